@@ -1,0 +1,64 @@
+"""Builds libcc3d_b200.so (hand-written sm_100a CUDA + C-ABI) in-tree with nvcc.
+
+  python connected-components-3d_b200/build.py [--force]
+
+The .so lands next to the Python host layer (cc3d_b200/libcc3d_b200.so); it is git-ignored but
+travels to the GPU box with gpurun. Translation units compile in parallel.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+OUT = os.path.join(HERE, "cc3d_b200", "libcc3d_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+UNITS = ["cc3d_b200.cu", "inst_u8.cu", "inst_u16.cu", "inst_u32.cu", "inst_u64.cu", "inst_f32.cu", "inst_f64.cu"]
+
+
+def _stale(target, deps):
+  if not os.path.exists(target):
+    return True
+  t = os.path.getmtime(target)
+  return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+  os.makedirs(OBJ, exist_ok=True)
+  headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+  headers.append(os.path.join(HERE, "..", "include", "cc3d_b200.h"))
+  jobs = []
+  for u in UNITS:
+    src = os.path.join(CSRC, u)
+    obj = os.path.join(OBJ, u.replace(".cu", ".o"))
+    if force or _stale(obj, [src] + headers):
+      jobs.append((src, obj))
+
+  def compile_one(job):
+    src, obj = job
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+      raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return r.stderr
+
+  with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+    logs = list(ex.map(compile_one, jobs))
+  objs = [os.path.join(OBJ, u.replace(".cu", ".o")) for u in UNITS]
+  if jobs or force or _stale(OUT, objs):
+    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+      raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+  if verbose:
+    for l in logs:
+      print(l)
+  return OUT
+
+
+if __name__ == "__main__":
+  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

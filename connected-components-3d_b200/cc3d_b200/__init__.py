@@ -1,0 +1,453 @@
+"""cc3d_b200 — B200-native drop-in for the hot path of seung-lab/connected-components-3d.
+
+    import cc3d_b200 as cc3d
+    labels, N = cc3d.connected_components(volume, connectivity=26, return_N=True)
+    stats = cc3d.statistics(labels)
+    clean = cc3d.dust(volume, threshold=100)
+
+Host layer = the reference's Cython/Python boundary logic (argument validation, layout
+normalisation, out-dtype rule; cc3d/fastcc3d.pyx:245-626, 682-938 and cc3d/__init__.py:71-155)
+re-expressed over the C-ABI in include/cc3d_b200.h. All compute runs in hand-written sm_100a CUDA
+kernels (csrc/); there is no CPU fallback. Inputs may be numpy arrays (staged through device
+memory), CPU torch tensors, or CUDA torch tensors (zero copy, result stays on the device).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Optional, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import CC3DB200Error
+
+__all__ = [
+  "connected_components", "statistics", "dust", "estimate_provisional_labels",
+  "DimensionError", "CC3DB200Error", "last_timings", "set_timing",
+]
+
+
+class DimensionError(Exception):
+  """The array has the wrong number of dimensions."""
+  pass
+
+
+_UNSIGNED = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
+_OUT_KIND = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}
+
+
+def _kind_of(dtype) -> int:
+  dtype = np.dtype(dtype)
+  if dtype == np.float32:
+    return _lib.F32
+  if dtype == np.float64:
+    return _lib.F64
+  if dtype == bool or np.issubdtype(dtype, np.integer):
+    return {1: _lib.U8, 2: _lib.U16, 4: _lib.U32, 8: _lib.U64}[dtype.itemsize]
+  raise TypeError(
+    f"Type {dtype} is not currently supported. "
+    f"Supported: bool, int8, int16, int32, int64, uint8, uint16, uint32, uint64, float16, float32, float64"
+  )
+
+
+def set_timing(enabled: bool) -> None:
+  """Record per-kernel CUDA-event timings for the following calls (see last_timings)."""
+  _lib.lib().cc3d_b200_set_timing(int(bool(enabled)))
+
+
+def last_timings():
+  return _lib.last_timings()
+
+
+# ----------------------------------------------------------------------------------------------
+# torch interop helpers (torch is optional: only touched when a tensor is passed in)
+# ----------------------------------------------------------------------------------------------
+def _is_torch(x) -> bool:
+  return hasattr(x, "cpu") and hasattr(x, "data_ptr")
+
+
+def _torch_np_dtype(t):
+  import torch
+  table = {
+    torch.bool: np.bool_, torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16,
+    torch.int32: np.int32, torch.int64: np.int64, torch.float16: np.float16,
+    torch.float32: np.float32, torch.float64: np.float64,
+  }
+  for name in ("uint16", "uint32", "uint64"):
+    if hasattr(torch, name):
+      table[getattr(torch, name)] = getattr(np, name)
+  if t.dtype not in table:
+    raise TypeError(f"Type {t.dtype} is not currently supported.")
+  return np.dtype(table[t.dtype])
+
+
+def _torch_dtype(np_dtype):
+  import torch
+  return {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64,
+          np.dtype(np.uint8): torch.uint8}[np.dtype(np_dtype)]
+
+
+def _torch_order(t) -> Tuple[Any, str]:
+  """Returns (tensor that is dense in memory, 'C' or 'F')."""
+  if t.is_contiguous():
+    return t, "C"
+  if t.ndim > 1 and t.permute(*reversed(range(t.ndim))).is_contiguous():
+    return t, "F"
+  return t.contiguous(), "C"
+
+
+# ----------------------------------------------------------------------------------------------
+# estimate_provisional_labels (fastcc3d.pyx:169-242)
+# ----------------------------------------------------------------------------------------------
+def estimate_provisional_labels(data: np.ndarray) -> Tuple[int, int, int]:
+  if _is_torch(data):
+    data = data.cpu().numpy()
+  sx = data.shape[0] if data.flags.f_contiguous else data.shape[-1]
+  if not (data.flags.f_contiguous or data.flags.c_contiguous):
+    data = np.ascontiguousarray(data)
+  kind = _kind_of(data.dtype)
+  epl, first, last = ctypes.c_uint64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+  rows = data.size // sx if sx else 0
+  _lib.check(_lib.lib().cc3d_b200_prepass(
+    data.ctypes.data, kind, sx, rows, 1, _lib.HOST,
+    ctypes.byref(epl), ctypes.byref(first), ctypes.byref(last), None, None, None))
+  return int(epl.value), int(first.value), int(last.value)
+
+
+def _even_ceil(n: int) -> int:
+  return n << 1 if n & 1 else n  # (sic) fastcc3d.pyx:163-166
+
+
+# ----------------------------------------------------------------------------------------------
+# connected_components (fastcc3d.pyx:245-626)
+# ----------------------------------------------------------------------------------------------
+def connected_components(
+  data, max_labels: int = -1, connectivity: int = 26, return_N: bool = False,
+  delta: Union[int, float] = 0, out_dtype: Optional[Any] = None, out_file=None,
+  periodic_boundary: bool = False, binary_image: bool = False,
+):
+  """Connected components of a 1D/2D/3D image; same contract as cc3d.connected_components.
+
+  connectivity: 6/18/26 (3D) or 4/8 (2D); delta > 0 joins values differing by <= delta;
+  binary_image treats non-zero as foreground; periodic_boundary wraps 4/8/6-connected images.
+  Components are numbered 1..N in order of first appearance in memory order. `max_labels` is
+  accepted and ignored, as in the reference (fastcc3d.pyx:263-268, 388).
+  """
+  L = _lib.lib()
+  is_torch = _is_torch(data)
+  on_device = False
+  tensor = None
+  if is_torch:
+    if data.is_cuda:
+      on_device = True
+      tensor, order = _torch_order(data.detach())
+      shape_in = tuple(tensor.shape)
+      dtype = _torch_np_dtype(tensor)
+      size = tensor.numel()
+    else:
+      data = data.cpu().numpy()
+
+  if not on_device:
+    shape_in = tuple(data.shape)
+    dtype = data.dtype
+    size = data.size
+
+  dims = len(shape_in)
+  if dims not in (1, 2, 3):
+    raise DimensionError("Only 1D, 2D, and 3D arrays supported. Got: " + str(dims))
+  if dims == 2 and connectivity not in (4, 8, 6, 18, 26):
+    raise ValueError("Only 4, 8, and 6, 18, 26 connectivities are supported for 2D images. Got: " + str(connectivity))
+  elif dims != 2 and connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  if periodic_boundary and connectivity not in (4, 8, 6):
+    raise ValueError(f"periodic_boundary is not yet implemented for {connectivity}-connectivity.")
+  if periodic_boundary and delta != 0:
+    raise ValueError("periodic_boundary is not yet implemented continuous data.")
+
+  if size == 0:
+    odt = dtype if out_dtype is None else out_dtype
+    out_labels = np.zeros(shape=(0,), dtype=odt)
+    if is_torch:
+      import torch
+      out_labels = torch.from_numpy(out_labels)
+      if on_device:
+        out_labels = out_labels.to(tensor.device)
+    return (out_labels, 0) if return_N else out_labels
+
+  if not on_device:
+    order = "F" if data.flags.f_contiguous else "C"
+    if not data.flags.c_contiguous and not data.flags.f_contiguous:
+      data = np.copy(data, order=order)
+
+  shape3 = list(shape_in)
+  while len(shape3) < 3:  # C: new leading axes, F: new trailing axes (fastcc3d.pyx:337-341)
+    shape3 = [1] + shape3 if order == "C" else shape3 + [1]
+
+  if dtype == np.float16:
+    if delta == 0:
+      dtype = np.dtype(np.uint16)
+    else:
+      raise TypeError("float16 is not supported for continuous images (delta != 0).")
+
+  sx, sy, sz = (shape3[::-1] if order == "C" else shape3)  # x = fastest memory axis
+  voxels = sx * sy * sz
+  kind = _kind_of(dtype)
+  orig_dtype = np.dtype(dtype)
+  binary_image = bool(binary_image) or orig_dtype == bool
+
+  if np.issubdtype(orig_dtype, np.floating):
+    delta = float(delta)
+    is_max_delta = (delta == np.finfo(orig_dtype).max)
+  else:
+    delta = int(delta)
+    is_max_delta = (orig_dtype != bool) and (delta == np.iinfo(orig_dtype).max)
+  epl_skipped = binary_image                      # fastcc3d.pyx:381-386
+  binary_image = binary_image or is_max_delta     # fastcc3d.pyx:390-395
+
+  # delta as one element of the kernel's element type (signed ints run as their unsigned views)
+  kdtype = orig_dtype
+  if orig_dtype == bool:
+    kdtype = np.dtype(np.uint8)
+  elif np.issubdtype(orig_dtype, np.signedinteger):
+    kdtype = np.dtype(_UNSIGNED[orig_dtype.itemsize])
+  with np.errstate(over="ignore"):
+    if np.issubdtype(kdtype, np.floating):
+      delta_arr = np.array([delta], dtype=kdtype)
+    else:
+      delta_arr = np.array([delta & ((1 << (8 * kdtype.itemsize)) - 1)], dtype=kdtype)
+
+  if on_device:
+    in_ptr, space = tensor.data_ptr(), _lib.DEVICE
+    import torch
+    stream = ctypes.c_void_p(torch.cuda.current_stream(tensor.device).cuda_stream)
+    dev_guard = torch.cuda.device(tensor.device)
+  else:
+    in_ptr, space = data.ctypes.data, _lib.HOST
+    stream = None
+    dev_guard = None
+
+  def resolve(periodic):
+    info = _lib.ResolveInfo()
+    sess = ctypes.c_void_p()
+    _lib.check(L.cc3d_b200_label_resolve(
+      in_ptr, kind, sx, sy, sz, int(connectivity), delta_arr.ctypes.data, int(binary_image),
+      int(periodic), space, stream, ctypes.byref(info), ctypes.byref(sess)))
+    return info, sess
+
+  if dev_guard is not None:
+    dev_guard.__enter__()
+  try:
+    info, sess = resolve(bool(periodic_boundary))
+    try:
+      if epl_skipped:
+        epl, first_row, last_row = voxels, 0, sy
+      else:
+        epl, first_row, last_row = int(info.epl), int(info.first_foreground_row), int(info.last_foreground_row)
+      # A single foreground row is labelled by a fast path that ignores periodic_boundary
+      # (fastcc3d.pyx:469-470, 644-679); reproduce that by labelling without the wrap.
+      if periodic_boundary and delta == 0 and first_row == last_row and first_row >= 0:
+        L.cc3d_b200_session_release(sess)
+        sess = None
+        info, sess = resolve(False)
+
+      max_lab = min(epl, voxels)
+      uf_voxels = _even_ceil(shape3[0]) * _even_ceil(shape3[1]) * _even_ceil(shape3[2])
+      if binary_image:
+        if connectivity in (4, 6):
+          max_lab = min(max_lab, (uf_voxels // 2) + 1)
+        else:  # (sic) 8 and 18 take the 26-connected bound, fastcc3d.pyx:412
+          max_lab = min(max_lab, (uf_voxels // 8) + 1)
+
+      if out_dtype is not None:
+        out_dtype = np.dtype(out_dtype)
+        if out_dtype not in (np.uint16, np.uint32, np.uint64):
+          raise ValueError(
+            f"Explicitly defined out_dtype ({out_dtype}) must be one of: np.uint16, np.uint32, np.uint64")
+        if np.iinfo(out_dtype).max < max_lab:
+          raise ValueError(
+            f"Explicitly defined out_dtype ({out_dtype}) is too small "
+            f"to contain the estimated maximum number of labels ({max_lab}).")
+      elif max_lab < np.iinfo(np.uint16).max:
+        out_dtype = np.dtype(np.uint16)
+      elif max_lab < np.iinfo(np.uint32).max:
+        out_dtype = np.dtype(np.uint32)
+      else:
+        out_dtype = np.dtype(np.uint64)
+
+      N = int(info.N)
+      if on_device:
+        import torch
+        out_flat = torch.empty((voxels,), dtype=_torch_dtype(out_dtype), device=tensor.device)
+        s2, sess = sess, None
+        _lib.check(L.cc3d_b200_label_write(s2, out_flat.data_ptr(), _OUT_KIND[out_dtype], _lib.DEVICE, stream))
+      else:
+        if out_file is None:
+          out_flat = np.empty((voxels,), dtype=out_dtype)
+        else:
+          import os
+          if isinstance(out_file, str):
+            with open(out_file, "wb") as f:
+              os.ftruncate(f.fileno(), voxels * np.dtype(out_dtype).itemsize)
+          out_flat = np.memmap(out_file, order="F", dtype=out_dtype, shape=(voxels,))
+        s2, sess = sess, None
+        _lib.check(L.cc3d_b200_label_write(s2, out_flat.ctypes.data, _OUT_KIND[out_dtype], _lib.HOST, stream))
+    finally:
+      if sess is not None and sess.value:
+        L.cc3d_b200_session_release(sess)
+  finally:
+    if dev_guard is not None:
+      dev_guard.__exit__(None, None, None)
+
+  # _final_reshape (fastcc3d.pyx:628-642)
+  if on_device:
+    if order == "C":
+      out_labels = out_flat.reshape(shape_in)
+    else:
+      out_labels = out_flat.reshape(tuple(reversed(shape_in))).permute(*reversed(range(dims)))
+  else:
+    out_labels = out_flat.reshape(shape_in, order=order)
+    if is_torch:
+      import torch
+      out_labels = torch.from_numpy(out_labels)
+
+  if return_N:
+    return (out_labels, N)
+  return out_labels
+
+
+# ----------------------------------------------------------------------------------------------
+# statistics (fastcc3d.pyx:682-938)
+# ----------------------------------------------------------------------------------------------
+def _statistics_arrays(out_labels, N: Optional[int] = None):
+  """Raw per-label arrays in ARRAY axes: counts u32[N+1], bbox u32[N+1, 2*ndim], sums u64[N+1, ndim]."""
+  L = _lib.lib()
+  ndim = out_labels.ndim
+  shape3 = list(out_labels.shape) + [1] * (3 - ndim)
+  forder = out_labels.flags.f_contiguous
+  if not (out_labels.flags.f_contiguous or out_labels.flags.c_contiguous):
+    out_labels = np.ascontiguousarray(out_labels)
+    forder = False
+  mem = shape3 if forder else shape3[::-1]
+  if N is None:
+    N = int(np.max(out_labels))
+  counts = np.empty(N + 1, dtype=np.uint32)
+  bbox = np.empty((N + 1, 6), dtype=np.uint32)
+  sums = np.empty((N + 1, 3), dtype=np.uint64)
+  _lib.check(L.cc3d_b200_statistics(
+    out_labels.ctypes.data, _kind_of(out_labels.dtype), mem[0], mem[1], mem[2], N,
+    counts.ctypes.data, bbox.ctypes.data, sums.ctypes.data, _lib.HOST, None))
+  if not forder:  # memory axes (x fastest) -> array axes
+    sums = sums[:, ::-1]
+    bbox = bbox.reshape(N + 1, 3, 2)[:, ::-1, :].reshape(N + 1, 6)
+  return counts, bbox[:, : 2 * ndim], sums[:, :ndim]
+
+
+def statistics(out_labels, no_slice_conversion: bool = False) -> dict:
+  """Voxel counts, bounding boxes and centroids per label; same contract as cc3d.statistics."""
+  if _is_torch(out_labels):
+    out_labels = out_labels.cpu().numpy()
+  while out_labels.ndim < 2:
+    out_labels = out_labels[..., np.newaxis]
+  if out_labels.dtype == bool:
+    out_labels = out_labels.view(np.uint8)
+  voxels = out_labels.size
+  if voxels == 0:
+    return {"voxel_counts": None, "bounding_boxes": None, "centroids": None}
+  N = int(np.max(out_labels))
+  if N > voxels:
+    raise ValueError(
+      f"Statistics can only be computed on volumes containing labels with values lower than the number of voxels. Max: {N}")
+  if np.issubdtype(out_labels.dtype, np.signedinteger):
+    N_min = int(np.min(out_labels))
+    if N_min < 0:
+      raise ValueError(
+        f"Statistics can only be computed on volumes containing labels with values >= 0. Min: {N_min}")
+    out_labels = out_labels.view(_UNSIGNED[out_labels.dtype.itemsize])
+  ndim = out_labels.ndim
+  shape3 = list(out_labels.shape) + [1] * (3 - ndim)
+  bdtype = np.uint32 if max(shape3) > np.iinfo(np.uint16).max else np.uint16
+
+  counts, bbox32, sums = _statistics_arrays(out_labels, N)
+  with np.errstate(invalid="ignore", divide="ignore"):
+    centroids = sums.astype(np.float64) / counts[:, None].astype(np.float64)
+  centroids[counts == 0] = np.nan
+  bbxes = np.where(bbox32 == np.iinfo(np.uint32).max, np.iinfo(bdtype).max, bbox32).astype(bdtype)
+  bbxes = np.ascontiguousarray(bbxes)
+  output = {
+    "voxel_counts": counts,
+    "bounding_boxes": bbxes,
+    "centroids": np.ascontiguousarray(centroids),
+  }
+  if no_slice_conversion:
+    return output
+  slices = []
+  for row in bbxes:
+    mins, maxs = row[0::2], row[1::2]
+    if all(int(m) < voxels for m in mins):  # fastcc3d.pyx:837, 931
+      slices.append(tuple(slice(int(a), int(b) + 1) for a, b in zip(mins, maxs)))
+    else:
+      slices.append(None)
+  output["bounding_boxes"] = slices
+  return output
+
+
+# ----------------------------------------------------------------------------------------------
+# dust (cc3d/__init__.py:71-155)
+# ----------------------------------------------------------------------------------------------
+def _view_as_unsigned(img):
+  if np.issubdtype(img.dtype, np.unsignedinteger) or img.dtype == bool:
+    return img
+  if np.issubdtype(img.dtype, np.signedinteger):
+    return img.view(_UNSIGNED[img.dtype.itemsize])
+  return img
+
+
+def dust(img, threshold, connectivity: int = 26, in_place: bool = False, binary_image: bool = False,
+         precomputed_ccl: bool = False, invert: bool = False, return_N: bool = False):
+  """Remove connected components smaller than threshold (or outside [lo, hi)); same contract as cc3d.dust."""
+  L = _lib.lib()
+  orig_dtype = img.dtype
+  img = _view_as_unsigned(img)
+  if not in_place:
+    img = np.copy(img)
+
+  if precomputed_ccl:
+    cc_labels = img
+    N = int(np.max(cc_labels))
+  else:
+    cc_labels, N = connected_components(img, connectivity=connectivity, return_N=True, binary_image=bool(binary_image))
+
+  stats = statistics(cc_labels, no_slice_conversion=True)
+  mask_sizes = stats["voxel_counts"]
+  del stats
+
+  sizes = mask_sizes[1:N + 1].astype(np.int64)
+  if isinstance(threshold, (tuple, list)):
+    masked = ~((threshold[0] <= sizes) & (sizes < threshold[1]))
+  else:
+    masked = sizes < threshold
+  n_mask = int(np.count_nonzero(masked))
+
+  dust_N = n_mask if invert else N - n_mask
+  if n_mask == 0:
+    if invert:
+      img = np.zeros(img.shape, dtype=img.dtype, order="F")
+    return (img, dust_N) if return_N else img
+
+  # np.isin(cc_labels, to_mask, invert=invert) -> zero where the mask is True (__init__.py:148-150)
+  keep = np.ones(N + 1, dtype=np.uint8)
+  keep[1:][masked] = 0
+  if invert:
+    keep = 1 - keep  # background (label 0) is "not in to_mask" -> masked when inverted
+  if not (img.flags.c_contiguous or img.flags.f_contiguous):
+    raise ValueError("dust requires a contiguous image")
+  same_layout = (cc_labels.flags.c_contiguous and img.flags.c_contiguous) or (cc_labels.flags.f_contiguous and img.flags.f_contiguous)
+  if not same_layout:
+    cc_labels = np.asarray(cc_labels, order="C" if img.flags.c_contiguous else "F")
+  if img.itemsize not in (1, 2, 4, 8) or img.dtype.kind not in "buif":
+    raise TypeError(f"Type {img.dtype} is not currently supported.")
+  _lib.check(L.cc3d_b200_mask_by_label(
+    img.ctypes.data, img.itemsize, cc_labels.ctypes.data, _kind_of(cc_labels.dtype), img.size,
+    keep.ctypes.data, N, _lib.HOST, None))
+  img = img.view(orig_dtype)
+  return (img, dust_N) if return_N else img

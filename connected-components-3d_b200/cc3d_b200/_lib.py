@@ -1,0 +1,83 @@
+"""ctypes binding of libcc3d_b200.so (C-ABI declared in include/cc3d_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or fails, the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcc3d_b200.so")
+
+HOST, DEVICE = 0, 1
+U8, U16, U32, U64, F32, F64 = range(6)
+
+
+class ResolveInfo(ctypes.Structure):
+  _fields_ = [
+    ("N", ctypes.c_uint64),
+    ("epl", ctypes.c_uint64),
+    ("first_foreground_row", ctypes.c_int64),
+    ("last_foreground_row", ctypes.c_int64),
+  ]
+
+
+class CC3DB200Error(RuntimeError):
+  def __init__(self, code, message):
+    super().__init__(f"cc3d_b200 error {code}: {message}")
+    self.code = code
+
+
+_lib = None
+
+
+def lib():
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise ImportError(
+      f"{LIB_PATH} not found: build it with `python connected-components-3d_b200/build.py` "
+      "(cc3d_b200 has no CPU fallback)"
+    )
+  L = ctypes.CDLL(LIB_PATH)
+  vp, i64, u64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int
+  p = ctypes.POINTER
+  L.cc3d_b200_last_error.restype = ctypes.c_char_p
+  L.cc3d_b200_version.restype = ctypes.c_char_p
+  L.cc3d_b200_prepass.restype = ci
+  L.cc3d_b200_prepass.argtypes = [vp, ci, i64, i64, i64, ci, p(u64), p(i64), p(i64), vp, vp, vp]
+  L.cc3d_b200_label_resolve.restype = ci
+  L.cc3d_b200_label_resolve.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, ci, vp, p(ResolveInfo), p(vp)]
+  L.cc3d_b200_label_write.restype = ci
+  L.cc3d_b200_label_write.argtypes = [vp, vp, ci, ci, vp]
+  L.cc3d_b200_session_release.restype = None
+  L.cc3d_b200_session_release.argtypes = [vp]
+  L.cc3d_b200_label.restype = ci
+  L.cc3d_b200_label.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, vp, ci, ci, p(u64), vp]
+  L.cc3d_b200_statistics.restype = ci
+  L.cc3d_b200_statistics.argtypes = [vp, ci, i64, i64, i64, u64, vp, vp, vp, ci, vp]
+  L.cc3d_b200_mask_by_label.restype = ci
+  L.cc3d_b200_mask_by_label.argtypes = [vp, ci, vp, ci, i64, vp, u64, ci, vp]
+  L.cc3d_b200_workspace_bytes.restype = ctypes.c_size_t
+  L.cc3d_b200_release_workspace.restype = None
+  L.cc3d_b200_set_timing.restype = None
+  L.cc3d_b200_set_timing.argtypes = [ci]
+  L.cc3d_b200_last_timings.restype = ci
+  L.cc3d_b200_last_timings.argtypes = [p(ctypes.c_char_p), p(ctypes.c_float), ci]
+  _lib = L
+  return L
+
+
+def check(rc):
+  if rc != 0:
+    raise CC3DB200Error(rc, lib().cc3d_b200_last_error().decode())
+
+
+def last_timings():
+  L = lib()
+  names = (ctypes.c_char_p * 64)()
+  ms = (ctypes.c_float * 64)()
+  n = L.cc3d_b200_last_timings(names, ms, 64)
+  return [(names[i].decode(), float(ms[i])) for i in range(n)]

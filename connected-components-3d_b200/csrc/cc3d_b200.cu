@@ -1,0 +1,555 @@
+// cc3d_b200.cu — C-ABI (include/cc3d_b200.h) and host orchestration of the kernel pipeline.
+// No CPU fallback exists: every entry point runs CUDA kernels or fails with an error code.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cc3d_b200.h"
+#include "cc3d_dispatch.cuh"
+#include "cc3d_misc.cuh"
+#include "cc3d_resolve.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_OK(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(CC3D_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+size_t kind_size(int kind) {
+  switch (kind) {
+    case CC3D_B200_U8: return 1;
+    case CC3D_B200_U16: return 2;
+    case CC3D_B200_U32: case CC3D_B200_F32: return 4;
+    case CC3D_B200_U64: case CC3D_B200_F64: return 8;
+  }
+  return 0;
+}
+
+// ---- device arena: one cached allocation reused across calls ----
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  int device = -1;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    void* p = base + off;
+    off += bytes;
+    return p;
+  }
+};
+std::mutex g_pool_mu;
+Arena g_cached;  // at most one idle arena is kept
+
+int arena_acquire(size_t bytes, Arena* out) {
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_cached.base && g_cached.device == dev && g_cached.cap >= bytes) {
+      *out = g_cached; out->off = 0;
+      g_cached = Arena();
+      return 0;
+    }
+    if (g_cached.base) { cudaFree(g_cached.base); g_cached = Arena(); }
+  }
+  Arena a;
+  a.device = dev;
+  a.cap = bytes + (bytes >> 4) + (1 << 20);
+  cudaError_t e = cudaMalloc((void**)&a.base, a.cap);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
+  *out = a;
+  return 0;
+}
+void arena_release(Arena& a) {
+  if (!a.base) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_cached.base) {
+    if (g_cached.cap >= a.cap) { cudaFree(a.base); a = Arena(); return; }
+    cudaFree(g_cached.base);
+  }
+  g_cached = a; g_cached.off = 0;
+  a = Arena();
+}
+
+// ---- optional per-kernel timing ----
+thread_local bool g_timing = false;
+struct Mark { const char* name; cudaEvent_t ev; };
+thread_local std::vector<Mark> g_marks;
+thread_local std::vector<std::pair<const char*, float>> g_last_timings;
+void mark(const char* name, cudaStream_t s) {
+  if (!g_timing) return;
+  Mark m; m.name = name;
+  cudaEventCreate(&m.ev);
+  cudaEventRecord(m.ev, s);
+  g_marks.push_back(m);
+}
+void marks_begin(cudaStream_t s) { if (g_timing) { for (auto& m : g_marks) cudaEventDestroy(m.ev); g_marks.clear(); mark("start", s); } }
+void marks_collect(bool append) {
+  if (!g_timing) return;
+  if (!append) g_last_timings.clear();
+  for (size_t i = 1; i < g_marks.size(); i++) {
+    float ms = 0;
+    cudaEventSynchronize(g_marks[i].ev);
+    cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev);
+    g_last_timings.push_back({g_marks[i].name, ms});
+  }
+  for (auto& m : g_marks) cudaEventDestroy(m.ev);
+  g_marks.clear();
+}
+
+__global__ void k_init_counters(Counters* c) { c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; }
+
+Geom make_geom(i64 sx, i64 sy, i64 sz) {
+  Geom g;
+  g.sx = sx; g.sy = sy; g.sz = sz;
+  int TZ = (int)std::min<i64>(8, sz);
+  int TY = (int)std::min<i64>(64 / TZ, sy);
+  g.TY = TY; g.TZ = TZ;
+  g.ntx = (sx + CC_TX - 1) / CC_TX;
+  g.nty = (sy + TY - 1) / TY;
+  g.ntz = (sz + TZ - 1) / TZ;
+  g.W = (sx + 31) / 32;
+  return g;
+}
+
+int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n, u64* total_dev, cudaStream_t s) {
+  const i64 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  k_scan_reduce<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n);
+  k_scan_blocks<<<1, 1024, 0, s>>>(bsum, nb, total_dev);
+  k_scan_apply<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, prefix, n);
+  return 0;
+}
+
+}  // namespace
+
+struct cc3d_b200_session {
+  Arena arena;
+  Geom g;
+  i64 voxels = 0;
+  u32* L = nullptr;
+  u32* LR = nullptr;
+  u64 N = 0;
+};
+
+// (definitions below inherit C linkage from their declarations in include/cc3d_b200.h)
+
+const char* cc3d_b200_last_error(void) { return g_err.c_str(); }
+const char* cc3d_b200_version(void) { return "cc3d_b200 0.1 (sm_100a)"; }
+void cc3d_b200_set_timing(int enabled) { g_timing = enabled != 0; }
+int cc3d_b200_last_timings(const char** names, float* ms, int cap) {
+  int n = 0;
+  for (auto& t : g_last_timings) { if (n >= cap) break; names[n] = t.first; ms[n] = t.second; n++; }
+  return n;
+}
+size_t cc3d_b200_workspace_bytes(void) { std::lock_guard<std::mutex> lk(g_pool_mu); return g_cached.cap; }
+void cc3d_b200_release_workspace(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_cached.base) cudaFree(g_cached.base);
+  g_cached = Arena();
+}
+
+static int check_shape(i64 sx, i64 sy, i64 sz) {
+  if (sx < 0 || sy < 0 || sz < 0) return fail(CC3D_B200_ERR_ARGUMENT, "negative dimension");
+  if (sx >= (1ll << 31) || sy >= (1ll << 31) || sz >= (1ll << 31)) return fail(CC3D_B200_ERR_ARGUMENT, "dimension >= 2^31");
+  return 0;
+}
+
+template <typename T>
+static int prepass_typed(const T* in, const Geom& g, Counters* ctr, T* range2, Arena& ar, cudaStream_t s) {
+  const int blocks = 148 * 8;
+  T* pmin = (T*)ar.take(sizeof(T) * blocks);
+  T* pmax = (T*)ar.take(sizeof(T) * blocks);
+  k_prepass<T><<<blocks, 256, 0, s>>>(in, g, ctr, pmin, pmax);
+  k_minmax_final<T><<<1, 32, 0, s>>>(pmin, pmax, blocks, range2);
+  return 0;
+}
+
+static int prepass_dispatch(const void* in, int kind, const Geom& g, Counters* ctr, void* range2, Arena& ar, cudaStream_t s) {
+  switch (kind) {
+    case CC3D_B200_U8: return prepass_typed((const uint8_t*)in, g, ctr, (uint8_t*)range2, ar, s);
+    case CC3D_B200_U16: return prepass_typed((const uint16_t*)in, g, ctr, (uint16_t*)range2, ar, s);
+    case CC3D_B200_U32: return prepass_typed((const uint32_t*)in, g, ctr, (uint32_t*)range2, ar, s);
+    case CC3D_B200_U64: return prepass_typed((const uint64_t*)in, g, ctr, (uint64_t*)range2, ar, s);
+    case CC3D_B200_F32: return prepass_typed((const float*)in, g, ctr, (float*)range2, ar, s);
+    case CC3D_B200_F64: return prepass_typed((const double*)in, g, ctr, (double*)range2, ar, s);
+  }
+  return -1;
+}
+
+int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int mem_space,
+                      uint64_t* epl, int64_t* first_row, int64_t* last_row, void* vmin, void* vmax, void* stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  const size_t es = kind_size(in_kind);
+  if (!es) return fail(CC3D_B200_ERR_KIND, "unsupported input kind");
+  const i64 voxels = sx * sy * sz;
+  if (epl) *epl = 0;
+  if (first_row) *first_row = -1;
+  if (last_row) *last_row = -1;
+  if (voxels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar;
+  const size_t need = (mem_space == CC3D_B200_HOST ? (size_t)voxels * es : 0) + (1 << 16);
+  if (int rc = arena_acquire(need, &ar)) return rc;
+  const void* din = in;
+  if (mem_space == CC3D_B200_HOST) {
+    void* d = ar.take((size_t)voxels * es);
+    cudaError_t e = cudaMemcpyAsync(d, in, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    din = d;
+  }
+  Counters* ctr = (Counters*)ar.take(sizeof(Counters));
+  void* range2 = ar.take(16);
+  Geom g = make_geom(sx, sy, sz);
+  k_init_counters<<<1, 1, 0, s>>>(ctr);
+  prepass_dispatch(din, in_kind, g, ctr, range2, ar, s);
+  Counters h;
+  unsigned char hr[16];
+  cudaError_t e = cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hr, range2, 16, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e));
+  if (epl) *epl = h.epl;
+  if (first_row) *first_row = h.epl ? h.first_row : -1;
+  if (last_row) *last_row = h.epl ? h.last_row : -1;
+  if (vmin) memcpy(vmin, hr, es);
+  if (vmax) memcpy(vmax, hr + es, es);
+  return 0;
+}
+
+static int label_stage_dispatch(int kind, const LabelArgs& a) {
+  switch (kind) {
+    case CC3D_B200_U8: return run_label_stage<uint8_t>(a);
+    case CC3D_B200_U16: return run_label_stage<uint16_t>(a);
+    case CC3D_B200_U32: return run_label_stage<uint32_t>(a);
+    case CC3D_B200_U64: return run_label_stage<uint64_t>(a);
+    case CC3D_B200_F32: return run_label_stage<float>(a);
+    case CC3D_B200_F64: return run_label_stage<double>(a);
+  }
+  return -1;
+}
+
+template <typename T>
+static void c8_mask_typed(const T* in, unsigned char* mask, i64 sx, i64 sy, const void* delta, const void* range, cudaStream_t s) {
+  T d;
+  memcpy(&d, delta, sizeof(T));
+  const i64 n = sx * sy;
+  k_c8_mask<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, mask, sx, sy, d, (const T*)range);
+}
+
+int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                            const void* delta, int binary_image, int periodic_boundary, int mem_space,
+                            void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session) {
+  if (!info || !session) return fail(CC3D_B200_ERR_ARGUMENT, "info/session must not be NULL");
+  *session = nullptr;
+  info->N = 0; info->epl = 0; info->first_foreground_row = -1; info->last_foreground_row = -1;
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  const size_t es = kind_size(in_kind);
+  if (!es) return fail(CC3D_B200_ERR_KIND, "unsupported input kind");
+  if (connectivity != 4 && connectivity != 8 && connectivity != 6 && connectivity != 18 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "Only 4 and 8 2D and 6, 18, and 26 3D connectivities are supported.");
+  if ((connectivity == 4 || connectivity == 8) && sz != 1)
+    return fail(CC3D_B200_ERR_2D_NEEDS_SZ1, "sz must be 1 for 2D connectivities.");
+  // dispatch precedence of cc3d_continuous.hpp:394-455: binary -> delta == 0 -> continuous
+  bool delta_zero = true;
+  if (delta) { for (size_t i = 0; i < es; i++) if (((const unsigned char*)delta)[i]) delta_zero = false; }
+  if (delta && !delta_zero && (in_kind == CC3D_B200_F32 || in_kind == CC3D_B200_F64)) {
+    // -0.0 compares equal to 0
+    double d = in_kind == CC3D_B200_F32 ? (double)*(const float*)delta : *(const double*)delta;
+    if (d == 0.0) delta_zero = true;
+  }
+  int mode = binary_image ? MODE_NONZERO : (delta_zero ? MODE_EQ : MODE_DELTA);
+  if (mode == MODE_DELTA && periodic_boundary)
+    return fail(CC3D_B200_ERR_PERIODIC_CONTINUOUS, "periodic_boundary is not currently supported for continuous data.");
+  const bool c8 = (mode == MODE_DELTA && connectivity == 8);
+  const bool block_order = (mode == MODE_NONZERO && connectivity == 8);
+
+  const i64 voxels = sx * sy * sz;
+  cc3d_b200_session* S = new cc3d_b200_session();
+  S->voxels = voxels;
+  if (voxels == 0) { *session = S; return 0; }
+  if ((u64)voxels >= 0xFFFFFFFFull) {
+    delete S;
+    return fail(CC3D_B200_ERR_TOO_LARGE, "volume has >= 2^32-1 voxels; use the sharded path");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  Geom g = make_geom(sx, sy, sz);
+  S->g = g;
+  const i64 rows = sy * sz;
+  const i64 nwords = rows * g.W;
+  const i64 nslots = rows * (g.ntx - 1);
+  const i64 nb = (nwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  const i64 nblocks2d = block_order ? ((sx + 1) / 2) * ((sy + 1) / 2) : 0;
+  const i64 nbwords = (nblocks2d + 31) / 32;
+
+  size_t need = 4096;
+  auto add = [&](size_t b) { need += ((b + 255) & ~size_t(255)) + 256; };
+  if (mem_space == CC3D_B200_HOST) add((size_t)voxels * es);
+  if (c8) add((size_t)voxels);
+  add((size_t)voxels * 4);          // L
+  add((size_t)nwords * 4 * 4);      // LR GR cnt prefix
+  add((size_t)nslots * 4 + 4);      // XS
+  add((size_t)(nb + 1) * 8);        // bsum
+  add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
+  if (block_order) { add((size_t)voxels * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
+  if (int rc = arena_acquire(need, &S->arena)) { delete S; return rc; }
+  Arena& ar = S->arena;
+
+  marks_begin(s);
+  const void* din = in;
+  if (mem_space == CC3D_B200_HOST) {
+    void* d = ar.take((size_t)voxels * es);
+    cudaError_t e = cudaMemcpyAsync(d, in, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    din = d;
+    mark("H2D", s);
+  }
+  u32* L = (u32*)ar.take((size_t)voxels * 4);
+  u32* LR = (u32*)ar.take((size_t)nwords * 4);
+  u32* GR = (u32*)ar.take((size_t)nwords * 4);
+  u32* cnt = (u32*)ar.take((size_t)nwords * 4);
+  u32* prefix = (u32*)ar.take((size_t)nwords * 4);
+  u32* XS = (u32*)ar.take((size_t)nslots * 4 + 4);
+  u64* bsum = (u64*)ar.take((size_t)(nb + 1) * 8);
+  Counters* ctr = (Counters*)ar.take(sizeof(Counters));
+  S->L = L; S->LR = LR;
+
+  k_init_counters<<<1, 1, 0, s>>>(ctr);
+
+  LabelArgs a;
+  a.L = L; a.LR = LR; a.XS = XS; a.ctr = ctr; a.g = g;
+  a.connectivity = connectivity; a.periodic = periodic_boundary; a.stream = s;
+  a.mark = g_timing ? mark : nullptr;
+  memset(a.delta, 0, 8);
+  if (delta) memcpy(a.delta, delta, es);
+  int rc;
+  if (c8) {
+    // epl + value range, then the reference's per-pixel edge rule as a bitfield, then mask-mode labelling
+    void* range2 = ar.take(16);
+    unsigned char* maskbuf = (unsigned char*)ar.take((size_t)voxels);
+    prepass_dispatch(din, in_kind, g, ctr, range2, ar, s);
+    switch (in_kind) {
+      case CC3D_B200_U8: c8_mask_typed((const uint8_t*)din, maskbuf, sx, sy, delta, range2, s); break;
+      case CC3D_B200_U16: c8_mask_typed((const uint16_t*)din, maskbuf, sx, sy, delta, range2, s); break;
+      case CC3D_B200_U32: c8_mask_typed((const uint32_t*)din, maskbuf, sx, sy, delta, range2, s); break;
+      case CC3D_B200_U64: c8_mask_typed((const uint64_t*)din, maskbuf, sx, sy, delta, range2, s); break;
+      case CC3D_B200_F32: c8_mask_typed((const float*)din, maskbuf, sx, sy, delta, range2, s); break;
+      case CC3D_B200_F64: c8_mask_typed((const double*)din, maskbuf, sx, sy, delta, range2, s); break;
+    }
+    mark("c8_mask", s);
+    a.in = maskbuf; a.mode = MODE_MASK;
+    rc = run_label_stage<uint8_t>(a);
+  } else {
+    a.in = din; a.mode = mode;
+    rc = label_stage_dispatch(in_kind, a);
+  }
+  if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
+
+  const unsigned wblocks = (unsigned)((nwords + 255) / 256);
+  k_compress<<<wblocks, 256, 0, s>>>(L, LR, GR, cnt, g, nwords);
+  mark("C1_compress", s);
+  scan_counts(cnt, prefix, bsum, nwords, &ctr->N, s);
+  mark("C2_scan", s);
+  if (block_order) {
+    u32* K = (u32*)ar.take((size_t)voxels * 4);
+    u32* BK = (u32*)ar.take((size_t)nbwords * 4);
+    u32* bcnt = (u32*)ar.take((size_t)nbwords * 4);
+    u32* bprefix = (u32*)ar.take((size_t)nbwords * 4);
+    u64* bsum2 = (u64*)ar.take(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8);
+    u64* dummyN = (u64*)ar.take(8);
+    cudaMemsetAsync(BK, 0, (size_t)nbwords * 4, s);
+    k_blockkey_init<<<wblocks, 256, 0, s>>>(K, GR, g, nwords);
+    k_blockkey_min<<<(unsigned)((nwords * 32 + 255) / 256), 256, 0, s>>>(L, LR, K, g);
+    k_blockkey_mark<<<wblocks, 256, 0, s>>>(K, GR, BK, g, nwords);
+    k_popc<<<(unsigned)((nbwords + 255) / 256), 256, 0, s>>>(BK, bcnt, nbwords);
+    scan_counts(bcnt, bprefix, bsum2, nbwords, dummyN, s);
+    k_assign_blockorder<<<wblocks, 256, 0, s>>>(L, LR, GR, K, BK, bprefix, g, nwords);
+    mark("C3_assign_blockorder", s);
+  } else {
+    k_assign<<<wblocks, 256, 0, s>>>(L, LR, GR, prefix, g, nwords);
+    mark("C3_assign", s);
+  }
+  Counters h;
+  cudaError_t e = cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e)); }
+  marks_collect(false);
+  S->N = h.N;
+  info->N = h.N;
+  info->epl = h.epl;
+  info->first_foreground_row = h.epl ? h.first_row : -1;
+  info->last_foreground_row = h.epl ? h.last_row : -1;
+  *session = S;
+  return 0;
+}
+
+void cc3d_b200_session_release(cc3d_b200_session* S) {
+  if (!S) return;
+  arena_release(S->arena);
+  delete S;
+}
+
+int cc3d_b200_label_write(cc3d_b200_session* S, void* out, int out_kind, int mem_space, void* stream) {
+  if (!S) return fail(CC3D_B200_ERR_ARGUMENT, "NULL session");
+  const size_t os = (out_kind == CC3D_B200_U16) ? 2 : (out_kind == CC3D_B200_U32 ? 4 : (out_kind == CC3D_B200_U64 ? 8 : 0));
+  if (!os) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_KIND, "out kind must be u16, u32 or u64"); }
+  if (S->voxels == 0) { cc3d_b200_session_release(S); return 0; }
+  if ((os == 2 && S->N > 0xFFFFull) || (os == 4 && S->N > 0xFFFFFFFFull)) {
+    cc3d_b200_session_release(S);
+    return fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const Geom& g = S->g;
+  void* dout = out;
+  if (mem_space == CC3D_B200_HOST) {
+    // the arena was sized for the resolve phase; the output staging buffer may need its own allocation
+    if (S->arena.off + (size_t)S->voxels * os + 512 <= S->arena.cap) dout = S->arena.take((size_t)S->voxels * os);
+    else {
+      cudaError_t e = cudaMalloc(&dout, (size_t)S->voxels * os);
+      if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+  }
+  marks_begin(s);
+  const unsigned blocks = (unsigned)((g.sy * g.sz * g.W * 32 + 255) / 256);
+  if (os == 2) k_write<uint16_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g);
+  else if (os == 4) k_write<uint32_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g);
+  else k_write<uint64_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g);
+  mark("D_write", s);
+  cudaError_t e = cudaSuccess;
+  if (mem_space == CC3D_B200_HOST) {
+    e = cudaMemcpyAsync(out, dout, (size_t)S->voxels * os, cudaMemcpyDeviceToHost, s);
+    mark("D2H", s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  marks_collect(true);
+  if (mem_space == CC3D_B200_HOST) {
+    const char* b = S->arena.base;
+    if (!((const char*)dout >= b && (const char*)dout < b + S->arena.cap)) cudaFree(dout);
+  }
+  cc3d_b200_session_release(S);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("label_write: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                    const void* delta, int binary_image, int periodic_boundary, void* out, int out_kind,
+                    int mem_space, uint64_t* N, void* stream) {
+  cc3d_b200_resolve_info info;
+  cc3d_b200_session* S = nullptr;
+  int rc = cc3d_b200_label_resolve(in, in_kind, sx, sy, sz, connectivity, delta, binary_image, periodic_boundary,
+                                   mem_space, stream, &info, &S);
+  if (rc) return rc;
+  if (N) *N = info.N;
+  return cc3d_b200_label_write(S, out, out_kind, mem_space, stream);
+}
+
+template <typename LT>
+static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts, u32* bbox, u64* sums, cudaStream_t s) {
+  static bool attr = false;
+  auto k = k_statistics<LT>;
+  if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable)); attr = true; }
+  k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
+  k<<<148 * 2, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums);
+  return 0;
+}
+
+int cc3d_b200_statistics(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, uint64_t N,
+                         uint32_t* counts, uint32_t* bbox, uint64_t* sums, int mem_space, void* stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  const size_t es = kind_size(kind);
+  if (!es || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "labels must be u8/u16/u32/u64");
+  if (N >= 0xFFFFFFFEull) return fail(CC3D_B200_ERR_TOO_LARGE, "N must be < 2^32-2");
+  const i64 voxels = sx * sy * sz;
+  if (voxels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  Geom g = make_geom(sx, sy, sz);
+  Arena ar;
+  const void* dl = labels;
+  u32 *dc = counts, *db = bbox;
+  u64* ds = sums;
+  const size_t n1 = (size_t)N + 1;
+  if (mem_space == CC3D_B200_HOST) {
+    if (int rc = arena_acquire((size_t)voxels * es + n1 * (4 + 24 + 24) + 4096, &ar)) return rc;
+    void* d = ar.take((size_t)voxels * es);
+    dc = (u32*)ar.take(n1 * 4); db = (u32*)ar.take(n1 * 24); ds = (u64*)ar.take(n1 * 24);
+    cudaError_t e = cudaMemcpyAsync(d, labels, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    dl = d;
+  }
+  switch (kind) {
+    case CC3D_B200_U8: statistics_typed((const uint8_t*)dl, g, N, dc, db, ds, s); break;
+    case CC3D_B200_U16: statistics_typed((const uint16_t*)dl, g, N, dc, db, ds, s); break;
+    case CC3D_B200_U32: statistics_typed((const uint32_t*)dl, g, N, dc, db, ds, s); break;
+    default: statistics_typed((const uint64_t*)dl, g, N, dc, db, ds, s); break;
+  }
+  cudaError_t e = cudaSuccess;
+  if (mem_space == CC3D_B200_HOST) {
+    e = cudaMemcpyAsync(counts, dc, n1 * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bbox, db, n1 * 24, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums, ds, n1 * 24, cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("statistics: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+template <typename IT>
+static void mask_typed(IT* img, const void* labels, int label_kind, const unsigned char* keep, u64 N, i64 n, cudaStream_t s) {
+  const unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 32);
+  switch (label_kind) {
+    case CC3D_B200_U8: k_mask_by_label<IT, uint8_t><<<blocks, 256, 0, s>>>(img, (const uint8_t*)labels, keep, N, n); break;
+    case CC3D_B200_U16: k_mask_by_label<IT, uint16_t><<<blocks, 256, 0, s>>>(img, (const uint16_t*)labels, keep, N, n); break;
+    case CC3D_B200_U32: k_mask_by_label<IT, uint32_t><<<blocks, 256, 0, s>>>(img, (const uint32_t*)labels, keep, N, n); break;
+    default: k_mask_by_label<IT, uint64_t><<<blocks, 256, 0, s>>>(img, (const uint64_t*)labels, keep, N, n); break;
+  }
+}
+
+int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int label_kind, int64_t voxels,
+                            const uint8_t* keep, uint64_t N, int mem_space, void* stream) {
+  const size_t ls = kind_size(label_kind);
+  if (!ls || label_kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "labels must be u8/u16/u32/u64");
+  if (img_itemsize != 1 && img_itemsize != 2 && img_itemsize != 4 && img_itemsize != 8)
+    return fail(CC3D_B200_ERR_KIND, "img itemsize must be 1, 2, 4 or 8");
+  if (voxels <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar;
+  void* dimg = img; const void* dl = labels; const unsigned char* dk = keep;
+  if (mem_space == CC3D_B200_HOST) {
+    if (int rc = arena_acquire((size_t)voxels * (img_itemsize + ls) + N + 1 + 4096, &ar)) return rc;
+    dimg = ar.take((size_t)voxels * img_itemsize);
+    void* l = ar.take((size_t)voxels * ls);
+    unsigned char* k = (unsigned char*)ar.take(N + 1);
+    cudaMemcpyAsync(dimg, img, (size_t)voxels * img_itemsize, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(l, labels, (size_t)voxels * ls, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(k, keep, N + 1, cudaMemcpyHostToDevice, s);
+    dl = l; dk = k;
+  }
+  switch (img_itemsize) {
+    case 1: mask_typed((uint8_t*)dimg, dl, label_kind, dk, N, voxels, s); break;
+    case 2: mask_typed((uint16_t*)dimg, dl, label_kind, dk, N, voxels, s); break;
+    case 4: mask_typed((uint32_t*)dimg, dl, label_kind, dk, N, voxels, s); break;
+    default: mask_typed((uint64_t*)dimg, dl, label_kind, dk, N, voxels, s); break;
+  }
+  cudaError_t e = cudaSuccess;
+  if (mem_space == CC3D_B200_HOST) e = cudaMemcpyAsync(img, dimg, (size_t)voxels * img_itemsize, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("mask_by_label: ") + cudaGetErrorString(e));
+  return 0;
+}
+

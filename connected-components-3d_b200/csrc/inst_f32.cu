@@ -1,0 +1,5 @@
+// Instantiates the labelling-stage kernels (A, B1, B2, P) for element type float.
+#define CC3D_INSTANTIATE
+#include <cstring>
+#include "cc3d_dispatch.cuh"
+template int run_label_stage<float>(const LabelArgs&);

@@ -1,0 +1,124 @@
+/* cc3d_b200.h — C-ABI of the B200-native connected-components engine.
+ *
+ * Drop-in boundary for the hot path of seung-lab/connected-components-3d (cc3d 4.x): these entry
+ * points replace the C++ template the reference's Cython layer binds,
+ *
+ *   cc3d::connected_components3d<T,OUT>(T* in_labels, sx, sy, sz, max_labels, connectivity, delta,
+ *                                      OUT* out_labels, size_t& N, periodic_boundary, binary_image)
+ *   declared  cc3d/fastcc3d.pyx:67-74, defined cc3d/cc3d_continuous.hpp:394-455,
+ *   18 instantiations at cc3d/fastcc3d.pyx:471-608,
+ *
+ * plus the pre-pass cc3d::estimate_provisional_label_count<T> (cc3d/cc3d.hpp:287-315, bound at
+ * cc3d/fastcc3d.pyx:60-66) and the Cython statistics loops (cc3d/fastcc3d.pyx:771-938) and the
+ * masking step of dust (cc3d/__init__.py:121-151).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only. `x` is the fastest-varying memory axis (the reference reverses
+ *     C-order shapes before the call, fastcc3d.pyx:352-359), so index = x + sx*(y + sy*z).
+ *   - `mem_space`: CC3D_B200_HOST pointers are staged through device memory inside the call;
+ *     CC3D_B200_DEVICE pointers are used in place (zero copy).
+ *   - `stream` is a cudaStream_t (NULL = default stream). Calls are synchronous with respect to
+ *     the host on return unless stated otherwise.
+ *   - All functions return 0 on success or a negative cc3d_b200_status; cc3d_b200_last_error()
+ *     gives the message (thread-local).
+ *   - Signed integers are passed as their unsigned views, bool as u8, float16 (delta==0) as u16,
+ *     exactly as the reference does (fastcc3d.pyx:346-350, 472-563).
+ */
+#ifndef CC3D_B200_H
+#define CC3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CC3D_B200_U8 = 0, CC3D_B200_U16 = 1, CC3D_B200_U32 = 2, CC3D_B200_U64 = 3,
+  CC3D_B200_F32 = 4, CC3D_B200_F64 = 5
+} cc3d_b200_kind;
+
+typedef enum { CC3D_B200_HOST = 0, CC3D_B200_DEVICE = 1 } cc3d_b200_mem_space;
+
+typedef enum {
+  CC3D_B200_OK = 0,
+  CC3D_B200_ERR_CONNECTIVITY = -1, /* "Only 4 and 8 2D and 6, 18, and 26 3D connectivities are supported." cc3d.hpp:1469 */
+  CC3D_B200_ERR_2D_NEEDS_SZ1 = -2, /* "sz must be 1 for 2D connectivities." cc3d.hpp:1451-1452 */
+  CC3D_B200_ERR_PERIODIC_CONTINUOUS = -3, /* cc3d_continuous.hpp:423-425 */
+  CC3D_B200_ERR_KIND = -4,
+  CC3D_B200_ERR_TOO_LARGE = -5,    /* more voxels than one call supports (use the sharded path) */
+  CC3D_B200_ERR_CUDA = -6,
+  CC3D_B200_ERR_ARGUMENT = -7,
+  CC3D_B200_ERR_OUT_RANGE = -8     /* N does not fit the requested out kind */
+} cc3d_b200_status;
+
+/* Results of the resolve phase that the caller needs before it can allocate the output
+ * (the reference's out-dtype rule depends on epl, fastcc3d.pyx:373-434). */
+typedef struct {
+  uint64_t N;                 /* number of connected components */
+  uint64_t epl;               /* cc3d.hpp:287-315 transition count (0 for mask mode) */
+  int64_t first_foreground_row; /* -1 when there is no foreground */
+  int64_t last_foreground_row;
+} cc3d_b200_resolve_info;
+
+typedef struct cc3d_b200_session cc3d_b200_session;
+
+const char* cc3d_b200_last_error(void);
+const char* cc3d_b200_version(void);
+
+/* Row a1: estimate_provisional_label_count (cc3d.hpp:287-315; fastcc3d.pyx:169-242).
+ * Also returns the value range needed by the continuous 2D-8 path (vmin/vmax may be NULL; each
+ * points at one element of the input kind). */
+int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int mem_space,
+                      uint64_t* epl, int64_t* first_foreground_row, int64_t* last_foreground_row,
+                      void* vmin, void* vmax, void* stream);
+
+/* Rows a3-a11, phase 1: label + merge + resolve. Leaves the resolved union-find forest in the
+ * session and reports N / epl so that the caller can apply the out-dtype rule and allocate.
+ * `delta` points at one element of the input kind (ignored when binary_image != 0).
+ * Dispatch precedence is the reference's: binary -> delta == 0 -> continuous. */
+int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz,
+                            int connectivity, const void* delta, int binary_image,
+                            int periodic_boundary, int mem_space, void* stream,
+                            cc3d_b200_resolve_info* info, cc3d_b200_session** session);
+
+/* Rows a10/a12, phase 2: write final labels 1..N (first-appearance order) as out_kind
+ * (CC3D_B200_U16/U32/U64). May be called once per session; releases the session. */
+int cc3d_b200_label_write(cc3d_b200_session* session, void* out, int out_kind, int mem_space,
+                          void* stream);
+
+/* Drops a session without writing. */
+void cc3d_b200_session_release(cc3d_b200_session* session);
+
+/* One-shot convenience: resolve + write into a caller-chosen out kind. */
+int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                    const void* delta, int binary_image, int periodic_boundary, void* out,
+                    int out_kind, int mem_space, uint64_t* N, void* stream);
+
+/* Row a13: per-label statistics in MEMORY axes (x fastest). counts[N+1] (uint32, wraps like the
+ * reference), bbox[(N+1)*6] uint32 as xmin,xmax,ymin,ymax,zmin,zmax (absent label: min=UINT32_MAX,
+ * max=0), sums[(N+1)*3] uint64 coordinate sums (centroid = sum / count, exact below 2^53).
+ * Labels > N are ignored. Output arrays live in the same mem_space as `labels`. */
+int cc3d_b200_statistics(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, uint64_t N,
+                         uint32_t* counts, uint32_t* bbox, uint64_t* sums, int mem_space, void* stream);
+
+/* Row a14: masking step of dust: img[i] = keep[labels[i]] ? img[i] : 0, in place.
+ * keep has N+1 bytes (index = label). img_itemsize in {1,2,4,8}. */
+int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int label_kind,
+                            int64_t voxels, const uint8_t* keep, uint64_t N, int mem_space, void* stream);
+
+/* Device-memory workspace currently cached by the library on the active device (bytes), and a
+ * call that frees it. */
+size_t cc3d_b200_workspace_bytes(void);
+void cc3d_b200_release_workspace(void);
+
+/* Per-kernel device times (ms) of the last label call on this thread, for bench/profiling.
+ * names[i] points at static strings; returns the number of entries filled (<= cap). */
+int cc3d_b200_last_timings(const char** names, float* ms, int cap);
+void cc3d_b200_set_timing(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CC3D_B200_H */
