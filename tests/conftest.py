@@ -1,0 +1,43 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "connected-components-3d_b200")):
+  if p not in sys.path:
+    sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+  config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu():
+  try:
+    import torch
+    return torch.cuda.is_available()
+  except Exception:
+    return False
+
+
+def pytest_collection_modifyitems(config, items):
+  if _has_gpu():
+    return
+  skip = pytest.mark.skip(reason="no CUDA device")
+  for item in items:
+    if "gpu" in item.keywords:
+      item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+  from oracle import oracle
+  oracle.build()
+  return oracle
+
+
+@pytest.fixture(scope="session")
+def cc3d():
+  import cc3d_b200
+  return cc3d_b200

@@ -1,0 +1,73 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/cc3d_b200.h declares (no compute calls - there is no GPU here), and argument validation
+that happens before any CUDA call behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cc3d_b200.h")
+
+
+def declared_symbols():
+  src = open(HEADER).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  return sorted(set(re.findall(r"\b(cc3d_b200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+  syms = declared_symbols()
+  for s in ["cc3d_b200_prepass", "cc3d_b200_label_resolve", "cc3d_b200_label_write", "cc3d_b200_label",
+            "cc3d_b200_statistics", "cc3d_b200_mask_by_label", "cc3d_b200_last_error"]:
+    assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+  from cc3d_b200 import _lib
+  assert os.path.exists(_lib.LIB_PATH), "build with python connected-components-3d_b200/build.py"
+  L = ctypes.CDLL(_lib.LIB_PATH)
+  for s in declared_symbols():
+    assert hasattr(L, s), f"{s} declared in include/cc3d_b200.h but not exported"
+  assert b"sm_100a" in L.cc3d_b200_version.__call__.__self__.restype.__class__.__name__.encode() or True
+  _lib.lib()
+  assert "sm_100a" in _lib.lib().cc3d_b200_version().decode()
+
+
+def test_library_contains_sm100a_code():
+  from cc3d_b200 import _lib
+  import subprocess
+  out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True)
+  if out.returncode != 0:
+    pytest.skip("cuobjdump unavailable")
+  assert "sm_100a" in out.stdout
+
+
+def test_python_validation_matches_reference_errors(cc3d):
+  with pytest.raises(cc3d.DimensionError):
+    cc3d.connected_components(np.zeros((2, 2, 2, 2), np.uint8))
+  with pytest.raises(ValueError):
+    cc3d.connected_components(np.zeros((4, 4, 4), np.uint8), connectivity=8)
+  with pytest.raises(ValueError):
+    cc3d.connected_components(np.zeros((4, 4), np.uint8), connectivity=5)
+  with pytest.raises(ValueError):
+    cc3d.connected_components(np.zeros((4, 4, 4), np.uint8), connectivity=26, periodic_boundary=True)
+  with pytest.raises(ValueError):
+    cc3d.connected_components(np.zeros((4, 4, 4), np.uint8), connectivity=6, periodic_boundary=True, delta=1)
+  out, N = cc3d.connected_components(np.zeros((0, 0), np.uint32), return_N=True)
+  assert out.size == 0 and N == 0 and out.dtype == np.uint32
+  assert cc3d.statistics(np.zeros((0, 0), np.uint32)) == {"voxel_counts": None, "bounding_boxes": None, "centroids": None}
+
+
+def test_no_cpu_fallback_without_gpu(cc3d):
+  """On a box without a CUDA device the product path must fail loudly, never compute on the CPU."""
+  try:
+    import torch
+    if torch.cuda.is_available():
+      pytest.skip("GPU present")
+  except ImportError:
+    pass
+  with pytest.raises(cc3d.CC3DB200Error):
+    cc3d.connected_components(np.ones((4, 4, 4), np.uint8))

@@ -1,0 +1,126 @@
+"""CPU tests: the oracle (plain-C restatement, oracle/cc3d_oracle.c) is pinned against
+(1) golden vectors generated from the unmodified reference (tests/golden/, make_golden.py),
+(2) the reference itself when oracle/_ref is built here, and (3) an independent graph spec."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_labels, call_kwargs, golden_manifest, load_golden, spec_oracle, blobs
+
+MANIFEST = golden_manifest()
+
+
+@pytest.mark.parametrize("case", MANIFEST, ids=[c["name"] for c in MANIFEST])
+def test_oracle_matches_golden(oracle_mod, case):
+  x, labels, N, z = load_golden(case["name"])
+  out, No = oracle_mod.connected_components(x, return_N=True, **call_kwargs(case["kw"]))
+  assert_same_labels(labels, N, out, No, case["name"])
+
+
+@pytest.mark.parametrize("case", MANIFEST[::3], ids=[c["name"] for c in MANIFEST[::3]])
+def test_oracle_statistics_match_golden(oracle_mod, case):
+  x, labels, N, z = load_golden(case["name"])
+  st = oracle_mod.statistics(labels, no_slice_conversion=True)
+  assert np.array_equal(st["voxel_counts"], z["voxel_counts"])
+  assert np.array_equal(st["bounding_boxes"], z["bounding_boxes"])
+  assert st["bounding_boxes"].dtype == z["bounding_boxes"].dtype
+  assert np.array_equal(st["centroids"], z["centroids"], equal_nan=True)
+
+
+def test_oracle_vs_reference_fuzz(oracle_mod):
+  ref = oracle_mod.reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built (needs /root/reference)")
+  rng = np.random.default_rng(7)
+  dtypes = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int64, np.float32, np.float64, bool]
+  checked = 0
+  for it in range(400):
+    dims = int(rng.integers(1, 4))
+    shape = tuple(int(rng.integers(1, 13)) for _ in range(dims))
+    dt = dtypes[rng.integers(len(dtypes))]
+    order = "F" if rng.random() < 0.5 else "C"
+    x = (rng.random(shape) < 0.5) if dt == bool else rng.integers(0, 4, shape).astype(dt)
+    x = np.asarray(x, order=order)
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    c = conns[rng.integers(len(conns))]
+    kw = {}
+    mode = int(rng.integers(0, 4))
+    fast = x.shape[0] if order == "F" else x.shape[-1]
+    if mode == 1:
+      kw["binary_image"] = True
+      x = np.asarray((x != 0).astype(x.dtype), order=order)
+    elif mode == 2 and dt != bool:
+      kw["delta"] = int(rng.integers(1, 3))
+    elif mode == 3 and c in (4, 8, 6):
+      kw["periodic_boundary"] = True
+    if (kw.get("binary_image") or dt == bool) and c == 8 and fast % 2 == 1:
+      continue  # reference defect D1
+    try:
+      a, Na = ref.connected_components(x, connectivity=c, return_N=True, **kw)
+    except RuntimeError:
+      continue  # reference union-find overflow on tiny binary inputs (defect D3)
+    b, Nb = oracle_mod.connected_components(x, connectivity=c, return_N=True, **kw)
+    assert_same_labels(a, Na, b, Nb, f"{shape} {dt} {order} {c} {kw}")
+    checked += 1
+  assert checked > 300
+
+
+@pytest.mark.parametrize("conn,mode", [(26, "eq"), (18, "eq"), (6, "eq"), (26, "nonzero"), (6, "delta"), (26, "delta")])
+def test_oracle_vs_graph_spec(oracle_mod, conn, mode):
+  rng = np.random.default_rng(conn * 7 + len(mode))
+  for shape in [(9, 8, 7), (16, 5, 6), (5, 17, 3)]:
+    if mode == "delta":
+      x = np.asfortranarray((blobs(rng, shape, 3, 2) * 10 + rng.integers(0, 4, shape)).astype(np.uint8))
+      a, Na = oracle_mod.connected_components(x, connectivity=conn, delta=3, return_N=True)
+      b, Nb = spec_oracle(x, conn, "delta", 3)
+    elif mode == "nonzero":
+      x = np.asfortranarray((rng.random(shape) < 0.4).astype(np.uint8))
+      a, Na = oracle_mod.connected_components(x, connectivity=conn, binary_image=True, return_N=True)
+      b, Nb = spec_oracle(x, conn, "nonzero")
+    else:
+      x = np.asfortranarray(rng.integers(0, 3, shape).astype(np.uint16))
+      a, Na = oracle_mod.connected_components(x, connectivity=conn, return_N=True)
+      b, Nb = spec_oracle(x, conn, "eq")
+    assert Na == Nb
+    assert np.array_equal(a, b)
+
+
+def test_oracle_periodic_vs_torus_spec(oracle_mod):
+  rng = np.random.default_rng(3)
+  for conn, shape in [(6, (7, 6, 5)), (4, (9, 8)), (8, (9, 8))]:
+    x = np.asfortranarray(rng.integers(0, 3, shape).astype(np.uint8))
+    if x.reshape(-1, order="F")[: shape[0]].any() and np.count_nonzero(x.any(axis=0)) <= 1:
+      continue
+    a, Na = oracle_mod.connected_components(x, connectivity=conn, periodic_boundary=True, return_N=True)
+    b, Nb = spec_oracle(x, conn, "eq", periodic=True)
+    assert Na == Nb and np.array_equal(a, b)
+
+
+def test_oracle_dtype_rule_and_errors(oracle_mod):
+  x = np.zeros((8, 8, 8), np.uint8)
+  assert oracle_mod.connected_components(x).dtype == np.uint16
+  assert oracle_mod.connected_components(x, out_dtype=np.uint64).dtype == np.uint64
+  with pytest.raises(ValueError):
+    oracle_mod.connected_components(x, out_dtype=np.uint8)
+  big = (np.arange(41 ** 3, dtype=np.uint32) + 1).reshape(41, 41, 41)
+  with pytest.raises(ValueError):
+    oracle_mod.connected_components(big, out_dtype=np.uint16)
+  assert oracle_mod.connected_components(big).dtype == np.uint32
+  with pytest.raises(TypeError):
+    oracle_mod.connected_components(np.ones((4, 4), np.float16), delta=1)
+  out, N = oracle_mod.connected_components(np.zeros((0, 0), np.uint32), return_N=True)
+  assert out.size == 0 and N == 0
+
+
+def test_oracle_dust_matches_reference(oracle_mod):
+  ref = oracle_mod.reference_module()
+  rng = np.random.default_rng(11)
+  x = np.asfortranarray(rng.integers(0, 3, (20, 20, 20)).astype(np.uint8))
+  out, dN = oracle_mod.dust(x, threshold=5, connectivity=6, return_N=True)
+  lab, N = oracle_mod.connected_components(x, connectivity=6, return_N=True)
+  cnt = oracle_mod.statistics(lab, no_slice_conversion=True)["voxel_counts"]
+  keep = cnt >= 5
+  keep[0] = False
+  assert np.array_equal(out, x * keep[lab])
+  assert dN == int(np.count_nonzero(keep))
+  if ref is not None:
+    assert np.array_equal(ref.statistics(lab, no_slice_conversion=True)["voxel_counts"], cnt)

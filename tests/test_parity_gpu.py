@@ -1,0 +1,267 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Every call goes through the C-ABI
+(libcc3d_b200.so via the Python host layer); results are compared bit-exactly with
+ - the golden vectors generated from the unmodified reference (tests/golden/),
+ - the plain-C oracle (oracle/cc3d_oracle.c) on seeded random inputs,
+ - the reference build itself (oracle/_ref) when it travelled with the repo,
+ - size-independent properties at BASELINE.json's full sizes."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import assert_same_labels, blobs, call_kwargs, golden_manifest, load_golden, spec_oracle
+
+pytestmark = pytest.mark.gpu
+MANIFEST = golden_manifest()
+
+
+@pytest.mark.parametrize("case", MANIFEST, ids=[c["name"] for c in MANIFEST])
+def test_golden_labels(cc3d, case):
+  x, labels, N, z = load_golden(case["name"])
+  out, No = cc3d.connected_components(x, return_N=True, **call_kwargs(case["kw"]))
+  assert_same_labels(labels, N, out, No, case["name"])
+
+
+@pytest.mark.parametrize("case", MANIFEST, ids=[c["name"] for c in MANIFEST])
+def test_golden_statistics(cc3d, case):
+  x, labels, N, z = load_golden(case["name"])
+  st = cc3d.statistics(labels, no_slice_conversion=True)
+  assert st["voxel_counts"].dtype == z["voxel_counts"].dtype
+  assert np.array_equal(st["voxel_counts"], z["voxel_counts"])
+  assert st["bounding_boxes"].dtype == z["bounding_boxes"].dtype
+  assert np.array_equal(st["bounding_boxes"], z["bounding_boxes"])
+  assert np.array_equal(st["centroids"], z["centroids"], equal_nan=True)
+
+
+def _truth(oracle_mod):
+  ref = oracle_mod.reference_module()
+  return ref if ref is not None else oracle_mod
+
+
+def _fuzz(cc3d, truth, seed, ncase, maxdim):
+  rng = np.random.default_rng(seed)
+  dtypes = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64, np.float32, np.float64, bool]
+  checked = 0
+  for it in range(ncase):
+    dims = int(rng.integers(1, 4))
+    shape = tuple(int(rng.integers(1, maxdim)) for _ in range(dims))
+    if dims == 2 and rng.random() < 0.4:
+      shape = (int(rng.integers(1, 400)), int(rng.integers(1, 400)))
+    dt = dtypes[rng.integers(len(dtypes))]
+    order = "F" if rng.random() < 0.5 else "C"
+    nvals = int(rng.integers(2, 6))
+    if dt == bool:
+      x = rng.random(shape) < rng.random()
+    elif rng.random() < 0.4:
+      x = blobs(rng, shape, nvals, int(rng.integers(2, 6))).astype(dt)
+    else:
+      x = rng.integers(0, nvals, shape).astype(dt)
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    c = conns[rng.integers(len(conns))]
+    mode = int(rng.integers(0, 4))
+    kw = {}
+    if mode == 1:
+      kw["binary_image"] = True
+      x = (x != 0).astype(x.dtype)
+    elif mode == 2 and dt != bool:
+      if np.issubdtype(dt, np.floating):
+        x = ((x * 3 + rng.random(shape) * 2.5) * (x != 0)).astype(dt)
+        kw["delta"] = float(rng.random() * 3)
+      else:
+        x = (x * 3 + rng.integers(0, 3, shape) * (x != 0)).astype(dt)
+        kw["delta"] = int(rng.integers(1, 4))
+    elif mode == 3 and c in (4, 8, 6):
+      kw["periodic_boundary"] = True
+    x = np.asarray(x, order=order)
+    fast = x.shape[0] if order == "F" else x.shape[-1]
+    if (kw.get("binary_image") or dt == bool) and c == 8 and fast % 2 == 1:
+      continue  # reference defect D1: stale labels for odd sx
+    try:
+      a, Na = truth.connected_components(x, connectivity=c, return_N=True, **kw)
+    except RuntimeError:
+      continue  # reference union-find overflow (defect D3)
+    b, Nb = cc3d.connected_components(x, connectivity=c, return_N=True, **kw)
+    assert_same_labels(a, Na, b, Nb, f"{shape} {np.dtype(dt)} {order} conn={c} {kw}")
+    checked += 1
+  return checked
+
+
+def test_differential_fuzz_small(cc3d, oracle_mod):
+  assert _fuzz(cc3d, _truth(oracle_mod), seed=101, ncase=500, maxdim=24) > 400
+
+
+def test_differential_fuzz_seams(cc3d, oracle_mod):
+  """Shapes that cross several 64x8x8 tiles in every axis."""
+  assert _fuzz(cc3d, _truth(oracle_mod), seed=202, ncase=150, maxdim=150) > 100
+
+
+def test_c_oracle_agrees_too(cc3d, oracle_mod):
+  assert _fuzz(cc3d, oracle_mod, seed=303, ncase=200, maxdim=40) > 150
+
+
+@pytest.mark.parametrize("conn", [6, 18, 26])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_3d_all_different(cc3d, conn, order):
+  # automated_test.py:261-270
+  x = (np.arange(100 * 99 * 98, dtype=np.uint32) + 1).reshape((100, 99, 98), order=order)
+  out, N = cc3d.connected_components(x, connectivity=conn, return_N=True)
+  assert N == x.size and out.dtype == np.uint32 and out.shape == x.shape
+  assert np.array_equal(out.reshape(-1, order=order), np.arange(1, x.size + 1, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("conn", [6, 18, 26])
+def test_scipy_equality_random_binary(cc3d, conn):
+  # automated_test.py:499-554: numbering equals scipy.ndimage.label on C-ordered bool volumes
+  import scipy.ndimage
+  rng = np.random.default_rng(conn)
+  x = rng.random((128, 128, 128)) < 0.5
+  structure = {6: None, 18: scipy.ndimage.generate_binary_structure(3, 2), 26: np.ones((3, 3, 3))}[conn]
+  want, n = scipy.ndimage.label(x, structure=structure)
+  out, N = cc3d.connected_components(x, connectivity=conn, return_N=True)
+  assert N == n and np.array_equal(out, want)
+
+
+def test_binary_equals_multilabel_on_mask(cc3d):
+  # automated_test.py:1644-1661
+  rng = np.random.default_rng(5)
+  x = rng.integers(0, 4, (96, 80, 72)).astype(np.uint8)
+  for conn in (6, 18, 26):
+    a, Na = cc3d.connected_components(x, connectivity=conn, binary_image=True, return_N=True)
+    b, Nb = cc3d.connected_components((x > 0).astype(np.uint8), connectivity=conn, return_N=True)
+    assert Na == Nb and np.array_equal(a, b)
+
+
+def test_graph_spec_multilabel_and_continuous(cc3d):
+  rng = np.random.default_rng(9)
+  x = np.asfortranarray(blobs(rng, (70, 40, 30), 4, 3).astype(np.uint32))
+  for conn in (6, 18, 26):
+    a, Na = cc3d.connected_components(x, connectivity=conn, return_N=True)
+    b, Nb = spec_oracle(x, conn, "eq")
+    assert Na == Nb and np.array_equal(a, b)
+  xf = np.asfortranarray(((blobs(rng, (70, 40, 30), 3, 5) + 1) * 64 + rng.uniform(-4, 4, (70, 40, 30))).astype(np.float32))
+  for conn in (6, 26):
+    a, Na = cc3d.connected_components(xf, connectivity=conn, delta=10, return_N=True)
+    b, Nb = spec_oracle(xf, conn, "delta", 10)
+    assert Na == Nb and np.array_equal(a, b)
+
+
+def test_dtype_rule_and_special_cases(cc3d):
+  assert cc3d.connected_components(np.zeros((64, 64, 64), np.uint8)).dtype == np.uint16
+  for od in (np.uint16, np.uint32, np.uint64):
+    assert cc3d.connected_components(np.zeros((32, 32, 32), np.uint8), out_dtype=od).dtype == od
+  with pytest.raises(ValueError):
+    cc3d.connected_components(np.zeros((8, 8, 8), np.uint8), out_dtype=np.uint8)
+  with pytest.raises(ValueError):
+    cc3d.connected_components((np.arange(41 ** 3, dtype=np.uint32) + 1).reshape(41, 41, 41), out_dtype=np.uint16)
+  out = cc3d.connected_components((np.arange(40 ** 3, dtype=np.uint32) + 1).reshape(40, 40, 40))
+  assert out.dtype == np.uint16
+  out, N = cc3d.connected_components(np.array([[[1, 1, 1, 1]]]), return_N=True)
+  assert N == 1 and np.all(out == 1)
+  # test_epl_special_case (automated_test.py:453-483)
+  x = np.zeros((10, 10, 10), np.uint8, order="F"); x[:, 5, 5] = 1
+  assert cc3d.estimate_provisional_labels(x) == (1, 55, 55)
+  out = cc3d.connected_components(x)
+  assert out.dtype == np.uint16 and np.array_equal(out, x)
+  with pytest.raises(TypeError):
+    cc3d.connected_components(np.ones((4, 4), np.float16), delta=1)
+
+
+def test_estimate_provisional_labels_matches_oracle(cc3d, oracle_mod):
+  rng = np.random.default_rng(13)
+  for dt in (np.uint8, np.uint32, np.int64, np.float32, np.float64):
+    for order in "CF":
+      x = np.asarray(blobs(rng, (70, 33, 9), 4, 3).astype(dt), order=order)
+      assert cc3d.estimate_provisional_labels(x) == oracle_mod.estimate_provisional_labels(x)
+  assert cc3d.estimate_provisional_labels(np.zeros((5, 5, 5), np.uint8)) == (0, -1, -1)
+
+
+def test_statistics_and_dust_against_oracle(cc3d, oracle_mod):
+  rng = np.random.default_rng(17)
+  for shape, order in [((50, 40, 30), "F"), ((50, 40, 30), "C"), ((300, 200), "F"), ((300, 200), "C")]:
+    img = np.asarray(blobs(rng, shape, 5, 3).astype(np.uint32), order=order)
+    lab, N = cc3d.connected_components(img, connectivity=6, return_N=True)
+    a, b = cc3d.statistics(lab), oracle_mod.statistics(lab)
+    assert np.array_equal(a["voxel_counts"], b["voxel_counts"])
+    assert a["bounding_boxes"] == b["bounding_boxes"]
+    assert np.array_equal(a["centroids"], b["centroids"], equal_nan=True)
+    for thr, inv in [(30, False), (30, True), ((10, 200), False), ((10, 200), True), (0, False)]:
+      da, na = cc3d.dust(img, thr, connectivity=6, invert=inv, return_N=True)
+      db, nb = oracle_mod.dust(img, thr, connectivity=6, invert=inv, return_N=True)
+      assert na == nb and da.dtype == db.dtype and np.array_equal(da, db), (shape, order, thr, inv)
+  # signed input comes back signed (cc3d/__init__.py:102-103,151)
+  img = rng.integers(0, 3, (40, 40, 40)).astype(np.int16)
+  out = cc3d.dust(img, 20)
+  assert out.dtype == np.int16 and np.array_equal(out, oracle_mod.dust(img, 20))
+
+
+def test_statistics_absent_labels_and_big_dims(cc3d, oracle_mod):
+  lab = np.zeros((10, 10), np.uint32); lab[2:4, 5:9] = 7
+  a, b = cc3d.statistics(lab), oracle_mod.statistics(lab)
+  assert np.array_equal(a["voxel_counts"], b["voxel_counts"]) and a["bounding_boxes"] == b["bounding_boxes"]
+  assert np.array_equal(a["centroids"], b["centroids"], equal_nan=True)
+  wide = np.zeros((70000, 2), np.uint8); wide[66000:, 1] = 1
+  a = cc3d.statistics(wide, no_slice_conversion=True)
+  assert a["bounding_boxes"].dtype == np.uint32 and list(a["bounding_boxes"][1]) == [66000, 69999, 1, 1]
+
+
+def test_torch_cpu_and_cuda_tensors(cc3d):
+  import torch
+  rng = np.random.default_rng(21)
+  x = blobs(rng, (40, 50, 60), 4, 3).astype(np.int32)
+  want, N = cc3d.connected_components(x, return_N=True)
+  t = torch.from_numpy(x)
+  got, n = cc3d.connected_components(t, return_N=True)          # CPU tensor in -> CPU tensor out
+  assert isinstance(got, torch.Tensor) and n == N and np.array_equal(got.numpy(), want)
+  got, n = cc3d.connected_components(t.cuda(), return_N=True)   # device tensor: zero copy, stays on device
+  assert got.is_cuda and n == N and np.array_equal(got.cpu().numpy(), want)
+  tf = t.cuda().permute(2, 1, 0)                                # Fortran-ordered view
+  wantf, Nf = cc3d.connected_components(np.asfortranarray(x.transpose(2, 1, 0)), return_N=True)
+  gotf, nf = cc3d.connected_components(tf, return_N=True)
+  assert nf == Nf and np.array_equal(gotf.cpu().numpy(), wantf)
+
+
+def test_full_size_properties_512(cc3d):
+  """BASELINE configs at full size: size-independent properties (idempotence, binary==multilabel,
+  label range, N == number of distinct labels)."""
+  import torch
+  import benchdata
+  x = benchdata.random_binary((512, 512, 512), 0.5, 1, "cuda")
+  for conn in (6, 26):
+    lab, N = cc3d.connected_components(x, connectivity=conn, return_N=True)
+    labb, Nb = cc3d.connected_components(x, connectivity=conn, binary_image=True, return_N=True)
+    l64 = lab.to(torch.int64)
+    assert N == Nb and torch.equal(l64, labb.to(torch.int64))
+    assert int(l64.max()) == N and bool(((l64 > 0) == (x > 0)).all())
+    again, N2 = cc3d.connected_components(lab.to(torch.int32), connectivity=conn, return_N=True)
+    assert N2 == N and torch.equal(again.to(torch.int64), l64)   # idempotent: relabelling a labelling is the identity
+    first = torch.unique(l64[l64 > 0], sorted=False)
+    assert first.numel() == N
+  v = benchdata.voronoi_multilabel((512, 512, 512), cell=40, seed=2, device="cuda", dtype=torch.int32)
+  lab, N = cc3d.connected_components(v, connectivity=26, return_N=True)
+  l64 = lab.to(torch.int64).reshape(-1)
+  # first-appearance numbering: the running maximum of the labels in memory order increases by at most 1
+  cm = torch.cummax(l64, 0).values
+  assert int(cm[0]) <= 1 and int((cm[1:] - cm[:-1]).max()) <= 1 and int(cm[-1]) == N
+
+
+def test_connectomics_known_answers(cc3d):
+  """config #1: N and sha256 of the labelling of the reference's own benchmark volume."""
+  from oracle import decode_connectomics
+  vol = decode_connectomics.load_fixture()
+  if vol is None:
+    pytest.skip("oracle/_ref/connectomics_512_u32.npz did not travel")
+  assert hashlib.sha256(vol.tobytes(order="F")).hexdigest() == decode_connectomics.SHA
+  assert cc3d.estimate_provisional_labels(vol) == (4730127, 0, 262143)
+  out, N = cc3d.connected_components(vol, connectivity=26, return_N=True)
+  assert N == 3619 and out.dtype == np.uint32
+  assert hashlib.sha256(out.tobytes(order="F")).hexdigest() == "8e11e41a9a83a8fe3f59f84f016665e6a8d1f9036b9533286f12e04b421c8d49"
+  st = cc3d.statistics(out, no_slice_conversion=True)
+  assert list(st["voxel_counts"][:5]) == [1018433, 36827584, 3695, 151, 4336]
+  assert list(st["bounding_boxes"][1]) == [0, 511, 0, 511, 0, 357]
+  assert np.allclose(st["centroids"][1], [281.75905283, 164.67780751, 144.57447961], rtol=0, atol=1e-8)
+  out6, N6 = cc3d.connected_components(vol, connectivity=6, return_N=True)
+  assert N6 == 4744
+  assert hashlib.sha256(out6.tobytes(order="F")).hexdigest() == "cef5d8cecd2ac9b119323dfce62df3020d3be2520e4672003f50c864013a0ccc"
+  assert cc3d.connected_components(vol, connectivity=18, return_N=True)[1] == 3657
+  _, kept = cc3d.dust(vol, threshold=100, connectivity=26, return_N=True)
+  assert kept == 2810
