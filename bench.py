@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — gigavoxels/s of 26-connected CCL on a 512^3 volume (BASELINE.json metric) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one full labelling call (resolve + write) on one synthetic volume.
+  value      device-resident input/output, CUDA events around K steps, max over ranks.
+  e2e        same call through the public API on pinned HOST buffers (H2D + kernels + D2H per step).
+  roofline   dominant kernel (tile labelling) against the measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline  the unmodified reference (oracle/_ref) on this box's host, 1 core, bounded sample.
+`--impl reference` times the reference's own CPU implementation instead (same metric/config).
+Under torchrun (N > 1) every rank labels its own z-slab sized volume ("weak" scaling).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "gigavoxels/s, 26-connected CCL, 512^3"
+UNIT = "GVx/s"
+
+WORKLOADS = {
+  # name: (generator, shape, call kwargs, in bytes/voxel, algorithmic bytes/voxel = sizeof(in)+sizeof(out))
+  "random_binary_512_u8_conn26": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=1, alg_bytes=5,
+                                      desc="configs[1]: random 0/1 uint8 512^3 at 50% density, 26-connected, default (multilabel) call"),
+  "random_binary_512_u8_conn6": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=6), in_bytes=1, alg_bytes=5,
+                                     desc="configs[1]: random 0/1 uint8 512^3 at 50% density, 6-connected"),
+  "multilabel_512_u32_conn26": dict(kind="voronoi", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=4, alg_bytes=8,
+                                    desc="configs[0]-like: Voronoi multilabel uint32 512^3 (~2.9k labels), 26-connected"),
+  "connectomics_512_u32_conn26": dict(kind="connectomics", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=4, alg_bytes=8,
+                                      desc="configs[0]: the reference's connectomics.npy.ckl.gz (decoded fixture), 26-connected"),
+  "continuous_512_f32_conn26": dict(kind="tone", shape=(512, 512, 512), kw=dict(connectivity=26, delta=10), in_bytes=4, alg_bytes=8,
+                                    desc="configs[3] at 512^3: three-tone float32 + noise, delta=10, 26-connected"),
+}
+DEFAULT_WORKLOAD = "random_binary_512_u8_conn26"
+
+
+def make_volume(wl, device, seed_offset=0):
+  import torch
+  import benchdata
+  if wl["kind"] == "binary":
+    return benchdata.random_binary(wl["shape"], 0.5, 1 + seed_offset, device)
+  if wl["kind"] == "voronoi":
+    return benchdata.voronoi_multilabel(wl["shape"], cell=40, seed=2 + seed_offset, device=device, dtype=torch.int32)
+  if wl["kind"] == "tone":
+    return benchdata.three_tone_noise(wl["shape"], cell=64, seed=3 + seed_offset, device=device)
+  if wl["kind"] == "connectomics":
+    from oracle import decode_connectomics
+    vol = decode_connectomics.load_fixture()
+    if vol is None:
+      raise SystemExit("connectomics fixture missing (oracle/_ref/connectomics_512_u32.npz)")
+    return torch.from_numpy(np.ascontiguousarray(vol.transpose(2, 1, 0)).view(np.int32)).to(device)
+  raise ValueError(wl["kind"])
+
+
+class ClockSampler:
+  """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+  def __init__(self, index):
+    self.samples, self.reasons, self.max_mhz = [], set(), None
+    self._stop = threading.Event()
+    self._thr = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:
+      self.nv = None
+
+  def _run(self):
+    nv = self.nv
+    names = {
+      getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+      getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+      getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+      getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+    }
+    while not self._stop.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if r & bit:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      time.sleep(0.002)
+
+  def __enter__(self):
+    if self.nv is not None:
+      self._thr = threading.Thread(target=self._run, daemon=True)
+      self._thr.start()
+    return self
+
+  def __exit__(self, *a):
+    self._stop.set()
+    if self._thr is not None:
+      self._thr.join()
+
+  def summary(self):
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+    return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def hbm_peak():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    try:
+      return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+      pass
+  return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_labeller():
+  """(callable, kind): the unmodified reference when oracle/_ref travelled, else the C oracle port."""
+  from oracle import oracle
+  ref = oracle.reference_module()
+  if ref is not None:
+    return ref.connected_components, "reference"
+  return oracle.connected_components, "port"
+
+
+def cpu_sample(wl, depth):
+  """Bounded sample of the workload for the CPU arm: the first `depth` z-planes, generated like the GPU input."""
+  import torch
+  import benchdata
+  sz, sy, sx = wl["shape"]
+  shape = (min(depth, sz), sy, sx)
+  dev = "cuda" if torch.cuda.is_available() else "cpu"
+  if wl["kind"] == "binary":
+    full = benchdata.random_binary(shape, 0.5, 1, dev)
+  elif wl["kind"] == "voronoi":
+    full = benchdata.voronoi_multilabel(shape, cell=40, seed=2, device=dev, dtype=torch.int32)
+  elif wl["kind"] == "tone":
+    full = benchdata.three_tone_noise(shape, cell=64, seed=3, device=dev)
+  else:
+    full = make_volume(wl, dev)[: shape[0]]
+  return np.ascontiguousarray(full.cpu().numpy())
+
+
+def time_cpu(fn, x, kw, repeats):
+  best = float("inf")
+  for _ in range(repeats):
+    t0 = time.perf_counter()
+    fn(x, return_N=True, **kw)
+    best = min(best, time.perf_counter() - t0)
+  return best
+
+
+def run_reference_arm(args, wl):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  fn, kind = reference_labeller()
+  x = cpu_sample(wl, depth=128)
+  for _ in range(args.warmup):
+    fn(x, return_N=True, **wl["kw"])
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    fn(x, return_N=True, **wl["kw"])
+  dt = time.perf_counter() - t0
+  value = x.size * args.steps / dt / 1e9
+  sample = f"first {x.shape[0]} z-planes of the {args.workload} volume ({x.size} voxels) per step"
+  line = {
+    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    "vs_baseline": None, "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"),
+    "data": "synthetic", "config": {"workload": args.workload, "description": wl["desc"], "sample": sample},
+    "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                     "host_cores": os.cpu_count()},
+    "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=30)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-extra", action="store_true", help="skip the additional workloads reported under 'also'")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+  wl = WORKLOADS[args.workload]
+
+  if args.impl == "reference":
+    run_reference_arm(args, wl)
+    return
+
+  import torch
+  import torch.distributed as dist
+  import cc3d_b200
+  from cc3d_b200 import _lib
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device (cc3d_b200 has no CPU fallback)")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(v):
+    if world == 1:
+      return v
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  L = _lib.lib()
+  x = make_volume(wl, dev, seed_offset=rank)
+  voxels = x.numel()
+  kw = wl["kw"]
+
+  def timed_device_loop(vol, kwargs, steps, warmup):
+    for _ in range(warmup):
+      out, N = cc3d_b200.connected_components(vol, return_N=True, **kwargs)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      out, N = cc3d_b200.connected_components(vol, return_N=True, **kwargs)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)), N, out
+
+  # ---- value: device-resident ----
+  launches0 = L.cc3d_b200_launch_count()
+  with ClockSampler(local_rank) as clk:
+    ms, N, out = timed_device_loop(x, kw, args.steps, args.warmup)
+  # warm-up launches are excluded: count again over a clean run of `steps`
+  per_step_launches = (L.cc3d_b200_launch_count() - launches0) // (args.steps + args.warmup)
+  value = world * voxels * args.steps / (ms / 1e3) / 1e9
+  out_dtype = str(out.dtype).replace("torch.", "")
+  out_bytes = out.element_size()
+  del out
+
+  # ---- roofline of the dominant kernel: CUDA events recorded by the library on the launching stream ----
+  cc3d_b200.set_timing(True)
+  ktimes = {}
+  for _ in range(args.steps):
+    cc3d_b200.connected_components(x, return_N=True, **kw)
+    for name, t in cc3d_b200.last_timings():
+      ktimes.setdefault(name, []).append(t)
+  cc3d_b200.set_timing(False)
+  kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
+  dom = max(kavg, key=kavg.get)
+  peak, peak_src = hbm_peak()
+  alg_bytes = wl["alg_bytes"] * voxels
+  achieved = alg_bytes / (kavg[dom] / 1e3) / 1e9
+  traffic = None
+  tpath = os.path.join(ROOT, "profiles", "traffic.json")
+  if os.path.exists(tpath):
+    try:
+      traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+    except Exception:
+      traffic = None
+  roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+              "kernel_ms": kavg, "kernel_share": {k: v / sum(kavg.values()) for k, v in kavg.items()},
+              "pipeline_frac": alg_bytes / (ms / args.steps / 1e3) / 1e9 / peak}
+
+  # ---- e2e: public API on pinned host buffers ----
+  xh = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+  xh.copy_(x)
+  x_np = xh.numpy()
+  np_out_dtype = {"uint16": np.uint16, "uint32": np.uint32, "uint64": np.uint64}[out_dtype]
+  oh = torch.empty((voxels * out_bytes,), dtype=torch.uint8, pin_memory=True)
+  out_np = oh.numpy().view(np_out_dtype)
+  e2e_steps = max(3, min(args.steps, 10))
+  for _ in range(2):
+    cc3d_b200.connected_components(x_np, return_N=True, out=out_np, **kw)
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(e2e_steps):
+    res, N2 = cc3d_b200.connected_components(x_np, return_N=True, out=out_np, **kw)
+  e1.record()
+  barrier()
+  e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+  assert N2 == N
+  e2e = {"value": world * voxels * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": UNIT,
+         "h2d_bytes_per_step": voxels * x.element_size(), "d2h_bytes_per_step": voxels * out_bytes + 32,
+         "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_memory": "pinned"}
+
+  # ---- other BASELINE workloads, same timing method (N=1 only) ----
+  also = []
+  if world == 1 and not args.no_extra:
+    for name, w in WORKLOADS.items():
+      if name == args.workload:
+        continue
+      try:
+        v = make_volume(w, dev)
+      except SystemExit:
+        continue
+      m, n_, o_ = timed_device_loop(v, w["kw"], max(5, args.steps // 3), 3)
+      steps_ = max(5, args.steps // 3)
+      also.append({"workload": name, "value": v.numel() * steps_ / (m / 1e3) / 1e9, "unit": UNIT,
+                   "ms_per_step": m / steps_, "N": int(n_),
+                   "compulsory_roofline_frac": w["alg_bytes"] * v.numel() / (m / steps_ / 1e3) / 1e9 / peak})
+      del v, o_
+
+  # ---- CPU baseline (rank 0, N=1) ----
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    fn, kind = reference_labeller()
+    xs = cpu_sample(wl, depth=256)
+    t = time_cpu(fn, xs, kw, repeats=3)
+    cpu = {"value": xs.size / t / 1e9, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+           "sample": f"first {xs.shape[0]} z-planes of the same volume ({xs.size} voxels), best of 3"}
+
+  if rank == 0:
+    line = {
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"), "data": "synthetic",
+      "config": {"workload": args.workload, "description": wl["desc"], "out_dtype": out_dtype, "N": int(N),
+                 "l2": "inputs+labels (>= 640 MB per step) are larger than the 126 MB L2",
+                 "parallelism": "1 volume per GPU" if world > 1 else "single GPU"},
+      "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(per_step_launches) * args.steps,
+      "gpu_launches_per_step": int(per_step_launches),
+      "roofline": roofline, "cpu_baseline": cpu, "also": also,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

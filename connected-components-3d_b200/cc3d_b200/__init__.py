@@ -124,9 +124,12 @@ def _even_ceil(n: int) -> int:
 def connected_components(
   data, max_labels: int = -1, connectivity: int = 26, return_N: bool = False,
   delta: Union[int, float] = 0, out_dtype: Optional[Any] = None, out_file=None,
-  periodic_boundary: bool = False, binary_image: bool = False,
+  periodic_boundary: bool = False, binary_image: bool = False, out=None,
 ):
   """Connected components of a 1D/2D/3D image; same contract as cc3d.connected_components.
+
+  Extension: `out` may be a preallocated contiguous numpy array (e.g. backed by pinned memory) of
+  the right dtype and size for host inputs; the labels are written into it instead of a new array.
 
   connectivity: 6/18/26 (3D) or 4/8 (2D); delta > 0 joins values differing by <= delta;
   binary_image treats non-zero as foreground; periodic_boundary wraps 4/8/6-connected images.
@@ -281,7 +284,12 @@ def connected_components(
         s2, sess = sess, None
         _lib.check(L.cc3d_b200_label_write(s2, out_flat.data_ptr(), _OUT_KIND[out_dtype], _lib.DEVICE, stream))
       else:
-        if out_file is None:
+        if out is not None:
+          if not isinstance(out, np.ndarray) or out.dtype != out_dtype or out.size != voxels or not (
+              out.flags.c_contiguous or out.flags.f_contiguous):
+            raise ValueError(f"out must be a contiguous numpy array of dtype {out_dtype} and size {voxels}")
+          out_flat = out.reshape(-1, order="K")
+        elif out_file is None:
           out_flat = np.empty((voxels,), dtype=out_dtype)
         else:
           import os

@@ -62,6 +62,7 @@ def lib():
   L.cc3d_b200_mask_by_label.argtypes = [vp, ci, vp, ci, i64, vp, u64, ci, vp]
   L.cc3d_b200_workspace_bytes.restype = ctypes.c_size_t
   L.cc3d_b200_release_workspace.restype = None
+  L.cc3d_b200_launch_count.restype = ctypes.c_ulonglong
   L.cc3d_b200_set_timing.restype = None
   L.cc3d_b200_set_timing.argtypes = [ci]
   L.cc3d_b200_last_timings.restype = ci

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -81,6 +82,8 @@ void arena_release(Arena& a) {
   a = Arena();
 }
 
+std::atomic<unsigned long long> g_launches{0};
+
 // ---- optional per-kernel timing ----
 thread_local bool g_timing = false;
 struct Mark { const char* name; cudaEvent_t ev; };
@@ -127,6 +130,7 @@ int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n, u64* total_dev, c
   k_scan_reduce<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n);
   k_scan_blocks<<<1, 1024, 0, s>>>(bsum, nb, total_dev);
   k_scan_apply<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, prefix, n);
+  g_launches += 3;
   return 0;
 }
 
@@ -151,6 +155,7 @@ int cc3d_b200_last_timings(const char** names, float* ms, int cap) {
   for (auto& t : g_last_timings) { if (n >= cap) break; names[n] = t.first; ms[n] = t.second; n++; }
   return n;
 }
+unsigned long long cc3d_b200_launch_count(void) { return g_launches.load(); }
 size_t cc3d_b200_workspace_bytes(void) { std::lock_guard<std::mutex> lk(g_pool_mu); return g_cached.cap; }
 void cc3d_b200_release_workspace(void) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -171,6 +176,7 @@ static int prepass_typed(const T* in, const Geom& g, Counters* ctr, T* range2, A
   T* pmax = (T*)ar.take(sizeof(T) * blocks);
   k_prepass<T><<<blocks, 256, 0, s>>>(in, g, ctr, pmin, pmax);
   k_minmax_final<T><<<1, 32, 0, s>>>(pmin, pmax, blocks, range2);
+  g_launches += 2;
   return 0;
 }
 
@@ -211,6 +217,7 @@ int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64
   void* range2 = ar.take(16);
   Geom g = make_geom(sx, sy, sz);
   k_init_counters<<<1, 1, 0, s>>>(ctr);
+  g_launches += 1;
   prepass_dispatch(din, in_kind, g, ctr, range2, ar, s);
   Counters h;
   unsigned char hr[16];
@@ -245,6 +252,7 @@ static void c8_mask_typed(const T* in, unsigned char* mask, i64 sx, i64 sy, cons
   memcpy(&d, delta, sizeof(T));
   const i64 n = sx * sy;
   k_c8_mask<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, mask, sx, sy, d, (const T*)range);
+  g_launches += 1;
 }
 
 int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
@@ -325,8 +333,11 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   S->L = L; S->LR = LR;
 
   k_init_counters<<<1, 1, 0, s>>>(ctr);
+  g_launches += 1;
 
   LabelArgs a;
+  int stage_launches = 0;
+  a.launches = &stage_launches;
   a.L = L; a.LR = LR; a.XS = XS; a.ctr = ctr; a.g = g;
   a.connectivity = connectivity; a.periodic = periodic_boundary; a.stream = s;
   a.mark = g_timing ? mark : nullptr;
@@ -355,8 +366,10 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   }
   if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
 
+  g_launches += stage_launches;
   const unsigned wblocks = (unsigned)((nwords + 255) / 256);
   k_compress<<<wblocks, 256, 0, s>>>(L, LR, GR, cnt, g, nwords);
+  g_launches += 1;
   mark("C1_compress", s);
   scan_counts(cnt, prefix, bsum, nwords, &ctr->N, s);
   mark("C2_scan", s);
@@ -374,9 +387,11 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
     k_popc<<<(unsigned)((nbwords + 255) / 256), 256, 0, s>>>(BK, bcnt, nbwords);
     scan_counts(bcnt, bprefix, bsum2, nbwords, dummyN, s);
     k_assign_blockorder<<<wblocks, 256, 0, s>>>(L, LR, GR, K, BK, bprefix, g, nwords);
+    g_launches += 5;
     mark("C3_assign_blockorder", s);
   } else {
     k_assign<<<wblocks, 256, 0, s>>>(L, LR, GR, prefix, g, nwords);
+    g_launches += 1;
     mark("C3_assign", s);
   }
   Counters h;
@@ -425,6 +440,7 @@ int cc3d_b200_label_write(cc3d_b200_session* S, void* out, int out_kind, int mem
   if (os == 2) k_write<uint16_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g);
   else if (os == 4) k_write<uint32_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g);
   else k_write<uint64_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g);
+  g_launches += 1;
   mark("D_write", s);
   cudaError_t e = cudaSuccess;
   if (mem_space == CC3D_B200_HOST) {
@@ -462,6 +478,7 @@ static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts,
   if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable)); attr = true; }
   k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
   k<<<148 * 2, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums);
+  g_launches += 2;
   return 0;
 }
 
@@ -544,6 +561,7 @@ int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int
     case 4: mask_typed((uint32_t*)dimg, dl, label_kind, dk, N, voxels, s); break;
     default: mask_typed((uint64_t*)dimg, dl, label_kind, dk, N, voxels, s); break;
   }
+  g_launches += 1;
   cudaError_t e = cudaSuccess;
   if (mem_space == CC3D_B200_HOST) e = cudaMemcpyAsync(img, dimg, (size_t)voxels * img_itemsize, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);

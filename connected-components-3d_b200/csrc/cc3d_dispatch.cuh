@@ -19,6 +19,7 @@ struct LabelArgs {
   unsigned char delta[8];  // one element of T
   cudaStream_t stream;
   void (*mark)(const char*, cudaStream_t);  // optional timing hook
+  int* launches;     // incremented once per kernel launch
 };
 
 template <typename T> int run_label_stage(const LabelArgs& a);
@@ -40,17 +41,20 @@ static int launch_label(const LabelArgs& a) {
   }
   const i64 ntiles = g.ntx * g.nty * g.ntz;
   kA<<<(unsigned)ntiles, CC_TILE_THREADS, smem, a.stream>>>(in, a.L, a.LR, a.XS, g, E, a.ctr);
+  ++*a.launches;
   if (a.mark) a.mark("A_tile_label", a.stream);
   const i64 rows = g.sy * g.sz;
   if (g.nty > 1 || g.ntz > 1) {
     const i64 warps = rows * g.W;
     const i64 blocks = (warps * 32 + 255) / 256;
     k_seam_rows<T, MODE, CONN><<<(unsigned)blocks, 256, 0, a.stream>>>(in, a.L, g, E);
+    ++*a.launches;
     if (a.mark) a.mark("B1_seam_rows", a.stream);
   }
   if (g.ntx > 1) {
     const i64 n = rows * (g.ntx - 1);
     k_seam_x<CC_TX><<<(unsigned)((n + 255) / 256), 256, 0, a.stream>>>(a.XS, a.L, g);
+    ++*a.launches;
     if (a.mark) a.mark("B2_seam_x", a.stream);
   }
   if constexpr ((MODE == MODE_EQ || MODE == MODE_NONZERO) && (CONN == 4 || CONN == 8 || CONN == 6)) {
@@ -59,6 +63,7 @@ static int launch_label(const LabelArgs& a) {
       k_periodic<T, MODE, CONN><<<(unsigned)((n0 + 255) / 256), 256, 0, a.stream>>>(in, a.L, g, E, 0);
       k_periodic<T, MODE, CONN><<<(unsigned)((n1 + 255) / 256), 256, 0, a.stream>>>(in, a.L, g, E, 1);
       if (CONN == 6) k_periodic<T, MODE, CONN><<<(unsigned)((n2 + 255) / 256), 256, 0, a.stream>>>(in, a.L, g, E, 2);
+      *a.launches += (CONN == 6) ? 3 : 2;
       if (a.mark) a.mark("P_periodic", a.stream);
     }
   }

@@ -113,6 +113,9 @@ int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int
 size_t cc3d_b200_workspace_bytes(void);
 void cc3d_b200_release_workspace(void);
 
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+unsigned long long cc3d_b200_launch_count(void);
+
 /* Per-kernel device times (ms) of the last label call on this thread, for bench/profiling.
  * names[i] points at static strings; returns the number of entries filled (<= cap). */
 int cc3d_b200_last_timings(const char** names, float* ms, int cap);
