@@ -288,7 +288,9 @@ def connected_components(
           if not isinstance(out, np.ndarray) or out.dtype != out_dtype or out.size != voxels or not (
               out.flags.c_contiguous or out.flags.f_contiguous):
             raise ValueError(f"out must be a contiguous numpy array of dtype {out_dtype} and size {voxels}")
-          out_flat = out.reshape(-1, order="K")
+          out_flat = out.ravel(order="K")
+          if not np.shares_memory(out_flat, out):
+            raise ValueError("out must be contiguous")
         elif out_file is None:
           out_flat = np.empty((voxels,), dtype=out_dtype)
         else:

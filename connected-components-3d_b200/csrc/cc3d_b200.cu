@@ -115,8 +115,9 @@ __global__ void k_init_counters(Counters* c) { c->epl = 0; c->first_row = INT64_
 Geom make_geom(i64 sx, i64 sy, i64 sz) {
   Geom g;
   g.sx = sx; g.sy = sy; g.sz = sz;
-  int TZ = (int)std::min<i64>(8, sz);
-  int TY = (int)std::min<i64>(64 / TZ, sy);
+  // 64 rows per tile: 64x8x8 for volumes, 64x64x1 for single-plane images
+  int TZ = sz > 1 ? 8 : 1;
+  int TY = 64 / TZ;
   g.TY = TY; g.TZ = TZ;
   g.ntx = (sx + CC_TX - 1) / CC_TX;
   g.nty = (sy + TY - 1) / TY;

@@ -23,7 +23,6 @@ struct LabelArgs {
 };
 
 template <typename T> int run_label_stage(const LabelArgs& a);
-template <typename T> size_t label_tile_smem(int TY, int TZ) { return tile_smem_bytes<T, CC_TX>(TY, TZ); }
 
 #ifdef CC3D_INSTANTIATE
 template <typename T, int MODE, int CONN>
@@ -32,15 +31,23 @@ static int launch_label(const LabelArgs& a) {
   memcpy(&E.delta, a.delta, sizeof(T));
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
-  const size_t smem = tile_smem_bytes<T, CC_TX>(g.TY, g.TZ);
-  auto kA = k_tile_label<T, MODE, CONN, CC_TX>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
+  const size_t smem = tile_smem_bytes<T>();
   const i64 ntiles = g.ntx * g.nty * g.ntz;
-  kA<<<(unsigned)ntiles, CC_TILE_THREADS, smem, a.stream>>>(in, a.L, a.LR, a.XS, g, E, a.ctr);
+  // tile shape: 64x8x8 for volumes, 64x64x1 for images (2D connectivities only exist for sz == 1)
+  if (g.TZ == 1) {
+    auto kA = k_tile_label<T, MODE, CONN, 6, 0>;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    kA<<<(unsigned)ntiles, CC_TILE_THREADS, smem, a.stream>>>(in, a.L, a.LR, a.XS, g, E, a.ctr);
+  } else {
+    if constexpr (CONN == 4 || CONN == 8) { return -1; }
+    else {
+      auto kA = k_tile_label<T, MODE, CONN, 3, 3>;
+      static bool attr_set = false;
+      if (!attr_set) { cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+      kA<<<(unsigned)ntiles, CC_TILE_THREADS, smem, a.stream>>>(in, a.L, a.LR, a.XS, g, E, a.ctr);
+    }
+  }
   ++*a.launches;
   if (a.mark) a.mark("A_tile_label", a.stream);
   const i64 rows = g.sy * g.sz;

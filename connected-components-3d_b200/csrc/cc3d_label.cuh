@@ -4,160 +4,247 @@
 
 #define CC_TILE_THREADS 256
 
-// Shared-memory bytes kernel A needs for a TXxTYxTZ tile of T.
-template <typename T, int TX>
-__host__ __device__ constexpr size_t tile_smem_bytes(int TY, int TZ) {
-  // slab[TILE + rows] + slink[rows*NSEG] (u32) + sval[rows*(TX+2)] (T), T region 8-byte aligned
-  return (((size_t)TY * TZ * TX + (size_t)TY * TZ + (size_t)TY * TZ * (TX / 32)) * 4 + 7) / 8 * 8 +
-         (size_t)TY * TZ * (TX + 2) * sizeof(T);
+// Shared-memory bytes kernel A needs (TX = 64, 64 rows per tile).
+template <typename T>
+__host__ __device__ constexpr size_t tile_smem_bytes() {
+  // slab[4096 + 64] + slink[128] + sB[256] (u32) + sval[64][66] (T)
+  return (size_t)(4096 + 64 + 128 + 256) * 4 + (size_t)64 * 66 * sizeof(T);
+}
+
+template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return (T)__shfl_sync(CC_FULL, v, src); }
+template <typename T> __device__ __forceinline__ T shfl_up_t(T v) { return (T)__shfl_up_sync(CC_FULL, v, 1); }
+
+// path-compressing find for the shared-memory forest: the start node is re-pointed at the root
+__device__ __forceinline__ u32 uf_find_c(u32* A, u32 i) {
+  volatile u32* V = A;
+  u32 r = i, p;
+  while ((p = V[r]) != r) r = p;
+  if (r != i) atomicMin(&A[i], r);
+  return r;
+}
+static __device__ __noinline__ void uf_union_c(u32* A, u32 a, u32 b) {
+  bool done;
+  do {
+    a = uf_find_c(A, a);
+    b = uf_find_c(A, b);
+    if (a < b) { u32 old = atomicMin(&A[b], a); done = (old == b); b = old; }
+    else if (b < a) { u32 old = atomicMin(&A[a], b); done = (old == a); a = old; }
+    else done = true;
+  } while (!done);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel A. One CTA labels one tile entirely in shared memory.
-//  phase 0: coalesced load of the tile (+ the x0-1 halo column) into sval; voxels outside the volume = 0
-//  phase 1: x-runs by warp ballot: every voxel starts out pointing at the first voxel of its run
-//           inside its 32-wide segment (no atomics); epl transitions are counted here too
-//  phase 2: for each neighbour row of the backward neighbourhood, ballot the three candidate edges,
-//           drop the ones already implied by a neighbouring lane (same pair of runs), and union the rest
-//           with shared-memory atomicMin; the halo column joins through the same union-find with
-//           indices >= TILE so that it can never become a root
-//  phase 3: flatten, write L (global raster index of the local root), the local-root bitmap word and
-//           the x-seam slot (own-tile root that the halo voxel to the left belongs to)
+// Kernel A. One CTA (8 warps) labels one 64 x TY x TZ tile (TY*TZ = 64 rows) in shared memory;
+// warp w owns rows 8w..8w+7 (one z-plane of an 8x8 tile) and keeps their voxels in registers.
+//  phase 1: 16 coalesced loads per warp issued back to back (+ the x0-1 halo column), x-runs by ballot:
+//           every voxel starts out pointing at the first voxel of its run inside its 32-wide segment;
+//           the epl transition count (cc3d.hpp:300-303) falls out of the same ballots
+//  phase 2a: ballot masks of the two "straight" backward edges (dy=-1 and dz=-1) of every segment
+//  phase 2b: remaining neighbour rows, evaluated only on the lanes where they can matter (for the
+//           transitive predicates EQ/NONZERO a voxel that matches its -y or -z neighbour inherits that
+//           neighbour's diagonal connections), then redundancy elimination on the masks (an edge is
+//           dropped when a neighbouring lane / row already joins the same two runs) and shared-memory
+//           atomicMin unions for the few edges left; the halo column joins through the same forest
+//           with indices >= TILE so that it never becomes a root
+//  phase 3: flatten, write L (raster index of the local root), the local-root bitmap word and the
+//           x-seam slot (own-tile root that the halo voxel to the left belongs to)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MODE, int CONN, int TX>
+template <typename T, int MODE, int CONN, int TYL, int TZL>
 __global__ void __launch_bounds__(CC_TILE_THREADS)
 k_tile_label(const T* __restrict__ in, u32* __restrict__ L, u32* __restrict__ LR, u32* __restrict__ XS,
              Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr) {
-  constexpr int NSEG = TX / 32;
-  constexpr int SVX = TX + 2;
-  const int TY = g.TY, TZ = g.TZ;
-  const int rows = TY * TZ;
-  const int TILE = rows * TX;
+  constexpr int TX = 64, NSEG = 2, SVX = TX + 2;
+  constexpr int TY = 1 << TYL, TZ = 1 << TZL, ROWS = TY * TZ, TILE = ROWS * TX;
+  static_assert(ROWS == 64, "8 warps x 8 rows");
+  constexpr int RPW = 8;
+  constexpr bool TRANS = (MODE == MODE_EQ || MODE == MODE_NONZERO);
+  constexpr int NR = hood_rows(CONN);
+  constexpr bool HAS_Z = (NR >= 2) && (TZ > 1);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u32* slab = reinterpret_cast<u32*>(smem_raw);          // [TILE + rows]
-  u32* slink = slab + TILE + rows;                       // [rows * NSEG]
-  T* sval = reinterpret_cast<T*>(smem_raw + (((size_t)(TILE + rows + rows * NSEG) * 4 + 7) / 8 * 8));  // [rows][SVX]
+  u32* slab = reinterpret_cast<u32*>(smem_raw);   // [TILE + ROWS]
+  u32* slink = slab + TILE + ROWS;                // [ROWS * NSEG]   x-link masks
+  u32* sB = slink + ROWS * NSEG;                  // [ROWS * NSEG][2] dy=-1 / dz=-1 straight-edge masks
+  T* sval = reinterpret_cast<T*>(sB + ROWS * NSEG * 2);  // [ROWS][SVX]
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  constexpr int NWARPS = CC_TILE_THREADS / 32;
+  const int wrow0 = warp * RPW;
 
-  // tile origin
-  i64 t = blockIdx.x;
-  const i64 bx = t % g.ntx; t /= g.ntx;
-  const i64 by = t % g.nty;
-  const i64 bz = t / g.nty;
-  const i64 x0 = bx * TX, y0 = by * TY, z0 = bz * TZ;
+  unsigned t = blockIdx.x;
+  const unsigned ntx = (unsigned)g.ntx, nty = (unsigned)g.nty;
+  const unsigned bx = t % ntx; t /= ntx;
+  const unsigned by = t % nty;
+  const unsigned bz = t / nty;
+  const i64 x0 = (i64)bx * TX, y0 = (i64)by * TY, z0 = (i64)bz * TZ;
 
-  // ---- phase 0: load ----
-  for (int s = warp; s < rows * NSEG; s += NWARPS) {
-    const int row = s / NSEG, k = s - row * NSEG;
-    const int lz = row / TY, ly = row - lz * TY;
-    const i64 gx = x0 + k * 32 + lane, gy = y0 + ly, gz = z0 + lz;
-    T v = (T)0;
-    if (gx < g.sx && gy < g.sy && gz < g.sz) v = in[(gz * g.sy + gy) * g.sx + gx];
-    sval[row * SVX + 1 + k * 32 + lane] = v;
+  // ---- phase 1: load + x-runs ----
+  T v[RPW][NSEG];
+#pragma unroll
+  for (int j = 0; j < RPW; j++) {
+    const int row = wrow0 + j;
+    const i64 gy = y0 + (row & (TY - 1)), gz = z0 + (row >> TYL);
+    const bool rowok = gy < g.sy && gz < g.sz;
+    const T* src = in + ((gz * g.sy + gy) * g.sx + x0);
+#pragma unroll
+    for (int k = 0; k < NSEG; k++) {
+      const int lx = k * 32 + lane;
+      v[j][k] = (rowok && x0 + lx < g.sx) ? src[lx] : (T)0;
+    }
   }
-  for (int row = threadIdx.x; row < rows; row += CC_TILE_THREADS) {
-    const int lz = row / TY, ly = row - lz * TY;
-    const i64 gy = y0 + ly, gz = z0 + lz;
-    T v = (T)0;
-    if (x0 > 0 && gy < g.sy && gz < g.sz) v = in[(gz * g.sy + gy) * g.sx + x0 - 1];
-    sval[row * SVX] = v;
-    sval[row * SVX + TX + 1] = (T)0;
+  T hv = (T)0;
+  if (lane < RPW && x0 > 0) {
+    const int row = wrow0 + lane;
+    const i64 gy = y0 + (row & (TY - 1)), gz = z0 + (row >> TYL);
+    if (gy < g.sy && gz < g.sz) hv = in[(gz * g.sy + gy) * g.sx + x0 - 1];
   }
-  __syncthreads();
-
-  // ---- phase 1: x-runs ----
+  if (lane < RPW) {
+    sval[(wrow0 + lane) * SVX] = hv;
+    sval[(wrow0 + lane) * SVX + TX + 1] = (T)0;
+    slab[TILE + wrow0 + lane] = E.fg(hv) ? (u32)(TILE + wrow0 + lane) : CC_BG;
+  }
   u32 epl_local = 0;
-  i64 row_min = INT64_MAX, row_max = -1;
-  for (int s = warp; s < rows * NSEG; s += NWARPS) {
-    const int row = s / NSEG, k = s - row * NSEG;
-    const int lx = k * 32 + lane;
-    const T v = sval[row * SVX + 1 + lx];
-    const T vl = sval[row * SVX + lx];
-    const bool f = E.fg(v);
-    const bool link = (lx > 0) && f && E(v, vl, dir_code(-1, 0, 0));
-    const u32 m = __ballot_sync(CC_FULL, link);
-    u32 below = (~m & (CC_FULL >> (31 - lane))) | 1u;
-    const int start = 31 - __clz(below);
-    slab[row * TX + lx] = f ? (u32)(row * TX + k * 32 + start) : CC_BG;
-    if (lane == 0) slink[s] = m;
-    if constexpr (MODE != MODE_MASK) {
-      // cc3d.hpp:300-303: (row[0] != 0) + sum_x (row[x] != row[x-1] && row[x] != 0)
-      const bool tr = f && ((x0 + lx == 0) || (v != vl));
-      const u32 tm = __ballot_sync(CC_FULL, tr);
-      if (tm) {
-        epl_local += __popc(tm);
-        const int lz = row / TY, ly = row - lz * TY;
-        const i64 grow = (z0 + lz) * g.sy + (y0 + ly);
-        row_min = min(row_min, grow);
-        row_max = max(row_max, grow);
+  int row_min = ROWS, row_max = -1;
+#pragma unroll
+  for (int j = 0; j < RPW; j++) {
+    const int row = wrow0 + j;
+    const T hvj = shfl_t(hv, j);
+    const T t31 = shfl_t(v[j][0], 31);
+#pragma unroll
+    for (int k = 0; k < NSEG; k++) {
+      const int lx = k * 32 + lane;
+      const T cur = v[j][k];
+      sval[row * SVX + 1 + lx] = cur;
+      T vl = shfl_up_t(cur);
+      if (lane == 0) vl = (k == 0) ? hvj : t31;
+      const bool f = E.fg(cur);
+      const bool link = f && (k > 0 || lane > 0) && E(cur, vl, dir_code(-1, 0, 0));
+      const u32 m = __ballot_sync(CC_FULL, link);
+      const u32 below = (~m & (CC_FULL >> (31 - lane))) | 1u;
+      const int start = 31 - __clz(below);
+      slab[row * TX + lx] = f ? (u32)(row * TX + k * 32 + start) : CC_BG;
+      if (lane == 0) slink[row * NSEG + k] = m;
+      if constexpr (MODE != MODE_MASK) {
+        const bool tr = f && ((x0 + lx == 0) || (cur != vl));
+        const u32 tm = __ballot_sync(CC_FULL, tr);
+        if (tm) { epl_local += __popc(tm); row_min = min(row_min, row); row_max = max(row_max, row); }
       }
     }
   }
-  // halo column entries of the union-find
-  for (int row = threadIdx.x; row < rows; row += CC_TILE_THREADS)
-    slab[TILE + row] = E.fg(sval[row * SVX]) ? (u32)(TILE + row) : CC_BG;
   __syncthreads();
 
-  // ---- phase 2: unions ----
-  for (int s = warp; s < rows * NSEG; s += NWARPS) {
-    const int row = s / NSEG, k = s - row * NSEG;
-    const int lz = row / TY, ly = row - lz * TY;
+  // ---- phase 2a: straight-edge masks B0 (dy=-1) and B1 (dz=-1) ----
+  // (rolled loops from here on: the unrolled form is ~300 KB of SASS and thrashes the instruction cache)
+#pragma unroll 1
+  for (int s = wrow0 * NSEG; s < (wrow0 + RPW) * NSEG; s++) {
+    const int row = s >> 1, k = s & 1;
+    const int ly = row & (TY - 1), lz = row >> TYL;
+    const int lx = k * 32 + lane;
+    const T cur = sval[row * SVX + 1 + lx];
+    const bool f = E.fg(cur);
+    u32 B0 = 0, B1 = 0;
+    if (ly > 0) B0 = __ballot_sync(CC_FULL, f && E(cur, sval[(row - 1) * SVX + 1 + lx], dir_code(0, -1, 0)));
+    if constexpr (HAS_Z) {
+      if (lz > 0) B1 = __ballot_sync(CC_FULL, f && E(cur, sval[(row - TY) * SVX + 1 + lx], dir_code(0, 0, -1)));
+    }
+    if (lane == 0) { sB[s * 2] = B0; sB[s * 2 + 1] = B1; }
+  }
+  __syncthreads();
+
+  // ---- phase 2b: remaining edges, redundancy elimination, unions ----
+#pragma unroll 1
+  for (int s = wrow0 * NSEG; s < (wrow0 + RPW) * NSEG; s++) {
+    const int row = s >> 1, k = s & 1;
+    const int ly = row & (TY - 1), lz = row >> TYL;
     const int lx = k * 32 + lane;
     const u32 li = row * TX + lx;
-    const T v = sval[row * SVX + 1 + lx];
+    const T cur = sval[row * SVX + 1 + lx];
+    const bool f = E.fg(cur);
+    const u32 F = __ballot_sync(CC_FULL, f);
+    if (F == 0) continue;
     const u32 m_own = slink[s];
-    const u32 m_own_next = (k + 1 < NSEG) ? slink[s + 1] : 0u;
-    const u32 LRs1 = (m_own >> 1) | (m_own_next << 31);
-    if (k > 0 && lane == 0 && (m_own & 1u)) uf_union(slab, li, li - 1);  // run continues from the previous segment
-    if (!__any_sync(CC_FULL, E.fg(v))) continue;
-#pragma unroll
-    for (int r = 0; r < hood_rows(CONN); r++) {
-      constexpr int dummy = 0; (void)dummy;
+    const u32 LRs1 = (m_own >> 1) | ((k == 0 ? slink[s + 1] : 0u) << 31);
+    if (k > 0 && lane == 0 && (m_own & 1u)) uf_union_c(slab, li, li - 1);  // run continues from the previous segment
+    const u32 B0 = sB[s * 2], B1 = sB[s * 2 + 1];
+
+    // one neighbour row: edges a (dx-1), b (dx0, mask given or computed), c (dx+1); in-row elimination; unions
+    auto do_row = [&](const int r, const int row2, const bool have_b, u32 Bm, const u32 Bprev, const u32 Bnext,
+                      const u32 cand_b, const u32 cand_ac, const u32 kill_b) {
       const int dy = row_dy(r), dz = row_dz(r);
       const int dxm = hood_dx(CONN, r);
-      const int ly2 = ly + dy, lz2 = lz + dz;
-      if (ly2 < 0 || ly2 >= TY || lz2 < 0) continue;  // other tile: seam kernel
-      const int row2 = lz2 * TY + ly2;
       const T* q = sval + row2 * SVX + 1 + lx;
-      const bool f = E.fg(v);
-      const bool b = (dxm & 2) && f && E(v, q[0], dir_code(0, dy, dz));
-      const bool a = (dxm & 1) && f && lx > 0 && E(v, q[-1], dir_code(-1, dy, dz));
-      const bool c = (dxm & 4) && f && lx + 1 < TX && E(v, q[1], dir_code(1, dy, dz));
-      const u32 B = __ballot_sync(CC_FULL, b);
-      const u32 A = (dxm & 1) ? __ballot_sync(CC_FULL, a) : 0u;
-      const u32 C = (dxm & 4) ? __ballot_sync(CC_FULL, c) : 0u;
-      if ((A | B | C) == 0) continue;
+      if (!have_b) {
+        if (cand_b == 0 && cand_ac == 0) return;
+        Bm = __ballot_sync(CC_FULL, ((cand_b >> lane) & 1u) && E(cur, q[0], dir_code(0, dy, dz)));
+      }
+      u32 Am = 0, Cm = 0;
+      if ((dxm & 5) && cand_ac) {
+        const bool ca = (cand_ac >> lane) & 1u;
+        Am = __ballot_sync(CC_FULL, ca && lx > 0 && E(cur, q[-1], dir_code(-1, dy, dz)));
+        Cm = __ballot_sync(CC_FULL, ca && lx + 1 < TX && E(cur, q[1], dir_code(1, dy, dz)));
+      }
+      if ((Am | Bm | Cm) == 0) return;
       const u32 LP = slink[row2 * NSEG + k];
-      const u32 LP_next = (k + 1 < NSEG) ? slink[row2 * NSEG + k + 1] : 0u;
-      const u32 LPs1 = (LP >> 1) | (LP_next << 31);
-      const u32 Bl = B << 1;  // bit j: dx=0 edge exists at x_j - 1 (unknown across the segment start)
-      const u32 Br = B >> 1;  // bit j: dx=0 edge exists at x_j + 1
-      const u32 needB = B & ~(m_own & LP & Bl);
-      const u32 needA = A & ~(B & LP) & ~(m_own & Bl);
-      const u32 needC = C & ~(B & LPs1) & ~(LRs1 & Br);
+      const u32 LPs1 = (LP >> 1) | ((k == 0 ? slink[row2 * NSEG + 1] : 0u) << 31);
+      const u32 Bl = (Bm << 1) | (Bprev >> 31);
+      const u32 Br = (Bm >> 1) | (Bnext << 31);
+      const u32 needB = Bm & ~(m_own & LP & Bl) & ~kill_b;
+      const u32 needA = Am & ~(Bm & LP) & ~(m_own & Bl);
+      const u32 needC = Cm & ~(Bm & LPs1) & ~(LRs1 & Br);
       const u32 qi = row2 * TX + lx;
-      if ((needB >> lane) & 1u) uf_union(slab, li, qi);
-      if ((needA >> lane) & 1u) uf_union(slab, li, qi - 1);
-      if ((needC >> lane) & 1u) uf_union(slab, li, qi + 1);
+      if ((needB >> lane) & 1u) uf_union_c(slab, li, qi);
+      if ((needA >> lane) & 1u) uf_union_c(slab, li, qi - 1);
+      if ((needC >> lane) & 1u) uf_union_c(slab, li, qi + 1);
+    };
+
+    // R0: (dy=-1, dz=0)
+    if (ly > 0) {
+      const u32 Bprev = (k == 1) ? sB[(s - 1) * 2] : 0u, Bnext = (k == 0) ? sB[(s + 1) * 2] : 0u;
+      u32 cand_ac = F;
+      if constexpr (TRANS) cand_ac = (CONN == 26) ? (F & ~(B0 | B1)) : (F & ~B0);
+      do_row(0, row - 1, true, B0, Bprev, Bnext, 0u, cand_ac, 0u);
+    }
+    if constexpr (HAS_Z) {
+      if (lz > 0) {
+        // R1: (dy=0, dz=-1); square rule: (x,y,z)-(x,y-1,z)-(x,y-1,z-1)-(x,y,z-1) already closes the loop
+        {
+          const u32 Bprev = (k == 1) ? sB[(s - 1) * 2 + 1] : 0u, Bnext = (k == 0) ? sB[(s + 1) * 2 + 1] : 0u;
+          const u32 B1up = (ly > 0) ? sB[(s - NSEG) * 2 + 1] : 0u;
+          const u32 B0down = sB[(s - TY * NSEG) * 2];
+          u32 cand_ac = F;
+          if constexpr (TRANS) cand_ac = (CONN == 26) ? (F & ~(B0 | B1)) : (F & ~B1);
+          do_row(1, row - TY, true, B1, Bprev, Bnext, 0u, cand_ac, B0 & B1up & B0down);
+        }
+        if constexpr (NR >= 4) {
+          // R2: (dy=-1, dz=-1)
+          if (ly > 0) {
+            const u32 B1up = sB[(s - NSEG) * 2 + 1];
+            const u32 B0down = sB[(s - TY * NSEG) * 2];
+            const u32 cand = TRANS ? (F & ~(B0 | B1)) : F;
+            do_row(2, row - TY - 1, false, 0u, 0u, 0u, cand, cand, (B0 & B1up) | (B1 & B0down));
+          }
+          // R3: (dy=+1, dz=-1)
+          if (ly < TY - 1) {
+            const u32 B0d1 = sB[(s - TY * NSEG + NSEG) * 2];  // (x,y+1,z-1)-(x,y,z-1)
+            const u32 cand = TRANS ? (F & ~B1) : F;
+            do_row(3, row - TY + 1, false, 0u, 0u, 0u, cand, cand, B1 & B0d1);
+          }
+        }
+      }
     }
   }
   // halo column: edges between the halo voxel h=(x0-1,y,z) and own voxels (x0, y+ddy, z+ddz),
   // plus halo-halo links used to drop redundant x-seam slots.
-  if (x0 > 0) {
-    for (int row = threadIdx.x; row < rows; row += CC_TILE_THREADS) {
-      const T hv = sval[row * SVX];
-      if (!E.fg(hv)) continue;
-      const int lz = row / TY, ly = row - lz * TY;
+  if (x0 > 0 && threadIdx.x < ROWS) {
+    const int row = threadIdx.x;
+    const T hvv = sval[row * SVX];
+    if (E.fg(hvv)) {
+      const int ly = row & (TY - 1), lz = row >> TYL;
       const u32 hi = TILE + row;
-#pragma unroll
+#pragma unroll 1
       for (int ddz = -1; ddz <= 1; ddz++) {
-#pragma unroll
+#pragma unroll 1
         for (int ddy = -1; ddy <= 1; ddy++) {
-          // is (dx=+-1, ddy, ddz) part of this connectivity?
           const int nz = (ddy != 0) + (ddz != 0);
           bool allowed;
           if (CONN == 4 || CONN == 6) allowed = nz == 0;
@@ -171,30 +258,31 @@ k_tile_label(const T* __restrict__ in, u32* __restrict__ L, u32* __restrict__ LR
           const T ov = sval[row2 * SVX + 1];
           if (!E.fg(ov)) continue;
           bool e;
-          if (ddz > 0 || (ddz == 0 && ddy >= 0)) e = E(ov, hv, dir_code(-1, -ddy, -ddz));  // own voxel is later
-          else e = E(hv, ov, dir_code(1, ddy, ddz));                                        // halo voxel is later
-          if (e) uf_union(slab, hi, (u32)(row2 * TX));
+          if (ddz > 0 || (ddz == 0 && ddy >= 0)) e = E(ov, hvv, dir_code(-1, -ddy, -ddz));  // own voxel is later
+          else e = E(hvv, ov, dir_code(1, ddy, ddz));                                        // halo voxel is later
+          if (e) uf_union_c(slab, hi, (u32)(row2 * TX));
         }
       }
       if (ly > 0) {
         const T pv = sval[(row - 1) * SVX];
-        if (E.fg(pv) && E(hv, pv, dir_code(0, -1, 0))) uf_union(slab, hi, hi - 1);
+        if (E.fg(pv) && E(hvv, pv, dir_code(0, -1, 0))) uf_union_c(slab, hi, hi - 1);
       }
       if (CONN != 4 && CONN != 8 && lz > 0) {
         const T pv = sval[(row - TY) * SVX];
-        if (E.fg(pv) && E(hv, pv, dir_code(0, 0, -1))) uf_union(slab, hi, hi - TY);
+        if (E.fg(pv) && E(hvv, pv, dir_code(0, 0, -1))) uf_union_c(slab, hi, hi - TY);
       }
     }
   }
   __syncthreads();
 
   // ---- phase 3: flatten + write ----
-  for (int s = warp; s < rows * NSEG; s += NWARPS) {
-    const int row = s / NSEG, k = s - row * NSEG;
-    const int lz = row / TY, ly = row - lz * TY;
+#pragma unroll 1
+  for (int s = wrow0 * NSEG; s < (wrow0 + RPW) * NSEG; s++) {
+    const int row = s >> 1, k = s & 1;
+    const i64 gy = y0 + (row & (TY - 1)), gz = z0 + (row >> TYL);
+    const bool rowok = gy < g.sy && gz < g.sz;
+    const i64 rbase = (gz * g.sy + gy) * g.sx + x0;
     const int lx = k * 32 + lane;
-    const i64 gx = x0 + lx, gy = y0 + ly, gz = z0 + lz;
-    const bool inside = gx < g.sx && gy < g.sy && gz < g.sz;
     const u32 li = row * TX + lx;
     u32 l = slab[li];
     u32 out = CC_BG;
@@ -203,37 +291,34 @@ k_tile_label(const T* __restrict__ in, u32* __restrict__ L, u32* __restrict__ LR
       u32 p;
       while ((p = slab[l]) != l) l = p;
       is_root = (l == li);
-      const int rrow = l / TX, rlx = l - rrow * TX;
-      const int rlz = rrow / TY, rly = rrow - rlz * TY;
-      out = (u32)(((z0 + rlz) * g.sy + (y0 + rly)) * g.sx + x0 + rlx);
+      const int rrow = l >> 6, rlx = l & (TX - 1);
+      out = (u32)(((z0 + (rrow >> TYL)) * g.sy + (y0 + (rrow & (TY - 1)))) * g.sx + x0 + rlx);
     }
     const u32 rm = __ballot_sync(CC_FULL, is_root);
-    if (inside) L[(gz * g.sy + gy) * g.sx + gx] = out;
-    if (lane == 0 && gy < g.sy && gz < g.sz && x0 + k * 32 < g.sx)
-      LR[(gz * g.sy + gy) * g.W + ((x0 + k * 32) >> 5)] = rm;
+    if (rowok && x0 + lx < g.sx) L[rbase + lx] = out;
+    if (lane == 0 && rowok && x0 + k * 32 < g.sx) LR[(gz * g.sy + gy) * g.W + ((x0 + k * 32) >> 5)] = rm;
   }
-  if (x0 > 0) {
-    for (int row = threadIdx.x; row < rows; row += CC_TILE_THREADS) {
-      const int lz = row / TY, ly = row - lz * TY;
-      const i64 gy = y0 + ly, gz = z0 + lz;
-      if (gy >= g.sy || gz >= g.sz) continue;
+  if (x0 > 0 && threadIdx.x < ROWS) {
+    const int row = threadIdx.x;
+    const int ly = row & (TY - 1), lz = row >> TYL;
+    const i64 gy = y0 + ly, gz = z0 + lz;
+    if (gy < g.sy && gz < g.sz) {
       u32 out = CC_BG;
       u32 l = slab[TILE + row];
       if (l != CC_BG) {
         // skip when an earlier halo voxel of the same column is linked to this one (both tiles know that link)
-        const T hv = sval[row * SVX];
+        const T hvv = sval[row * SVX];
         bool covered = false;
-        if (ly > 0) { const T pv = sval[(row - 1) * SVX]; covered = E.fg(pv) && E(hv, pv, dir_code(0, -1, 0)); }
+        if (ly > 0) { const T pv = sval[(row - 1) * SVX]; covered = E.fg(pv) && E(hvv, pv, dir_code(0, -1, 0)); }
         if (!covered && CONN != 4 && CONN != 8 && lz > 0) {
-          const T pv = sval[(row - TY) * SVX]; covered = E.fg(pv) && E(hv, pv, dir_code(0, 0, -1));
+          const T pv = sval[(row - TY) * SVX]; covered = E.fg(pv) && E(hvv, pv, dir_code(0, 0, -1));
         }
         if (!covered) {
           u32 p;
           while ((p = slab[l]) != l) l = p;
           if (l < (u32)TILE) {
-            const int rrow = l / TX, rlx = l - rrow * TX;
-            const int rlz = rrow / TY, rly = rrow - rlz * TY;
-            out = (u32)(((z0 + rlz) * g.sy + (y0 + rly)) * g.sx + x0 + rlx);
+            const int rrow = l >> 6, rlx = l & (TX - 1);
+            out = (u32)(((z0 + (rrow >> TYL)) * g.sy + (y0 + (rrow & (TY - 1)))) * g.sx + x0 + rlx);
           }
         }
       }
@@ -244,19 +329,22 @@ k_tile_label(const T* __restrict__ in, u32* __restrict__ L, u32* __restrict__ LR
   if constexpr (MODE != MODE_MASK) {
     // block-level reduction of epl and the foreground row range
     __shared__ u32 s_epl;
-    __shared__ long long s_rmin, s_rmax;
-    if (threadIdx.x == 0) { s_epl = 0; s_rmin = INT64_MAX; s_rmax = -1; }
+    __shared__ int s_rmin, s_rmax;
+    if (threadIdx.x == 0) { s_epl = 0; s_rmin = ROWS; s_rmax = -1; }
     __syncthreads();
     if (lane == 0 && epl_local) {
       atomicAdd(&s_epl, epl_local);
-      atomicMin(&s_rmin, (long long)row_min);
-      atomicMax(&s_rmax, (long long)row_max);
+      atomicMin(&s_rmin, row_min);
+      atomicMax(&s_rmax, row_max);
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_epl) {
       atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)s_epl);
-      atomicMin((long long*)&ctr->first_row, s_rmin);
-      atomicMax((long long*)&ctr->last_row, s_rmax);
+      // rows of a tile are ordered like global rows, so the extreme local rows give the extreme global rows
+      const i64 gmin = (z0 + (s_rmin >> TYL)) * g.sy + (y0 + (s_rmin & (TY - 1)));
+      const i64 gmax = (z0 + (s_rmax >> TYL)) * g.sy + (y0 + (s_rmax & (TY - 1)));
+      atomicMin((long long*)&ctr->first_row, (long long)gmin);
+      atomicMax((long long*)&ctr->last_row, (long long)gmax);
     }
   }
 }
