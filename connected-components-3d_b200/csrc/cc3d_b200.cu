@@ -437,10 +437,12 @@ int cc3d_b200_label_write(cc3d_b200_session* S, void* out, int out_kind, int mem
     }
   }
   marks_begin(s);
-  const unsigned blocks = (unsigned)((g.sy * g.sz * g.W * 32 + 255) / 256);
-  if (os == 2) k_write<uint16_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g);
-  else if (os == 4) k_write<uint32_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g);
-  else k_write<uint64_t><<<blocks, 256, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g);
+  const unsigned nchunks = (unsigned)((g.sx + 511) / 512);
+  const unsigned blocks = (unsigned)(g.sy * g.sz) * nchunks;
+  const bool vec = (g.sx % 4 == 0) && (((uintptr_t)dout) % 32 == 0);
+  if (os == 2) { if (vec) k_write<uint16_t, true><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g, nchunks); else k_write<uint16_t, false><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g, nchunks); }
+  else if (os == 4) { if (vec) k_write<uint32_t, true><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g, nchunks); else k_write<uint32_t, false><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g, nchunks); }
+  else { if (vec) k_write<uint64_t, true><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g, nchunks); else k_write<uint64_t, false><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g, nchunks); }
   g_launches += 1;
   mark("D_write", s);
   cudaError_t e = cudaSuccess;

@@ -52,9 +52,8 @@ static int launch_label(const LabelArgs& a) {
   if (a.mark) a.mark("A_tile_label", a.stream);
   const i64 rows = g.sy * g.sz;
   if (g.nty > 1 || g.ntz > 1) {
-    const i64 warps = rows * g.W;
-    const i64 blocks = (warps * 32 + 255) / 256;
-    k_seam_rows<T, MODE, CONN><<<(unsigned)blocks, 256, 0, a.stream>>>(in, a.L, g, E);
+    const unsigned nchunks = (unsigned)((g.sx + 255) / 256);
+    k_seam_rows<T, MODE, CONN><<<(unsigned)rows * nchunks, 256, 0, a.stream>>>(in, a.L, g, E, nchunks);
     ++*a.launches;
     if (a.mark) a.mark("B1_seam_rows", a.stream);
   }

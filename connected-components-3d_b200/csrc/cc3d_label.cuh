@@ -350,73 +350,120 @@ k_tile_label(const T* __restrict__ in, u32* __restrict__ L, u32* __restrict__ LR
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel B1. Unions across y/z tile seams. One warp per (row, 32-voxel x segment); a row only does
-// work for those neighbour rows that live in a different (y,z) tile. Same ballot-based redundancy
-// elimination as kernel A, unions go to the global forest L with atomicMin.
+// Kernel B1. Unions across y/z tile seams, straight on the global forest L (atomicMin link-to-smaller).
+// One CTA per (row, 256-voxel chunk); CTAs of rows that touch no seam exit at once. A warp loads its
+// 32-voxel segment of the row P and of the rows U=(y-1,z), D=(y,z-1), UD=(y-1,z-1), DN=(y+1,z-1),
+// ballots the straight edges, and applies the same eliminations as kernel A so that only the first
+// voxel of every contact patch between two runs touches global memory:
+//   - x: an edge is implied by the same edge one voxel to the left when both runs continue
+//   - square: (P-D) is implied by (P-U),(U-UD),(D-UD) on z-seams; (P-U) by (P-D),(D-UD),(U-UD) on pure
+//     y-seam rows (kernel A keeps P-D there because it does not see across the y seam)
+//   - transitive predicates: diagonals only where the straight edges do not already connect
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256)
-k_seam_rows(const T* __restrict__ in, u32* __restrict__ L, Geom g, Edge<T, MODE> E) {
+k_seam_rows(const T* __restrict__ in, u32* __restrict__ L, Geom g, Edge<T, MODE> E, unsigned nchunks) {
+  constexpr bool TRANS = (MODE == MODE_EQ || MODE == MODE_NONZERO);
+  constexpr int NR = hood_rows(CONN);
+  const unsigned row = blockIdx.x / nchunks;
+  const unsigned chunk = blockIdx.x - row * nchunks;
+  const unsigned sy = (unsigned)g.sy;
+  const unsigned z = row / sy, y = row - z * sy;
+  const int ly = y & (g.TY - 1), lz = z & (g.TZ - 1);
+  const bool hasz = NR >= 2 && z > 0;
+  const bool xR0 = y > 0 && ly == 0;
+  const bool xR1 = hasz && lz == 0;
+  const bool xR2 = NR >= 4 && hasz && y > 0 && (ly == 0 || lz == 0);
+  const bool xR3 = NR >= 4 && hasz && y + 1 < sy && (ly == g.TY - 1 || lz == 0);
+  if (!(xR0 || xR1 || xR2 || xR3)) return;
+
   const int lane = threadIdx.x & 31;
-  const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const i64 nseg = g.W;
-  const i64 row = wid / nseg;
-  if (row >= g.sy * g.sz) return;
-  const i64 seg = wid - row * nseg;
-  const i64 z = row / g.sy, y = row - z * g.sy;
-  const int ly = (int)(y % g.TY), lz = (int)(z % g.TZ);
-  // does any neighbour row fall into another tile?
-  bool any = false;
-#pragma unroll
-  for (int r = 0; r < hood_rows(CONN); r++) {
-    const int dy = row_dy(r), dz = row_dz(r);
-    const i64 y2 = y + dy, z2 = z + dz;
-    if (y2 < 0 || y2 >= g.sy || z2 < 0) continue;
-    if (ly + dy < 0 || ly + dy >= g.TY || lz + dz < 0) any = true;
-  }
-  if (!any) return;
-
-  const i64 x = seg * 32 + lane;
+  const i64 x = (i64)chunk * 256 + threadIdx.x;
+  if (x - lane >= g.sx) return;
   const bool inx = x < g.sx;
-  const i64 base = row * g.sx;
-  const T v = inx ? in[base + x] : (T)0;
-  T vl = __shfl_up_sync(CC_FULL, v, 1);
-  if (lane == 0) vl = (x > 0 && inx) ? in[base + x - 1] : (T)0;
-  const bool f = E.fg(v);
-  if (!__any_sync(CC_FULL, f)) return;
-  const u32 m_own = __ballot_sync(CC_FULL, f && x > 0 && E(v, vl, dir_code(-1, 0, 0)));
-  const u32 LRs1 = m_own >> 1;
+  const i64 baseP = (i64)row * g.sx;
 
-#pragma unroll
-  for (int r = 0; r < hood_rows(CONN); r++) {
+  // a row segment with its left/right neighbours
+  struct Seg { T c, l, r; };
+  auto load = [&](i64 base, bool want) -> Seg {
+    Seg q; q.c = (T)0; q.l = (T)0; q.r = (T)0;
+    if (!want) return q;
+    q.c = inx ? in[base + x] : (T)0;
+    q.l = (T)__shfl_up_sync(CC_FULL, q.c, 1);
+    q.r = (T)__shfl_down_sync(CC_FULL, q.c, 1);
+    if (lane == 0) q.l = (x > 0 && inx) ? in[base + x - 1] : (T)0;
+    if (lane == 31) q.r = (x + 1 < g.sx) ? in[base + x + 1] : (T)0;
+    return q;
+  };
+  const Seg P = load(baseP, true);
+  const bool f = E.fg(P.c);
+  const u32 F = __ballot_sync(CC_FULL, f);
+  if (F == 0) return;
+  const bool haveU = y > 0, haveD = hasz, haveUD = hasz && y > 0, haveDN = NR >= 4 && hasz && y + 1 < sy;
+  const i64 sxy = g.sx * g.sy;
+  const Seg U = load(baseP - g.sx, haveU);
+  const Seg D = load(baseP - sxy, haveD);
+  const Seg UD = load(baseP - sxy - g.sx, haveUD && (xR2 || xR1 || xR0));
+  const Seg DN = load(baseP - sxy + g.sx, haveDN && xR3);
+
+  const int DXL = dir_code(-1, 0, 0);
+  const u32 LxP = __ballot_sync(CC_FULL, f && x > 0 && E(P.c, P.l, DXL));
+  const u32 LxPs1 = LxP >> 1;
+  const u32 B0 = haveU ? __ballot_sync(CC_FULL, f && E(P.c, U.c, dir_code(0, -1, 0))) : 0u;
+  const u32 B1 = haveD ? __ballot_sync(CC_FULL, f && E(P.c, D.c, dir_code(0, 0, -1))) : 0u;
+  const u32 B1u = haveUD ? __ballot_sync(CC_FULL, E.fg(U.c) && E(U.c, UD.c, dir_code(0, 0, -1))) : 0u;
+  const u32 B0d = haveUD ? __ballot_sync(CC_FULL, E.fg(D.c) && E(D.c, UD.c, dir_code(0, -1, 0))) : 0u;
+  const u32 pi = (u32)(baseP + x);
+
+  auto do_row = [&](const int r, const Seg& Q, const i64 baseQ, const bool have_b, u32 Bm, const u32 cand_b,
+                    const u32 cand_ac, const u32 kill_b) {
     const int dy = row_dy(r), dz = row_dz(r);
     const int dxm = hood_dx(CONN, r);
-    const i64 y2 = y + dy, z2 = z + dz;
-    if (y2 < 0 || y2 >= g.sy || z2 < 0) continue;
-    if (!(ly + dy < 0 || ly + dy >= g.TY || lz + dz < 0)) continue;  // same tile: kernel A did it
-    const i64 base2 = (z2 * g.sy + y2) * g.sx;
-    const T qb = inx ? in[base2 + x] : (T)0;
-    T qa = __shfl_up_sync(CC_FULL, qb, 1);
-    T qc = __shfl_down_sync(CC_FULL, qb, 1);
-    if (lane == 0) qa = (x > 0 && inx) ? in[base2 + x - 1] : (T)0;
-    if (lane == 31) qc = (x + 1 < g.sx) ? in[base2 + x + 1] : (T)0;
-    const bool b = (dxm & 2) && f && E(v, qb, dir_code(0, dy, dz));
-    const bool a = (dxm & 1) && f && x > 0 && E(v, qa, dir_code(-1, dy, dz));
-    const bool c = (dxm & 4) && f && x + 1 < g.sx && E(v, qc, dir_code(1, dy, dz));
-    const u32 B = __ballot_sync(CC_FULL, b);
-    const u32 A = (dxm & 1) ? __ballot_sync(CC_FULL, a) : 0u;
-    const u32 C = (dxm & 4) ? __ballot_sync(CC_FULL, c) : 0u;
-    if ((A | B | C) == 0) continue;
-    const u32 LP = __ballot_sync(CC_FULL, E.fg(qb) && x > 0 && E(qb, qa, dir_code(-1, 0, 0)));
-    const u32 LPs1 = LP >> 1;
-    const u32 Bl = B << 1, Br = B >> 1;
-    const u32 needB = B & ~(m_own & LP & Bl);
-    const u32 needA = A & ~(B & LP) & ~(m_own & Bl);
-    const u32 needC = C & ~(B & LPs1) & ~(LRs1 & Br);
-    const u32 pi = (u32)(base + x), qi = (u32)(base2 + x);
+    if (!have_b) {
+      if (cand_b == 0 && cand_ac == 0) return;
+      Bm = __ballot_sync(CC_FULL, ((cand_b >> lane) & 1u) && E(P.c, Q.c, dir_code(0, dy, dz)));
+    }
+    u32 Am = 0, Cm = 0;
+    if ((dxm & 5) && cand_ac) {
+      const bool ca = (cand_ac >> lane) & 1u;
+      Am = __ballot_sync(CC_FULL, ca && x > 0 && E(P.c, Q.l, dir_code(-1, dy, dz)));
+      Cm = __ballot_sync(CC_FULL, ca && x + 1 < g.sx && E(P.c, Q.r, dir_code(1, dy, dz)));
+    }
+    if ((Am | Bm | Cm) == 0) return;
+    const u32 LP = __ballot_sync(CC_FULL, E.fg(Q.c) && x > 0 && E(Q.c, Q.l, DXL));
+    const u32 Bl = Bm << 1, Br = Bm >> 1;
+    const u32 needB = Bm & ~(LxP & LP & Bl) & ~kill_b;
+    const u32 needA = Am & ~(Bm & LP) & ~(LxP & Bl);
+    const u32 needC = Cm & ~(Bm & (LP >> 1)) & ~(LxPs1 & Br);
+    const u32 qi = (u32)(baseQ + x);
     if ((needB >> lane) & 1u) uf_union(L, pi, qi);
     if ((needA >> lane) & 1u) uf_union(L, pi, qi - 1);
     if ((needC >> lane) & 1u) uf_union(L, pi, qi + 1);
+  };
+
+  if (xR0) {
+    u32 cand_ac = F;
+    if constexpr (TRANS) cand_ac = (CONN == 26) ? (F & ~(B0 | B1)) : (F & ~B0);
+    const u32 kill = (lz > 0) ? (B1 & B0d & B1u) : 0u;  // pure y-seam row: the z-1 side closes the square
+    do_row(0, U, baseP - g.sx, true, B0, 0u, cand_ac, kill);
+  }
+  if constexpr (NR >= 2) {
+    if (xR1) {
+      u32 cand_ac = F;
+      if constexpr (TRANS) cand_ac = (CONN == 26) ? (F & ~(B0 | B1)) : (F & ~B1);
+      do_row(1, D, baseP - sxy, true, B1, 0u, cand_ac, B0 & B1u & B0d);
+    }
+  }
+  if constexpr (NR >= 4) {
+    if (xR2) {
+      const u32 cand = TRANS ? (F & ~(B0 | B1)) : F;
+      do_row(2, UD, baseP - sxy - g.sx, false, 0u, cand, cand, (B0 & B1u) | (B1 & B0d));
+    }
+    if (xR3) {
+      const u32 B0dn = __ballot_sync(CC_FULL, E.fg(DN.c) && E(DN.c, D.c, dir_code(0, -1, 0)));
+      const u32 cand = TRANS ? (F & ~B1) : F;
+      do_row(3, DN, baseP - sxy + g.sx, false, 0u, cand, cand, B1 & B0dn);
+    }
   }
 }
 

@@ -171,24 +171,50 @@ k_assign(u32* __restrict__ L, const u32* __restrict__ LR, const u32* __restrict_
 }
 
 // D: final write. A voxel either is a local root (its L entry already is the label) or points at one.
-template <typename OUT>
-__global__ void __launch_bounds__(256)
-k_write(const u32* __restrict__ L, const u32* __restrict__ LR, OUT* __restrict__ out, Geom g) {
-  const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const i64 row = wid / g.W;
-  if (row >= g.sy * g.sz) return;
-  const i64 seg = wid - row * g.W;
-  const i64 x = seg * 32 + lane;
+// Each thread handles 4 consecutive voxels of one row (128-bit load of L, one gather per distinct
+// pointer, one vector store); a CTA of 128 threads covers a 512-voxel chunk of a row.
+template <typename OUT> struct Out4;
+template <> struct Out4<uint16_t> { typedef ushort4 type; };
+template <> struct Out4<uint32_t> { typedef uint4 type; };
+template <> struct Out4<uint64_t> { typedef ulonglong4 type; };
+
+template <typename OUT, bool VEC>
+__global__ void __launch_bounds__(128)
+k_write(const u32* __restrict__ L, const u32* __restrict__ LR, OUT* __restrict__ out, Geom g, unsigned nchunks) {
+  const unsigned row = blockIdx.x / nchunks;
+  const unsigned chunk = blockIdx.x - row * nchunks;
+  const i64 x = (i64)chunk * 512 + threadIdx.x * 4;
   if (x >= g.sx) return;
-  const i64 i = row * g.sx + x;
-  const u32 l = L[i];
-  u32 label = 0;
-  if (l != CC_BG) {
-    const u32 lr = LR[wid];
-    label = ((lr >> lane) & 1u) ? l : L[l];
+  const i64 base = (i64)row * g.sx + x;
+  const u32 lrw = LR[(i64)row * g.W + (x >> 5)] >> (x & 31);
+  u32 l[4];
+  if (VEC) {
+    const uint4 t = *reinterpret_cast<const uint4*>(L + base);
+    l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) l[i] = (x + i < g.sx) ? L[base + i] : CC_BG;
   }
-  out[i] = (OUT)label;
+  u32 lab[4];
+  u32 prev_ptr = CC_BG, prev_lab = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    u32 v = 0;
+    if (l[i] != CC_BG) {
+      if ((lrw >> i) & 1u) v = l[i];
+      else if (l[i] == prev_ptr) v = prev_lab;
+      else { v = __ldg(&L[l[i]]); prev_ptr = l[i]; prev_lab = v; }
+    }
+    lab[i] = v;
+  }
+  if (VEC) {
+    typename Out4<OUT>::type o;
+    o.x = (OUT)lab[0]; o.y = (OUT)lab[1]; o.z = (OUT)lab[2]; o.w = (OUT)lab[3];
+    *reinterpret_cast<typename Out4<OUT>::type*>(out + base) = o;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (x + i < g.sx) out[base + i] = (OUT)lab[i];
+  }
 }
 
 // ---- binary 2D 8-connected: number components by their first 2x2 block in block-raster order
