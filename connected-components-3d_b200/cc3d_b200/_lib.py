@@ -52,6 +52,14 @@ def lib():
   L.cc3d_b200_label_resolve.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, ci, vp, p(ResolveInfo), p(vp)]
   L.cc3d_b200_label_write.restype = ci
   L.cc3d_b200_label_write.argtypes = [vp, vp, ci, ci, vp]
+  L.cc3d_b200_label_write_rows.restype = ci
+  L.cc3d_b200_label_write_rows.argtypes = [vp, i64, i64, vp, ci, vp]
+  L.cc3d_b200_label_write_remap.restype = ci
+  L.cc3d_b200_label_write_remap.argtypes = [vp, vp, ci, u64, vp, ci, ci, vp]
+  L.cc3d_b200_face_pairs.restype = ci
+  L.cc3d_b200_face_pairs.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ci, vp, u64, p(u64), vp]
+  L.cc3d_b200_solve_pairs.restype = ci
+  L.cc3d_b200_solve_pairs.argtypes = [vp, i64, vp, vp, i64, vp]
   L.cc3d_b200_session_release.restype = None
   L.cc3d_b200_session_release.argtypes = [vp]
   L.cc3d_b200_label.restype = ci

@@ -1,0 +1,282 @@
+"""Sharded labelling: one volume split into z-slabs, one slab per rank (one process per GPU).
+
+    # every rank, inside an initialised torch.distributed process group (NCCL on GPUs):
+    labels_slab, N = cc3d_b200.sharded.connected_components_slab(my_slab, connectivity=26, return_N=True)
+
+`my_slab` is this rank's contiguous (sz_local, sy, sx) block of the volume (x fastest, slabs ordered
+by rank along the slowest memory axis). The result is this rank's block of the labelling the
+single-GPU / reference call would give for the WHOLE volume: same partition, same first-appearance
+numbering, same dtype rule. It is the GPU counterpart of the reference's out-of-core
+connected_components_stack (cc3d/__init__.py:353-501), except that the final numbering equals the
+monolithic one (the reference only promises equality after renumbering, automated_test.py:1628-1641).
+
+Steps:
+  1. every rank labels its slab locally (kernels A-C3); local labels 1..N_r are in local raster order
+  2. neighbours exchange ONE boundary plane (values + local labels) point to point over NVLink
+  3. the upper rank of each interface extracts the cross-face equivalences (k_face_pairs)
+  4. the small pair lists are all-gathered; every rank solves the same union-find (k_union_pairs)
+  5. a component is numbered by the lowest slab it touches: per-slab counts of owned components give
+     offsets, and a per-slab remap table (local label -> global label) is fused into the final write
+
+All tensor plumbing below is device agnostic torch code; the compute steps go through a backend
+(CUDA via the C-ABI by default; tests inject an oracle-based backend to cover this logic with gloo).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _lib
+
+
+def _even_ceil(n: int) -> int:
+  return n << 1 if n & 1 else n
+
+
+class CudaBackend:
+  """Compute steps on the GPU through libcc3d_b200.so (no CPU fallback)."""
+
+  def __init__(self):
+    import torch
+    self.torch = torch
+    self.L = _lib.lib()
+
+  def _stream(self, t):
+    return ctypes.c_void_p(self.torch.cuda.current_stream(t.device).cuda_stream)
+
+  def resolve(self, slab, kind, connectivity, delta_arr, binary_image):
+    sz, sy, sx = slab.shape
+    info = _lib.ResolveInfo()
+    sess = ctypes.c_void_p()
+    with self.torch.cuda.device(slab.device):
+      _lib.check(self.L.cc3d_b200_label_resolve(
+        slab.data_ptr(), kind, sx, sy, sz, int(connectivity), delta_arr.ctypes.data, int(binary_image), 0,
+        _lib.DEVICE, self._stream(slab), ctypes.byref(info), ctypes.byref(sess)))
+    return {"sess": sess, "N": int(info.N), "epl": int(info.epl), "shape": (sz, sy, sx), "device": slab.device}
+
+  def plane_labels(self, h, z):
+    sz, sy, sx = h["shape"]
+    out = self.torch.empty((sy, sx), dtype=self.torch.int32, device=h["device"])
+    with self.torch.cuda.device(h["device"]):
+      _lib.check(self.L.cc3d_b200_label_write_rows(h["sess"], z * sy, (z + 1) * sy, out.data_ptr(), _lib.DEVICE,
+                                                   self._stream(out)))
+    return out
+
+  def face_pairs(self, vals_upper, labs_upper, vals_lower, labs_lower, kind, connectivity, delta_arr, binary_image):
+    torch = self.torch
+    sy, sx = labs_upper.shape
+    cap = 2 * sy * sx + 1024
+    while True:
+      pairs = torch.empty((cap,), dtype=torch.int64, device=labs_upper.device)
+      count = ctypes.c_uint64(0)
+      with torch.cuda.device(labs_upper.device):
+        _lib.check(self.L.cc3d_b200_face_pairs(
+          vals_upper.data_ptr(), labs_upper.data_ptr(), vals_lower.data_ptr(), labs_lower.data_ptr(), kind, sx, sy,
+          int(connectivity), delta_arr.ctypes.data, int(binary_image), pairs.data_ptr(), cap, ctypes.byref(count),
+          self._stream(labs_upper)))
+      if count.value <= cap:
+        return pairs[: count.value]
+      cap = int(count.value)
+
+  def solve_pairs(self, n_nodes, a, b):
+    torch = self.torch
+    parent = torch.empty((n_nodes,), dtype=torch.int32, device=a.device)
+    a32, b32 = a.to(torch.int32).contiguous(), b.to(torch.int32).contiguous()
+    with torch.cuda.device(a.device):
+      _lib.check(self.L.cc3d_b200_solve_pairs(parent.data_ptr(), n_nodes, a32.data_ptr(), b32.data_ptr(), a32.numel(),
+                                              self._stream(parent)))
+    return parent.to(torch.int64)
+
+  def write_remap(self, h, remap, max_label, out_dtype):
+    torch = self.torch
+    sz, sy, sx = h["shape"]
+    tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}[out_dtype]
+    okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}[out_dtype]
+    out = torch.empty((sz, sy, sx), dtype=tdt, device=h["device"])
+    remap = remap.contiguous()
+    sess, h["sess"] = h["sess"], None
+    with torch.cuda.device(h["device"]):
+      _lib.check(self.L.cc3d_b200_label_write_remap(sess, remap.data_ptr(), _lib.U64, int(max_label), out.data_ptr(),
+                                                    okind, _lib.DEVICE, self._stream(out)))
+    return out
+
+  def release(self, h):
+    if h.get("sess") is not None:
+      self.L.cc3d_b200_session_release(h["sess"])
+      h["sess"] = None
+
+
+def _exchange_planes(dist, group, rank, world, send_tensors, like):
+  """Rank r sends `send_tensors` to r+1 and receives the same-shaped tensors from r-1 (or None)."""
+  import torch
+  ops, recv = [], None
+  if rank > 0:
+    recv = [torch.empty_like(t) for t in like]
+    for t in recv:
+      ops.append(dist.P2POp(dist.irecv, t, dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group))
+  if rank + 1 < world:
+    for t in send_tensors:
+      ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group))
+  if ops:
+    for req in dist.batch_isend_irecv(ops):
+      req.wait()
+  return recv
+
+
+def _all_gather_varlen(dist, group, world, t):
+  """all-gather 1-D int64 tensors of different lengths (counts first, then padded payload)."""
+  import torch
+  n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+  counts = [torch.zeros_like(n) for _ in range(world)]
+  dist.all_gather(counts, n, group=group)
+  counts = [int(c.item()) for c in counts]
+  m = max(counts)
+  if m == 0:
+    return t[:0]
+  pad = torch.zeros((m,), dtype=torch.int64, device=t.device)
+  pad[: t.numel()] = t
+  bufs = [torch.empty_like(pad) for _ in range(world)]
+  dist.all_gather(bufs, pad, group=group)
+  return torch.cat([b[:c] for b, c in zip(bufs, counts)])
+
+
+def connected_components_slab(slab, connectivity: int = 26, return_N: bool = False, delta=0,
+                              out_dtype: Optional[Any] = None, binary_image: bool = False, group=None,
+                              backend=None):
+  """Labels this rank's z-slab of a volume that is sharded over the ranks of `group`.
+
+  slab: 3-D tensor (sz_local, sy, sx), C-contiguous, same dtype/sy/sx on every rank.
+  Returns this rank's slab of the global labelling (and the global N).
+  """
+  import torch
+  import torch.distributed as dist
+  from . import _kind_of, _UNSIGNED
+
+  if connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  if slab.ndim != 3:
+    raise ValueError("slab must be a 3-D (sz_local, sy, sx) tensor")
+  if backend is None:
+    backend = CudaBackend()
+  distributed = dist.is_available() and dist.is_initialized()
+  rank = dist.get_rank(group) if distributed else 0
+  world = dist.get_world_size(group) if distributed else 1
+  slab = slab.contiguous()
+  dev = slab.device
+
+  from . import _torch_np_dtype
+  orig_dtype = _torch_np_dtype(slab)
+  if orig_dtype == np.float16:
+    if delta != 0:
+      raise TypeError("float16 is not supported for continuous images (delta != 0).")
+    orig_dtype = np.dtype(np.uint16)
+  kind = _kind_of(orig_dtype)
+  binary_image = bool(binary_image) or orig_dtype == bool
+  if np.issubdtype(orig_dtype, np.floating):
+    delta = float(delta)
+    is_max_delta = delta == np.finfo(orig_dtype).max
+  else:
+    delta = int(delta)
+    is_max_delta = (orig_dtype != bool) and delta == np.iinfo(orig_dtype).max
+  epl_skipped = binary_image
+  binary_image = binary_image or is_max_delta
+  kdtype = np.dtype(np.uint8) if orig_dtype == bool else (
+    np.dtype(_UNSIGNED[orig_dtype.itemsize]) if np.issubdtype(orig_dtype, np.signedinteger) else orig_dtype)
+  delta_arr = np.array([delta], dtype=kdtype) if np.issubdtype(kdtype, np.floating) else \
+    np.array([delta & ((1 << (8 * kdtype.itemsize)) - 1)], dtype=kdtype)
+
+  sz, sy, sx = slab.shape
+  h = backend.resolve(slab, kind, connectivity, delta_arr, binary_image)
+  try:
+    # ---- per-slab facts every rank needs ----
+    mine = torch.tensor([h["N"], h["epl"], sz], dtype=torch.int64, device=dev)
+    if world > 1:
+      allv = [torch.zeros_like(mine) for _ in range(world)]
+      dist.all_gather(allv, mine, group=group)
+      facts = torch.stack(allv).cpu()
+    else:
+      facts = mine.cpu()[None]
+    N_r = facts[:, 0]
+    offsets = torch.cumsum(N_r, 0) - N_r            # global id of (slab r, label l) = offsets[r] + l, l >= 1
+    total_ids = int(N_r.sum())
+    sz_total = int(facts[:, 2].sum())
+    voxels_total = sz_total * sy * sx
+    epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
+
+    # ---- boundary plane exchange + cross-face equivalences ----
+    pairs = torch.zeros((0,), dtype=torch.int64, device=dev)
+    if world > 1:
+      top_vals = slab[sz - 1].contiguous().view(torch.uint8) if sz > 0 else None
+      top_labs = backend.plane_labels(h, sz - 1)
+      recv = _exchange_planes(dist, group, rank, world, [top_vals, top_labs], [top_vals, top_labs])
+      if rank > 0:
+        low_vals = recv[0].view(slab.dtype)
+        low_labs = recv[1]
+        up_labs = backend.plane_labels(h, 0)
+        packed = backend.face_pairs(slab[0].contiguous(), up_labs, low_vals, low_labs, kind, connectivity, delta_arr,
+                                    binary_image)
+        packed = torch.unique(packed)
+        lo = (packed >> 32) + int(offsets[rank - 1])
+        up = (packed & 0xFFFFFFFF) + int(offsets[rank])
+        pairs = torch.stack([lo, up], 1).reshape(-1)
+      pairs = _all_gather_varlen(dist, group, world, pairs)
+    a, b = pairs[0::2], pairs[1::2]
+
+    # ---- every rank solves the same small union-find over the ids that touch an interface ----
+    remap = torch.arange(h["N"] + 1, dtype=torch.int64, device=dev)
+    owned = N_r.clone()
+    if a.numel() > 0:
+      nodes = torch.unique(torch.cat([a, b]))                      # sorted: id order == global raster order
+      ia, ib = torch.searchsorted(nodes, a), torch.searchsorted(nodes, b)
+      parent = backend.solve_pairs(nodes.numel(), ia, ib)          # smallest node of each set
+      bounds = (offsets + N_r).to(dev)                             # last id of every slab
+      node_slab = torch.searchsorted(bounds, nodes)                # ids are 1-based: id <= bounds[r]
+      nonowned = parent != torch.arange(nodes.numel(), device=dev)
+      per_slab_nonowned = torch.zeros((world,), dtype=torch.int64, device=dev).index_add_(
+        0, node_slab, nonowned.to(torch.int64))
+      owned = N_r - per_slab_nonowned.cpu()
+    base = torch.cumsum(owned, 0) - owned
+    N_total = int(owned.sum())
+    if a.numel() > 0:
+      cs = torch.cumsum(nonowned.to(torch.int64), 0) - nonowned.to(torch.int64)  # non-owned nodes before j
+      first_of_slab = torch.searchsorted(node_slab, torch.arange(world, device=dev))
+      cs_start = torch.cat([cs, cs.new_zeros(1)])[first_of_slab.clamp(max=nodes.numel())]
+      before_in_slab = cs - cs_start[node_slab]
+      node_label = nodes - offsets.to(dev)[node_slab]
+      final_owned = base.to(dev)[node_slab] + node_label - before_in_slab   # valid for owned (root) nodes
+      final = final_owned[parent]
+      my = node_slab == rank
+      my_labels = node_label[my]
+      flags = torch.zeros((h["N"] + 1,), dtype=torch.int64, device=dev)
+      flags[my_labels[nonowned[my]]] = 1
+      remap = int(base[rank]) + remap - torch.cumsum(flags, 0)
+      remap[my_labels] = final[my]
+    else:
+      remap = int(base[rank]) + remap
+    remap[0] = 0
+
+    # ---- out-dtype rule of the monolithic call (fastcc3d.pyx:388-434) ----
+    max_lab = min(epl_total, voxels_total)
+    if binary_image:
+      uf = _even_ceil(sz_total) * _even_ceil(sy) * _even_ceil(sx)
+      max_lab = min(max_lab, uf // 2 + 1) if connectivity == 6 else min(max_lab, uf // 8 + 1)
+    if out_dtype is not None:
+      out_dtype = np.dtype(out_dtype)
+      if out_dtype not in (np.uint16, np.uint32, np.uint64):
+        raise ValueError(f"Explicitly defined out_dtype ({out_dtype}) must be one of: np.uint16, np.uint32, np.uint64")
+      if np.iinfo(out_dtype).max < max_lab:
+        raise ValueError(f"Explicitly defined out_dtype ({out_dtype}) is too small "
+                         f"to contain the estimated maximum number of labels ({max_lab}).")
+    elif max_lab < np.iinfo(np.uint16).max:
+      out_dtype = np.dtype(np.uint16)
+    elif max_lab < np.iinfo(np.uint32).max:
+      out_dtype = np.dtype(np.uint32)
+    else:
+      out_dtype = np.dtype(np.uint64)
+
+    out = backend.write_remap(h, remap, N_total, out_dtype)
+  finally:
+    backend.release(h)
+  return (out, N_total) if return_N else out

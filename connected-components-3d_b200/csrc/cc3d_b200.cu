@@ -416,49 +416,152 @@ void cc3d_b200_session_release(cc3d_b200_session* S) {
   delete S;
 }
 
-int cc3d_b200_label_write(cc3d_b200_session* S, void* out, int out_kind, int mem_space, void* stream) {
+template <typename OUT>
+static void launch_write(const cc3d_b200_session* S, OUT* dout, unsigned row0, unsigned nrows, const void* remap,
+                         int remap_kind, cudaStream_t s) {
+  const Geom& g = S->g;
+  const unsigned nchunks = (unsigned)((g.sx + 511) / 512);
+  const unsigned blocks = nrows * nchunks;
+  const bool vec = (g.sx % 4 == 0) && (((uintptr_t)dout) % 32 == 0);
+#define CC_LAUNCH_WRITE(V, R) k_write<OUT, V, R><<<blocks, 128, 0, s>>>(S->L, S->LR, dout, g, nchunks, row0, remap)
+  if (!remap) { if (vec) CC_LAUNCH_WRITE(true, 0); else CC_LAUNCH_WRITE(false, 0); }
+  else if (remap_kind == CC3D_B200_U32) { if (vec) CC_LAUNCH_WRITE(true, 1); else CC_LAUNCH_WRITE(false, 1); }
+  else { if (vec) CC_LAUNCH_WRITE(true, 2); else CC_LAUNCH_WRITE(false, 2); }
+#undef CC_LAUNCH_WRITE
+  g_launches += 1;
+}
+
+// shared implementation of label_write / label_write_rows / label_write_remap
+static int write_impl(cc3d_b200_session* S, void* out, int out_kind, int mem_space, void* stream, i64 row0, i64 nrows,
+                      const void* remap, int remap_kind, u64 max_label, bool release) {
   if (!S) return fail(CC3D_B200_ERR_ARGUMENT, "NULL session");
+  auto done = [&](int rc) { if (release) cc3d_b200_session_release(S); return rc; };
   const size_t os = (out_kind == CC3D_B200_U16) ? 2 : (out_kind == CC3D_B200_U32 ? 4 : (out_kind == CC3D_B200_U64 ? 8 : 0));
-  if (!os) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_KIND, "out kind must be u16, u32 or u64"); }
-  if (S->voxels == 0) { cc3d_b200_session_release(S); return 0; }
-  if ((os == 2 && S->N > 0xFFFFull) || (os == 4 && S->N > 0xFFFFFFFFull)) {
-    cc3d_b200_session_release(S);
-    return fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind");
-  }
+  if (!os) return done(fail(CC3D_B200_ERR_KIND, "out kind must be u16, u32 or u64"));
+  if (S->voxels == 0 || nrows == 0) return done(0);
+  if (row0 < 0 || nrows < 0 || row0 + nrows > S->g.sy * S->g.sz) return done(fail(CC3D_B200_ERR_ARGUMENT, "row range outside the volume"));
+  if (remap && remap_kind != CC3D_B200_U32 && remap_kind != CC3D_B200_U64) return done(fail(CC3D_B200_ERR_KIND, "remap kind must be u32 or u64"));
+  if ((os == 2 && max_label > 0xFFFFull) || (os == 4 && max_label > 0xFFFFFFFFull))
+    return done(fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind"));
   cudaStream_t s = (cudaStream_t)stream;
   const Geom& g = S->g;
+  const size_t nvox = (size_t)nrows * (size_t)g.sx;
   void* dout = out;
+  const void* dremap = remap;
+  void* tmp_out = nullptr;
+  void* tmp_remap = nullptr;
   if (mem_space == CC3D_B200_HOST) {
-    // the arena was sized for the resolve phase; the output staging buffer may need its own allocation
-    if (S->arena.off + (size_t)S->voxels * os + 512 <= S->arena.cap) dout = S->arena.take((size_t)S->voxels * os);
+    // the arena was sized for the resolve phase; staging buffers may need their own allocation
+    if (S->arena.off + nvox * os + 512 <= S->arena.cap) dout = S->arena.take(nvox * os);
     else {
-      cudaError_t e = cudaMalloc(&dout, (size_t)S->voxels * os);
-      if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+      cudaError_t e = cudaMalloc(&tmp_out, nvox * os);
+      if (e != cudaSuccess) return done(fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)));
+      dout = tmp_out;
+    }
+    if (remap) {
+      const size_t rb = (size_t)(S->N + 1) * (remap_kind == CC3D_B200_U32 ? 4 : 8);
+      cudaError_t e = cudaMalloc(&tmp_remap, rb);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp_remap, remap, rb, cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) { if (tmp_out) cudaFree(tmp_out); return done(fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e))); }
+      dremap = tmp_remap;
     }
   }
   marks_begin(s);
-  const unsigned nchunks = (unsigned)((g.sx + 511) / 512);
-  const unsigned blocks = (unsigned)(g.sy * g.sz) * nchunks;
-  const bool vec = (g.sx % 4 == 0) && (((uintptr_t)dout) % 32 == 0);
-  if (os == 2) { if (vec) k_write<uint16_t, true><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g, nchunks); else k_write<uint16_t, false><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint16_t*)dout, g, nchunks); }
-  else if (os == 4) { if (vec) k_write<uint32_t, true><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g, nchunks); else k_write<uint32_t, false><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint32_t*)dout, g, nchunks); }
-  else { if (vec) k_write<uint64_t, true><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g, nchunks); else k_write<uint64_t, false><<<blocks, 128, 0, s>>>(S->L, S->LR, (uint64_t*)dout, g, nchunks); }
-  g_launches += 1;
+  if (os == 2) launch_write<uint16_t>(S, (uint16_t*)dout, (unsigned)row0, (unsigned)nrows, dremap, remap_kind, s);
+  else if (os == 4) launch_write<uint32_t>(S, (uint32_t*)dout, (unsigned)row0, (unsigned)nrows, dremap, remap_kind, s);
+  else launch_write<uint64_t>(S, (uint64_t*)dout, (unsigned)row0, (unsigned)nrows, dremap, remap_kind, s);
   mark("D_write", s);
   cudaError_t e = cudaSuccess;
   if (mem_space == CC3D_B200_HOST) {
-    e = cudaMemcpyAsync(out, dout, (size_t)S->voxels * os, cudaMemcpyDeviceToHost, s);
+    e = cudaMemcpyAsync(out, dout, nvox * os, cudaMemcpyDeviceToHost, s);
     mark("D2H", s);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
   marks_collect(true);
-  if (mem_space == CC3D_B200_HOST) {
-    const char* b = S->arena.base;
-    if (!((const char*)dout >= b && (const char*)dout < b + S->arena.cap)) cudaFree(dout);
+  if (tmp_out) cudaFree(tmp_out);
+  if (tmp_remap) cudaFree(tmp_remap);
+  if (e != cudaSuccess) return done(fail(CC3D_B200_ERR_CUDA, std::string("label_write: ") + cudaGetErrorString(e)));
+  return done(0);
+}
+
+int cc3d_b200_label_write(cc3d_b200_session* S, void* out, int out_kind, int mem_space, void* stream) {
+  if (!S) return fail(CC3D_B200_ERR_ARGUMENT, "NULL session");
+  return write_impl(S, out, out_kind, mem_space, stream, 0, S->g.sy * S->g.sz, nullptr, 0, S->N, true);
+}
+
+int cc3d_b200_label_write_rows(cc3d_b200_session* S, int64_t row_begin, int64_t row_end, uint32_t* out, int mem_space,
+                               void* stream) {
+  return write_impl(S, out, CC3D_B200_U32, mem_space, stream, row_begin, row_end - row_begin, nullptr, 0, 0, false);
+}
+
+int cc3d_b200_label_write_remap(cc3d_b200_session* S, const void* remap, int remap_kind, uint64_t max_label, void* out,
+                                int out_kind, int mem_space, void* stream) {
+  if (!S) return fail(CC3D_B200_ERR_ARGUMENT, "NULL session");
+  if (!remap) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "NULL remap table"); }
+  return write_impl(S, out, out_kind, mem_space, stream, 0, S->g.sy * S->g.sz, remap, remap_kind, max_label, true);
+}
+
+template <typename T>
+static void face_pairs_typed(const T* vP, const u32* lP, const T* vQ, const u32* lQ, i64 sx, i64 sy, int connectivity,
+                             int mode, const void* delta, u64* pairs, unsigned long long cap, unsigned long long* count,
+                             cudaStream_t s) {
+  const i64 n = sx * sy;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (mode == MODE_EQ) { Edge<T, MODE_EQ> E; E.delta = (T)0; k_face_pairs<T, MODE_EQ><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
+  else if (mode == MODE_NONZERO) { Edge<T, MODE_NONZERO> E; E.delta = (T)0; k_face_pairs<T, MODE_NONZERO><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
+  else { Edge<T, MODE_DELTA> E; memcpy(&E.delta, delta, sizeof(T)); k_face_pairs<T, MODE_DELTA><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
+  g_launches += 1;
+}
+
+int cc3d_b200_face_pairs(const void* values_upper, const uint32_t* labels_upper, const void* values_lower,
+                         const uint32_t* labels_lower, int in_kind, int64_t sx, int64_t sy, int connectivity,
+                         const void* delta, int binary_image, uint64_t* pairs, uint64_t capacity, uint64_t* count,
+                         void* stream) {
+  const size_t es = kind_size(in_kind);
+  if (!es) return fail(CC3D_B200_ERR_KIND, "unsupported input kind");
+  if (connectivity != 6 && connectivity != 18 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "sharded volumes support 6, 18 and 26 connectivity");
+  if (!count) return fail(CC3D_B200_ERR_ARGUMENT, "count must not be NULL");
+  *count = 0;
+  if (sx * sy == 0) return 0;
+  bool delta_zero = true;
+  if (delta) { for (size_t i = 0; i < es; i++) if (((const unsigned char*)delta)[i]) delta_zero = false; }
+  const int mode = binary_image ? MODE_NONZERO : (delta_zero ? MODE_EQ : MODE_DELTA);
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* dcount = nullptr;
+  CUDA_OK(cudaMalloc((void**)&dcount, 8));
+  cudaMemsetAsync(dcount, 0, 8, s);
+  const u32 *lP = labels_upper, *lQ = labels_lower;
+  switch (in_kind) {
+    case CC3D_B200_U8: face_pairs_typed((const uint8_t*)values_upper, lP, (const uint8_t*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s); break;
+    case CC3D_B200_U16: face_pairs_typed((const uint16_t*)values_upper, lP, (const uint16_t*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s); break;
+    case CC3D_B200_U32: face_pairs_typed((const uint32_t*)values_upper, lP, (const uint32_t*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s); break;
+    case CC3D_B200_U64: face_pairs_typed((const uint64_t*)values_upper, lP, (const uint64_t*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s); break;
+    case CC3D_B200_F32: face_pairs_typed((const float*)values_upper, lP, (const float*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s); break;
+    default: face_pairs_typed((const double*)values_upper, lP, (const double*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s); break;
   }
-  cc3d_b200_session_release(S);
-  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("label_write: ") + cudaGetErrorString(e));
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, dcount, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(dcount);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("face_pairs: ") + cudaGetErrorString(e));
+  *count = h;
+  return 0;
+}
+
+int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, const uint32_t* b, int64_t n_pairs,
+                          void* stream) {
+  if (n_nodes <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_iota<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(parent, n_nodes);
+  if (n_pairs > 0) k_union_pairs<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(parent, a, b, n_pairs);
+  k_flatten<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(parent, n_nodes);
+  g_launches += 3;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("solve_pairs: ") + cudaGetErrorString(e));
   return 0;
 }
 

@@ -178,14 +178,19 @@ template <> struct Out4<uint16_t> { typedef ushort4 type; };
 template <> struct Out4<uint32_t> { typedef uint4 type; };
 template <> struct Out4<uint64_t> { typedef ulonglong4 type; };
 
-template <typename OUT, bool VEC>
+// REMAP: 0 = write the local label, 1/2 = write remap[label] from a u32/u64 table (sharded volumes:
+// per-slab label -> global label). row0 = first row to write; out is indexed relative to row0.
+template <typename OUT, bool VEC, int REMAP>
 __global__ void __launch_bounds__(128)
-k_write(const u32* __restrict__ L, const u32* __restrict__ LR, OUT* __restrict__ out, Geom g, unsigned nchunks) {
-  const unsigned row = blockIdx.x / nchunks;
-  const unsigned chunk = blockIdx.x - row * nchunks;
+k_write(const u32* __restrict__ L, const u32* __restrict__ LR, OUT* __restrict__ out, Geom g, unsigned nchunks,
+        unsigned row0, const void* __restrict__ remap) {
+  const unsigned rrel = blockIdx.x / nchunks;
+  const unsigned chunk = blockIdx.x - rrel * nchunks;
+  const unsigned row = row0 + rrel;
   const i64 x = (i64)chunk * 512 + threadIdx.x * 4;
   if (x >= g.sx) return;
   const i64 base = (i64)row * g.sx + x;
+  const i64 obase = (i64)rrel * g.sx + x;
   const u32 lrw = LR[(i64)row * g.W + (x >> 5)] >> (x & 31);
   u32 l[4];
   if (VEC) {
@@ -195,26 +200,107 @@ k_write(const u32* __restrict__ L, const u32* __restrict__ LR, OUT* __restrict__
 #pragma unroll
     for (int i = 0; i < 4; i++) l[i] = (x + i < g.sx) ? L[base + i] : CC_BG;
   }
-  u32 lab[4];
-  u32 prev_ptr = CC_BG, prev_lab = 0;
+  OUT lab[4];
+  u32 prev_ptr = CC_BG;
+  OUT prev_lab = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    u32 v = 0;
+    OUT v = 0;
     if (l[i] != CC_BG) {
-      if ((lrw >> i) & 1u) v = l[i];
-      else if (l[i] == prev_ptr) v = prev_lab;
-      else { v = __ldg(&L[l[i]]); prev_ptr = l[i]; prev_lab = v; }
+      const bool isroot = (lrw >> i) & 1u;
+      if (!isroot && l[i] == prev_ptr) v = prev_lab;
+      else {
+        const u32 loc = isroot ? l[i] : __ldg(&L[l[i]]);
+        if (REMAP == 1) v = (OUT)__ldg(reinterpret_cast<const u32*>(remap) + loc);
+        else if (REMAP == 2) v = (OUT)__ldg(reinterpret_cast<const u64*>(remap) + loc);
+        else v = (OUT)loc;
+        if (!isroot) { prev_ptr = l[i]; prev_lab = v; }
+      }
     }
     lab[i] = v;
   }
   if (VEC) {
     typename Out4<OUT>::type o;
-    o.x = (OUT)lab[0]; o.y = (OUT)lab[1]; o.z = (OUT)lab[2]; o.w = (OUT)lab[3];
-    *reinterpret_cast<typename Out4<OUT>::type*>(out + base) = o;
+    o.x = lab[0]; o.y = lab[1]; o.z = lab[2]; o.w = lab[3];
+    *reinterpret_cast<typename Out4<OUT>::type*>(out + obase) = o;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) if (x + i < g.sx) out[base + i] = (OUT)lab[i];
+    for (int i = 0; i < 4; i++) if (x + i < g.sx) out[obase + i] = lab[i];
   }
+}
+
+// ---- sharded volumes (z-slabs): equivalences across one slab interface ----
+// P = first plane of the upper slab (later in raster order), Q = last plane of the lower slab.
+// Emits (label in Q's slab, label in P's slab) for every edge of the chosen predicate/neighbourhood
+// between the two planes, skipping an edge when the voxel to the left already produced the same pair.
+// Replaces the Python face loops of connected_components_stack (cc3d/__init__.py:425-468).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __restrict__ vQ, const u32* __restrict__ lQ,
+             i64 sx, i64 sy, int connectivity, Edge<T, MODE> E, u64* __restrict__ pairs, unsigned long long cap,
+             unsigned long long* __restrict__ count) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  u64 mine[9];
+  int n = 0;
+  if (i < sx * sy) {
+    const i64 y = i / sx, x = i - y * sx;
+    const T p = vP[i];
+    if (E.fg(p)) {
+      const u32 lp = lP[i];
+      const bool left_same = x > 0 && lP[i - 1] == lp;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          const int nz = (dx != 0) + (dy != 0);
+          if (connectivity == 6 && nz > 0) continue;
+          if (connectivity == 18 && nz > 1) continue;
+          const i64 xx = x + dx, yy = y + dy;
+          if (xx < 0 || xx >= sx || yy < 0 || yy >= sy) continue;
+          const i64 qi = yy * sx + xx;
+          const T q = vQ[qi];
+          if (!E(p, q, dir_code(dx, dy, -1))) continue;
+          const u32 lq = lQ[qi];
+          // the voxel to the left emits the same (lq, lp) through the same direction
+          if (left_same && xx > 0 && lQ[qi - 1] == lq && E(vP[i - 1], vQ[qi - 1], dir_code(dx, dy, -1))) continue;
+          mine[n++] = ((u64)lq << 32) | lp;
+        }
+      }
+    }
+  }
+  // warp-aggregated append
+  u32 total = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(CC_FULL, total, o);
+    if (lane >= o) total += t;
+  }
+  const u32 wtotal = __shfl_sync(CC_FULL, total, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && wtotal) base = atomicAdd(count, (unsigned long long)wtotal);
+  base = __shfl_sync(CC_FULL, base, 31);
+  const unsigned long long off = base + total - n;
+  for (int k = 0; k < n; k++)
+    if (off + k < cap) pairs[off + k] = mine[k];
+}
+
+// union-find over compact node ids (pairs given as two u32 arrays); parent must hold 0..n-1 on entry
+__global__ void __launch_bounds__(256) k_iota(u32* __restrict__ p, i64 n) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (u32)i;
+}
+__global__ void __launch_bounds__(256)
+k_union_pairs(u32* __restrict__ parent, const u32* __restrict__ a, const u32* __restrict__ b, i64 n) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) uf_union(parent, a[i], b[i]);
+}
+__global__ void __launch_bounds__(256) k_flatten(u32* __restrict__ parent, i64 n) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 r = (u32)i, p;
+  while ((p = __ldcg(&parent[r])) != r) r = p;
+  parent[i] = r;
 }
 
 // ---- binary 2D 8-connected: number components by their first 2x2 block in block-raster order

@@ -88,6 +88,34 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
 int cc3d_b200_label_write(cc3d_b200_session* session, void* out, int out_kind, int mem_space,
                           void* stream);
 
+/* Sharded volumes (z-slabs across GPUs); device pointers only where noted.
+ * label_write_rows: local labels (uint32, 1..N of this session) of rows [row_begin,row_end) into a
+ * compact buffer; keeps the session. Used to publish a slab's boundary planes. */
+int cc3d_b200_label_write_rows(cc3d_b200_session* session, int64_t row_begin, int64_t row_end, uint32_t* out,
+                               int mem_space, void* stream);
+
+/* label_write_remap: out[i] = remap[local label of i] (remap has N+1 entries of remap_kind u32/u64,
+ * remap[0] = 0; max_label = largest value in remap, checked against out_kind). Releases the session. */
+int cc3d_b200_label_write_remap(cc3d_b200_session* session, const void* remap, int remap_kind, uint64_t max_label,
+                                void* out, int out_kind, int mem_space, void* stream);
+
+/* Equivalences across one slab interface (DEVICE pointers): `upper` = first plane of the slab that
+ * comes later in memory, `lower` = last plane of the slab before it; values of in_kind, labels = the
+ * slabs' local labels. Appends (lower_label << 32 | upper_label) for every edge between the planes
+ * (6/18/26 neighbourhood, same predicate as label_resolve) to pairs[capacity]; *count receives the
+ * number of pairs produced (if > capacity the list was truncated: call again with more room).
+ * GPU analogue of the face loops in connected_components_stack (cc3d/__init__.py:425-468). */
+int cc3d_b200_face_pairs(const void* values_upper, const uint32_t* labels_upper, const void* values_lower,
+                         const uint32_t* labels_lower, int in_kind, int64_t sx, int64_t sy, int connectivity,
+                         const void* delta, int binary_image, uint64_t* pairs, uint64_t capacity, uint64_t* count,
+                         void* stream);
+
+/* Union-find over n_nodes compact node ids joined by n_pairs (a[i], b[i]) pairs (DEVICE pointers):
+ * parent[i] = smallest node id of i's set. Replaces the Python DisjointSet of
+ * connected_components_stack (cc3d/__init__.py:296-321). */
+int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, const uint32_t* b, int64_t n_pairs,
+                          void* stream);
+
 /* Drops a session without writing. */
 void cc3d_b200_session_release(cc3d_b200_session* session);
 
