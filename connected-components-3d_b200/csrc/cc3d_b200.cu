@@ -110,19 +110,14 @@ void marks_collect(bool append) {
   g_marks.clear();
 }
 
-__global__ void k_init_counters(Counters* c) { c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; }
+__global__ void k_init_counters(Counters* c) { c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; c->nruns = 0; }
 
 Geom make_geom(i64 sx, i64 sy, i64 sz) {
   Geom g;
   g.sx = sx; g.sy = sy; g.sz = sz;
-  // 64 rows per tile: 64x8x8 for volumes, 64x64x1 for single-plane images
-  int TZ = sz > 1 ? 8 : 1;
-  int TY = 64 / TZ;
-  g.TY = TY; g.TZ = TZ;
-  g.ntx = (sx + CC_TX - 1) / CC_TX;
-  g.nty = (sy + TY - 1) / TY;
-  g.ntz = (sz + TZ - 1) / TZ;
   g.W = (sx + 31) / 32;
+  g.rows = sy * sz;
+  g.nwords = g.rows * g.W;
   return g;
 }
 
@@ -141,8 +136,8 @@ struct cc3d_b200_session {
   Arena arena;
   Geom g;
   i64 voxels = 0;
-  u32* L = nullptr;
-  u32* LR = nullptr;
+  u32* L = nullptr;   // final label of every run, at the run's first voxel
+  u32* M = nullptr;   // edge bitmaps (F and X planes are what the expansion needs)
   u64 N = 0;
 };
 
@@ -235,24 +230,22 @@ int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64
   return 0;
 }
 
-static int label_stage_dispatch(int kind, const LabelArgs& a) {
-  switch (kind) {
-    case CC3D_B200_U8: return run_label_stage<uint8_t>(a);
-    case CC3D_B200_U16: return run_label_stage<uint16_t>(a);
-    case CC3D_B200_U32: return run_label_stage<uint32_t>(a);
-    case CC3D_B200_U64: return run_label_stage<uint64_t>(a);
-    case CC3D_B200_F32: return run_label_stage<float>(a);
-    case CC3D_B200_F64: return run_label_stage<double>(a);
+#define CC_KIND_SWITCH(kind, CALL)                                  \
+  switch (kind) {                                                    \
+    case CC3D_B200_U8: { typedef uint8_t KT; CALL; break; }          \
+    case CC3D_B200_U16: { typedef uint16_t KT; CALL; break; }        \
+    case CC3D_B200_U32: { typedef uint32_t KT; CALL; break; }        \
+    case CC3D_B200_U64: { typedef uint64_t KT; CALL; break; }        \
+    case CC3D_B200_F32: { typedef float KT; CALL; break; }           \
+    case CC3D_B200_F64: { typedef double KT; CALL; break; }          \
   }
-  return -1;
-}
 
 template <typename T>
-static void c8_mask_typed(const T* in, unsigned char* mask, i64 sx, i64 sy, const void* delta, const void* range, cudaStream_t s) {
+static void c8_edges_typed(const T* in, u32* M, const Geom& g, const void* delta, const void* range, cudaStream_t s) {
   T d;
   memcpy(&d, delta, sizeof(T));
-  const i64 n = sx * sy;
-  k_c8_mask<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, mask, sx, sy, d, (const T*)range);
+  const i64 nthreads = g.nwords * 32;
+  k_c8_edges<T><<<(unsigned)((nthreads + 255) / 256), 256, 0, s>>>(in, M, g, d, (const T*)range);
   g_launches += 1;
 }
 
@@ -294,23 +287,24 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   cudaStream_t s = (cudaStream_t)stream;
   Geom g = make_geom(sx, sy, sz);
   S->g = g;
-  const i64 rows = sy * sz;
-  const i64 nwords = rows * g.W;
-  const i64 nslots = rows * (g.ntx - 1);
+  const i64 nwords = g.nwords;
   const i64 nb = (nwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  // upper bound on the number of x-runs: every voxel (multilabel / continuous), every other voxel (binary)
+  const i64 maxruns = (mode == MODE_NONZERO) ? g.rows * ((sx + 1) / 2) : voxels;
+  const i64 nwords2 = (maxruns + 31) / 32;            // root-flag words
+  const i64 nb2 = (nwords2 + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
   const i64 nblocks2d = block_order ? ((sx + 1) / 2) * ((sy + 1) / 2) : 0;
   const i64 nbwords = (nblocks2d + 31) / 32;
 
   size_t need = 4096;
   auto add = [&](size_t b) { need += ((b + 255) & ~size_t(255)) + 256; };
   if (mem_space == CC3D_B200_HOST) add((size_t)voxels * es);
-  if (c8) add((size_t)voxels);
-  add((size_t)voxels * 4);          // L
-  add((size_t)nwords * 4 * 4);      // LR GR cnt prefix
-  add((size_t)nslots * 4 + 4);      // XS
-  add((size_t)(nb + 1) * 8);        // bsum
+  add((size_t)maxruns * 4);                // L
+  add((size_t)nwords * 4 * PL_COUNT);      // M
+  add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
+  add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
-  if (block_order) { add((size_t)voxels * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
+  if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
   if (int rc = arena_acquire(need, &S->arena)) { delete S; return rc; }
   Arena& ar = S->arena;
 
@@ -323,15 +317,15 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
     din = d;
     mark("H2D", s);
   }
-  u32* L = (u32*)ar.take((size_t)voxels * 4);
-  u32* LR = (u32*)ar.take((size_t)nwords * 4);
-  u32* GR = (u32*)ar.take((size_t)nwords * 4);
-  u32* cnt = (u32*)ar.take((size_t)nwords * 4);
-  u32* prefix = (u32*)ar.take((size_t)nwords * 4);
-  u32* XS = (u32*)ar.take((size_t)nslots * 4 + 4);
+  u32* M = (u32*)ar.take((size_t)nwords * 4 * PL_COUNT);
+  u32* L = (u32*)ar.take((size_t)maxruns * 4);
+  u32* GR = (u32*)ar.take((size_t)nwords2 * 4);
+  u32* cnt = (u32*)ar.take((size_t)nwords2 * 4);
+  u32* prefix = (u32*)ar.take((size_t)nwords2 * 4);
   u64* bsum = (u64*)ar.take((size_t)(nb + 1) * 8);
+  u64* bsum2 = (u64*)ar.take((size_t)(nb2 + 1) * 8);
   Counters* ctr = (Counters*)ar.take(sizeof(Counters));
-  S->L = L; S->LR = LR;
+  S->L = L; S->M = M;
 
   k_init_counters<<<1, 1, 0, s>>>(ctr);
   g_launches += 1;
@@ -339,59 +333,66 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   LabelArgs a;
   int stage_launches = 0;
   a.launches = &stage_launches;
-  a.L = L; a.LR = LR; a.XS = XS; a.ctr = ctr; a.g = g;
-  a.connectivity = connectivity; a.periodic = periodic_boundary; a.stream = s;
-  a.mark = g_timing ? mark : nullptr;
+  a.in = din; a.M = M; a.L = L; a.ctr = ctr; a.g = g; a.mode = mode;
+  a.connectivity = connectivity; a.stream = s;
   memset(a.delta, 0, 8);
   if (delta) memcpy(a.delta, delta, es);
-  int rc;
+  int rc = 0;
+  // A: face bitmaps
   if (c8) {
-    // epl + value range, then the reference's per-pixel edge rule as a bitfield, then mask-mode labelling
+    // epl + value range, then the reference's per-pixel edge rule straight into the bitmaps
     void* range2 = ar.take(16);
-    unsigned char* maskbuf = (unsigned char*)ar.take((size_t)voxels);
     prepass_dispatch(din, in_kind, g, ctr, range2, ar, s);
-    switch (in_kind) {
-      case CC3D_B200_U8: c8_mask_typed((const uint8_t*)din, maskbuf, sx, sy, delta, range2, s); break;
-      case CC3D_B200_U16: c8_mask_typed((const uint16_t*)din, maskbuf, sx, sy, delta, range2, s); break;
-      case CC3D_B200_U32: c8_mask_typed((const uint32_t*)din, maskbuf, sx, sy, delta, range2, s); break;
-      case CC3D_B200_U64: c8_mask_typed((const uint64_t*)din, maskbuf, sx, sy, delta, range2, s); break;
-      case CC3D_B200_F32: c8_mask_typed((const float*)din, maskbuf, sx, sy, delta, range2, s); break;
-      case CC3D_B200_F64: c8_mask_typed((const double*)din, maskbuf, sx, sy, delta, range2, s); break;
-    }
-    mark("c8_mask", s);
-    a.in = maskbuf; a.mode = MODE_MASK;
-    rc = run_label_stage<uint8_t>(a);
+    CC_KIND_SWITCH(in_kind, c8_edges_typed((const KT*)din, M, g, delta, range2, s));
+    a.mode = MODE_MASK;
+    mark("A_c8_edges", s);
   } else {
-    a.in = din; a.mode = mode;
-    rc = label_stage_dispatch(in_kind, a);
+    rc = -1;
+    CC_KIND_SWITCH(in_kind, rc = run_faces_stage<KT>(a));
+    mark("A_faces", s);
+  }
+  if (rc == 0) {
+    // S: number the runs
+    u32* RS = M + (size_t)PL_RS * nwords;
+    scan_counts(RS, RS, bsum, nwords, &ctr->nruns, s);
+    k_iota_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, &ctr->nruns);
+    g_launches += 1;
+    mark("S_scan_runs", s);
+    // B: unions
+    rc = -1;
+    CC_KIND_SWITCH(in_kind, rc = run_union_stage<KT>(a));
+    mark("B_union", s);
+  }
+  if (rc == 0 && periodic_boundary && (connectivity == 4 || connectivity == 8 || connectivity == 6)) {
+    CC_KIND_SWITCH(in_kind, rc = run_periodic_stage<KT>(a));
+    mark("P_periodic", s);
   }
   if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
 
   g_launches += stage_launches;
-  const unsigned wblocks = (unsigned)((nwords + 255) / 256);
-  k_compress<<<wblocks, 256, 0, s>>>(L, LR, GR, cnt, g, nwords);
+  k_compress<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, GR, cnt, &ctr->nruns, (u32)nwords2);
   g_launches += 1;
   mark("C1_compress", s);
-  scan_counts(cnt, prefix, bsum, nwords, &ctr->N, s);
+  scan_counts(cnt, prefix, bsum2, nwords2, &ctr->N, s);
   mark("C2_scan", s);
   if (block_order) {
-    u32* K = (u32*)ar.take((size_t)voxels * 4);
+    u32* K = (u32*)ar.take((size_t)maxruns * 4);
     u32* BK = (u32*)ar.take((size_t)nbwords * 4);
     u32* bcnt = (u32*)ar.take((size_t)nbwords * 4);
     u32* bprefix = (u32*)ar.take((size_t)nbwords * 4);
-    u64* bsum2 = (u64*)ar.take(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8);
+    u64* bsum3 = (u64*)ar.take(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8);
     u64* dummyN = (u64*)ar.take(8);
     cudaMemsetAsync(BK, 0, (size_t)nbwords * 4, s);
-    k_blockkey_init<<<wblocks, 256, 0, s>>>(K, GR, g, nwords);
-    k_blockkey_min<<<(unsigned)((nwords * 32 + 255) / 256), 256, 0, s>>>(L, LR, K, g);
-    k_blockkey_mark<<<wblocks, 256, 0, s>>>(K, GR, BK, g, nwords);
+    k_fill_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(K, CC_BG, &ctr->nruns);
+    k_blockkey_min<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(L, M, K, g);
+    k_blockkey_mark<<<CC_GRID_BLOCKS, 256, 0, s>>>(K, GR, BK, &ctr->nruns);
     k_popc<<<(unsigned)((nbwords + 255) / 256), 256, 0, s>>>(BK, bcnt, nbwords);
-    scan_counts(bcnt, bprefix, bsum2, nbwords, dummyN, s);
-    k_assign_blockorder<<<wblocks, 256, 0, s>>>(L, LR, GR, K, BK, bprefix, g, nwords);
+    scan_counts(bcnt, bprefix, bsum3, nbwords, dummyN, s);
+    k_assign_blockorder<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, K, BK, bprefix, &ctr->nruns);
     g_launches += 5;
     mark("C3_assign_blockorder", s);
   } else {
-    k_assign<<<wblocks, 256, 0, s>>>(L, LR, GR, prefix, g, nwords);
+    k_assign<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, GR, prefix, &ctr->nruns);
     g_launches += 1;
     mark("C3_assign", s);
   }
@@ -417,17 +418,15 @@ void cc3d_b200_session_release(cc3d_b200_session* S) {
 }
 
 template <typename OUT>
-static void launch_write(const cc3d_b200_session* S, OUT* dout, unsigned row0, unsigned nrows, const void* remap,
+static void launch_write(const cc3d_b200_session* S, OUT* dout, i64 row0, i64 nrows, const void* remap,
                          int remap_kind, cudaStream_t s) {
   const Geom& g = S->g;
-  const unsigned nchunks = (unsigned)((g.sx + 511) / 512);
-  const unsigned blocks = nrows * nchunks;
-  const bool vec = (g.sx % 4 == 0) && (((uintptr_t)dout) % 32 == 0);
-#define CC_LAUNCH_WRITE(V, R) k_write<OUT, V, R><<<blocks, 128, 0, s>>>(S->L, S->LR, dout, g, nchunks, row0, remap)
-  if (!remap) { if (vec) CC_LAUNCH_WRITE(true, 0); else CC_LAUNCH_WRITE(false, 0); }
-  else if (remap_kind == CC3D_B200_U32) { if (vec) CC_LAUNCH_WRITE(true, 1); else CC_LAUNCH_WRITE(false, 1); }
-  else { if (vec) CC_LAUNCH_WRITE(true, 2); else CC_LAUNCH_WRITE(false, 2); }
-#undef CC_LAUNCH_WRITE
+  const unsigned nchunks = (unsigned)((g.W + 31) / 32);
+  const i64 nwarps = nrows * nchunks;
+  const unsigned blocks = (unsigned)((nwarps + 7) / 8);
+  if (!remap) k_expand<OUT, 0><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap);
+  else if (remap_kind == CC3D_B200_U32) k_expand<OUT, 1><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap);
+  else k_expand<OUT, 2><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap);
   g_launches += 1;
 }
 
@@ -467,10 +466,10 @@ static int write_impl(cc3d_b200_session* S, void* out, int out_kind, int mem_spa
     }
   }
   marks_begin(s);
-  if (os == 2) launch_write<uint16_t>(S, (uint16_t*)dout, (unsigned)row0, (unsigned)nrows, dremap, remap_kind, s);
-  else if (os == 4) launch_write<uint32_t>(S, (uint32_t*)dout, (unsigned)row0, (unsigned)nrows, dremap, remap_kind, s);
-  else launch_write<uint64_t>(S, (uint64_t*)dout, (unsigned)row0, (unsigned)nrows, dremap, remap_kind, s);
-  mark("D_write", s);
+  if (os == 2) launch_write<uint16_t>(S, (uint16_t*)dout, row0, nrows, dremap, remap_kind, s);
+  else if (os == 4) launch_write<uint32_t>(S, (uint32_t*)dout, row0, nrows, dremap, remap_kind, s);
+  else launch_write<uint64_t>(S, (uint64_t*)dout, row0, nrows, dremap, remap_kind, s);
+  mark("D_expand", s);
   cudaError_t e = cudaSuccess;
   if (mem_space == CC3D_B200_HOST) {
     e = cudaMemcpyAsync(out, dout, nvox * os, cudaMemcpyDeviceToHost, s);

@@ -1,17 +1,32 @@
 // cc3d_common.cuh — shared types for the B200 connected-components kernels.
 //
-// Pipeline (one volume, x fastest, index i = x + sx*(y + sy*z), voxels < 2^32-1):
-//   A  k_tile_label   : TXxTYxTZ tiles labelled in shared memory; L[i] = raster index of the tile-local
-//                       root (the tile component's minimum raster index), LR bitmap = local roots,
-//                       XS slots = x-seam equivalences found through the one-column halo.
-//   B1 k_seam_rows    : unions across y/z tile seams (atomicMin link-to-smaller on L).
-//   B2 k_seam_x       : unions recorded in XS (x tile seams).
-//   P  k_periodic     : torus wrap unions (4/8/6-connected, delta == 0).
-//   C1 k_compress     : every local root -> its global root; GR bitmap = global roots (+ popcounts).
-//   C2 scan           : exclusive scan of GR popcounts -> rank of every global root = first-appearance
-//                       order of its component (roots are minimum raster indices).
-//   C3 k_assign       : L[local root] = final label.
-//   D  k_write        : out[i] = final label in the out dtype.
+// Pipeline (one volume, x fastest, voxel index i = x + sx*(y + sy*z), voxels < 2^32-1).
+// The volume is reduced to FACE BITMAPS: one 32-bit word per 32 consecutive voxels of a row for the
+// foreground (F) and for the three straight backward edges (X: joined to x-1, Y: to y-1, Z: to z-1).
+// The nodes of the union-find are x-RUNS (maximal chains of x-links inside a row). Runs are numbered
+// densely in raster order (run table), so the forest, the root flags and the final labels are dense
+// arrays of one entry per run that stay L2-resident; the minimum run of a component is the run of
+// its first voxel in raster order.
+//
+//   A  k_faces      : the only pass over the input. One voxel per lane, three compares + four
+//                     ballots per 32 voxels -> F/X/Y/Z words, run starts per word, and the epl
+//                     transition count (cc3d.hpp:287-315).
+//   S  scan         : exclusive scan of run starts per word -> RS (id of the first run that starts in
+//                     a word); L[i] = i for every run.
+//   B  k_union      : one thread per bitmap word, everything word-parallel. Straight edges: an edge
+//                     is dropped when kept edges already join the same two runs (x rule, square rule).
+//                     Diagonal edges (8/18/26): a diagonal can only matter when no voxel "between" its
+//                     end points joins them, which is decided from the face bitmaps of the neighbour
+//                     rows; the handful of candidates left compare their two voxel values.
+//                     Kept edges do a lock-free atomicMin link-to-smaller union of two run ids.
+//   P  k_periodic   : torus wrap unions (4/8/6-connected, delta == 0).
+//   C1 k_compress   : every run -> its root; root flags (+ popcounts).
+//   C2 scan         : exclusive scan of root flags -> rank of every root = first-appearance order of
+//                     its component.
+//   C3 k_assign     : L[run] = final label.
+//   D  k_expand     : out[i] = label of i's run, in the out dtype (the only dense write).
+// Dense traffic is sizeof(T) + sizeof(OUT) bytes per voxel (the compulsory bytes); everything between
+// A and D touches bitmaps (1/8 byte per voxel and plane) and the run table.
 // Replaces cc3d.hpp:64-149 (DisjointSet), :245-285 (relabel), :344-1421 (decision-tree kernels),
 // cc3d_binary.hpp:31-1263, cc3d_continuous.hpp:90-392.
 #pragma once
@@ -27,14 +42,17 @@ typedef int64_t i64;
 
 enum { MODE_EQ = 0, MODE_NONZERO = 1, MODE_DELTA = 2, MODE_MASK = 3 };
 
-// Backward-direction codes (bit positions in MODE_MASK inputs). Order follows the reference's
-// compute_neighborhood (cc3d_continuous.hpp:38-73).
+// Backward-direction codes. Order follows the reference's compute_neighborhood
+// (cc3d_continuous.hpp:38-73).
 __host__ __device__ constexpr int dir_code(int dx, int dy, int dz) {
   return (dz == 0) ? ((dy == 0) ? 0 /*(-1,0,0)*/ : (dx == 0 ? 1 : (dx < 0 ? 3 : 4)))
                    : ((dy == 0) ? (dx == 0 ? 2 : (dx < 0 ? 7 : 8))
                                 : (dy < 0 ? (dx == 0 ? 5 : (dx < 0 ? 9 : 10))
                                           : (dx == 0 ? 6 : (dx < 0 ? 11 : 12))));
 }
+// Bitmap planes. RS holds the number of runs that start in the word until the scan turns it into the
+// id of the first of them. A0/C0 are only written by the continuous 2D-8 path (explicit diagonals).
+enum { PL_F = 0, PL_X = 1, PL_Y = 2, PL_Z = 3, PL_RS = 4, PL_A0 = 5, PL_C0 = 6, PL_COUNT = 7 };
 
 // Neighbour rows of a voxel's backward neighbourhood other than its own row:
 // R0=(dy-1,dz0) R1=(dy0,dz-1) R2=(dy-1,dz-1) R3=(dy+1,dz-1); dx mask bit0: dx=-1, bit1: dx=0, bit2: dx=+1.
@@ -46,14 +64,12 @@ __host__ __device__ constexpr int hood_dx(int conn, int r) {
        : conn == 18 ? (r < 2 ? 7 : 2)
        : 7;
 }
-__host__ __device__ constexpr int row_dy(int r) { return r == 0 ? -1 : (r == 1 ? 0 : (r == 2 ? -1 : 1)); }
-__host__ __device__ constexpr int row_dz(int r) { return r == 0 ? 0 : -1; }
 
 struct Geom {
-  i64 sx, sy, sz;     // volume
-  int TY, TZ;         // tile extent in y and z (TX is a template parameter)
-  i64 ntx, nty, ntz;  // tiles per axis
-  i64 W;              // bitmap words per row = ceil(sx/32)
+  i64 sx, sy, sz;  // volume
+  i64 W;           // bitmap words per row = ceil(sx/32)
+  i64 rows;        // sy * sz
+  i64 nwords;      // rows * W = words per bitmap plane
 };
 
 struct Counters {      // device-side results of a labelling pass
@@ -61,32 +77,27 @@ struct Counters {      // device-side results of a labelling pass
   i64 first_row;       // initialised to INT64_MAX
   i64 last_row;        // initialised to -1
   u64 N;
+  u64 nruns;           // number of x-runs (scan S)
 };
 
 template <typename T> struct is_float_t { static constexpr bool value = false; };
 template <> struct is_float_t<float> { static constexpr bool value = true; };
 template <> struct is_float_t<double> { static constexpr bool value = true; };
 
-// Edge predicate between a voxel p and an EARLIER (in raster order) neighbour q.
+// Edge predicate between a voxel p and a neighbour q (out-of-volume neighbours are passed as 0).
 //   EQ      : v[p] == v[q] != 0                      (cc3d.hpp multilabel kernels)
 //   NONZERO : v[p] != 0 && v[q] != 0                 (cc3d_binary.hpp)
 //   DELTA   : both non-zero and |v[p]-v[q]| <= delta in T arithmetic (cc3d_continuous.hpp:79-88)
-//   MASK    : bit `dir` of p's value (precomputed backward-edge bitfield; top bit = foreground)
 template <typename T, int MODE> struct Edge {
   T delta;
-  __device__ __forceinline__ bool fg(T v) const {
-    if constexpr (MODE == MODE_MASK) return (v >> (8 * sizeof(T) - 1)) & 1;
-    else return v != (T)0;
-  }
-  __device__ __forceinline__ bool operator()(T p, T q, int dir) const {
+  __device__ __forceinline__ bool fg(T v) const { return v != (T)0; }
+  __device__ __forceinline__ bool operator()(T p, T q) const {
     if constexpr (MODE == MODE_EQ) { return p == q && p != (T)0; }
     else if constexpr (MODE == MODE_NONZERO) { return p != (T)0 && q != (T)0; }
-    else if constexpr (MODE == MODE_DELTA) {
+    else {
       if (p == (T)0 || q == (T)0) return false;
       if constexpr (is_float_t<T>::value) { return fabs(p - q) <= delta; }
       else { return (p > q ? (T)(p - q) : (T)(q - p)) <= delta; }
-    } else {
-      return (p >> dir) & 1;
     }
   }
 };
@@ -107,4 +118,37 @@ __device__ __forceinline__ void uf_union(u32* A, u32 a, u32 b) {
     else if (b < a) { u32 old = atomicMin(&A[a], b); done = (old == a); a = old; }
     else done = true;
   } while (!done);
+}
+
+// Lock-free union with path halving: a find re-points every node it passes at its grandparent.
+// A stale write can only replace a parent by another ancestor, which keeps every set intact.
+__device__ __forceinline__ u32 uf_find_h(u32* A, u32 i) {
+  volatile u32* V = A;
+  u32 p = V[i];
+  while (p != i) {
+    const u32 gp = V[p];
+    if (gp == p) return p;
+    V[i] = gp;
+    i = gp;
+    p = V[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void uf_union_h(u32* A, u32 a, u32 b) {
+  bool done;
+  do {
+    a = uf_find_h(A, a);
+    b = uf_find_h(A, b);
+    if (a < b) { u32 old = atomicMin(&A[b], a); done = (old == b); b = old; }
+    else if (b < a) { u32 old = atomicMin(&A[a], b); done = (old == a); a = old; }
+    else done = true;
+  } while (!done);
+}
+
+// Id of the run that contains foreground voxel x of the row whose first word is j0 (= row * W):
+// runs are numbered in raster order, so it is the last run that started at or before x.
+__device__ __forceinline__ u32 run_id(const u32* __restrict__ M, const Geom& g, u32 j0, u32 x) {
+  const u32 j = j0 + (x >> 5);
+  const u32 S = __ldg(M + PL_F * g.nwords + j) & ~__ldg(M + PL_X * g.nwords + j);
+  return __ldg(M + PL_RS * g.nwords + j) + __popc(S & (CC_FULL >> (31 - (x & 31)))) - 1u;
 }

@@ -1,5 +1,5 @@
-// cc3d_misc.cuh — pre-pass (epl / foreground rows / value range), the continuous 2D-8 edge-mask
-// builder, per-label statistics and the dust masking kernel.
+// cc3d_misc.cuh — pre-pass (epl / foreground rows / value range), per-label statistics and the
+// dust masking kernel.
 #pragma once
 #include "cc3d_common.cuh"
 
@@ -66,46 +66,6 @@ __global__ void k_minmax_final(const T* __restrict__ part_min, const T* __restri
     if (b > mx) mx = b;
   }
   if (threadIdx.x == 0) { out2[0] = mn; out2[1] = mx; }
-}
-
-// ---- continuous 2D 8-connected (cc3d_continuous.hpp:270-392): the reference's raster rule picks the
-// backward edges of every pixel from its neighbourhood AND the global value range (gmin/gmax
-// shortcut, :298-303, 341-349). We evaluate exactly that rule per pixel into an edge bitfield
-// (bit = dir_code, top bit = foreground) and label the bitfield with MODE_MASK. ----
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_c8_mask(const T* __restrict__ in, unsigned char* __restrict__ mask, i64 sx, i64 sy, T delta, const T* __restrict__ range) {
-  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= sx * sy) return;
-  const i64 y = i / sx, x = i - y * sx;
-  const T cur = in[i];
-  unsigned m = 0;
-  if (cur != (T)0) {
-    m = 0x80u;
-    const T gmin = range[0], gmax = range[1];
-    auto match = [&](T a, T b) -> bool {
-      if constexpr (is_float_t<T>::value) return fabs(a - b) <= delta;
-      else return (a > b ? (T)(a - b) : (T)(b - a)) <= delta;
-    };
-    bool shortcut = false;
-    T vB = (T)0;
-    if (y > 0) {
-      vB = in[i - sx];
-      if (cur == vB) shortcut = true;
-      else if (vB != (T)0) {
-        const T lo = cur < vB ? cur : vB, hi = cur > vB ? cur : vB;
-        if ((lo - gmin <= delta) && (gmax - hi <= delta)) shortcut = true;
-      }
-    }
-    if (shortcut) m |= 1u << dir_code(0, -1, 0);
-    else {
-      if (y > 0 && vB != (T)0 && match(cur, vB)) m |= 1u << dir_code(0, -1, 0);
-      if (x > 0 && y > 0) { const T q = in[i - sx - 1]; if (q != (T)0 && match(cur, q)) m |= 1u << dir_code(-1, -1, 0); }
-      if (x < sx - 1 && y > 0) { const T q = in[i - sx + 1]; if (q != (T)0 && match(cur, q)) m |= 1u << dir_code(1, -1, 0); }
-      if (x > 0) { const T q = in[i - 1]; if (q != (T)0 && match(cur, q)) m |= 1u << dir_code(-1, 0, 0); }
-    }
-  }
-  mask[i] = (unsigned char)m;
 }
 
 // ---- row a13: statistics (fastcc3d.pyx:771-938). Memory-axis coordinates. Runs of equal labels inside

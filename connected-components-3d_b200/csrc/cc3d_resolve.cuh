@@ -1,32 +1,37 @@
-// cc3d_resolve.cuh — kernels C1 (compress), C2 (scan), C3 (assign), D (write) and the
-// block-order renumbering used by the binary 2D 8-connected path. See cc3d_common.cuh.
+// cc3d_resolve.cuh — run-table kernels: S (scan of run starts), C1 (compress), C2 (scan of roots),
+// C3 (assign), D (expand), the block-order renumbering used by the binary 2D 8-connected path, and the
+// face-pair kernels of the sharded path. See cc3d_common.cuh.
 #pragma once
 #include "cc3d_common.cuh"
 
-// C1: one thread per word of the local-root bitmap. Every local root is pointed straight at its
-// global root; the word of global roots and its popcount are emitted for the scan.
+#define CC_GRID_BLOCKS (148 * 8)   // grid of the kernels that loop over a device-side count
+
+// L[i] = i for every run (the count comes from scan S)
+__global__ void __launch_bounds__(256) k_iota_n(u32* __restrict__ L, const u64* __restrict__ n_dev) {
+  const u32 n = (u32)*n_dev;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) L[i] = i;
+}
+
+// C1: one lane per run. Every run is pointed straight at its root; 32 root flags per word (ballot) and
+// the word's popcount are emitted for the scan. Words past the last run are cleared (nwords2 is the
+// host-side upper bound the scan runs over).
 __global__ void __launch_bounds__(256)
-k_compress(u32* __restrict__ L, const u32* __restrict__ LR, u32* __restrict__ GR, u32* __restrict__ cnt,
-           Geom g, i64 nwords) {
-  const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwords) return;
-  u32 bits = LR[w];
-  u32 gr = 0;
-  if (bits) {
-    const i64 row = w / g.W;
-    const i64 base = row * g.sx + (w - row * g.W) * 32;
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const u32 l = (u32)(base + b);
-      u32 r = l, p;
+k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restrict__ n_dev, u32 nwords2) {
+  const u32 n = (u32)*n_dev;
+  const int lane = threadIdx.x & 31;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 wd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wd < nwords2; wd += nwarps) {
+    const u32 i = (wd << 5) + lane;
+    bool isroot = false;
+    if (i < n) {
+      u32 r = i, p;
       while ((p = __ldcg(&L[r])) != r) r = p;
-      if (r == l) gr |= 1u << b;
-      else L[l] = r;
+      if (r == i) isroot = true;
+      else L[i] = r;
     }
+    const u32 m = __ballot_sync(CC_FULL, isroot);
+    if (lane == 0) { GR[wd] = m; cnt[wd] = __popc(m); }
   }
-  GR[w] = gr;
-  cnt[w] = __popc(gr);
 }
 
 // C2: exclusive scan of u32 counts, three small kernels (block reduce, scan of block sums, apply).
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ bsum, i6
 
 // prefix[i] = exclusive prefix of cnt (mod 2^32 is fine: ranks are < voxels < 2^32)
 __global__ void __launch_bounds__(CC_SCAN_THREADS)
-k_scan_apply(const u32* __restrict__ cnt, const u64* __restrict__ bsum, u32* __restrict__ prefix, i64 n) {
+k_scan_apply(const u32* cnt, const u64* __restrict__ bsum, u32* prefix, i64 n) {  // cnt may alias prefix
   const i64 base = (i64)blockIdx.x * CC_SCAN_CHUNK + (i64)threadIdx.x * CC_SCAN_ITEMS;
   u32 v[CC_SCAN_ITEMS];
   u32 s = 0;
@@ -141,91 +146,60 @@ __device__ __forceinline__ u32 rank_in_bitmap(const u32* __restrict__ bm, const 
   return prefix[word] + __popc(bm[word] & ((1u << bit) - 1u));
 }
 
-// C3: every local root gets its component's final label (1-based rank of its global root).
+// C3: every run gets its component's final label (1-based rank of its root).
 __global__ void __launch_bounds__(256)
-k_assign(u32* __restrict__ L, const u32* __restrict__ LR, const u32* __restrict__ GR,
-         const u32* __restrict__ prefix, Geom g, i64 nwords) {
-  const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwords) return;
-  u32 bits = LR[w];
-  if (!bits) return;
-  const i64 row = w / g.W;
-  const i64 base = row * g.sx + (w - row * g.W) * 32;
-  const u32 gw = GR[w];
-  const u32 pw = prefix[w];
-  while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    const u32 l = (u32)(base + b);
-    u32 label;
-    if ((gw >> b) & 1u) {
-      label = pw + __popc(gw & ((1u << b) - 1u)) + 1u;
-    } else {
-      const u32 r = L[l];
-      const i64 rrow = r / g.sx;
-      const i64 rx = r - rrow * g.sx;
-      label = rank_in_bitmap(GR, prefix, rrow * g.W + (rx >> 5), (int)(rx & 31)) + 1u;
-    }
-    L[l] = label;
+k_assign(u32* __restrict__ L, const u32* __restrict__ GR, const u32* __restrict__ prefix, const u64* __restrict__ n_dev) {
+  const u32 n = (u32)*n_dev;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool isroot = (GR[i >> 5] >> (i & 31)) & 1u;
+    const u32 r = isroot ? i : L[i];
+    L[i] = rank_in_bitmap(GR, prefix, r >> 5, (int)(r & 31)) + 1u;
   }
 }
 
-// D: final write. A voxel either is a local root (its L entry already is the label) or points at one.
-// Each thread handles 4 consecutive voxels of one row (128-bit load of L, one gather per distinct
-// pointer, one vector store); a CTA of 128 threads covers a 512-voxel chunk of a row.
-template <typename OUT> struct Out4;
-template <> struct Out4<uint16_t> { typedef ushort4 type; };
-template <> struct Out4<uint32_t> { typedef uint4 type; };
-template <> struct Out4<uint64_t> { typedef ulonglong4 type; };
-
-// REMAP: 0 = write the local label, 1/2 = write remap[label] from a u32/u64 table (sharded volumes:
+// D: the only dense write. One warp per (row, 32-word chunk): lane j first takes word j of the F / X /
+// RS bitmaps; then the warp walks the words, one voxel per lane: the voxel's run is the last run that
+// started at or before it (popcount), one mostly warp-uniform L2-resident load of the run's label, one
+// coalesced store.
+// REMAP: 0 = write the label, 1/2 = write remap[label] from a u32/u64 table (sharded volumes:
 // per-slab label -> global label). row0 = first row to write; out is indexed relative to row0.
-template <typename OUT, bool VEC, int REMAP>
-__global__ void __launch_bounds__(128)
-k_write(const u32* __restrict__ L, const u32* __restrict__ LR, OUT* __restrict__ out, Geom g, unsigned nchunks,
-        unsigned row0, const void* __restrict__ remap) {
-  const unsigned rrel = blockIdx.x / nchunks;
-  const unsigned chunk = blockIdx.x - rrel * nchunks;
-  const unsigned row = row0 + rrel;
-  const i64 x = (i64)chunk * 512 + threadIdx.x * 4;
-  if (x >= g.sx) return;
-  const i64 base = (i64)row * g.sx + x;
-  const i64 obase = (i64)rrel * g.sx + x;
-  const u32 lrw = LR[(i64)row * g.W + (x >> 5)] >> (x & 31);
-  u32 l[4];
-  if (VEC) {
-    const uint4 t = *reinterpret_cast<const uint4*>(L + base);
-    l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) l[i] = (x + i < g.sx) ? L[base + i] : CC_BG;
+template <typename OUT, int REMAP>
+__global__ void __launch_bounds__(256)
+k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__ out, Geom g, unsigned nchunks,
+         u32 row0, u32 nwarps_total, const void* __restrict__ remap) {
+  const int lane = threadIdx.x & 31;
+  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= nwarps_total) return;
+  const u32 rrel = wid / nchunks;
+  const u32 chunk = wid - rrel * nchunks;
+  const u32 row = row0 + rrel;
+  const u32 W = (u32)g.W, sx = (u32)g.sx;
+  const u32 wl = (chunk << 5) + lane;
+  const size_t nw = (size_t)g.nwords;
+  u32 F = 0, S = 0, RS = 0;
+  if (wl < W) {
+    const u32 j = row * W + wl;
+    F = __ldg(M + PL_F * nw + j);
+    S = F & ~__ldg(M + PL_X * nw + j);
+    RS = __ldg(M + PL_RS * nw + j) - 1u;
   }
-  OUT lab[4];
-  u32 prev_ptr = CC_BG;
-  OUT prev_lab = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
+  const int nwd = (int)min(32u, W - (chunk << 5));
+  OUT* orow = out + (size_t)rrel * sx;
+  const u32 below = CC_FULL >> (31 - lane);
+  u32 x = (chunk << 10) + lane;
+#pragma unroll 4
+  for (int j = 0; j < nwd; j++, x += 32) {
+    const u32 Fj = __shfl_sync(CC_FULL, F, j);
+    const u32 Sj = __shfl_sync(CC_FULL, S, j);
+    const u32 Rj = __shfl_sync(CC_FULL, RS, j);
     OUT v = 0;
-    if (l[i] != CC_BG) {
-      const bool isroot = (lrw >> i) & 1u;
-      if (!isroot && l[i] == prev_ptr) v = prev_lab;
-      else {
-        const u32 loc = isroot ? l[i] : __ldg(&L[l[i]]);
-        if (REMAP == 1) v = (OUT)__ldg(reinterpret_cast<const u32*>(remap) + loc);
-        else if (REMAP == 2) v = (OUT)__ldg(reinterpret_cast<const u64*>(remap) + loc);
-        else v = (OUT)loc;
-        if (!isroot) { prev_ptr = l[i]; prev_lab = v; }
-      }
+    if ((Fj >> lane) & 1u) {
+      const u32 lab = L[Rj + __popc(Sj & below)];
+      if (REMAP == 1) v = (OUT)__ldg(reinterpret_cast<const u32*>(remap) + lab);
+      else if (REMAP == 2) v = (OUT)__ldg(reinterpret_cast<const u64*>(remap) + lab);
+      else v = (OUT)lab;
     }
-    lab[i] = v;
-  }
-  if (VEC) {
-    typename Out4<OUT>::type o;
-    o.x = lab[0]; o.y = lab[1]; o.z = lab[2]; o.w = lab[3];
-    *reinterpret_cast<typename Out4<OUT>::type*>(out + obase) = o;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) if (x + i < g.sx) out[obase + i] = lab[i];
+    if (x < sx) orow[x] = v;
   }
 }
 
@@ -260,10 +234,10 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
           if (xx < 0 || xx >= sx || yy < 0 || yy >= sy) continue;
           const i64 qi = yy * sx + xx;
           const T q = vQ[qi];
-          if (!E(p, q, dir_code(dx, dy, -1))) continue;
+          if (!E(p, q)) continue;
           const u32 lq = lQ[qi];
           // the voxel to the left emits the same (lq, lp) through the same direction
-          if (left_same && xx > 0 && lQ[qi - 1] == lq && E(vP[i - 1], vQ[qi - 1], dir_code(dx, dy, -1))) continue;
+          if (left_same && xx > 0 && lQ[qi - 1] == lq && E(vP[i - 1], vQ[qi - 1])) continue;
           mine[n++] = ((u64)lq << 32) | lp;
         }
       }
@@ -304,61 +278,42 @@ __global__ void __launch_bounds__(256) k_flatten(u32* __restrict__ parent, i64 n
 }
 
 // ---- binary 2D 8-connected: number components by their first 2x2 block in block-raster order
-// (cc3d_binary.hpp:1016-1023, 1215-1231). K[root] = min block key over the component. ----
+// (cc3d_binary.hpp:1016-1023, 1215-1231). K[root] = min block key over the component's runs. ----
+__global__ void __launch_bounds__(256) k_fill_n(u32* __restrict__ K, u32 v, const u64* __restrict__ n_dev) {
+  const u32 n = (u32)*n_dev;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) K[i] = v;
+}
+
+// one atomic per run: along a row the block key grows with x, so a run's minimum is at its start
 __global__ void __launch_bounds__(256)
-k_blockkey_init(u32* __restrict__ K, const u32* __restrict__ GR, Geom g, i64 nwords) {
-  const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwords) return;
-  u32 bits = GR[w];
-  const i64 row = w / g.W;
-  const i64 base = row * g.sx + (w - row * g.W) * 32;
+k_blockkey_min(const u32* __restrict__ L, const u32* __restrict__ M, u32* __restrict__ K, Geom g) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (u32)g.nwords) return;
+  const size_t nw = (size_t)g.nwords;
+  const u32 F = __ldg(M + PL_F * nw + i);
+  if (!F) return;
+  const u32 W = (u32)g.W;
+  const u32 row = i / W, w = i - row * W;
+  u32 bits = F & ~__ldg(M + PL_X * nw + i);
+  u32 id = __ldg(M + PL_RS * nw + i);
+  const u32 osx = ((u32)g.sx + 1) >> 1;
   while (bits) {
     const int b = __ffs(bits) - 1;
     bits &= bits - 1;
-    K[base + b] = CC_BG;
+    const u32 x = (w << 5) + b;
+    atomicMin(&K[L[id]], (x >> 1) + osx * (row >> 1));   // after k_compress L[id] is the root (roots: themselves)
+    id++;
   }
 }
 
 __global__ void __launch_bounds__(256)
-k_blockkey_min(const u32* __restrict__ L, const u32* __restrict__ LR, u32* __restrict__ K, Geom g) {
-  const i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const i64 row = wid / g.W;
-  if (row >= g.sy * g.sz) return;
-  const i64 seg = wid - row * g.W;
-  const i64 x = seg * 32 + lane;
-  u32 root = CC_BG;
-  if (x < g.sx) {
-    const i64 i = row * g.sx + x;
-    const u32 l = L[i];
-    if (l != CC_BG) {
-      const u32 lr = LR[wid];
-      // after k_compress: local roots hold their global root (or themselves)
-      root = ((lr >> lane) & 1u) ? l : L[l];
+k_blockkey_mark(const u32* __restrict__ K, const u32* __restrict__ GR, u32* __restrict__ BK, const u64* __restrict__ n_dev) {
+  const u32 n = (u32)*n_dev;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if ((GR[i >> 5] >> (i & 31)) & 1u) {
+      const u32 k = K[i];
+      atomicOr(&BK[k >> 5], 1u << (k & 31));
     }
-  }
-  // one atomic per run of equal roots inside the warp
-  const u32 prev = __shfl_up_sync(CC_FULL, root, 1);
-  const bool head = root != CC_BG && (lane == 0 || prev != root);
-  if (head) {
-    const i64 osx = (g.sx + 1) >> 1;
-    const u32 key = (u32)((x >> 1) + osx * (row >> 1));
-    atomicMin(&K[root], key);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_blockkey_mark(const u32* __restrict__ K, const u32* __restrict__ GR, u32* __restrict__ BK, Geom g, i64 nwords) {
-  const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwords) return;
-  u32 bits = GR[w];
-  const i64 row = w / g.W;
-  const i64 base = row * g.sx + (w - row * g.W) * 32;
-  while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    const u32 k = K[base + b];
-    atomicOr(&BK[k >> 5], 1u << (k & 31));
   }
 }
 
@@ -368,22 +323,11 @@ __global__ void __launch_bounds__(256) k_popc(const u32* __restrict__ bm, u32* _
 }
 
 __global__ void __launch_bounds__(256)
-k_assign_blockorder(u32* __restrict__ L, const u32* __restrict__ LR, const u32* __restrict__ GR,
-                    const u32* __restrict__ K, const u32* __restrict__ BK, const u32* __restrict__ bprefix,
-                    Geom g, i64 nwords) {
-  const i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwords) return;
-  u32 bits = LR[w];
-  if (!bits) return;
-  const i64 row = w / g.W;
-  const i64 base = row * g.sx + (w - row * g.W) * 32;
-  const u32 gw = GR[w];
-  while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    const u32 l = (u32)(base + b);
-    const u32 r = ((gw >> b) & 1u) ? l : L[l];
-    const u32 k = K[r];
-    L[l] = rank_in_bitmap(BK, bprefix, k >> 5, (int)(k & 31)) + 1u;
+k_assign_blockorder(u32* __restrict__ L, const u32* __restrict__ K, const u32* __restrict__ BK,
+                    const u32* __restrict__ bprefix, const u64* __restrict__ n_dev) {
+  const u32 n = (u32)*n_dev;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 k = K[L[i]];
+    L[i] = rank_in_bitmap(BK, bprefix, k >> 5, (int)(k & 31)) + 1u;
   }
 }

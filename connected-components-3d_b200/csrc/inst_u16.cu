@@ -1,5 +1,7 @@
-// Instantiates the labelling-stage kernels (A, B1, B2, P) for element type uint16_t.
+// Instantiates the type-dependent kernels (A: face bitmaps, B: unions, P: periodic wrap) for element type uint16_t.
 #define CC3D_INSTANTIATE
 #include <cstring>
 #include "cc3d_dispatch.cuh"
-template int run_label_stage<uint16_t>(const LabelArgs&);
+template int run_faces_stage<uint16_t>(const LabelArgs&);
+template int run_union_stage<uint16_t>(const LabelArgs&);
+template int run_periodic_stage<uint16_t>(const LabelArgs&);

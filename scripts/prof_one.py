@@ -1,4 +1,4 @@
-"""One device-resident labelling call per workload for ncu captures (debug helper for gpurun)."""
+"""One labelling call on a device-resident workload (target of ncu runs under gpurun)."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,6 +14,10 @@ elif wl == "binary":
     x = benchdata.random_binary((n, n, n), 0.5, 1, "cuda")
 elif wl == "tone":
     x = benchdata.three_tone_noise((n, n, n), cell=64, seed=3, device="cuda")
+elif wl == "connectomics":
+    from oracle import decode_connectomics
+    vol = decode_connectomics.load_fixture()
+    x = torch.from_numpy(np.ascontiguousarray(vol.transpose(2, 1, 0)).view(np.int32)).cuda()
 kw = {}
 if os.environ.get("DELTA"): kw["delta"] = float(os.environ["DELTA"])
 if os.environ.get("BINARY"): kw["binary_image"] = True
