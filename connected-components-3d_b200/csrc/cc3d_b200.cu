@@ -118,14 +118,30 @@ Geom make_geom(i64 sx, i64 sy, i64 sz) {
   g.W = (sx + 31) / 32;
   g.rows = sy * sz;
   g.nwords = g.rows * g.W;
+  auto pad4 = [](i64 n) { return (n + 3) & ~i64(3); };
+  g.offRS = 4 * g.nwords;
+  g.offA0 = g.offRS + pad4(g.nwords + 1);
+  g.offC0 = g.offA0 + pad4(g.nwords);
+  // union tile: 512 words = 2^tw words x 2^ty rows x 2^tz planes
+  int tw = 0;
+  while (tw < 4 && (i64(1) << tw) < g.W) tw++;
+  g.tw = tw;
+  g.tz = sz > 1 ? 2 : 0;
+  g.ty = 9 - g.tw - g.tz;
   return g;
 }
+size_t bitmap_words(const Geom& g, bool with_diagonals) {
+  return (size_t)(with_diagonals ? g.offC0 + ((g.nwords + 3) & ~i64(3)) : g.offA0);
+}
 
-int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n, u64* total_dev, cudaStream_t s) {
-  const i64 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
-  k_scan_reduce<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n);
-  k_scan_blocks<<<1, 1024, 0, s>>>(bsum, nb, total_dev);
-  k_scan_apply<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, prefix, n);
+// exclusive scan of n counts (n on the host, or ceil(*n_dev / 2^shift) when n_dev is given; n_max bounds it)
+int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_dev, int shift, u64* total_dev,
+                u32* total32_dev, cudaStream_t s) {
+  const i64 nb = (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  const unsigned grid = (unsigned)std::min<i64>(nb, CC_GRID_BLOCKS);
+  k_scan_reduce<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n_max, n_dev, shift);
+  k_scan_blocks<<<1, 1024, 0, s>>>(bsum, n_max, n_dev, shift, total_dev, total32_dev);
+  k_scan_apply<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, prefix, n_max, n_dev, shift);
   g_launches += 3;
   return 0;
 }
@@ -300,7 +316,7 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   auto add = [&](size_t b) { need += ((b + 255) & ~size_t(255)) + 256; };
   if (mem_space == CC3D_B200_HOST) add((size_t)voxels * es);
   add((size_t)maxruns * 4);                // L
-  add((size_t)nwords * 4 * PL_COUNT);      // M
+  add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
   add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
@@ -317,7 +333,7 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
     din = d;
     mark("H2D", s);
   }
-  u32* M = (u32*)ar.take((size_t)nwords * 4 * PL_COUNT);
+  u32* M = (u32*)ar.take(bitmap_words(g, c8) * 4);
   u32* L = (u32*)ar.take((size_t)maxruns * 4);
   u32* GR = (u32*)ar.take((size_t)nwords2 * 4);
   u32* cnt = (u32*)ar.take((size_t)nwords2 * 4);
@@ -353,10 +369,8 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   }
   if (rc == 0) {
     // S: number the runs
-    u32* RS = M + (size_t)PL_RS * nwords;
-    scan_counts(RS, RS, bsum, nwords, &ctr->nruns, s);
-    k_iota_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, &ctr->nruns);
-    g_launches += 1;
+    u32* RS = M + g.offRS;
+    scan_counts(RS, RS, bsum, nwords, nullptr, 0, &ctr->nruns, RS + nwords, s);
     mark("S_scan_runs", s);
     // B: unions
     rc = -1;
@@ -370,10 +384,10 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
 
   g_launches += stage_launches;
-  k_compress<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, GR, cnt, &ctr->nruns, (u32)nwords2);
+  k_compress<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, GR, cnt, &ctr->nruns);
   g_launches += 1;
   mark("C1_compress", s);
-  scan_counts(cnt, prefix, bsum2, nwords2, &ctr->N, s);
+  scan_counts(cnt, prefix, bsum2, nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s);
   mark("C2_scan", s);
   if (block_order) {
     u32* K = (u32*)ar.take((size_t)maxruns * 4);
@@ -387,7 +401,7 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
     k_blockkey_min<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(L, M, K, g);
     k_blockkey_mark<<<CC_GRID_BLOCKS, 256, 0, s>>>(K, GR, BK, &ctr->nruns);
     k_popc<<<(unsigned)((nbwords + 255) / 256), 256, 0, s>>>(BK, bcnt, nbwords);
-    scan_counts(bcnt, bprefix, bsum3, nbwords, dummyN, s);
+    scan_counts(bcnt, bprefix, bsum3, nbwords, nullptr, 0, dummyN, nullptr, s);
     k_assign_blockorder<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, K, BK, bprefix, &ctr->nruns);
     g_launches += 5;
     mark("C3_assign_blockorder", s);

@@ -50,9 +50,16 @@ __host__ __device__ constexpr int dir_code(int dx, int dy, int dz) {
                                 : (dy < 0 ? (dx == 0 ? 5 : (dx < 0 ? 9 : 10))
                                           : (dx == 0 ? 6 : (dx < 0 ? 11 : 12))));
 }
-// Bitmap planes. RS holds the number of runs that start in the word until the scan turns it into the
-// id of the first of them. A0/C0 are only written by the continuous 2D-8 path (explicit diagonals).
-enum { PL_F = 0, PL_X = 1, PL_Y = 2, PL_Z = 3, PL_RS = 4, PL_A0 = 5, PL_C0 = 6, PL_COUNT = 7 };
+// Bitmap storage M (u32 words): [0, 4*nwords) holds one uint4 {F, X, Y, Z} per bitmap word (one 16-byte
+// access gives all four faces of a word); RS (nwords + 1 entries: runs that start in the word, turned by
+// the scan into the id of the first of them, RS[nwords] = number of runs) follows at g.offRS; A0 / C0
+// (explicit in-plane diagonals, continuous 2D-8 path only) at g.offA0 / g.offC0.
+struct Q4 { u32 F, X, Y, Z; };
+__device__ __forceinline__ Q4 ldq(const u32* __restrict__ M, u32 j) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(M) + j);
+  Q4 q; q.F = v.x; q.X = v.y; q.Y = v.z; q.Z = v.w;
+  return q;
+}
 
 // Neighbour rows of a voxel's backward neighbourhood other than its own row:
 // R0=(dy-1,dz0) R1=(dy0,dz-1) R2=(dy-1,dz-1) R3=(dy+1,dz-1); dx mask bit0: dx=-1, bit1: dx=0, bit2: dx=+1.
@@ -70,7 +77,11 @@ struct Geom {
   i64 W;           // bitmap words per row = ceil(sx/32)
   i64 rows;        // sy * sz
   i64 nwords;      // rows * W = words per bitmap plane
+  i64 offRS, offA0, offC0;   // word offsets into M
+  int tw, ty, tz;  // log2 of the union tile extent in words (x), rows (y) and planes (z); tw+ty+tz = 9
 };
+#define CC_TILE_WORDS 512
+#define CC_TILE_NODES (CC_TILE_WORDS * 32)   // a 32-voxel word starts at most 32 runs (multilabel)
 
 struct Counters {      // device-side results of a labelling pass
   u64 epl;
@@ -149,6 +160,6 @@ __device__ __forceinline__ void uf_union_h(u32* A, u32 a, u32 b) {
 // runs are numbered in raster order, so it is the last run that started at or before x.
 __device__ __forceinline__ u32 run_id(const u32* __restrict__ M, const Geom& g, u32 j0, u32 x) {
   const u32 j = j0 + (x >> 5);
-  const u32 S = __ldg(M + PL_F * g.nwords + j) & ~__ldg(M + PL_X * g.nwords + j);
-  return __ldg(M + PL_RS * g.nwords + j) + __popc(S & (CC_FULL >> (31 - (x & 31)))) - 1u;
+  const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)j);   // {F, X}
+  return __ldg(M + g.offRS + j) + __popc(fx.x & ~fx.y & (CC_FULL >> (31 - (x & 31)))) - 1u;
 }

@@ -53,9 +53,16 @@ template <typename T, int MODE, int CONN>
 static int launch_union(const LabelArgs& a) {
   Edge<T, MODE> E;
   memcpy(&E.delta, a.delta, sizeof(T));
-  const unsigned blocks = (unsigned)((a.g.nwords + 255) / 256);
-  k_union<T, MODE, CONN><<<blocks, 256, 0, a.stream>>>(static_cast<const T*>(a.in), a.M, a.L, a.g, E);
-  ++*a.launches;
+  const Geom& g = a.g;
+  const T* in = static_cast<const T*>(a.in);
+  const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
+  const size_t smem = (size_t)(CC_TILE_NODES + CC_TILE_WORDS) * 4;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty);
+  if (ntx * nty * ntz > 1)
+    k_union_global<T, MODE, CONN><<<(unsigned)((g.nwords + 255) / 256), 256, 0, a.stream>>>(in, a.M, a.L, g, E);
+  *a.launches += (ntx * nty * ntz > 1) ? 2 : 1;
   return 0;
 }
 

@@ -16,7 +16,8 @@ template <> __device__ __forceinline__ uint64_t shfl_up1(uint64_t v) { return (u
 // Kernel A. One warp owns one bitmap-word column (32 voxels in x) of one z-plane and walks CC_FACE_YCH
 // rows down y, one voxel per lane. The row above stays in registers; the loads of CC_FACE_UNR rows
 // (this plane and plane z-1) are issued back to back before any of them is used. Per row: three
-// compares and four ballots (F, X, Y, Z); lane 0 stores the words. HASZ = 3D connectivity.
+// compares and four ballots (F, X, Y, Z); lane 0 stores the four words with one 16-byte store.
+// The row body is branch free (rows past the chunk end are predicated off). HASZ = 3D connectivity.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool HASZ>
 __global__ void __launch_bounds__(CC_FACE_WARPS * 32)
@@ -26,8 +27,7 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
   const int warp = threadIdx.x >> 5;
   const unsigned task = blockIdx.x * CC_FACE_WARPS + warp;
 
-  u32 epl = 0;
-  long long rmin = INT64_MAX, rmax = -1;
+  u32 epl = 0, rfirst = 0xFFFFFFFFu, rlast = 0, anyfg = 0;
   if (task < ntasks) {
     const u32 W = (u32)g.W, sx = (u32)g.sx, sy = (u32)g.sy;
     const u32 w = task % W;
@@ -38,82 +38,70 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
     const u32 x = (w << 5) + lane;
     const bool inx = x < sx;
     const bool edge = lane == 0 && x > 0;
-    u32* __restrict__ mF = M + (size_t)PL_F * g.nwords;
-    u32* __restrict__ mX = M + (size_t)PL_X * g.nwords;
-    u32* __restrict__ mY = M + (size_t)PL_Y * g.nwords;
-    u32* __restrict__ mZ = M + (size_t)PL_Z * g.nwords;
-    u32* __restrict__ mR = M + (size_t)PL_RS * g.nwords;
-    const bool hasz = HASZ && z > 0;
-    const T* col = in + ((size_t)z * sy * sx + x);       // (x, 0, z)
-    const T* colD = col - (size_t)sy * sx;               // (x, 0, z-1), only dereferenced when hasz
+    const bool inz = HASZ && z > 0 && inx;
+    const u32 plane = sy * sx;
+    u32 off = (z * sy + y0) * sx + x;          // voxel (x, y0, z); voxels < 2^32
+    u32 row = z * sy + y0;
+    u32 idx = row * W + w;
+    uint4* __restrict__ MQ = reinterpret_cast<uint4*>(M);
+    u32* __restrict__ RS = M + g.offRS;
     T up = (T)0;
-    if (y0 > 0 && inx) up = col[(size_t)(y0 - 1) * sx];
-    u32 idx = (z * sy + y0) * W + w;
+    if (y0 > 0 && inx) up = in[off - sx];
 
     for (u32 yb = y0; yb < y1; yb += CC_FACE_UNR) {
       T pc[CC_FACE_UNR], pe[CC_FACE_UNR], dc[CC_FACE_UNR];
 #pragma unroll
       for (int k = 0; k < CC_FACE_UNR; k++) {
-        const u32 y = yb + k;
-        pc[k] = (T)0; pe[k] = (T)0; dc[k] = (T)0;
-        if (y < y1) {
-          const size_t o = (size_t)y * sx;
-          if (inx) pc[k] = col[o];
-          if (edge) pe[k] = col[o - 1];
-          if (hasz && inx) dc[k] = colD[o];
-        }
+        const bool valid = yb + k < y1;
+        const u32 o = off + k * sx;
+        pc[k] = (valid && inx) ? in[o] : (T)0;
+        pe[k] = (valid && edge) ? in[o - 1] : (T)0;
+        dc[k] = (valid && inz) ? in[o - plane] : (T)0;
       }
 #pragma unroll
       for (int k = 0; k < CC_FACE_UNR; k++) {
-        const u32 y = yb + k;
-        if (y < y1) {
-          const T c = pc[k];
-          T l = shfl_up1(c);
-          if (lane == 0) l = pe[k];
-          const bool f = E.fg(c);
-          const u32 F = __ballot_sync(CC_FULL, f);
-          u32 X = 0, Y = 0, Z = 0, S = 0;
-          if (F) {
-            X = __ballot_sync(CC_FULL, E(c, l));
-            Y = __ballot_sync(CC_FULL, E(c, up));
-            if (hasz) Z = __ballot_sync(CC_FULL, E(c, dc[k]));
-            S = F & ~X;
-            // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
-            if constexpr (MODE == MODE_EQ) epl += __popc(S);
-            else epl += __popc(__ballot_sync(CC_FULL, f && c != l));
-            const long long row = (long long)(z * sy + y);
-            rmin = min(rmin, row);
-            rmax = row;
-          }
-          if (lane == 0) {
-            mF[idx] = F;
-            mX[idx] = X;
-            mY[idx] = Y;
-            if (HASZ) mZ[idx] = Z;
-            mR[idx] = __popc(S);
-          }
-          up = c;
-          idx += W;
+        const T c = pc[k];
+        T l = shfl_up1(c);
+        if (lane == 0) l = pe[k];
+        const bool f = E.fg(c);
+        const u32 F = __ballot_sync(CC_FULL, f);
+        const u32 X = __ballot_sync(CC_FULL, E(c, l));
+        const u32 Y = __ballot_sync(CC_FULL, E(c, up));
+        const u32 Z = HASZ ? __ballot_sync(CC_FULL, E(c, dc[k])) : 0u;
+        const u32 ns = __popc(F & ~X);
+        // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
+        if constexpr (MODE == MODE_EQ) epl += ns;
+        else epl += __popc(__ballot_sync(CC_FULL, f && c != l));
+        rfirst = F ? min(rfirst, row) : rfirst;
+        rlast = F ? row : rlast;
+        anyfg |= F;
+        if (lane == 0 && yb + k < y1) {
+          MQ[idx] = make_uint4(F, X, Y, Z);
+          RS[idx] = ns;
         }
+        up = c;
+        idx += W;
+        row++;
       }
+      off += CC_FACE_UNR * sx;
     }
   }
 
   // block-level reduction of epl and the foreground row range
-  __shared__ u32 s_epl;
-  __shared__ long long s_rmin, s_rmax;
-  if (threadIdx.x == 0) { s_epl = 0; s_rmin = INT64_MAX; s_rmax = -1; }
+  __shared__ u32 s_epl, s_rmin, s_rmax, s_any;
+  if (threadIdx.x == 0) { s_epl = 0; s_rmin = 0xFFFFFFFFu; s_rmax = 0; s_any = 0; }
   __syncthreads();
-  if (lane == 0 && rmax >= 0) {
+  if (lane == 0 && anyfg) {
     atomicAdd(&s_epl, epl);
-    atomicMin(&s_rmin, rmin);
-    atomicMax(&s_rmax, rmax);
+    atomicMin(&s_rmin, rfirst);
+    atomicMax(&s_rmax, rlast);
+    s_any = 1;
   }
   __syncthreads();
-  if (threadIdx.x == 0 && s_rmax >= 0) {
+  if (threadIdx.x == 0 && s_any) {
     if (s_epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)s_epl);
-    atomicMin((long long*)&ctr->first_row, s_rmin);
-    atomicMax((long long*)&ctr->last_row, s_rmax);
+    atomicMin((long long*)&ctr->first_row, (long long)s_rmin);
+    atomicMax((long long*)&ctr->last_row, (long long)s_rmax);
   }
 }
 
@@ -166,9 +154,8 @@ k_c8_edges(const T* __restrict__ in, u32* __restrict__ M, Geom g, T delta, const
   const u32 A0 = __ballot_sync(CC_FULL, eA);
   const u32 C0 = __ballot_sync(CC_FULL, eC);
   if (lane == 0) {
-    const i64 nw = g.nwords;
-    M[PL_F * nw + idx] = F; M[PL_X * nw + idx] = X; M[PL_Y * nw + idx] = Y;
-    M[PL_A0 * nw + idx] = A0; M[PL_C0 * nw + idx] = C0;
-    M[PL_RS * nw + idx] = __popc(F & ~X);
+    reinterpret_cast<uint4*>(M)[idx] = make_uint4(F, X, Y, 0u);
+    M[g.offA0 + idx] = A0; M[g.offC0 + idx] = C0;
+    M[g.offRS + idx] = __popc(F & ~X);
   }
 }

@@ -6,18 +6,17 @@
 
 #define CC_GRID_BLOCKS (148 * 8)   // grid of the kernels that loop over a device-side count
 
-// L[i] = i for every run (the count comes from scan S)
-__global__ void __launch_bounds__(256) k_iota_n(u32* __restrict__ L, const u64* __restrict__ n_dev) {
-  const u32 n = (u32)*n_dev;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) L[i] = i;
+// Length of a device-sized array: n_dev == nullptr -> n_host, else ceil(*n_dev / 2^shift)
+__device__ __forceinline__ u32 dev_len(i64 n_host, const u64* __restrict__ n_dev, int shift) {
+  return n_dev ? (u32)((*n_dev + ((1ull << shift) - 1)) >> shift) : (u32)n_host;
 }
 
 // C1: one lane per run. Every run is pointed straight at its root; 32 root flags per word (ballot) and
-// the word's popcount are emitted for the scan. Words past the last run are cleared (nwords2 is the
-// host-side upper bound the scan runs over).
+// the word's popcount are emitted for the scan.
 __global__ void __launch_bounds__(256)
-k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restrict__ n_dev, u32 nwords2) {
+k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restrict__ n_dev) {
   const u32 n = (u32)*n_dev;
+  const u32 nwords2 = (n + 31) >> 5;
   const int lane = threadIdx.x & 31;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
   for (u32 wd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wd < nwords2; wd += nwarps) {
@@ -34,7 +33,9 @@ k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, con
   }
 }
 
-// C2: exclusive scan of u32 counts, three small kernels (block reduce, scan of block sums, apply).
+// C2 / S: exclusive scan of u32 counts, three small kernels (block reduce, scan of block sums, apply).
+// The length is either a host value or derived from a device-side count (see dev_len); the kernels
+// loop over 4096-element chunks, so the grid does not depend on the length.
 #define CC_SCAN_THREADS 256
 #define CC_SCAN_ITEMS 16
 #define CC_SCAN_CHUNK (CC_SCAN_THREADS * CC_SCAN_ITEMS)
@@ -70,34 +71,42 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total) {
 }
 
 __global__ void __launch_bounds__(CC_SCAN_THREADS)
-k_scan_reduce(const u32* __restrict__ cnt, u64* __restrict__ bsum, i64 n) {
-  const i64 base = (i64)blockIdx.x * CC_SCAN_CHUNK;
-  u32 s = 0;
+k_scan_reduce(const u32* __restrict__ cnt, u64* __restrict__ bsum, i64 n_host, const u64* __restrict__ n_dev, int shift) {
+  const u32 n = dev_len(n_host, n_dev, shift);
+  const u32 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  for (u32 blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+    const u32 base = blk * CC_SCAN_CHUNK;
+    u32 s = 0;
 #pragma unroll
-  for (int k = 0; k < CC_SCAN_ITEMS; k++) {
-    const i64 i = base + k * CC_SCAN_THREADS + threadIdx.x;
-    if (i < n) s += cnt[i];
+    for (int k = 0; k < CC_SCAN_ITEMS; k++) {
+      const u32 i = base + k * CC_SCAN_THREADS + threadIdx.x;
+      if (i < n) s += cnt[i];
+    }
+    u32 tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) bsum[blk] = tot;
   }
-  u32 tot;
-  block_exclusive_scan(s, &tot);
-  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 
-// single block: exclusive scan of the block sums (64-bit), total -> *N
-__global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ bsum, i64 nb, u64* __restrict__ N) {
+// single block: exclusive scan of the block sums (64-bit), total -> *N (and *N32 when given)
+__global__ void __launch_bounds__(1024)
+k_scan_blocks(u64* __restrict__ bsum, i64 n_host, const u64* __restrict__ n_dev, int shift, u64* __restrict__ N,
+              u32* __restrict__ N32) {
   __shared__ u64 carry;
   __shared__ u64 wsum[32];
+  const u32 n = dev_len(n_host, n_dev, shift);
+  const u32 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (i64 base = 0; base < nb; base += 1024) {
-    const i64 i = base + threadIdx.x;
+  for (u32 base = 0; base < nb; base += 1024) {
+    const u32 i = base + threadIdx.x;
     const u64 v = i < nb ? bsum[i] : 0;
     u64 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const u64 n = __shfl_up_sync(CC_FULL, inc, o);
-      if (lane >= o) inc += n;
+      const u64 t = __shfl_up_sync(CC_FULL, inc, o);
+      if (lane >= o) inc += t;
     }
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
@@ -106,8 +115,8 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ bsum, i6
       u64 si = s;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const u64 n = __shfl_up_sync(CC_FULL, si, o);
-        if (lane >= o) si += n;
+        const u64 t = __shfl_up_sync(CC_FULL, si, o);
+        if (lane >= o) si += t;
       }
       wsum[lane] = si - s;
     }
@@ -118,27 +127,44 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(u64* __restrict__ bsum, i6
     if (threadIdx.x == 1023) carry = c + wsum[warp] + inc;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *N = carry;
+  if (threadIdx.x == 0) { *N = carry; if (N32) *N32 = (u32)carry; }
 }
 
-// prefix[i] = exclusive prefix of cnt (mod 2^32 is fine: ranks are < voxels < 2^32)
+// prefix[i] = exclusive prefix of cnt (mod 2^32 is fine: ranks are < voxels < 2^32); cnt may alias prefix
 __global__ void __launch_bounds__(CC_SCAN_THREADS)
-k_scan_apply(const u32* cnt, const u64* __restrict__ bsum, u32* prefix, i64 n) {  // cnt may alias prefix
-  const i64 base = (i64)blockIdx.x * CC_SCAN_CHUNK + (i64)threadIdx.x * CC_SCAN_ITEMS;
-  u32 v[CC_SCAN_ITEMS];
-  u32 s = 0;
+k_scan_apply(const u32* cnt, const u64* __restrict__ bsum, u32* prefix, i64 n_host, const u64* __restrict__ n_dev, int shift) {
+  const u32 n = dev_len(n_host, n_dev, shift);
+  const u32 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  for (u32 blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+    const u32 base = blk * CC_SCAN_CHUNK + threadIdx.x * CC_SCAN_ITEMS;
+    u32 v[CC_SCAN_ITEMS];
+    u32 s = 0;
+    if (base + CC_SCAN_ITEMS <= n) {
+      const uint4* p = reinterpret_cast<const uint4*>(cnt + base);
 #pragma unroll
-  for (int k = 0; k < CC_SCAN_ITEMS; k++) {
-    const i64 i = base + k;
-    v[k] = i < n ? cnt[i] : 0;
-    s += v[k];
-  }
-  u32 ex = block_exclusive_scan(s, nullptr) + (u32)bsum[blockIdx.x];
+      for (int k = 0; k < CC_SCAN_ITEMS / 4; k++) {
+        const uint4 t = p[k];
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+      }
+    } else {
 #pragma unroll
-  for (int k = 0; k < CC_SCAN_ITEMS; k++) {
-    const i64 i = base + k;
-    if (i < n) prefix[i] = ex;
-    ex += v[k];
+      for (int k = 0; k < CC_SCAN_ITEMS; k++) v[k] = (base + k < n) ? cnt[base + k] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < CC_SCAN_ITEMS; k++) s += v[k];
+    u32 ex = block_exclusive_scan(s, nullptr) + (u32)bsum[blk];
+    if (base + CC_SCAN_ITEMS <= n) {
+      uint4* q = reinterpret_cast<uint4*>(prefix + base);
+#pragma unroll
+      for (int k = 0; k < CC_SCAN_ITEMS / 4; k++) {
+        uint4 t;
+        t.x = ex; ex += v[4 * k]; t.y = ex; ex += v[4 * k + 1]; t.z = ex; ex += v[4 * k + 2]; t.w = ex; ex += v[4 * k + 3];
+        q[k] = t;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CC_SCAN_ITEMS; k++) { if (base + k < n) prefix[base + k] = ex; ex += v[k]; }
+    }
   }
 }
 
@@ -175,13 +201,13 @@ k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__
   const u32 row = row0 + rrel;
   const u32 W = (u32)g.W, sx = (u32)g.sx;
   const u32 wl = (chunk << 5) + lane;
-  const size_t nw = (size_t)g.nwords;
   u32 F = 0, S = 0, RS = 0;
   if (wl < W) {
     const u32 j = row * W + wl;
-    F = __ldg(M + PL_F * nw + j);
-    S = F & ~__ldg(M + PL_X * nw + j);
-    RS = __ldg(M + PL_RS * nw + j) - 1u;
+    const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)j);
+    F = fx.x;
+    S = fx.x & ~fx.y;
+    RS = __ldg(M + g.offRS + j) - 1u;
   }
   const int nwd = (int)min(32u, W - (chunk << 5));
   OUT* orow = out + (size_t)rrel * sx;
@@ -289,13 +315,12 @@ __global__ void __launch_bounds__(256)
 k_blockkey_min(const u32* __restrict__ L, const u32* __restrict__ M, u32* __restrict__ K, Geom g) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (u32)g.nwords) return;
-  const size_t nw = (size_t)g.nwords;
-  const u32 F = __ldg(M + PL_F * nw + i);
-  if (!F) return;
+  const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)i);
+  if (!fx.x) return;
   const u32 W = (u32)g.W;
   const u32 row = i / W, w = i - row * W;
-  u32 bits = F & ~__ldg(M + PL_X * nw + i);
-  u32 id = __ldg(M + PL_RS * nw + i);
+  u32 bits = fx.x & ~fx.y;
+  u32 id = __ldg(M + g.offRS + i);
   const u32 osx = ((u32)g.sx + 1) >> 1;
   while (bits) {
     const int b = __ffs(bits) - 1;
