@@ -110,7 +110,10 @@ void marks_collect(bool append) {
   g_marks.clear();
 }
 
-__global__ void k_init_counters(Counters* c) { c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; c->nruns = 0; }
+__global__ void k_init_counters(Counters* c, u32* ctl) {
+  c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; c->nruns = 0;
+  if (ctl) { ctl[0] = 0; ctl[1] = 0; }
+}
 
 Geom make_geom(i64 sx, i64 sy, i64 sz) {
   Geom g;
@@ -228,7 +231,7 @@ int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64
   Counters* ctr = (Counters*)ar.take(sizeof(Counters));
   void* range2 = ar.take(16);
   Geom g = make_geom(sx, sy, sz);
-  k_init_counters<<<1, 1, 0, s>>>(ctr);
+  k_init_counters<<<1, 1, 0, s>>>(ctr, nullptr);
   g_launches += 1;
   prepass_dispatch(din, in_kind, g, ctr, range2, ar, s);
   Counters h;
@@ -319,6 +322,8 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
   add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
+  const size_t gqcap = (size_t)std::min<i64>(8 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
+  add(gqcap * 8); add(64);
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
   if (int rc = arena_acquire(need, &S->arena)) { delete S; return rc; }
@@ -341,12 +346,15 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   u64* bsum = (u64*)ar.take((size_t)(nb + 1) * 8);
   u64* bsum2 = (u64*)ar.take((size_t)(nb2 + 1) * 8);
   Counters* ctr = (Counters*)ar.take(sizeof(Counters));
+  u64* gqbuf = (u64*)ar.take(gqcap * 8);
+  u32* gqctl = (u32*)ar.take(64);   // [0] count, [1] overflow flag
   S->L = L; S->M = M;
 
-  k_init_counters<<<1, 1, 0, s>>>(ctr);
+  k_init_counters<<<1, 1, 0, s>>>(ctr, gqctl);
   g_launches += 1;
 
   LabelArgs a;
+  a.GQ.q = gqbuf; a.GQ.count = gqctl; a.GQ.ovf = gqctl + 1; a.GQ.cap = (u32)gqcap;
   int stage_launches = 0;
   a.launches = &stage_launches;
   a.in = din; a.M = M; a.L = L; a.ctr = ctr; a.g = g; a.mode = mode;

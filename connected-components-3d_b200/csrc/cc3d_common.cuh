@@ -81,7 +81,9 @@ struct Geom {
   int tw, ty, tz;  // log2 of the union tile extent in words (x), rows (y) and planes (z); tw+ty+tz = 9
 };
 #define CC_TILE_WORDS 512
-#define CC_TILE_NODES (CC_TILE_WORDS * 32)   // a 32-voxel word starts at most 32 runs (multilabel)
+#define CC_TILE_LAB 8192     // shared-memory forest: runs a tile can resolve locally (16 per word)
+#define CC_TILE_LQ 2048      // queue of tile-local edges (packed 16+16 bit local run ids)
+#define CC_TILE_GQ 1024      // staging buffer of edges that leave the tile (64-bit: two run ids)
 
 struct Counters {      // device-side results of a labelling pass
   u64 epl;
@@ -155,6 +157,42 @@ __device__ __forceinline__ void uf_union_h(u32* A, u32 a, u32 b) {
     else done = true;
   } while (!done);
 }
+
+// Block-wide exclusive scan helper (256 threads) shared by the scan kernels and the union tiles.
+#define CC_SCAN_THREADS 256
+#define CC_SCAN_ITEMS 16
+#define CC_SCAN_CHUNK (CC_SCAN_THREADS * CC_SCAN_ITEMS)
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total) {
+  __shared__ u32 wsum[CC_SCAN_THREADS / 32];
+  __shared__ u32 wtot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 n = __shfl_up_sync(CC_FULL, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    u32 s = lane < CC_SCAN_THREADS / 32 ? wsum[lane] : 0;
+    u32 si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 n = __shfl_up_sync(CC_FULL, si, o);
+      if (lane >= o) si += n;
+    }
+    if (lane < CC_SCAN_THREADS / 32) wsum[lane] = si - s;
+    if (lane == 31) wtot = si;
+  }
+  __syncthreads();
+  const u32 r = inc - v + wsum[warp];
+  if (total) *total = wtot;
+  __syncthreads();
+  return r;
+}
+
 
 // Id of the run that contains foreground voxel x of the row whose first word is j0 (= row * W):
 // runs are numbered in raster order, so it is the last run that started at or before x.

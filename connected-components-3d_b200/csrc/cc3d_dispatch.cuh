@@ -15,8 +15,10 @@ struct LabelArgs {
   int connectivity;  // 4, 8, 6, 18, 26
   unsigned char delta[8];  // one element of T
   cudaStream_t stream;
+  EdgeQueue GQ;      // edges that leave their union tile
   int* launches;     // incremented once per kernel launch
 };
+#define CC_QUEUE_BLOCKS (148 * 8)
 
 template <typename T> int run_faces_stage(const LabelArgs& a);     // kernel A
 template <typename T> int run_union_stage(const LabelArgs& a);     // kernel B
@@ -56,13 +58,13 @@ static int launch_union(const LabelArgs& a) {
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
-  const size_t smem = (size_t)(CC_TILE_NODES + CC_TILE_WORDS) * 4;
+  const size_t smem = (size_t)(CC_TILE_LAB + CC_TILE_LQ + 2 * CC_TILE_GQ + 2 * CC_TILE_WORDS) * 4;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty);
-  if (ntx * nty * ntz > 1)
-    k_union_global<T, MODE, CONN><<<(unsigned)((g.nwords + 255) / 256), 256, 0, a.stream>>>(in, a.M, a.L, g, E);
-  *a.launches += (ntx * nty * ntz > 1) ? 2 : 1;
+  k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+  k_union_queue<<<CC_QUEUE_BLOCKS, 256, 0, a.stream>>>(a.L, a.GQ);
+  k_union_global<T, MODE, CONN><<<(unsigned)((g.nwords + 255) / 256), 256, 0, a.stream>>>(in, a.M, a.L, g, E, a.GQ.ovf);
+  *a.launches += 3;
   return 0;
 }
 

@@ -36,40 +36,6 @@ k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, con
 // C2 / S: exclusive scan of u32 counts, three small kernels (block reduce, scan of block sums, apply).
 // The length is either a host value or derived from a device-side count (see dev_len); the kernels
 // loop over 4096-element chunks, so the grid does not depend on the length.
-#define CC_SCAN_THREADS 256
-#define CC_SCAN_ITEMS 16
-#define CC_SCAN_CHUNK (CC_SCAN_THREADS * CC_SCAN_ITEMS)
-
-__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total) {
-  __shared__ u32 wsum[CC_SCAN_THREADS / 32];
-  __shared__ u32 wtot;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  u32 inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const u32 n = __shfl_up_sync(CC_FULL, inc, o);
-    if (lane >= o) inc += n;
-  }
-  if (lane == 31) wsum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    u32 s = lane < CC_SCAN_THREADS / 32 ? wsum[lane] : 0;
-    u32 si = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 n = __shfl_up_sync(CC_FULL, si, o);
-      if (lane >= o) si += n;
-    }
-    if (lane < CC_SCAN_THREADS / 32) wsum[lane] = si - s;
-    if (lane == 31) wtot = si;
-  }
-  __syncthreads();
-  const u32 r = inc - v + wsum[warp];
-  if (total) *total = wtot;
-  __syncthreads();
-  return r;
-}
-
 __global__ void __launch_bounds__(CC_SCAN_THREADS)
 k_scan_reduce(const u32* __restrict__ cnt, u64* __restrict__ bsum, i64 n_host, const u64* __restrict__ n_dev, int shift) {
   const u32 n = dev_len(n_host, n_dev, shift);

@@ -1,4 +1,5 @@
-// cc3d_union.cuh — kernels B1/B2 (word-parallel edge elimination + unions) and kernel P (periodic wrap).
+// cc3d_union.cuh — kernels B1/B2 (word-parallel edge elimination, tile-local and global unions) and
+// kernel P (periodic wrap).
 // See cc3d_common.cuh for the pipeline.
 #pragma once
 #include "cc3d_common.cuh"
@@ -30,7 +31,8 @@ struct R3 { S3 F, X, Y, Z; };
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CONN, typename EMIT>
 __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u32* __restrict__ M, const Geom& g,
-                                              const Edge<T, MODE>& E, const u32 i, EMIT&& emit) {
+                                              const Edge<T, MODE>& E, const u32 i, const u32 row, const u32 w,
+                                              const u32 y, const u32 z, EMIT&& emit) {
   constexpr int NR = hood_rows(CONN);
   constexpr bool DIAG0 = CONN == 8 || CONN == 18 || CONN == 26;
   constexpr bool DIAGZ = CONN == 18 || CONN == 26;
@@ -39,13 +41,12 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
   const Q4 P = ldq(M, i);
   if (P.F == 0) return;
   const u32 W = (u32)g.W, sy = (u32)g.sy, sx = (u32)g.sx;
-  const u32 row = i / W, w = i - row * W;
-  const u32 z = row / sy, y = row - z * sy;
   const u32 x0 = w << 5;
   const bool hasL = w > 0, hasR = w + 1 < W;
   const bool hasU = y > 0, hasD = NR >= 2 && z > 0, hasV = y + 1 < sy;
   const u32 WS = W * sy;                  // words per plane
   const Q4 Z4 = {0u, 0u, 0u, 0u};
+  const u32* __restrict__ RS = M + g.offRS;
 
   // faces of the words left and right of word j (0 outside the row)
   auto sh3 = [](u32 c, u32 lw, u32 rw) -> S3 { S3 s; s.c = c; s.l = (c << 1) | (lw >> 31); s.r = (c >> 1) | (rw << 31); return s; };
@@ -58,21 +59,29 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
     return o;
   };
 
-  const u32 RSp = __ldg(M + g.offRS + i);
+  const u32 RSp = __ldg(RS + i) - 1u;
   const u32 Sp = P.F & ~P.X;
-  auto pid = [&](int b) -> u32 { return RSp + __popc(Sp & (CC_FULL >> (31 - b))) - 1u; };
+  auto pid = [&](int b) -> u32 { return RSp + __popc(Sp & (CC_FULL >> (31 - b))); };
   auto joined = [&](int b, u32 rowQ, u32 xq) -> bool {   // value test of a diagonal candidate
     if constexpr (MODE == MODE_NONZERO || MODE == MODE_MASK) return true;
     else return E(in[row * sx + x0 + b], in[rowQ * sx + xq]);
   };
-  auto diag = [&](u32 cand, u32 rowQ, int dx) {
+  auto diag = [&](u32 cand, int dy, int dz, int dx) {
+    const u32 rowQ = row + dy + dz * (int)sy;
     while (cand) {
       const int b = __ffs(cand) - 1; cand &= cand - 1;
-      if (joined(b, rowQ, x0 + b + dx)) emit(b, pid(b), rowQ, x0 + b + dx);
+      const u32 xq = x0 + b + dx;
+      if (joined(b, rowQ, xq)) emit(pid(b), run_id(M, g, rowQ * W, xq), dy, dz, xq);
     }
   };
-  auto straight = [&](u32 need, u32 rowQ) {
-    while (need) { const int b = __ffs(need) - 1; need &= need - 1; emit(b, pid(b), rowQ, x0 + b); }
+  // straight edge to the same x of row Q (faces Qf, run counter RSq = RS[word of Q] - 1)
+  auto straight = [&](u32 need, const Q4& Qf, u32 RSq, int dy, int dz) {
+    const u32 Sq = Qf.F & ~Qf.X;
+    while (need) {
+      const int b = __ffs(need) - 1; need &= need - 1;
+      const u32 below = CC_FULL >> (31 - b);
+      emit(RSp + __popc(Sp & below), RSq + __popc(Sq & below), dy, dz, x0 + b);
+    }
   };
 
   // ---- straight edges ----
@@ -80,14 +89,20 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
   const Q4 U = hasU ? ldq(M, i - W) : Z4;
   const Q4 D = hasD ? ldq(M, i - WS) : Z4;
   const u32 Yl = (P.Y << 1) | (Pl.Y >> 31), Zl = (P.Z << 1) | (Pl.Z >> 31);
-  if (hasU) straight(P.Y & ~(P.X & U.X & Yl), row - 1);
-  if (hasD) straight(P.Z & ~(P.X & D.X & Zl) & ~(P.Y & U.Z & D.Y), row - sy);
+  if (hasU) {
+    const u32 need = P.Y & ~(P.X & U.X & Yl);
+    if (need) straight(need, U, __ldg(RS + i - W) - 1u, -1, 0);
+  }
+  if (hasD) {
+    const u32 need = P.Z & ~(P.X & D.X & Zl) & ~(P.Y & U.Z & D.Y);
+    if (need) straight(need, D, __ldg(RS + i - WS) - 1u, 0, -1);
+  }
 
   // ---- diagonal edges ----
   if constexpr (MODE == MODE_MASK) {
     if (hasU) {
-      diag(__ldg(M + g.offA0 + i), row - 1, -1);
-      diag(__ldg(M + g.offC0 + i), row - 1, +1);
+      diag(__ldg(M + g.offA0 + i), -1, 0, -1);
+      diag(__ldg(M + g.offC0 + i), -1, 0, +1);
     }
     return;
   }
@@ -111,8 +126,8 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
       A0 = Fp & RU.F.l & ~(Xp.c & Yp.l) & ~(Yp.c & RU.X.c);
       C0 = Fp & RU.F.r & ~(Xp.r & Yp.r) & ~(Yp.c & RU.X.r);
     }
-    diag(A0, row - 1, -1);
-    diag(C0, row - 1, +1);
+    diag(A0, -1, 0, -1);
+    diag(C0, -1, 0, +1);
   }
   if constexpr (DIAGZ) {
     if (wantz) {
@@ -128,8 +143,8 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
         A1 = Fp & RD.F.l & ~(Xp.c & Zp.l) & ~(Zp.c & XD.c);
         C1 = Fp & RD.F.r & ~(Xp.r & Zp.r) & ~(Zp.c & XD.r);
       }
-      diag(A1, row - sy, -1);
-      diag(C1, row - sy, +1);
+      diag(A1, 0, -1, -1);
+      diag(C1, 0, -1, +1);
       // (dy=-1, dz=-1): B2, A2, C2
       if (hasU && (!TRANS || (Fp & ~(Yp.c | Zp.c)))) {
         const R3 RUD = row3(iD - W);
@@ -137,7 +152,7 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
         u32 B2;
         if constexpr (TRANS) B2 = Fp & FUD.c & ~(Yp.c | ZU.c | Zp.c | YD.c);
         else B2 = Fp & FUD.c & ~(Yp.c & ZU.c) & ~(Zp.c & YD.c);
-        diag(B2, row - sy - 1, 0);
+        diag(B2, -1, -1, 0);
         if constexpr (CORNER) {
           u32 A2, C2;
           if constexpr (TRANS) {
@@ -149,8 +164,8 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
             C2 = Fp & FUD.r & ~(Xp.r & Yp.r & ZU.r) & ~(Xp.r & Zp.r & YD.r) & ~(Yp.c & XU.r & ZU.r)
                  & ~(Yp.c & ZU.c & XUD.r) & ~(Zp.c & XD.r & YD.r) & ~(Zp.c & YD.c & XUD.r);
           }
-          diag(A2, row - sy - 1, -1);
-          diag(C2, row - sy - 1, +1);
+          diag(A2, -1, -1, -1);
+          diag(C2, -1, -1, +1);
         }
       }
       // (dy=+1, dz=-1): B3, A3, C3
@@ -163,7 +178,7 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
           u32 B3;
           if constexpr (TRANS) B3 = Fp & FDN.c & ~(YV.c | ZV.c | Zp.c | YDN.c);
           else B3 = Fp & FDN.c & ~(YV.c & ZV.c) & ~(Zp.c & YDN.c);
-          diag(B3, row - sy + 1, 0);
+          diag(B3, +1, -1, 0);
           if constexpr (CORNER) {
             u32 A3, C3;
             if constexpr (TRANS) {
@@ -175,8 +190,8 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
               C3 = Fp & FDN.r & ~(Xp.r & YV.r & ZV.r) & ~(Xp.r & Zp.r & YDN.r) & ~(YV.c & XV.r & ZV.r)
                    & ~(YV.c & ZV.c & XDN.r) & ~(Zp.c & XD.r & YDN.r) & ~(Zp.c & YDN.c & XDN.r);
             }
-            diag(A3, row - sy + 1, -1);
-            diag(C3, row - sy + 1, +1);
+            diag(A3, +1, -1, -1);
+            diag(C3, +1, -1, +1);
           }
         }
       }
@@ -184,64 +199,127 @@ __device__ __forceinline__ void for_each_edge(const T* __restrict__ in, const u3
   }
 }
 
-// Union tiles: 2^tw words x 2^ty rows x 2^tz planes = CC_TILE_WORDS words. A run belongs to the tile its
-// first voxel lies in; an edge is tile-local when both of its runs belong to the same tile.
-struct TilePos { u32 tx, ty, tz; };
-__device__ __forceinline__ TilePos tile_of(const Geom& g, u32 w, u32 y, u32 z) {
-  TilePos t; t.tx = w >> g.tw; t.ty = y >> g.ty; t.tz = z >> g.tz; return t;
-}
+// ---------------------------------------------------------------------------------------------
+// Kernel B1. One CTA per union tile (2^tw words x 2^ty rows x 2^tz planes = CC_TILE_WORDS words).
+// A run belongs to the tile its first voxel lies in; an edge is tile-local when both of its runs belong
+// to the tile. The runs that start in a tile row segment (2^tw words of one row) have contiguous ids
+// [RS[first word], RS[word after the segment]), so an exclusive scan of the segment sizes gives dense
+// local ids that keep the raster order of the runs (link-to-smaller stays valid).
+//   phase 1: one thread per word enumerates the edges (for_each_edge) and only classifies them:
+//            tile-local edges go to a shared-memory queue, the others to a staging buffer
+//   phase 2: the queue is worked off by all threads, one edge each (balanced): union-find in shared memory
+//   phase 3: every run of the tile gets L[run] = run id of its tile root; the staged edges are appended
+//            to the global edge queue GQ for kernel B2
+// A tile with more than CC_TILE_LAB runs sends all its edges to B2. If GQ overflows, *ovf is raised
+// and kernel B2s redoes every edge on the global forest.
+// ---------------------------------------------------------------------------------------------
+struct EdgeQueue { u64* q; u32* count; u32* ovf; u32 cap; };
 
-// ---------------------------------------------------------------------------------------------
-// Kernel B1. One CTA per union tile, union-find in shared memory. A tile row segment (2^tw words of one
-// row) owns the contiguous run ids [RS[first word], RS[first word] + cap), so local node = segment *
-// cap + (run id - first id of the segment) keeps the raster order of the runs (link-to-smaller stays
-// valid). Tile-local edges are united in shared memory; every run of the tile then gets L[run] = run id
-// of its tile root. Edges that leave the tile are left to kernel B2.
-// ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256)
 k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
-             u32 ntx, u32 nty) {
-  extern __shared__ u32 smem_u32[];
-  u32* lab = smem_u32;                          // [CC_TILE_NODES]
-  u32* segRS = smem_u32 + CC_TILE_NODES;        // [CC_TILE_WORDS] first run id of every row segment
+             u32 ntx, u32 nty, EdgeQueue GQ) {
+  extern __shared__ __align__(16) u32 smem_u32[];
+  u32* lab = smem_u32;                                   // [CC_TILE_LAB]
+  u32* lq = lab + CC_TILE_LAB;                           // [CC_TILE_LQ]
+  u64* gq = reinterpret_cast<u64*>(lq + CC_TILE_LQ);     // [CC_TILE_GQ]
+  u32* segRS = lq + CC_TILE_LQ + 2 * CC_TILE_GQ;         // [CC_TILE_WORDS] first run id of every row segment
+  u32* segLB = segRS + CC_TILE_WORDS;                    // [CC_TILE_WORDS] first local id of every row segment
+  __shared__ u32 s_ln, s_gn, s_gbase, s_total;
   const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
   const u32 TW = 1u << g.tw, TY = 1u << g.ty;
   const u32 nseg = CC_TILE_WORDS >> g.tw;        // TY * TZ
-  const u32 capl = g.tw + 5;                     // log2(runs a segment can hold)
   u32 t = blockIdx.x;
   const u32 bx = t % ntx; t /= ntx;
   const u32 by = t % nty;
   const u32 bz = t / nty;
   const u32 w0 = bx << g.tw, y0 = by << g.ty, z0 = bz << g.tz;
+  const u32 wend = min(w0 + TW, W);
+  const u32* __restrict__ RS = M + g.offRS;
 
-  for (u32 r = threadIdx.x; r < nseg; r += blockDim.x) {
-    const u32 y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
-    segRS[r] = (y < sy && z < sz) ? __ldg(M + g.offRS + (z * sy + y) * W + w0) : 0xFFFFFFFFu;
+  // segment tables (two segments per thread; nseg <= 512)
+  {
+    u32 c[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const u32 r = 2 * threadIdx.x + k;
+      c[k] = 0;
+      if (r < nseg) {
+        const u32 y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+        u32 first = 0xFFFFFFFFu;
+        if (y < sy && z < sz) {
+          const u32 j = (z * sy + y) * W;
+          first = __ldg(RS + j + w0);
+          c[k] = __ldg(RS + j + wend) - first;
+        }
+        segRS[r] = first;
+      }
+    }
+    if (threadIdx.x == 0) { s_ln = 0; s_gn = 0; }
+    u32 total;
+    const u32 ex = block_exclusive_scan(c[0] + c[1], &total);
+    if (2 * threadIdx.x < nseg) segLB[2 * threadIdx.x] = ex;
+    if (2 * threadIdx.x + 1 < nseg) segLB[2 * threadIdx.x + 1] = ex + c[0];
+    if (threadIdx.x == 0) s_total = total;
   }
-  for (u32 k = threadIdx.x; k < CC_TILE_NODES; k += blockDim.x) lab[k] = k;
+  __syncthreads();
+  const u32 total = s_total;
+  const bool local_ok = total <= CC_TILE_LAB;
+  if (local_ok) for (u32 k = threadIdx.x; k < total; k += blockDim.x) lab[k] = k;
   __syncthreads();
 
+  auto push_global = [&](u32 gp, u32 gq_) {
+    const u32 pos = atomicAdd(GQ.count, 1u);
+    if (pos < GQ.cap) GQ.q[pos] = (u64)gp | ((u64)gq_ << 32);
+    else *GQ.ovf = 1u;
+  };
+
+  // ---- phase 1: enumerate + classify ----
 #pragma unroll 1
   for (u32 q = threadIdx.x; q < CC_TILE_WORDS; q += blockDim.x) {
     const u32 wx = q & (TW - 1), r = q >> g.tw;
-    const u32 w = w0 + wx, y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+    const int ly = (int)(r & (TY - 1)), lz = (int)(r >> g.ty);
+    const u32 w = w0 + wx, y = y0 + ly, z = z0 + lz;
     if (w >= W || y >= sy || z >= sz) continue;
-    const u32 i = (z * sy + y) * W + w;
-    const u32 base = segRS[r];
-    for_each_edge<T, MODE, CONN>(in, M, g, E, i, [&](int b, u32 gp, u32 rowQ, u32 xq) {
-      if (gp < base) return;                                    // p's run started left of the tile
-      const u32 zq = rowQ / sy, yq = rowQ - zq * sy;
-      if ((xq >> 5) >> g.tw != bx || yq >> g.ty != by || zq >> g.tz != bz) return;
-      const u32 rq = ((zq - z0) << g.ty) + (yq - y0);
-      const u32 gq = run_id(M, g, rowQ * W, xq);
-      if (gq < segRS[rq]) return;
-      uf_union_h(lab, (r << capl) + (gp - base), (rq << capl) + (gq - segRS[rq]));
+    const u32 row = z * sy + y;
+    const u32 baseP = segRS[r], lbP = segLB[r];
+    for_each_edge<T, MODE, CONN>(in, M, g, E, row * W + w, row, w, y, z, [&](u32 gp, u32 gq_, int dy, int dz, u32 xq) {
+      bool local = local_ok && gp >= baseP;
+      u32 rq = 0;
+      if (local) {
+        const int lyq = ly + dy, lzq = lz + dz;
+        local = ((xq >> 5) >> g.tw) == bx && lyq >= 0 && lyq < (int)TY && lzq >= 0;
+        if (local) { rq = ((u32)lzq << g.ty) + (u32)lyq; local = gq_ >= segRS[rq]; }
+      }
+      if (local) {
+        const u32 lp = lbP + (gp - baseP), lq_ = segLB[rq] + (gq_ - segRS[rq]);
+        const u32 pos = atomicAdd(&s_ln, 1u);
+        if (pos < CC_TILE_LQ) lq[pos] = lp | (lq_ << 16);
+        else uf_union_h(lab, lp, lq_);
+      } else {
+        const u32 pos = atomicAdd(&s_gn, 1u);
+        if (pos < CC_TILE_GQ) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+        else push_global(gp, gq_);
+      }
     });
   }
   __syncthreads();
 
-  // flatten: every run that starts in the tile -> run id of its tile root
+  // ---- phase 2: tile-local unions, one queued edge per thread and step ----
+  const u32 ln = min(s_ln, (u32)CC_TILE_LQ), gn = min(s_gn, (u32)CC_TILE_GQ);
+  if (threadIdx.x == 0 && gn) s_gbase = atomicAdd(GQ.count, gn);
+  for (u32 e = threadIdx.x; e < ln; e += blockDim.x) {
+    const u32 v = lq[e];
+    uf_union_h(lab, v & 0xFFFFu, v >> 16);
+  }
+  __syncthreads();
+
+  // ---- phase 3: staged edges -> global queue; runs -> tile roots ----
+  for (u32 e = threadIdx.x; e < gn; e += blockDim.x) {
+    const u32 pos = s_gbase + e;
+    if (pos < GQ.cap) GQ.q[pos] = gq[e];
+    else *GQ.ovf = 1u;
+  }
 #pragma unroll 1
   for (u32 q = threadIdx.x; q < CC_TILE_WORDS; q += blockDim.x) {
     const u32 wx = q & (TW - 1), r = q >> g.tw;
@@ -251,40 +329,48 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
     const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)i);
     const int n = __popc(fx.x & ~fx.y);
     if (n == 0) continue;
-    const u32 g0 = __ldg(M + g.offRS + i);
-    const u32 base = segRS[r];
+    const u32 g0 = __ldg(RS + i);
+    if (!local_ok) { for (int k = 0; k < n; k++) L[g0 + k] = g0 + k; continue; }
+    const u32 l0 = segLB[r] + (g0 - segRS[r]);
     for (int k = 0; k < n; k++) {
-      u32 l = (r << capl) + (g0 + k - base), p;
+      u32 l = l0 + k, p;
       while ((p = lab[l]) != l) l = p;
-      L[g0 + k] = segRS[l >> capl] + (l & ((1u << capl) - 1u));
+      u32 root = g0 + k;
+      if (l != l0 + (u32)k) {
+        // segment of the root: last segment whose first local id is <= l
+        u32 lo = 0, hi = nseg - 1;
+        while (lo < hi) { const u32 mid = (lo + hi + 1) >> 1; if (segLB[mid] <= l) lo = mid; else hi = mid - 1; }
+        root = segRS[lo] + (l - segLB[lo]);
+      }
+      L[g0 + k] = root;
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Kernel B2. One thread per bitmap word: the edges that are not tile-local (same test as B1) are united
-// on the global forest L (atomicMin link-to-smaller with path halving).
-// ---------------------------------------------------------------------------------------------
+// Kernel B2. One thread per queued edge: union on the global forest L (atomicMin link-to-smaller with
+// path halving). Tile roots are at most one hop away, so the finds are short.
+static __global__ void __launch_bounds__(256) k_union_queue(u32* __restrict__ L, EdgeQueue GQ) {
+  const u32 n = min(*GQ.count, GQ.cap);
+  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const u64 v = GQ.q[e];
+    uf_union_h(L, (u32)v, (u32)(v >> 32));
+  }
+}
+
+// Kernel B2s (fallback, does nothing unless the edge queue overflowed): one thread per bitmap word,
+// every edge is united on the global forest.
 template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256)
-k_union_global(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E) {
+k_union_global(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
+               const u32* __restrict__ ovf) {
+  if (*ovf == 0) return;
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (u32)g.nwords) return;
   const u32 W = (u32)g.W, sy = (u32)g.sy;
   const u32 row = i / W, w = i - row * W;
   const u32 z = row / sy, y = row - z * sy;
-  const u32 bx = w >> g.tw, by = y >> g.ty, bz = z >> g.tz;
-  const u32 w0 = bx << g.tw;
-  u32 base = 0xFFFFFFFFu;   // first run id of p's tile row segment, loaded on demand
-  for_each_edge<T, MODE, CONN>(in, M, g, E, i, [&](int b, u32 gp, u32 rowQ, u32 xq) {
-    const u32 gq = run_id(M, g, rowQ * W, xq);
-    const u32 zq = rowQ / sy, yq = rowQ - zq * sy;
-    if ((xq >> 5) >> g.tw == bx && yq >> g.ty == by && zq >> g.tz == bz) {
-      if (base == 0xFFFFFFFFu) base = __ldg(M + g.offRS + row * W + w0);
-      if (gp >= base && gq >= __ldg(M + g.offRS + rowQ * W + w0)) return;   // tile-local: done by B1
-    }
-    uf_union_h(L, gp, gq);
-  });
+  for_each_edge<T, MODE, CONN>(in, M, g, E, i, row, w, y, z,
+                               [&](u32 gp, u32 gq_, int, int, u32) { uf_union_h(L, gp, gq_); });
 }
 
 // ---------------------------------------------------------------------------------------------
