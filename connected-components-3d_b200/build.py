@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "cc3d_b200", "libcc3d_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+EXTRA = os.environ.get("CC3D_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 UNITS = ["cc3d_b200.cu", "inst_u8.cu", "inst_u16.cu", "inst_u32.cu", "inst_u64.cu", "inst_f32.cu", "inst_f64.cu"]
 

@@ -112,7 +112,7 @@ void marks_collect(bool append) {
 
 __global__ void k_init_counters(Counters* c, u32* ctl) {
   c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; c->nruns = 0;
-  if (ctl) { ctl[0] = 0; ctl[1] = 0; }
+  if (ctl) { for (int k = 0; k < 8; k++) ctl[k] = 0; }
 }
 
 Geom make_geom(i64 sx, i64 sy, i64 sz) {
@@ -424,6 +424,10 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e)); }
   marks_collect(false);
+#ifdef CC_STATS
+  { u32 hc[8]; cudaMemcpy(hc, gqctl, 32, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[cc3d stats] runs=%llu queued=%u ovf=%u hops=%u finds=%u nontrivial=%u\n", (unsigned long long)h.nruns, hc[0], hc[1], hc[2], hc[3], hc[4]); }
+#endif
   S->N = h.N;
   info->N = h.N;
   info->epl = h.epl;

@@ -81,7 +81,7 @@ struct Geom {
   int tw, ty, tz;  // log2 of the union tile extent in words (x), rows (y) and planes (z); tw+ty+tz = 9
 };
 #define CC_TILE_WORDS 512
-#define CC_TILE_LAB 8192     // shared-memory forest: runs a tile can resolve locally (16 per word)
+#define CC_TILE_NODES (CC_TILE_WORDS * 16)   // shared-memory forest: 16 runs per word (the binary maximum)
 #define CC_TILE_LQ 2048      // queue of tile-local edges (packed 16+16 bit local run ids)
 #define CC_TILE_GQ 1024      // staging buffer of edges that leave the tile (64-bit: two run ids)
 
@@ -133,17 +133,19 @@ __device__ __forceinline__ void uf_union(u32* A, u32 a, u32 b) {
   } while (!done);
 }
 
-// Lock-free union with path halving: a find re-points every node it passes at its grandparent.
-// A stale write can only replace a parent by another ancestor, which keeps every set intact.
+// Global forest (one u32 per run). Finds use ordinary L1-cached loads: a stale parent is still an
+// ancestor (parents only ever move up), so a find may stop early but never leaves the set, and the
+// link itself is an atomicMin whose return value is always current. This keeps the millions of finds
+// that end at the root of a giant component out of one L2 slice. Path halving: every find re-points
+// the nodes it passes at their grandparents.
 __device__ __forceinline__ u32 uf_find_h(u32* A, u32 i) {
-  volatile u32* V = A;
-  u32 p = V[i];
+  u32 p = __ldca(A + i);
   while (p != i) {
-    const u32 gp = V[p];
+    const u32 gp = __ldca(A + p);
     if (gp == p) return p;
-    V[i] = gp;
+    A[i] = gp;
     i = gp;
-    p = V[i];
+    p = __ldca(A + i);
   }
   return i;
 }
@@ -154,6 +156,43 @@ __device__ __forceinline__ void uf_union_h(u32* A, u32 a, u32 b) {
     b = uf_find_h(A, b);
     if (a < b) { u32 old = atomicMin(&A[b], a); done = (old == b); b = old; }
     else if (b < a) { u32 old = atomicMin(&A[a], b); done = (old == a); a = old; }
+    else done = true;
+  } while (!done);
+}
+
+// Shared-memory forest of a union tile: 16-bit parents (a tile holds at most 2^14 runs), link =
+// compare-and-swap minimum on the containing 32-bit word.
+__device__ __forceinline__ u32 sm_find16(volatile uint16_t* A, u32 i) {
+  u32 p = A[i];
+  while (p != i) {
+    const u32 gp = A[p];
+    if (gp == p) return p;
+    A[i] = (uint16_t)gp;
+    i = gp;
+    p = A[i];
+  }
+  return i;
+}
+__device__ __forceinline__ u32 sm_min16(uint16_t* A, u32 idx, u32 val) {   // returns the previous value
+  u32* Wd = reinterpret_cast<u32*>(A) + (idx >> 1);
+  const int sh = (idx & 1) * 16;
+  u32 old = *reinterpret_cast<volatile u32*>(Wd);
+  while (true) {
+    const u32 cur = (old >> sh) & 0xFFFFu;
+    if (val >= cur) return cur;
+    const u32 nw = (old & ~(0xFFFFu << sh)) | (val << sh);
+    const u32 prev = atomicCAS(Wd, old, nw);
+    if (prev == old) return cur;
+    old = prev;
+  }
+}
+__device__ __forceinline__ void sm_union16(uint16_t* A, u32 a, u32 b) {
+  bool done;
+  do {
+    a = sm_find16(A, a);
+    b = sm_find16(A, b);
+    if (a < b) { u32 old = sm_min16(A, b, a); done = (old == b); b = old; }
+    else if (b < a) { u32 old = sm_min16(A, a, b); done = (old == a); a = old; }
     else done = true;
   } while (!done);
 }

@@ -58,7 +58,7 @@ static int launch_union(const LabelArgs& a) {
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
-  const size_t smem = (size_t)(CC_TILE_LAB + CC_TILE_LQ + 2 * CC_TILE_GQ + 2 * CC_TILE_WORDS) * 4;
+  const size_t smem = (size_t)(CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * CC_TILE_GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2) * 4;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);

@@ -38,52 +38,82 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
     const u32 x = (w << 5) + lane;
     const bool inx = x < sx;
     const bool edge = lane == 0 && x > 0;
-    const bool inz = HASZ && z > 0 && inx;
+    const bool hasz = HASZ && z > 0;
     const u32 plane = sy * sx;
-    u32 off = (z * sy + y0) * sx + x;          // voxel (x, y0, z); voxels < 2^32
-    u32 row = z * sy + y0;
-    u32 idx = row * W + w;
+    const u32 row0 = z * sy + y0;
+    const u32 off0 = row0 * sx + (inx ? x : 0);   // voxel (x, y0, z); voxels < 2^32
+    u32 idx = row0 * W + w;
     uint4* __restrict__ MQ = reinterpret_cast<uint4*>(M);
     u32* __restrict__ RS = M + g.offRS;
+    const T* __restrict__ p = in + off0;           // walks down the column
     T up = (T)0;
-    if (y0 > 0 && inx) up = in[off - sx];
+    if (y0 > 0 && inx) up = *(p - sx);
+    u32 rowbits = 0;                               // bit k: row y0 + k has foreground
 
-    for (u32 yb = y0; yb < y1; yb += CC_FACE_UNR) {
+    // one row: faces of the 32 voxels c (left neighbour l, -y neighbour up, -z neighbour d)
+    auto step = [&](const T c, const T pe, const T d, const u32 k, const bool store) {
+      T l = shfl_up1(c);
+      if (lane == 0) l = pe;
+      const bool f = E.fg(c);
+      const u32 F = __ballot_sync(CC_FULL, f);
+      const u32 X = __ballot_sync(CC_FULL, E(c, l));
+      const u32 Y = __ballot_sync(CC_FULL, E(c, up));
+      const u32 Z = HASZ ? __ballot_sync(CC_FULL, E(c, d)) : 0u;
+      const u32 ns = __popc(F & ~X);
+      // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
+      if constexpr (MODE == MODE_EQ) epl += ns;
+      else epl += __popc(__ballot_sync(CC_FULL, f && c != l));
+      if (F) rowbits |= 1u << k;
+      if (store && lane == 0) {
+        MQ[idx] = make_uint4(F, X, Y, Z);
+        RS[idx] = ns;
+      }
+      up = c;
+      idx += W;
+    };
+
+    u32 yb = y0;
+    if ((w << 5) + 32 <= sx && yb + CC_FACE_UNR <= y1) {   // warp-uniform: the whole word lies inside the row
+      // full groups of CC_FACE_UNR rows, software pipelined: the unpredicated loads of the next group are
+      // issued before the current group is evaluated
       T pc[CC_FACE_UNR], pe[CC_FACE_UNR], dc[CC_FACE_UNR];
+      auto load_group = [&](T* a, T* b, T* c, const T* q) {
 #pragma unroll
-      for (int k = 0; k < CC_FACE_UNR; k++) {
-        const bool valid = yb + k < y1;
-        const u32 o = off + k * sx;
-        pc[k] = (valid && inx) ? in[o] : (T)0;
-        pe[k] = (valid && edge) ? in[o - 1] : (T)0;
-        dc[k] = (valid && inz) ? in[o - plane] : (T)0;
-      }
-#pragma unroll
-      for (int k = 0; k < CC_FACE_UNR; k++) {
-        const T c = pc[k];
-        T l = shfl_up1(c);
-        if (lane == 0) l = pe[k];
-        const bool f = E.fg(c);
-        const u32 F = __ballot_sync(CC_FULL, f);
-        const u32 X = __ballot_sync(CC_FULL, E(c, l));
-        const u32 Y = __ballot_sync(CC_FULL, E(c, up));
-        const u32 Z = HASZ ? __ballot_sync(CC_FULL, E(c, dc[k])) : 0u;
-        const u32 ns = __popc(F & ~X);
-        // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
-        if constexpr (MODE == MODE_EQ) epl += ns;
-        else epl += __popc(__ballot_sync(CC_FULL, f && c != l));
-        rfirst = F ? min(rfirst, row) : rfirst;
-        rlast = F ? row : rlast;
-        anyfg |= F;
-        if (lane == 0 && yb + k < y1) {
-          MQ[idx] = make_uint4(F, X, Y, Z);
-          RS[idx] = ns;
+        for (int k = 0; k < CC_FACE_UNR; k++) {
+          a[k] = q[k * sx];
+          b[k] = (T)0;
+          if (edge) b[k] = *(q + k * sx - 1);
+          c[k] = (T)0;
+          if (hasz) c[k] = *(q + k * sx - plane);
         }
-        up = c;
-        idx += W;
-        row++;
+      };
+      load_group(pc, pe, dc, p);
+      for (; yb + 2 * CC_FACE_UNR <= y1; yb += CC_FACE_UNR) {
+        T npc[CC_FACE_UNR], npe[CC_FACE_UNR], ndc[CC_FACE_UNR];
+        load_group(npc, npe, ndc, p + CC_FACE_UNR * sx);
+#pragma unroll
+        for (int k = 0; k < CC_FACE_UNR; k++) step(pc[k], pe[k], dc[k], yb - y0 + k, true);
+#pragma unroll
+        for (int k = 0; k < CC_FACE_UNR; k++) { pc[k] = npc[k]; pe[k] = npe[k]; dc[k] = ndc[k]; }
+        p += CC_FACE_UNR * sx;
       }
-      off += CC_FACE_UNR * sx;
+#pragma unroll
+      for (int k = 0; k < CC_FACE_UNR; k++) step(pc[k], pe[k], dc[k], yb - y0 + k, true);
+      p += CC_FACE_UNR * sx;
+      yb += CC_FACE_UNR;
+    }
+    // remaining rows, and every row of a partial last word (lanes past sx hold 0)
+    for (; yb < y1; yb++) {
+      T c = (T)0, e = (T)0, d = (T)0;
+      if (inx) { c = *p; if (hasz) d = *(p - plane); }
+      if (edge) e = *(p - 1);
+      step(c, e, d, yb - y0, true);
+      p += sx;
+    }
+    if (rowbits) {
+      anyfg = 1;
+      rfirst = row0 + __ffs(rowbits) - 1;
+      rlast = row0 + 31 - __clz(rowbits);
     }
   }
 

@@ -159,7 +159,9 @@ template <typename OUT, int REMAP>
 __global__ void __launch_bounds__(256)
 k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__ out, Geom g, unsigned nchunks,
          u32 row0, u32 nwarps_total, const void* __restrict__ remap) {
+  __shared__ uint4 s_words[8][32];   // per warp: {F, run starts, id of the run that enters the word, -}
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= nwarps_total) return;
   const u32 rrel = wid / nchunks;
@@ -167,31 +169,39 @@ k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__
   const u32 row = row0 + rrel;
   const u32 W = (u32)g.W, sx = (u32)g.sx;
   const u32 wl = (chunk << 5) + lane;
-  u32 F = 0, S = 0, RS = 0;
-  if (wl < W) {
-    const u32 j = row * W + wl;
-    const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)j);
-    F = fx.x;
-    S = fx.x & ~fx.y;
-    RS = __ldg(M + g.offRS + j) - 1u;
+  {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (wl < W) {
+      const u32 j = row * W + wl;
+      const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)j);
+      v.x = fx.x;
+      v.y = fx.x & ~fx.y;
+      v.z = __ldg(M + g.offRS + j) - 1u;
+    }
+    s_words[warp][lane] = v;
   }
-  const int nwd = (int)min(32u, W - (chunk << 5));
-  OUT* orow = out + (size_t)rrel * sx;
+  __syncwarp();
+  const u32 nwd = min(32u, W - (chunk << 5));
   const u32 below = CC_FULL >> (31 - lane);
+  const u32 bit = 1u << lane;
   u32 x = (chunk << 10) + lane;
-#pragma unroll 4
-  for (int j = 0; j < nwd; j++, x += 32) {
-    const u32 Fj = __shfl_sync(CC_FULL, F, j);
-    const u32 Sj = __shfl_sync(CC_FULL, S, j);
-    const u32 Rj = __shfl_sync(CC_FULL, RS, j);
+  OUT* __restrict__ o = out + ((size_t)rrel * sx + x);
+  auto label_of = [&](const uint4 wv) -> OUT {
     OUT v = 0;
-    if ((Fj >> lane) & 1u) {
-      const u32 lab = L[Rj + __popc(Sj & below)];
+    if (wv.x & bit) {
+      const u32 lab = L[wv.z + __popc(wv.y & below)];
       if (REMAP == 1) v = (OUT)__ldg(reinterpret_cast<const u32*>(remap) + lab);
       else if (REMAP == 2) v = (OUT)__ldg(reinterpret_cast<const u64*>(remap) + lab);
       else v = (OUT)lab;
     }
-    if (x < sx) orow[x] = v;
+    return v;
+  };
+  const u32 nfull = (x - lane + (nwd << 5) <= sx) ? nwd : nwd - 1;   // words that lie fully inside the row
+#pragma unroll 4
+  for (u32 j = 0; j < nfull; j++) o[j << 5] = label_of(s_words[warp][j]);
+  if (nfull < nwd) {
+    const OUT v = label_of(s_words[warp][nfull]);
+    if (x + (nfull << 5) < sx) o[nfull << 5] = v;
   }
 }
 
