@@ -28,19 +28,22 @@ METRIC = "gigavoxels/s, 26-connected CCL, 512^3"
 UNIT = "GVx/s"
 
 WORKLOADS = {
-  # name: (generator, shape, call kwargs, in bytes/voxel, algorithmic bytes/voxel = sizeof(in)+sizeof(out))
-  "random_binary_512_u8_conn26": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=1, alg_bytes=5,
-                                      desc="configs[1]: random 0/1 uint8 512^3 at 50% density, 26-connected, default (multilabel) call"),
-  "random_binary_512_u8_conn6": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=6), in_bytes=1, alg_bytes=5,
-                                     desc="configs[1]: random 0/1 uint8 512^3 at 50% density, 6-connected"),
+  # name: generator kind, shape, call kwargs, algorithmic bytes/voxel = sizeof(in) + sizeof(out)
   "multilabel_512_u32_conn26": dict(kind="voronoi", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=4, alg_bytes=8,
-                                    desc="configs[0]-like: Voronoi multilabel uint32 512^3 (~2.9k labels), 26-connected"),
+                                    desc="512^3 uint32 multilabel (synthetic Voronoi cells, ~2.9k labels), 26-connected, return_N=True: "
+                                         "the configuration BASELINE.json's roofline target is quoted on (configs[0] shape)"),
   "connectomics_512_u32_conn26": dict(kind="connectomics", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=4, alg_bytes=8,
                                       desc="configs[0]: the reference's connectomics.npy.ckl.gz (decoded fixture), 26-connected"),
+  "random_binary_512_u8_conn26": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=26, binary_image=True), in_bytes=1, alg_bytes=5,
+                                      desc="configs[1]: random 0/1 uint8 512^3 at 50% density, 26-connected, binary_image=True"),
+  "random_binary_512_u8_conn26_multilabel_call": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=26), in_bytes=1, alg_bytes=5,
+                                                      desc="configs[1]: same volume through the default (multilabel) call"),
+  "random_binary_512_u8_conn6": dict(kind="binary", shape=(512, 512, 512), kw=dict(connectivity=6, binary_image=True), in_bytes=1, alg_bytes=5,
+                                     desc="configs[1]: random 0/1 uint8 512^3 at 50% density, 6-connected, binary_image=True"),
   "continuous_512_f32_conn26": dict(kind="tone", shape=(512, 512, 512), kw=dict(connectivity=26, delta=10), in_bytes=4, alg_bytes=8,
                                     desc="configs[3] at 512^3: three-tone float32 + noise, delta=10, 26-connected"),
 }
-DEFAULT_WORKLOAD = "random_binary_512_u8_conn26"
+DEFAULT_WORKLOAD = "multilabel_512_u32_conn26"
 
 
 def make_volume(wl, device, seed_offset=0):
@@ -281,6 +284,7 @@ def main():
       traffic = None
   roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
               "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+              "note": "achieved = (sizeof(in)+sizeof(out)) * voxels / duration of the dominant kernel; pipeline_frac = same bytes / whole step",
               "kernel_ms": kavg, "kernel_share": {k: v / sum(kavg.values()) for k, v in kavg.items()},
               "pipeline_frac": alg_bytes / (ms / args.steps / 1e3) / 1e9 / peak}
 
@@ -339,7 +343,7 @@ def main():
       "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"), "data": "synthetic",
       "config": {"workload": args.workload, "description": wl["desc"], "out_dtype": out_dtype, "N": int(N),
-                 "l2": "inputs+labels (>= 640 MB per step) are larger than the 126 MB L2",
+                 "l2": "input + output of one step (>= 640 MB) are larger than the 126 MB L2",
                  "parallelism": "1 volume per GPU" if world > 1 else "single GPU"},
       "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(per_step_launches) * args.steps,
       "gpu_launches_per_step": int(per_step_launches),

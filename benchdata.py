@@ -18,27 +18,31 @@ def random_binary(shape, density=0.5, seed=1, device="cuda", dtype=torch.uint8):
   return out
 
 
-def voronoi_multilabel(shape, cell=40, seed=2, device="cuda", dtype=torch.int32, zero_fraction=0.0, id_bits=31):
+def voronoi_multilabel(shape, cell=40, seed=2, device="cuda", dtype=torch.int32, zero_fraction=0.0, id_bits=31,
+                       z_range=None):
   """configs[0]/[2]-like multilabel volume: jittered-grid Voronoi cells with random ids.
   shape = (sz, sy, sx), C-contiguous (x fastest). One seed per `cell`^3 coarse cell; every voxel takes
-  the id of the nearest seed among the 27 surrounding coarse cells."""
+  the id of the nearest seed among the 27 surrounding coarse cells.
+  z_range = (z0, z1): only that slab of the volume is generated (sharded volumes: every rank draws the
+  same seeds and fills its own planes)."""
   g = torch.Generator(device=device)
   g.manual_seed(seed)
   sz, sy, sx = shape
+  zlo, zhi = (0, sz) if z_range is None else z_range
   nz, ny, nx = (sz + cell - 1) // cell + 2, (sy + cell - 1) // cell + 2, (sx + cell - 1) // cell + 2
   jitter = torch.rand((3, nz, ny, nx), generator=g, device=device) * cell
   hi = (1 << id_bits) - 1
   ids = torch.randint(1, hi, (nz, ny, nx), generator=g, device=device, dtype=torch.int64)
   if zero_fraction > 0:
     ids = ids * (torch.rand((nz, ny, nx), generator=g, device=device) >= zero_fraction)
-  out = torch.empty(shape, dtype=dtype, device=device)
+  out = torch.empty((zhi - zlo, sy, sx), dtype=dtype, device=device)
   xs = torch.arange(sx, device=device, dtype=torch.float32)
   ys = torch.arange(sy, device=device, dtype=torch.float32)
   cx = (torch.arange(sx, device=device) // cell) + 1
   cy = (torch.arange(sy, device=device) // cell) + 1
   zchunk = max(1, (1 << 24) // (sy * sx))
-  for z0 in range(0, sz, zchunk):
-    z1 = min(sz, z0 + zchunk)
+  for z0 in range(zlo, zhi, zchunk):
+    z1 = min(zhi, z0 + zchunk)
     zs = torch.arange(z0, z1, device=device, dtype=torch.float32)
     cz = (torch.arange(z0, z1, device=device) // cell) + 1
     best = torch.full((z1 - z0, sy, sx), float("inf"), device=device)
@@ -54,7 +58,7 @@ def voronoi_multilabel(shape, cell=40, seed=2, device="cuda", dtype=torch.int32,
           closer = d < best
           best = torch.where(closer, d, best)
           best_id = torch.where(closer, ids[iz, iy, ix].expand_as(best_id), best_id)
-    out[z0:z1] = best_id.to(dtype)
+    out[z0 - zlo:z1 - zlo] = best_id.to(dtype)
   return out
 
 

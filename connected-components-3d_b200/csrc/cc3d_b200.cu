@@ -359,6 +359,7 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   a.launches = &stage_launches;
   a.in = din; a.M = M; a.L = L; a.ctr = ctr; a.g = g; a.mode = mode;
   a.connectivity = connectivity; a.stream = s;
+  a.mark = g_timing ? mark : nullptr;
   memset(a.delta, 0, 8);
   if (delta) memcpy(a.delta, delta, es);
   int rc = 0;
@@ -383,7 +384,6 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
     // B: unions
     rc = -1;
     CC_KIND_SWITCH(in_kind, rc = run_union_stage<KT>(a));
-    mark("B_union", s);
   }
   if (rc == 0 && periodic_boundary && (connectivity == 4 || connectivity == 8 || connectivity == 6)) {
     CC_KIND_SWITCH(in_kind, rc = run_periodic_stage<KT>(a));

@@ -1,0 +1,167 @@
+"""CPU tests of the sharded (z-slab) host logic: two gloo ranks label one slab each through
+cc3d_b200.sharded.connected_components_slab with an ORACLE backend (oracle/ is test infrastructure),
+and the concatenation must equal the monolithic oracle labelling bit for bit: same partition, same
+first-appearance numbering, same N, same out dtype. The compute steps of the product path (CudaBackend)
+are covered by the -m gpu tests; this file covers the exchange / union-find / renumbering plumbing."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+  """Same interface as cc3d_b200.sharded.CudaBackend, computed with the CPU oracle + numpy."""
+
+  def __init__(self):
+    import torch
+    self.torch = torch
+    from oracle import oracle
+    self.oracle = oracle
+
+  def _pred(self, kind_dtype, delta_arr, binary_image):
+    d = delta_arr[0]
+    if binary_image:
+      return lambda p, q: (p != 0) & (q != 0)
+    if d == 0:
+      return lambda p, q: (p == q) & (p != 0)
+    def f(p, q):
+      hi, lo = np.maximum(p, q), np.minimum(p, q)
+      return (p != 0) & (q != 0) & ((hi - lo) <= d)
+    return f
+
+  def resolve(self, slab, kind, connectivity, delta_arr, binary_image):
+    x = slab.numpy()
+    kw = dict(connectivity=connectivity, return_N=True, out_dtype=np.uint32)
+    if binary_image:
+      kw["binary_image"] = True
+    elif delta_arr[0] != 0:
+      kw["delta"] = delta_arr[0].item()
+    labels, N = self.oracle.connected_components(x, **kw)
+    epl = self.oracle.estimate_provisional_labels(x)[0]
+    return {"labels": labels, "N": int(N), "epl": int(epl), "shape": tuple(x.shape), "device": slab.device,
+            "values": x, "delta": delta_arr, "binary": binary_image}
+
+  def plane_labels(self, h, z):
+    return self.torch.from_numpy(h["labels"][z].astype(np.int32))
+
+  def face_pairs(self, vals_upper, labs_upper, vals_lower, labs_lower, kind, connectivity, delta_arr, binary_image):
+    P, Q = vals_upper.numpy(), vals_lower.numpy()
+    lP, lQ = labs_upper.numpy().astype(np.int64), labs_lower.numpy().astype(np.int64)
+    pred = self._pred(P.dtype, delta_arr, binary_image)
+    sy, sx = P.shape
+    out = []
+    for dy in (-1, 0, 1):
+      for dx in (-1, 0, 1):
+        nz = (dx != 0) + (dy != 0)
+        if connectivity == 6 and nz > 0:
+          continue
+        if connectivity == 18 and nz > 1:
+          continue
+        ys = slice(max(0, -dy), sy - max(0, dy)); yq = slice(max(0, dy), sy - max(0, -dy))
+        xs = slice(max(0, -dx), sx - max(0, dx)); xq = slice(max(0, dx), sx - max(0, -dx))
+        m = pred(P[ys, xs], Q[yq, xq])
+        out.append(((lQ[yq, xq][m] << 32) | lP[ys, xs][m]).ravel())
+    return self.torch.from_numpy(np.concatenate(out) if out else np.zeros(0, np.int64))
+
+  def solve_pairs(self, n_nodes, a, b):
+    parent = list(range(n_nodes))
+    def find(i):
+      while parent[i] != i:
+        parent[i] = parent[parent[i]]
+        i = parent[i]
+      return i
+    for x, y in zip(a.tolist(), b.tolist()):
+      rx, ry = find(x), find(y)
+      if rx < ry:
+        parent[ry] = rx
+      elif ry < rx:
+        parent[rx] = ry
+    return self.torch.tensor([find(i) for i in range(n_nodes)], dtype=self.torch.int64)
+
+  def write_remap(self, h, remap, max_label, out_dtype):
+    r = remap.numpy()
+    assert int(r.max(initial=0)) <= np.iinfo(out_dtype).max
+    out = r[h["labels"].astype(np.int64)].astype(out_dtype)
+    return self.torch.from_numpy(out.astype(np.int64))  # torch has limited unsigned support on CPU
+
+  def release(self, h):
+    pass
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _worker(rank, world, port, cases, results):
+  sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200"))
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import torch
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from cc3d_b200 import sharded
+  backend = OracleBackend()
+  try:
+    for ci, (vol, kw) in enumerate(cases):
+      bounds = np.linspace(0, vol.shape[0], world + 1).astype(int)
+      slab = torch.from_numpy(np.ascontiguousarray(vol[bounds[rank]:bounds[rank + 1]]))
+      out, N = sharded.connected_components_slab(slab, return_N=True, backend=backend, **kw)
+      results.put((ci, rank, out.numpy(), N))
+  finally:
+    dist.destroy_process_group()
+
+
+def _make_cases():
+  rng = np.random.default_rng(7)
+  cases = []
+  for it, conn in enumerate((6, 18, 26, 26, 6)):
+    shape = (int(rng.integers(6, 14)), int(rng.integers(5, 20)), int(rng.integers(5, 40)))
+    coarse = rng.integers(0, 4, tuple((s + 2) // 3 for s in shape))
+    vol = np.repeat(np.repeat(np.repeat(coarse, 3, 0), 3, 1), 3, 2)[:shape[0], :shape[1], :shape[2]]
+    kw = dict(connectivity=conn)
+    if it == 3:
+      vol = (rng.random(shape) < 0.45).astype(np.uint8)
+      kw["binary_image"] = True
+    elif it == 4:
+      vol = (vol * 10 + rng.integers(0, 3, shape)) * (vol != 0)
+      kw["delta"] = 2
+    cases.append((np.ascontiguousarray(vol.astype(np.uint8 if it == 3 else np.int32)), kw))
+  return cases
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_equal_monolithic_labelling(world):
+  import torch.multiprocessing as mp
+  sys.path.insert(0, ROOT)
+  from oracle import oracle
+  cases = _make_cases()
+  ctx = mp.get_context("spawn")
+  results = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(r, world, port, cases, results)) for r in range(world)]
+  for p in procs:
+    p.start()
+  got = {}
+  for _ in range(world * len(cases)):
+    ci, rank, out, N = results.get(timeout=120)
+    got[(ci, rank)] = (out, N)
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  for ci, (vol, kw) in enumerate(cases):
+    want, Nw = oracle.connected_components(vol, return_N=True, **kw)
+    parts = [got[(ci, r)][0] for r in range(world)]
+    for r in range(world):
+      assert got[(ci, r)][1] == Nw, f"case {ci} rank {r}: N {got[(ci, r)][1]} != {Nw}"
+    whole = np.concatenate(parts, axis=0)
+    assert np.array_equal(whole, want.astype(np.int64)), f"case {ci} ({kw}) differs from the monolithic labelling"
