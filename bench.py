@@ -9,7 +9,8 @@ A "step" is one full labelling call (resolve + write) on one synthetic volume.
   roofline   dominant kernel (tile labelling) against the measured HBM peak (MEASURED_PEAKS.json).
   cpu_baseline  the unmodified reference (oracle/_ref) on this box's host, 1 core, bounded sample.
 `--impl reference` times the reference's own CPU implementation instead (same metric/config).
-Under torchrun (N > 1) every rank labels its own z-slab sized volume ("weak" scaling).
+Under torchrun (N > 1) the ranks label ONE volume of N 512^3 z-slabs (cc3d_b200.sharded: per-slab labelling,
+NVLink face exchange, allgather of the face equivalences, global renumbering) - "weak" scaling, fixed work per GPU.
 """
 import argparse
 import json
@@ -46,15 +47,18 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "multilabel_512_u32_conn26"
 
 
-def make_volume(wl, device, seed_offset=0):
+def make_volume(wl, device, rank=0, world=1):
+  """One rank's volume. world > 1: rank r holds z-slab r of ONE volume of shape (world*sz, sy, sx)."""
   import torch
   import benchdata
+  sz, sy, sx = wl["shape"]
   if wl["kind"] == "binary":
-    return benchdata.random_binary(wl["shape"], 0.5, 1 + seed_offset, device)
+    return benchdata.random_binary(wl["shape"], 0.5, 1 + rank, device)
   if wl["kind"] == "voronoi":
-    return benchdata.voronoi_multilabel(wl["shape"], cell=40, seed=2 + seed_offset, device=device, dtype=torch.int32)
+    return benchdata.voronoi_multilabel((sz * world, sy, sx), cell=40, seed=2, device=device, dtype=torch.int32,
+                                        z_range=(rank * sz, (rank + 1) * sz))
   if wl["kind"] == "tone":
-    return benchdata.three_tone_noise(wl["shape"], cell=64, seed=3 + seed_offset, device=device)
+    return benchdata.three_tone_noise(wl["shape"], cell=64, seed=3 + rank, device=device)
   if wl["kind"] == "connectomics":
     from oracle import decode_connectomics
     vol = decode_connectomics.load_fixture()
@@ -235,18 +239,28 @@ def main():
     return float(t.item())
 
   L = _lib.lib()
-  x = make_volume(wl, dev, seed_offset=rank)
+  x = make_volume(wl, dev, rank, world)
   voxels = x.numel()
   kw = wl["kw"]
 
+  # N = 1: the plain call. N > 1: ONE volume of N z-slabs, one per rank, labelled globally (face exchange +
+  # allgather of the face equivalences); the result is identical to the single-GPU labelling of the whole volume.
+  if world > 1:
+    from cc3d_b200 import sharded
+    def label(vol, **kwargs):
+      return sharded.connected_components_slab(vol, return_N=True, **kwargs)
+  else:
+    def label(vol, **kwargs):
+      return cc3d_b200.connected_components(vol, return_N=True, **kwargs)
+
   def timed_device_loop(vol, kwargs, steps, warmup):
     for _ in range(warmup):
-      out, N = cc3d_b200.connected_components(vol, return_N=True, **kwargs)
+      out, N = label(vol, **kwargs)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-      out, N = cc3d_b200.connected_components(vol, return_N=True, **kwargs)
+      out, N = label(vol, **kwargs)
     e1.record()
     barrier()
     return max_over_ranks(e0.elapsed_time(e1)), N, out
@@ -266,7 +280,7 @@ def main():
   cc3d_b200.set_timing(True)
   ktimes = {}
   for _ in range(args.steps):
-    cc3d_b200.connected_components(x, return_N=True, **kw)
+    label(x, **kw)
     for name, t in cc3d_b200.last_timings():
       ktimes.setdefault(name, []).append(t)
   cc3d_b200.set_timing(False)
@@ -288,21 +302,31 @@ def main():
               "kernel_ms": kavg, "kernel_share": {k: v / sum(kavg.values()) for k, v in kavg.items()},
               "pipeline_frac": alg_bytes / (ms / args.steps / 1e3) / 1e9 / peak}
 
-  # ---- e2e: public API on pinned host buffers ----
+  # ---- e2e: public API on pinned host buffers (H2D + kernels + D2H inside the timed region) ----
   xh = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
   xh.copy_(x)
-  x_np = xh.numpy()
   np_out_dtype = {"uint16": np.uint16, "uint32": np.uint32, "uint64": np.uint64}[out_dtype]
   oh = torch.empty((voxels * out_bytes,), dtype=torch.uint8, pin_memory=True)
-  out_np = oh.numpy().view(np_out_dtype)
   e2e_steps = max(3, min(args.steps, 10))
+  if world == 1:
+    x_np = xh.numpy()
+    out_np = oh.numpy().view(np_out_dtype)
+    def e2e_step():
+      return cc3d_b200.connected_components(x_np, return_N=True, out=out_np, **kw)[1]
+  else:
+    def e2e_step():
+      xd = xh.to(dev, non_blocking=True)
+      o, n = label(xd, **kw)
+      oh.copy_(o.reshape(-1).view(torch.uint8), non_blocking=True)
+      torch.cuda.current_stream().synchronize()
+      return n
   for _ in range(2):
-    cc3d_b200.connected_components(x_np, return_N=True, out=out_np, **kw)
+    e2e_step()
   barrier()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
   for _ in range(e2e_steps):
-    res, N2 = cc3d_b200.connected_components(x_np, return_N=True, out=out_np, **kw)
+    N2 = e2e_step()
   e1.record()
   barrier()
   e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -344,7 +368,8 @@ def main():
       "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"), "data": "synthetic",
       "config": {"workload": args.workload, "description": wl["desc"], "out_dtype": out_dtype, "N": int(N),
                  "l2": "input + output of one step (>= 640 MB) are larger than the 126 MB L2",
-                 "parallelism": "1 volume per GPU" if world > 1 else "single GPU"},
+                 "parallelism": (f"one ({world}*512)x512x512 volume, one 512^3 z-slab per GPU (face exchange + allgather)"
+                                 if world > 1 else "single GPU")},
       "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(per_step_launches) * args.steps,
       "gpu_launches_per_step": int(per_step_launches),
       "roofline": roofline, "cpu_baseline": cpu, "also": also,

@@ -5,14 +5,13 @@ METRICS = [
   ("gpu__time_duration.sum", "time"),
   ("dram__bytes_read.sum", "dram_rd"),
   ("dram__bytes_write.sum", "dram_wr"),
-  ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
-  ("lts__t_bytes.sum", "l2_bytes"),
+  ("dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "dram_active%"),
+  ("dram__bytes.sum.per_second", "dram_bw"),
   ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
   ("smsp__inst_executed.sum", "warp_inst"),
   ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
   ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
   ("launch__registers_per_thread", "regs"),
-  ("smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "st_long_sb"),
   ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_lsb/iss"),
 ]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
