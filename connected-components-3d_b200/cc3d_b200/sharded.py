@@ -14,7 +14,8 @@ Steps:
   1. every rank labels its slab locally (kernels A-C3); local labels 1..N_r are in local raster order
   2. neighbours exchange ONE boundary plane (values + local labels) point to point over NVLink
   3. the upper rank of each interface extracts the cross-face equivalences (k_face_pairs)
-  4. the small pair lists are all-gathered; every rank solves the same union-find (k_union_pairs)
+  4. ONE all-gather carries every slab's facts (N, epl, depth) and its face pairs; every rank then solves
+     the same small union-find on the host (the interface graph has a few thousand nodes)
   5. a component is numbered by the lowest slab it touches: per-slab counts of owned components give
      offsets, and a per-slab remap table (local label -> global label) is fused into the final write
 
@@ -125,21 +126,42 @@ def _exchange_planes(dist, group, rank, world, send_tensors, like):
   return recv
 
 
-def _all_gather_varlen(dist, group, world, t):
-  """all-gather 1-D int64 tensors of different lengths (counts first, then padded payload)."""
+_PAIR_CAP = 16384   # pairs per rank that travel with the first (and normally only) all-gather
+
+
+def _gather_facts_and_pairs(dist, group, world, facts, pairs):
+  """ONE all-gather of [facts..., n_pairs, pairs padded to cap] per rank; repeated with a larger cap only if
+  some rank has more pairs than fit. Returns (facts[world, nf] int64 CPU, list of per-rank pair tensors on CPU)."""
   import torch
-  n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-  counts = [torch.zeros_like(n) for _ in range(world)]
-  dist.all_gather(counts, n, group=group)
-  counts = [int(c.item()) for c in counts]
-  m = max(counts)
-  if m == 0:
-    return t[:0]
-  pad = torch.zeros((m,), dtype=torch.int64, device=t.device)
-  pad[: t.numel()] = t
-  bufs = [torch.empty_like(pad) for _ in range(world)]
-  dist.all_gather(bufs, pad, group=group)
-  return torch.cat([b[:c] for b, c in zip(bufs, counts)])
+  nf = facts.numel()
+  cap = _PAIR_CAP
+  while True:
+    buf = torch.zeros((nf + 1 + cap,), dtype=torch.int64, device=pairs.device)
+    buf[:nf] = facts
+    buf[nf] = pairs.numel()
+    n = min(cap, pairs.numel())
+    buf[nf + 1: nf + 1 + n] = pairs[:n]
+    if world > 1:
+      bufs = [torch.empty_like(buf) for _ in range(world)]
+      dist.all_gather(bufs, buf, group=group)
+      allb = torch.stack(bufs).cpu()
+    else:
+      allb = buf.cpu()[None]
+    counts = allb[:, nf]
+    if int(counts.max()) <= cap:
+      return allb[:, :nf], [allb[r, nf + 1: nf + 1 + int(counts[r])] for r in range(world)]
+    cap = 1 << int(counts.max() - 1).bit_length()
+
+
+def _solve_pairs_host(n_nodes, ia, ib):
+  """parent[i] = smallest node of i's set (host side; the interface graph is small)."""
+  from scipy.sparse import coo_matrix
+  from scipy.sparse.csgraph import connected_components
+  g = coo_matrix((np.ones(ia.size, dtype=np.int8), (ia, ib)), shape=(n_nodes, n_nodes))
+  ncomp, lab = connected_components(g, directed=False)
+  mins = np.full(ncomp, n_nodes, dtype=np.int64)
+  np.minimum.at(mins, lab, np.arange(n_nodes, dtype=np.int64))
+  return mins[lab]
 
 
 def connected_components_slab(slab, connectivity: int = 26, return_N: bool = False, delta=0,
@@ -188,74 +210,84 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
     np.array([delta & ((1 << (8 * kdtype.itemsize)) - 1)], dtype=kdtype)
 
   sz, sy, sx = slab.shape
+  import os, time
+  _timing = os.environ.get("CC3D_SHARDED_TIMING") and rank == 0
+  _t = [time.perf_counter()]
+  def _lap(name):
+    if _timing:
+      if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+      _t.append(time.perf_counter())
+      print(f"  [sharded] {name}: {(_t[-1] - _t[-2]) * 1e3:.3f} ms", flush=True)
   h = backend.resolve(slab, kind, connectivity, delta_arr, binary_image)
+  _lap("resolve")
   try:
-    # ---- per-slab facts every rank needs ----
-    mine = torch.tensor([h["N"], h["epl"], sz], dtype=torch.int64, device=dev)
+    # ---- boundary plane exchange + cross-face equivalences (device side) ----
+    packed = torch.zeros((0,), dtype=torch.int64, device=dev)
     if world > 1:
-      allv = [torch.zeros_like(mine) for _ in range(world)]
-      dist.all_gather(allv, mine, group=group)
-      facts = torch.stack(allv).cpu()
-    else:
-      facts = mine.cpu()[None]
-    N_r = facts[:, 0]
-    offsets = torch.cumsum(N_r, 0) - N_r            # global id of (slab r, label l) = offsets[r] + l, l >= 1
-    total_ids = int(N_r.sum())
-    sz_total = int(facts[:, 2].sum())
-    voxels_total = sz_total * sy * sx
-    epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
-
-    # ---- boundary plane exchange + cross-face equivalences ----
-    pairs = torch.zeros((0,), dtype=torch.int64, device=dev)
-    if world > 1:
-      top_vals = slab[sz - 1].contiguous().view(torch.uint8) if sz > 0 else None
+      top_vals = slab[sz - 1].contiguous().view(torch.uint8)
       top_labs = backend.plane_labels(h, sz - 1)
+      _lap("plane_labels(top)")
       recv = _exchange_planes(dist, group, rank, world, [top_vals, top_labs], [top_vals, top_labs])
+      _lap("exchange")
       if rank > 0:
         low_vals = recv[0].view(slab.dtype)
         low_labs = recv[1]
         up_labs = backend.plane_labels(h, 0)
         packed = backend.face_pairs(slab[0].contiguous(), up_labs, low_vals, low_labs, kind, connectivity, delta_arr,
                                     binary_image)
-        packed = torch.unique(packed)
-        lo = (packed >> 32) + int(offsets[rank - 1])
-        up = (packed & 0xFFFFFFFF) + int(offsets[rank])
-        pairs = torch.stack([lo, up], 1).reshape(-1)
-      pairs = _all_gather_varlen(dist, group, world, pairs)
-    a, b = pairs[0::2], pairs[1::2]
+        # (lower label << 32 | upper label), local labels of the two slabs; duplicates are removed on the host
 
-    # ---- every rank solves the same small union-find over the ids that touch an interface ----
-    remap = torch.arange(h["N"] + 1, dtype=torch.int64, device=dev)
-    owned = N_r.clone()
-    if a.numel() > 0:
-      nodes = torch.unique(torch.cat([a, b]))                      # sorted: id order == global raster order
-      ia, ib = torch.searchsorted(nodes, a), torch.searchsorted(nodes, b)
-      parent = backend.solve_pairs(nodes.numel(), ia, ib)          # smallest node of each set
-      bounds = (offsets + N_r).to(dev)                             # last id of every slab
-      node_slab = torch.searchsorted(bounds, nodes)                # ids are 1-based: id <= bounds[r]
-      nonowned = parent != torch.arange(nodes.numel(), device=dev)
-      per_slab_nonowned = torch.zeros((world,), dtype=torch.int64, device=dev).index_add_(
-        0, node_slab, nonowned.to(torch.int64))
-      owned = N_r - per_slab_nonowned.cpu()
-    base = torch.cumsum(owned, 0) - owned
+    # ---- ONE all-gather: per-slab facts + face pairs; everything after it runs on the host ----
+    _lap("face_pairs+unique")
+    mine = torch.tensor([h["N"], h["epl"], sz], dtype=torch.int64, device=dev)
+    facts, pair_lists = _gather_facts_and_pairs(dist, group, world, mine, packed)
+    _lap("all_gather")
+    N_r = facts[:, 0]
+    offsets = torch.cumsum(N_r, 0) - N_r            # global id of (slab r, label l) = offsets[r] + l, l >= 1
+    sz_total = int(facts[:, 2].sum())
+    voxels_total = sz_total * sy * sx
+    epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
+    # ---- every rank solves the same small union-find over the ids that touch an interface (host, numpy) ----
+    N_r_np, off_np = N_r.numpy(), offsets.numpy()
+    glob = []
+    for r in range(1, world):
+      pr = np.unique(pair_lists[r].numpy())
+      if pr.size:
+        glob.append(np.stack([(pr >> 32) + off_np[r - 1], (pr & 0xFFFFFFFF) + off_np[r]], 1))
+    pairs_np = np.concatenate(glob) if glob else np.zeros((0, 2), dtype=np.int64)
+    a, b = pairs_np[:, 0], pairs_np[:, 1]
+    remap_np = np.arange(h["N"] + 1, dtype=np.int64)
+    owned = N_r_np.copy()
+    if a.size > 0:
+      nodes = np.unique(np.concatenate([a, b]))                    # sorted: id order == global raster order
+      ia, ib = np.searchsorted(nodes, a), np.searchsorted(nodes, b)
+      parent = _solve_pairs_host(nodes.size, ia, ib)               # smallest node of each set
+      bounds = off_np + N_r_np                                     # last id of every slab
+      node_slab = np.searchsorted(bounds, nodes)                   # ids are 1-based: id <= bounds[r]
+      nonowned = (parent != np.arange(nodes.size)).astype(np.int64)
+      owned = N_r_np - np.bincount(node_slab, weights=nonowned, minlength=world).astype(np.int64)
+    base = np.cumsum(owned) - owned
     N_total = int(owned.sum())
-    if a.numel() > 0:
-      cs = torch.cumsum(nonowned.to(torch.int64), 0) - nonowned.to(torch.int64)  # non-owned nodes before j
-      first_of_slab = torch.searchsorted(node_slab, torch.arange(world, device=dev))
-      cs_start = torch.cat([cs, cs.new_zeros(1)])[first_of_slab.clamp(max=nodes.numel())]
+    if a.size > 0:
+      cs = np.cumsum(nonowned) - nonowned                          # non-owned nodes before j
+      first_of_slab = np.searchsorted(node_slab, np.arange(world))
+      cs_start = np.concatenate([cs, [0]])[np.minimum(first_of_slab, nodes.size)]
       before_in_slab = cs - cs_start[node_slab]
-      node_label = nodes - offsets.to(dev)[node_slab]
-      final_owned = base.to(dev)[node_slab] + node_label - before_in_slab   # valid for owned (root) nodes
+      node_label = nodes - off_np[node_slab]
+      final_owned = base[node_slab] + node_label - before_in_slab  # valid for owned (root) nodes
       final = final_owned[parent]
       my = node_slab == rank
       my_labels = node_label[my]
-      flags = torch.zeros((h["N"] + 1,), dtype=torch.int64, device=dev)
-      flags[my_labels[nonowned[my]]] = 1
-      remap = int(base[rank]) + remap - torch.cumsum(flags, 0)
-      remap[my_labels] = final[my]
+      flags = np.zeros(h["N"] + 1, dtype=np.int64)
+      flags[my_labels[nonowned[my] != 0]] = 1
+      remap_np = int(base[rank]) + remap_np - np.cumsum(flags)
+      remap_np[my_labels] = final[my]
     else:
-      remap = int(base[rank]) + remap
-    remap[0] = 0
+      remap_np = int(base[rank]) + remap_np
+    remap_np[0] = 0
+    remap = torch.from_numpy(remap_np).to(dev)
+    _lap("host solve + remap")
 
     # ---- out-dtype rule of the monolithic call (fastcc3d.pyx:388-434) ----
     max_lab = min(epl_total, voxels_total)
@@ -277,6 +309,7 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
       out_dtype = np.dtype(np.uint64)
 
     out = backend.write_remap(h, remap, N_total, out_dtype)
+    _lap("write_remap")
   finally:
     backend.release(h)
   return (out, N_total) if return_N else out

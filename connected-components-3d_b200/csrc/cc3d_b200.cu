@@ -554,8 +554,16 @@ int cc3d_b200_face_pairs(const void* values_upper, const uint32_t* labels_upper,
   if (delta) { for (size_t i = 0; i < es; i++) if (((const unsigned char*)delta)[i]) delta_zero = false; }
   const int mode = binary_image ? MODE_NONZERO : (delta_zero ? MODE_EQ : MODE_DELTA);
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned long long* dcount = nullptr;
-  CUDA_OK(cudaMalloc((void**)&dcount, 8));
+  // one 8-byte device counter per device, allocated once (cudaMalloc/cudaFree would synchronise every call)
+  static unsigned long long* dcounts[64] = {nullptr};
+  int devid = 0;
+  CUDA_OK(cudaGetDevice(&devid));
+  if (devid < 0 || devid >= 64) return fail(CC3D_B200_ERR_ARGUMENT, "device index out of range");
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!dcounts[devid]) CUDA_OK(cudaMalloc((void**)&dcounts[devid], 8));
+  }
+  unsigned long long* dcount = dcounts[devid];
   cudaMemsetAsync(dcount, 0, 8, s);
   const u32 *lP = labels_upper, *lQ = labels_lower;
   switch (in_kind) {
@@ -570,7 +578,6 @@ int cc3d_b200_face_pairs(const void* values_upper, const uint32_t* labels_upper,
   cudaError_t e = cudaMemcpyAsync(&h, dcount, 8, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
-  cudaFree(dcount);
   if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("face_pairs: ") + cudaGetErrorString(e));
   *count = h;
   return 0;

@@ -64,8 +64,8 @@ static int launch_union(const LabelArgs& a) {
   if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   if (a.mark) a.mark("B1_union_tile", a.stream);
-  k_union_queue<<<CC_QUEUE_BLOCKS, 256, 0, a.stream>>>(a.L, a.GQ);
-  k_union_global<T, MODE, CONN><<<(unsigned)((g.nwords + 255) / 256), 256, 0, a.stream>>>(in, a.M, a.L, g, E, a.GQ.ovf);
+  k_union_queue<<<CC_QUEUE_BLOCKS * 4, 256, 0, a.stream>>>(a.L, a.GQ);
+  k_union_global<T, MODE, CONN><<<CC_QUEUE_BLOCKS, 256, 0, a.stream>>>(in, a.M, a.L, g, E, a.GQ.ovf);
   if (a.mark) a.mark("B2_union_queue", a.stream);
   *a.launches += 3;
   return 0;

@@ -24,7 +24,8 @@ k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, con
     bool isroot = false;
     if (i < n) {
       u32 r = i, p;
-      while ((p = __ldcg(&L[r])) != r) r = p;
+      // L1-cached loads: tile roots are shared by many runs; a stale parent is still an ancestor
+      while ((p = __ldca(&L[r])) != r) r = p;
       if (r == i) isroot = true;
       else L[i] = r;
     }
@@ -208,7 +209,7 @@ k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__
 // ---- sharded volumes (z-slabs): equivalences across one slab interface ----
 // P = first plane of the upper slab (later in raster order), Q = last plane of the lower slab.
 // Emits (label in Q's slab, label in P's slab) for every edge of the chosen predicate/neighbourhood
-// between the two planes, skipping an edge when the voxel to the left already produced the same pair.
+// between the two planes, skipping an edge when the voxel to the left or above already produced the same pair.
 // Replaces the Python face loops of connected_components_stack (cc3d/__init__.py:425-468).
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
@@ -225,6 +226,7 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
     if (E.fg(p)) {
       const u32 lp = lP[i];
       const bool left_same = x > 0 && lP[i - 1] == lp;
+      const bool up_same = y > 0 && lP[i - sx] == lp;
 #pragma unroll
       for (int dy = -1; dy <= 1; dy++) {
 #pragma unroll
@@ -240,6 +242,8 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
           const u32 lq = lQ[qi];
           // the voxel to the left emits the same (lq, lp) through the same direction
           if (left_same && xx > 0 && lQ[qi - 1] == lq && E(vP[i - 1], vQ[qi - 1])) continue;
+          // ... or the voxel above
+          if (up_same && yy > 0 && lQ[qi - sx] == lq && E(vP[i - sx], vQ[qi - sx])) continue;
           mine[n++] = ((u64)lq << 32) | lp;
         }
       }
@@ -302,7 +306,9 @@ k_blockkey_min(const u32* __restrict__ L, const u32* __restrict__ M, u32* __rest
     const int b = __ffs(bits) - 1;
     bits &= bits - 1;
     const u32 x = (w << 5) + b;
-    atomicMin(&K[L[id]], (x >> 1) + osx * (row >> 1));   // after k_compress L[id] is the root (roots: themselves)
+    const u32 root = L[id];                              // after k_compress L[id] is the root (roots: themselves)
+    const u32 key = (x >> 1) + osx * (row >> 1);
+    if (key < __ldcg(&K[root])) atomicMin(&K[root], key);  // the plain read keeps giant components off one address
     id++;
   }
 }

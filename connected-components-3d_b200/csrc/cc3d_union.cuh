@@ -459,16 +459,16 @@ __global__ void __launch_bounds__(256)
 k_union_global(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
                const u32* __restrict__ ovf) {
   if (*ovf == 0) return;
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (u32)g.nwords) return;
   const u32 W = (u32)g.W, sy = (u32)g.sy;
-  const u32 row = i / W, w = i - row * W;
-  const u32 z = row / sy, y = row - z * sy;
   WordEdges<T, MODE, CONN> we(in, M, g, E);
-  if (!we.load(i, row, w, y, z)) return;
   auto unite = [&](u32 gp, u32 gq_, int, int, u32) { uf_union_h(L, gp, gq_); };
-  we.straight(unite);
-  we.diagonals(unite);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < (u32)g.nwords; i += gridDim.x * blockDim.x) {
+    const u32 row = i / W, w = i - row * W;
+    const u32 z = row / sy, y = row - z * sy;
+    if (!we.load(i, row, w, y, z)) continue;
+    we.straight(unite);
+    we.diagonals(unite);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
