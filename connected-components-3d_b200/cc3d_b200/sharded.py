@@ -164,32 +164,9 @@ def _solve_pairs_host(n_nodes, ia, ib):
   return mins[lab]
 
 
-def connected_components_slab(slab, connectivity: int = 26, return_N: bool = False, delta=0,
-                              out_dtype: Optional[Any] = None, binary_image: bool = False, group=None,
-                              backend=None):
-  """Labels this rank's z-slab of a volume that is sharded over the ranks of `group`.
-
-  slab: 3-D tensor (sz_local, sy, sx), C-contiguous, same dtype/sy/sx on every rank.
-  Returns this rank's slab of the global labelling (and the global N).
-  """
-  import torch
-  import torch.distributed as dist
+def _normalise(orig_dtype, delta, binary_image):
+  """Predicate parameters exactly as the monolithic call derives them (fastcc3d.pyx:346-395)."""
   from . import _kind_of, _UNSIGNED
-
-  if connectivity not in (6, 18, 26):
-    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
-  if slab.ndim != 3:
-    raise ValueError("slab must be a 3-D (sz_local, sy, sx) tensor")
-  if backend is None:
-    backend = CudaBackend()
-  distributed = dist.is_available() and dist.is_initialized()
-  rank = dist.get_rank(group) if distributed else 0
-  world = dist.get_world_size(group) if distributed else 1
-  slab = slab.contiguous()
-  dev = slab.device
-
-  from . import _torch_np_dtype
-  orig_dtype = _torch_np_dtype(slab)
   if orig_dtype == np.float16:
     if delta != 0:
       raise TypeError("float16 is not supported for continuous images (delta != 0).")
@@ -208,6 +185,105 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
     np.dtype(_UNSIGNED[orig_dtype.itemsize]) if np.issubdtype(orig_dtype, np.signedinteger) else orig_dtype)
   delta_arr = np.array([delta], dtype=kdtype) if np.issubdtype(kdtype, np.floating) else \
     np.array([delta & ((1 << (8 * kdtype.itemsize)) - 1)], dtype=kdtype)
+  return kind, binary_image, epl_skipped, delta_arr
+
+
+def _global_numbering(N_r, pair_lists, want):
+  """Host side of the merge. N_r[r] = components of slab r (local labels 1..N_r), pair_lists[r] = packed
+  (label in slab r-1) << 32 | (label in slab r) equivalences across the interface below slab r.
+  A component is owned by the lowest slab it touches; owned components are numbered slab by slab in local
+  label order, which is the first-appearance order of the whole volume. Returns (N_total, {r: remap_r})
+  for the slabs in `want`, remap_r[local label] = global label, remap_r[0] = 0."""
+  world = len(N_r)
+  N_r = np.asarray(N_r, dtype=np.int64)
+  off = np.cumsum(N_r) - N_r                      # global id of (slab r, label l) = off[r] + l, l >= 1
+  glob = []
+  for r in range(1, world):
+    pr = np.unique(np.asarray(pair_lists[r], dtype=np.int64))
+    if pr.size:
+      glob.append(np.stack([(pr >> 32) + off[r - 1], (pr & 0xFFFFFFFF) + off[r]], 1))
+  pairs = np.concatenate(glob) if glob else np.zeros((0, 2), dtype=np.int64)
+  a, b = pairs[:, 0], pairs[:, 1]
+  owned = N_r.copy()
+  if a.size > 0:
+    nodes = np.unique(np.concatenate([a, b]))                    # sorted: id order == global raster order
+    ia, ib = np.searchsorted(nodes, a), np.searchsorted(nodes, b)
+    parent = _solve_pairs_host(nodes.size, ia, ib)               # smallest node of each set
+    bounds = off + N_r                                           # last id of every slab
+    node_slab = np.searchsorted(bounds, nodes)                   # ids are 1-based: id <= bounds[r]
+    nonowned = (parent != np.arange(nodes.size)).astype(np.int64)
+    owned = N_r - np.bincount(node_slab, weights=nonowned, minlength=world).astype(np.int64)
+    cs = np.cumsum(nonowned) - nonowned                          # non-owned nodes before j
+    first_of_slab = np.searchsorted(node_slab, np.arange(world))
+    cs_start = np.concatenate([cs, [0]])[np.minimum(first_of_slab, nodes.size)]
+    before_in_slab = cs - cs_start[node_slab]
+    node_label = nodes - off[node_slab]
+  base = np.cumsum(owned) - owned
+  if a.size > 0:
+    final_owned = base[node_slab] + node_label - before_in_slab  # valid for owned (root) nodes
+    final = final_owned[parent]
+  remaps = {}
+  for r in want:
+    remap = np.arange(N_r[r] + 1, dtype=np.int64)
+    if a.size > 0:
+      my = node_slab == r
+      my_labels = node_label[my]
+      flags = np.zeros(N_r[r] + 1, dtype=np.int64)
+      flags[my_labels[nonowned[my] != 0]] = 1
+      remap = int(base[r]) + remap - np.cumsum(flags)
+      remap[my_labels] = final[my]
+    else:
+      remap = int(base[r]) + remap
+    remap[0] = 0
+    remaps[r] = remap
+  return int(owned.sum()), remaps
+
+
+def _out_dtype_rule(out_dtype, epl_total, voxels_total, shape_total, binary_image, connectivity):
+  """Out-dtype rule of the monolithic call (fastcc3d.pyx:388-434)."""
+  max_lab = min(epl_total, voxels_total)
+  if binary_image:
+    uf = _even_ceil(shape_total[0]) * _even_ceil(shape_total[1]) * _even_ceil(shape_total[2])
+    max_lab = min(max_lab, uf // 2 + 1) if connectivity == 6 else min(max_lab, uf // 8 + 1)
+  if out_dtype is not None:
+    out_dtype = np.dtype(out_dtype)
+    if out_dtype not in (np.uint16, np.uint32, np.uint64):
+      raise ValueError(f"Explicitly defined out_dtype ({out_dtype}) must be one of: np.uint16, np.uint32, np.uint64")
+    if np.iinfo(out_dtype).max < max_lab:
+      raise ValueError(f"Explicitly defined out_dtype ({out_dtype}) is too small "
+                       f"to contain the estimated maximum number of labels ({max_lab}).")
+    return out_dtype
+  if max_lab < np.iinfo(np.uint16).max:
+    return np.dtype(np.uint16)
+  if max_lab < np.iinfo(np.uint32).max:
+    return np.dtype(np.uint32)
+  return np.dtype(np.uint64)
+
+
+def connected_components_slab(slab, connectivity: int = 26, return_N: bool = False, delta=0,
+                              out_dtype: Optional[Any] = None, binary_image: bool = False, group=None,
+                              backend=None):
+  """Labels this rank's z-slab of a volume that is sharded over the ranks of `group`.
+
+  slab: 3-D tensor (sz_local, sy, sx), C-contiguous, same dtype/sy/sx on every rank.
+  Returns this rank's slab of the global labelling (and the global N).
+  """
+  import torch
+  import torch.distributed as dist
+  from . import _torch_np_dtype
+
+  if connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  if slab.ndim != 3:
+    raise ValueError("slab must be a 3-D (sz_local, sy, sx) tensor")
+  if backend is None:
+    backend = CudaBackend()
+  distributed = dist.is_available() and dist.is_initialized()
+  rank = dist.get_rank(group) if distributed else 0
+  world = dist.get_world_size(group) if distributed else 1
+  slab = slab.contiguous()
+  dev = slab.device
+  kind, binary_image, epl_skipped, delta_arr = _normalise(_torch_np_dtype(slab), delta, binary_image)
 
   sz, sy, sx = slab.shape
   import os, time
@@ -234,82 +310,65 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
         low_vals = recv[0].view(slab.dtype)
         low_labs = recv[1]
         up_labs = backend.plane_labels(h, 0)
+        # (lower label << 32 | upper label), local labels of the two slabs; duplicates are removed on the host
         packed = backend.face_pairs(slab[0].contiguous(), up_labs, low_vals, low_labs, kind, connectivity, delta_arr,
                                     binary_image)
-        # (lower label << 32 | upper label), local labels of the two slabs; duplicates are removed on the host
+    _lap("face_pairs")
 
     # ---- ONE all-gather: per-slab facts + face pairs; everything after it runs on the host ----
-    _lap("face_pairs+unique")
     mine = torch.tensor([h["N"], h["epl"], sz], dtype=torch.int64, device=dev)
     facts, pair_lists = _gather_facts_and_pairs(dist, group, world, mine, packed)
     _lap("all_gather")
-    N_r = facts[:, 0]
-    offsets = torch.cumsum(N_r, 0) - N_r            # global id of (slab r, label l) = offsets[r] + l, l >= 1
+    facts = facts.numpy()
     sz_total = int(facts[:, 2].sum())
     voxels_total = sz_total * sy * sx
     epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
-    # ---- every rank solves the same small union-find over the ids that touch an interface (host, numpy) ----
-    N_r_np, off_np = N_r.numpy(), offsets.numpy()
-    glob = []
-    for r in range(1, world):
-      pr = np.unique(pair_lists[r].numpy())
-      if pr.size:
-        glob.append(np.stack([(pr >> 32) + off_np[r - 1], (pr & 0xFFFFFFFF) + off_np[r]], 1))
-    pairs_np = np.concatenate(glob) if glob else np.zeros((0, 2), dtype=np.int64)
-    a, b = pairs_np[:, 0], pairs_np[:, 1]
-    remap_np = np.arange(h["N"] + 1, dtype=np.int64)
-    owned = N_r_np.copy()
-    if a.size > 0:
-      nodes = np.unique(np.concatenate([a, b]))                    # sorted: id order == global raster order
-      ia, ib = np.searchsorted(nodes, a), np.searchsorted(nodes, b)
-      parent = _solve_pairs_host(nodes.size, ia, ib)               # smallest node of each set
-      bounds = off_np + N_r_np                                     # last id of every slab
-      node_slab = np.searchsorted(bounds, nodes)                   # ids are 1-based: id <= bounds[r]
-      nonowned = (parent != np.arange(nodes.size)).astype(np.int64)
-      owned = N_r_np - np.bincount(node_slab, weights=nonowned, minlength=world).astype(np.int64)
-    base = np.cumsum(owned) - owned
-    N_total = int(owned.sum())
-    if a.size > 0:
-      cs = np.cumsum(nonowned) - nonowned                          # non-owned nodes before j
-      first_of_slab = np.searchsorted(node_slab, np.arange(world))
-      cs_start = np.concatenate([cs, [0]])[np.minimum(first_of_slab, nodes.size)]
-      before_in_slab = cs - cs_start[node_slab]
-      node_label = nodes - off_np[node_slab]
-      final_owned = base[node_slab] + node_label - before_in_slab  # valid for owned (root) nodes
-      final = final_owned[parent]
-      my = node_slab == rank
-      my_labels = node_label[my]
-      flags = np.zeros(h["N"] + 1, dtype=np.int64)
-      flags[my_labels[nonowned[my] != 0]] = 1
-      remap_np = int(base[rank]) + remap_np - np.cumsum(flags)
-      remap_np[my_labels] = final[my]
-    else:
-      remap_np = int(base[rank]) + remap_np
-    remap_np[0] = 0
-    remap = torch.from_numpy(remap_np).to(dev)
+    # every rank solves the same small union-find over the labels that touch an interface
+    N_total, remaps = _global_numbering(facts[:, 0], [p.numpy() for p in pair_lists], [rank])
+    remap = torch.from_numpy(remaps[rank]).to(dev)
     _lap("host solve + remap")
-
-    # ---- out-dtype rule of the monolithic call (fastcc3d.pyx:388-434) ----
-    max_lab = min(epl_total, voxels_total)
-    if binary_image:
-      uf = _even_ceil(sz_total) * _even_ceil(sy) * _even_ceil(sx)
-      max_lab = min(max_lab, uf // 2 + 1) if connectivity == 6 else min(max_lab, uf // 8 + 1)
-    if out_dtype is not None:
-      out_dtype = np.dtype(out_dtype)
-      if out_dtype not in (np.uint16, np.uint32, np.uint64):
-        raise ValueError(f"Explicitly defined out_dtype ({out_dtype}) must be one of: np.uint16, np.uint32, np.uint64")
-      if np.iinfo(out_dtype).max < max_lab:
-        raise ValueError(f"Explicitly defined out_dtype ({out_dtype}) is too small "
-                         f"to contain the estimated maximum number of labels ({max_lab}).")
-    elif max_lab < np.iinfo(np.uint16).max:
-      out_dtype = np.dtype(np.uint16)
-    elif max_lab < np.iinfo(np.uint32).max:
-      out_dtype = np.dtype(np.uint32)
-    else:
-      out_dtype = np.dtype(np.uint64)
-
+    out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
     out = backend.write_remap(h, remap, N_total, out_dtype)
     _lap("write_remap")
   finally:
     backend.release(h)
   return (out, N_total) if return_N else out
+
+
+def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = False, delta=0,
+                               out_dtype: Optional[Any] = None, binary_image: bool = False, backend=None):
+  """Single-process variant: `slabs` is a list of consecutive z-slabs (sz_i, sy, sx) of ONE volume, all on
+  this process's device(s). Same merge as connected_components_slab without any collective; this is the
+  way to label a volume with more than 2^32-2 voxels on one GPU (each slab must stay below that).
+  Returns the list of labelled slabs (and the global N)."""
+  import torch
+  from . import _torch_np_dtype
+  if connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  if backend is None:
+    backend = CudaBackend()
+  slabs = [s.contiguous() for s in slabs]
+  kind, binary_image, epl_skipped, delta_arr = _normalise(_torch_np_dtype(slabs[0]), delta, binary_image)
+  sy, sx = slabs[0].shape[1:]
+  handles = []
+  try:
+    for s in slabs:
+      handles.append(backend.resolve(s, kind, connectivity, delta_arr, binary_image))
+    pair_lists = [np.zeros(0, dtype=np.int64)]
+    for r in range(1, len(slabs)):
+      low, up = slabs[r - 1], slabs[r]
+      packed = backend.face_pairs(up[0].contiguous(), backend.plane_labels(handles[r], 0),
+                                  low[low.shape[0] - 1].contiguous(), backend.plane_labels(handles[r - 1], low.shape[0] - 1),
+                                  kind, connectivity, delta_arr, binary_image)
+      pair_lists.append(packed.cpu().numpy())
+    N_total, remaps = _global_numbering([h["N"] for h in handles], pair_lists, range(len(slabs)))
+    sz_total = sum(int(s.shape[0]) for s in slabs)
+    voxels_total = sz_total * sy * sx
+    epl_total = voxels_total if epl_skipped else sum(h["epl"] for h in handles)
+    out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
+    outs = [backend.write_remap(h, torch.from_numpy(remaps[r]).to(slabs[r].device), N_total, out_dtype)
+            for r, h in enumerate(handles)]
+  finally:
+    for h in handles:
+      backend.release(h)
+  return (outs, N_total) if return_N else outs

@@ -265,3 +265,25 @@ def test_connectomics_known_answers(cc3d):
   assert cc3d.connected_components(vol, connectivity=18, return_N=True)[1] == 3657
   _, kept = cc3d.dust(vol, threshold=100, connectivity=26, return_N=True)
   assert kept == 2810
+
+
+@pytest.mark.parametrize("conn", [6, 18, 26])
+def test_virtual_slabs_equal_single_call(cc3d, conn):
+  """Sharded machinery on one GPU (cc3d_b200.sharded.connected_components_slabs): per-slab labelling, face pairs,
+  global renumbering and the remapped expand must reproduce the monolithic labelling bit for bit."""
+  import torch
+  from cc3d_b200 import sharded
+  rng = np.random.default_rng(conn)
+  coarse = rng.integers(0, 5, (20, 17, 23))
+  vol = np.repeat(np.repeat(np.repeat(coarse, 5, 0), 5, 1), 5, 2)[:97, :83, :111].astype(np.int32)
+  for kw in (dict(), dict(binary_image=True), dict(delta=1)):
+    x = vol if "delta" not in kw else (vol * 3 + rng.integers(0, 2, vol.shape)).astype(np.int32) * (vol != 0)
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    want, Nw = cc3d.connected_components(t, connectivity=conn, return_N=True, **kw)
+    for cuts in ([0, 97], [0, 40, 97], [0, 1, 2, 50, 96, 97]):
+      slabs = [t[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+      outs, N = sharded.connected_components_slabs(slabs, connectivity=conn, return_N=True, **kw)
+      got = torch.cat(outs, 0)
+      assert N == Nw and got.dtype == want.dtype
+      assert torch.equal(got.view(torch.int32) if got.dtype == torch.uint32 else got.to(torch.int64),
+                         want.view(torch.int32) if want.dtype == torch.uint32 else want.to(torch.int64)), (conn, kw, cuts)

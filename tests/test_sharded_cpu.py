@@ -165,3 +165,21 @@ def test_slabs_equal_monolithic_labelling(world):
       assert got[(ci, r)][1] == Nw, f"case {ci} rank {r}: N {got[(ci, r)][1]} != {Nw}"
     whole = np.concatenate(parts, axis=0)
     assert np.array_equal(whole, want.astype(np.int64)), f"case {ci} ({kw}) differs from the monolithic labelling"
+
+
+def test_single_process_slabs_equal_monolithic_labelling():
+  """connected_components_slabs: same merge without a process group (virtual slabs on one device)."""
+  sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200"))
+  sys.path.insert(0, ROOT)
+  import torch
+  from cc3d_b200 import sharded
+  from oracle import oracle
+  backend = OracleBackend()
+  for vol, kw in _make_cases():
+    for nslab in (1, 2, 4):
+      bounds = np.linspace(0, vol.shape[0], nslab + 1).astype(int)
+      slabs = [torch.from_numpy(np.ascontiguousarray(vol[bounds[r]:bounds[r + 1]])) for r in range(nslab)]
+      outs, N = sharded.connected_components_slabs(slabs, return_N=True, backend=backend, **kw)
+      want, Nw = oracle.connected_components(vol, return_N=True, **kw)
+      assert N == Nw
+      assert np.array_equal(np.concatenate([o.numpy() for o in outs], 0), want.astype(np.int64)), (kw, nslab)
