@@ -352,9 +352,68 @@ def _statistics_arrays(out_labels, N: Optional[int] = None):
   return counts, bbox[:, : 2 * ndim], sums[:, :ndim]
 
 
+def _statistics_arrays_device(t, N: int):
+  """Same as _statistics_arrays for a CUDA tensor (labels stay on the device; only the per-label arrays
+  come back)."""
+  import torch
+  L = _lib.lib()
+  t, order = _torch_order(t.detach())
+  ndim = t.ndim
+  shape3 = list(t.shape) + [1] * (3 - ndim)
+  mem = shape3 if order == "F" else shape3[::-1]
+  counts = torch.empty((N + 1,), dtype=torch.int32, device=t.device)
+  bbox = torch.empty((N + 1, 6), dtype=torch.int32, device=t.device)
+  sums = torch.empty((N + 1, 3), dtype=torch.int64, device=t.device)
+  stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+  with torch.cuda.device(t.device):
+    _lib.check(L.cc3d_b200_statistics(
+      t.data_ptr(), _kind_of(_torch_np_dtype(t)), mem[0], mem[1], mem[2], N,
+      counts.data_ptr(), bbox.data_ptr(), sums.data_ptr(), _lib.DEVICE, stream))
+  counts = counts.cpu().numpy().view(np.uint32)
+  bbox = bbox.cpu().numpy().view(np.uint32)
+  sums = sums.cpu().numpy().view(np.uint64)
+  if order != "F":  # memory axes (x fastest) -> array axes
+    sums = sums[:, ::-1]
+    bbox = bbox.reshape(N + 1, 3, 2)[:, ::-1, :].reshape(N + 1, 6)
+  return counts, bbox[:, : 2 * ndim], sums[:, :ndim]
+
+
+def _torch_max(t) -> int:
+  import torch
+  if t.numel() == 0:
+    return 0
+  if t.dtype in (getattr(torch, "uint16", None), getattr(torch, "uint32", None), getattr(torch, "uint64", None)):
+    signed = {2: torch.int16, 4: torch.int32, 8: torch.int64}[t.element_size()]
+    v = t.view(signed)
+    if int(v.min()) >= 0:
+      return int(v.max())
+    return int(t.cpu().numpy().max())
+  return int(t.max())
+
+
 def statistics(out_labels, no_slice_conversion: bool = False) -> dict:
-  """Voxel counts, bounding boxes and centroids per label; same contract as cc3d.statistics."""
+  """Voxel counts, bounding boxes and centroids per label; same contract as cc3d.statistics.
+  CUDA tensors are processed in place on their device."""
+  device_labels = None
   if _is_torch(out_labels):
+    if out_labels.is_cuda and out_labels.ndim >= 2 and out_labels.dtype != __import__("torch").bool:
+      device_labels = out_labels
+      voxels = out_labels.numel()
+      if voxels == 0:
+        return {"voxel_counts": None, "bounding_boxes": None, "centroids": None}
+      N = _torch_max(out_labels)
+      np_dtype = _torch_np_dtype(out_labels)
+      if np.issubdtype(np_dtype, np.signedinteger) and int(out_labels.min()) < 0:
+        raise ValueError(
+          f"Statistics can only be computed on volumes containing labels with values >= 0. Min: {int(out_labels.min())}")
+      if N > voxels:
+        raise ValueError(
+          f"Statistics can only be computed on volumes containing labels with values lower than the number of voxels. Max: {N}")
+      ndim = out_labels.ndim
+      shape3 = list(out_labels.shape) + [1] * (3 - ndim)
+      bdtype = np.uint32 if max(shape3) > np.iinfo(np.uint16).max else np.uint16
+      counts, bbox32, sums = _statistics_arrays_device(out_labels, N)
+      return _finish_statistics(counts, bbox32, sums, bdtype, voxels, no_slice_conversion)
     out_labels = out_labels.cpu().numpy()
   while out_labels.ndim < 2:
     out_labels = out_labels[..., np.newaxis]
@@ -378,6 +437,10 @@ def statistics(out_labels, no_slice_conversion: bool = False) -> dict:
   bdtype = np.uint32 if max(shape3) > np.iinfo(np.uint16).max else np.uint16
 
   counts, bbox32, sums = _statistics_arrays(out_labels, N)
+  return _finish_statistics(counts, bbox32, sums, bdtype, voxels, no_slice_conversion)
+
+
+def _finish_statistics(counts, bbox32, sums, bdtype, voxels, no_slice_conversion):
   with np.errstate(invalid="ignore", divide="ignore"):
     centroids = sums.astype(np.float64) / counts[:, None].astype(np.float64)
   centroids[counts == 0] = np.nan
@@ -414,8 +477,11 @@ def _view_as_unsigned(img):
 
 def dust(img, threshold, connectivity: int = 26, in_place: bool = False, binary_image: bool = False,
          precomputed_ccl: bool = False, invert: bool = False, return_N: bool = False):
-  """Remove connected components smaller than threshold (or outside [lo, hi)); same contract as cc3d.dust."""
+  """Remove connected components smaller than threshold (or outside [lo, hi)); same contract as cc3d.dust.
+  A CUDA tensor is processed entirely on its device (labelling, statistics and masking) and a tensor is returned."""
   L = _lib.lib()
+  if _is_torch(img) and img.is_cuda:
+    return _dust_device(img, threshold, connectivity, in_place, binary_image, precomputed_ccl, invert, return_N)
   orig_dtype = img.dtype
   img = _view_as_unsigned(img)
   if not in_place:
@@ -461,3 +527,43 @@ def dust(img, threshold, connectivity: int = 26, in_place: bool = False, binary_
     keep.ctypes.data, N, _lib.HOST, None))
   img = img.view(orig_dtype)
   return (img, dust_N) if return_N else img
+
+
+def _dust_device(img, threshold, connectivity, in_place, binary_image, precomputed_ccl, invert, return_N):
+  import torch
+  L = _lib.lib()
+  t, order = _torch_order(img.detach())
+  if not in_place or t.data_ptr() != img.data_ptr():
+    t = t.clone(memory_format=torch.preserve_format)
+  if precomputed_ccl:
+    cc_labels = t
+    N = _torch_max(t)
+  else:
+    cc_labels, N = connected_components(t, connectivity=connectivity, return_N=True, binary_image=bool(binary_image))
+  counts = statistics(cc_labels, no_slice_conversion=True)["voxel_counts"] if cc_labels.ndim >= 2 else \
+    statistics(cc_labels[..., None], no_slice_conversion=True)["voxel_counts"]
+  sizes = counts[1:N + 1].astype(np.int64)
+  if isinstance(threshold, (tuple, list)):
+    masked = ~((threshold[0] <= sizes) & (sizes < threshold[1]))
+  else:
+    masked = sizes < threshold
+  n_mask = int(np.count_nonzero(masked))
+  dust_N = n_mask if invert else N - n_mask
+  if n_mask == 0:
+    if invert:
+      t = torch.zeros_like(t)
+    return (t, dust_N) if return_N else t
+  keep = np.ones(N + 1, dtype=np.uint8)
+  keep[1:][masked] = 0
+  if invert:
+    keep = 1 - keep
+  keep_d = torch.from_numpy(keep).to(t.device)
+  lab, lorder = _torch_order(cc_labels)
+  if lorder != order:
+    raise ValueError("dust requires the image and its labels in the same memory layout")
+  stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+  with torch.cuda.device(t.device):
+    _lib.check(L.cc3d_b200_mask_by_label(
+      t.data_ptr(), t.element_size(), lab.data_ptr(), _kind_of(_torch_np_dtype(lab)), t.numel(),
+      keep_d.data_ptr(), N, _lib.DEVICE, stream))
+  return (t, dust_N) if return_N else t

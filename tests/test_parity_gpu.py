@@ -287,3 +287,22 @@ def test_virtual_slabs_equal_single_call(cc3d, conn):
       assert N == Nw and got.dtype == want.dtype
       assert torch.equal(got.view(torch.int32) if got.dtype == torch.uint32 else got.to(torch.int64),
                          want.view(torch.int32) if want.dtype == torch.uint32 else want.to(torch.int64)), (conn, kw, cuts)
+
+
+def test_statistics_and_dust_on_device_tensors(cc3d, oracle_mod):
+  """CUDA tensors stay on the device for statistics / dust; results equal the host path and the oracle."""
+  import torch
+  rng = np.random.default_rng(11)
+  coarse = rng.integers(0, 6, (14, 15, 16))
+  vol = np.repeat(np.repeat(np.repeat(coarse, 4, 0), 4, 1), 4, 2)[:53, :57, :61].astype(np.uint32)
+  vol[rng.random(vol.shape) < 0.02] = 7          # speckle -> small components for dust
+  labels, N = oracle_mod.connected_components(vol, return_N=True)
+  want = oracle_mod.statistics(labels, no_slice_conversion=True)
+  got = cc3d.statistics(torch.from_numpy(labels.astype(np.int32)).cuda(), no_slice_conversion=True)
+  assert np.array_equal(got["voxel_counts"], want["voxel_counts"])
+  assert np.array_equal(got["bounding_boxes"], want["bounding_boxes"]) and got["bounding_boxes"].dtype == want["bounding_boxes"].dtype
+  assert np.array_equal(got["centroids"], want["centroids"], equal_nan=True)
+  for kw in (dict(threshold=20), dict(threshold=(5, 50)), dict(threshold=20, invert=True), dict(threshold=30, connectivity=6)):
+    a, Na = oracle_mod.dust(vol, return_N=True, **kw)
+    b, Nb = cc3d.dust(torch.from_numpy(vol.view(np.int32)).cuda(), return_N=True, **kw)
+    assert Na == Nb and np.array_equal(a.view(np.int32), b.cpu().numpy()), kw
