@@ -352,6 +352,20 @@ def main():
                    "compulsory_roofline_frac": w["alg_bytes"] * v.numel() / (m / steps_ / 1e3) / 1e9 / peak})
       del v, o_
 
+  # ---- configs[2]: ONE 2048^3 uint64 Voronoi volume, z-slabs over the ranks (strong scaling; needs slabs < 2^32 voxels) ----
+  if world >= 4 and not args.no_extra:
+    import benchdata
+    n3 = 2048
+    szr = n3 // world
+    slab = benchdata.voronoi_multilabel((n3, n3, n3), cell=160, seed=2, device=dev, dtype=torch.int64, id_bits=62,
+                                        z_range=(rank * szr, (rank + 1) * szr))
+    m, n_, o_ = timed_device_loop(slab, dict(connectivity=26), 5, 2)
+    also.append({"workload": "voronoi_2048_u64_conn26_sharded", "description": "configs[2]: 2048^3 uint64 Voronoi (~2.9k labels), 26-connected, "
+                 f"z-slabs of {szr} planes over {world} GPUs, face exchange + allgather (strong scaling; 1 GPU with 8 virtual slabs: see DESIGN.md)",
+                 "value": float(n3) ** 3 * 5 / (m / 1e3) / 1e9, "unit": UNIT, "ms_per_step": m / 5, "N": int(n_),
+                 "compulsory_roofline_frac": 12 * float(n3) ** 3 / (m / 5 / 1e3) / 1e9 / (peak * world)})
+    del slab, o_
+
   # ---- CPU baseline (rank 0, N=1) ----
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

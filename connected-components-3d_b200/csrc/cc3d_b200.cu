@@ -322,7 +322,7 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
   add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
-  const size_t gqcap = (size_t)std::min<i64>(8 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
+  const size_t gqcap = (size_t)std::min<i64>(4 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
   add(gqcap * 8); add(64);
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
