@@ -71,6 +71,8 @@ def lib():
   L.cc3d_b200_workspace_bytes.restype = ctypes.c_size_t
   L.cc3d_b200_release_workspace.restype = None
   L.cc3d_b200_launch_count.restype = ctypes.c_ulonglong
+  L.cc3d_b200_debug_set_queue_capacity.restype = None
+  L.cc3d_b200_debug_set_queue_capacity.argtypes = [u64]
   L.cc3d_b200_set_timing.restype = None
   L.cc3d_b200_set_timing.argtypes = [ci]
   L.cc3d_b200_last_timings.restype = ci

@@ -83,6 +83,7 @@ void arena_release(Arena& a) {
 }
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_queue_cap_override{0};   // tests: force the global edge queue to overflow
 
 // ---- optional per-kernel timing ----
 thread_local bool g_timing = false;
@@ -171,6 +172,7 @@ int cc3d_b200_last_timings(const char** names, float* ms, int cap) {
   return n;
 }
 unsigned long long cc3d_b200_launch_count(void) { return g_launches.load(); }
+void cc3d_b200_debug_set_queue_capacity(uint64_t entries) { g_queue_cap_override.store(entries); }
 size_t cc3d_b200_workspace_bytes(void) { std::lock_guard<std::mutex> lk(g_pool_mu); return g_cached.cap; }
 void cc3d_b200_release_workspace(void) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -322,7 +324,8 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
   add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
   add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
-  const size_t gqcap = (size_t)std::min<i64>(4 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
+  size_t gqcap = (size_t)std::min<i64>(4 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
+  if (g_queue_cap_override.load()) gqcap = (size_t)g_queue_cap_override.load();
   add(gqcap * 8); add(64);
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }

@@ -306,3 +306,33 @@ def test_statistics_and_dust_on_device_tensors(cc3d, oracle_mod):
     a, Na = oracle_mod.dust(vol, return_N=True, **kw)
     b, Nb = cc3d.dust(torch.from_numpy(vol.view(np.int32)).cuda(), return_N=True, **kw)
     assert Na == Nb and np.array_equal(a.view(np.int32), b.cpu().numpy()), kw
+
+
+def test_edge_queue_overflow_fallback(cc3d, oracle_mod):
+  """With a global edge queue of 8 entries every volume that spans several union tiles overflows it; the
+  fallback kernel (every edge on the global forest) must give the same labelling."""
+  from cc3d_b200 import _lib
+  L = _lib.lib()
+  L.cc3d_b200_debug_set_queue_capacity(8)
+  try:
+    assert _fuzz(cc3d, _truth(oracle_mod), seed=404, ncase=120, maxdim=150) > 80
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 9, (70, 90, 130)).astype(np.uint32)      # > 16 runs per word: whole tiles go global
+    for conn in (6, 26):
+      a, Na = _truth(oracle_mod).connected_components(x, connectivity=conn, return_N=True)
+      b, Nb = cc3d.connected_components(x, connectivity=conn, return_N=True)
+      assert_same_labels(a, Na, b, Nb, f"overflow conn={conn}")
+  finally:
+    L.cc3d_b200_debug_set_queue_capacity(0)
+
+
+def test_many_runs_per_word_tiles(cc3d, oracle_mod):
+  """Multilabel rows with more than 16 runs per 32-voxel word do not fit the shared-memory forest of a tile;
+  those tiles send every edge to the global phase."""
+  rng = np.random.default_rng(6)
+  x = rng.integers(1, 4, (64, 96, 160)).astype(np.uint16)
+  x[:, :48] = np.repeat(np.repeat(np.repeat(rng.integers(0, 3, (16, 12, 40)), 4, 0), 4, 1), 4, 2)  # mixed: coarse half
+  for conn in (6, 18, 26):
+    a, Na = _truth(oracle_mod).connected_components(x, connectivity=conn, return_N=True)
+    b, Nb = cc3d.connected_components(x, connectivity=conn, return_N=True)
+    assert_same_labels(a, Na, b, Nb, f"dense runs conn={conn}")
