@@ -60,6 +60,8 @@ def lib():
   L.cc3d_b200_face_pairs.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ci, vp, u64, p(u64), vp]
   L.cc3d_b200_solve_pairs.restype = ci
   L.cc3d_b200_solve_pairs.argtypes = [vp, i64, vp, vp, i64, vp]
+  L.cc3d_b200_merge_slabs.restype = ci
+  L.cc3d_b200_merge_slabs.argtypes = [ci, vp, vp, vp, ci, vp, p(i64)]
   L.cc3d_b200_session_release.restype = None
   L.cc3d_b200_session_release.argtypes = [vp]
   L.cc3d_b200_label.restype = ci

@@ -239,6 +239,20 @@ def _global_numbering(N_r, pair_lists, want):
   return int(owned.sum()), remaps
 
 
+def _merge_native(N_r, pair_lists, rank):
+  """cc3d_b200_merge_slabs (C++): same result as _global_numbering for one slab, without the Python overhead."""
+  world = len(N_r)
+  n_labels = np.ascontiguousarray(N_r, dtype=np.int64)
+  arrs = [np.ascontiguousarray(p, dtype=np.uint64) for p in pair_lists]
+  ptrs = (ctypes.c_void_p * world)(*[a.ctypes.data if a.size else None for a in arrs])
+  n_pairs = np.array([a.size for a in arrs], dtype=np.int64)
+  remap = np.empty(int(n_labels[rank]) + 1, dtype=np.int64)
+  n_total = ctypes.c_int64(0)
+  _lib.check(_lib.lib().cc3d_b200_merge_slabs(world, n_labels.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p), n_pairs.ctypes.data,
+                                              int(rank), remap.ctypes.data, ctypes.byref(n_total)))
+  return int(n_total.value), remap
+
+
 def _out_dtype_rule(out_dtype, epl_total, voxels_total, shape_total, binary_image, connectivity):
   """Out-dtype rule of the monolithic call (fastcc3d.pyx:388-434)."""
   max_lab = min(epl_total, voxels_total)
@@ -303,13 +317,13 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
     if world > 1:
       top_vals = slab[sz - 1].contiguous().view(torch.uint8)
       top_labs = backend.plane_labels(h, sz - 1)
-      _lap("plane_labels(top)")
+      up_labs = backend.plane_labels(h, 0) if rank > 0 else None
+      _lap("plane_labels")
       recv = _exchange_planes(dist, group, rank, world, [top_vals, top_labs], [top_vals, top_labs])
       _lap("exchange")
       if rank > 0:
         low_vals = recv[0].view(slab.dtype)
         low_labs = recv[1]
-        up_labs = backend.plane_labels(h, 0)
         # (lower label << 32 | upper label), local labels of the two slabs; duplicates are removed on the host
         packed = backend.face_pairs(slab[0].contiguous(), up_labs, low_vals, low_labs, kind, connectivity, delta_arr,
                                     binary_image)
@@ -319,13 +333,15 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
     mine = torch.tensor([h["N"], h["epl"], sz], dtype=torch.int64, device=dev)
     facts, pair_lists = _gather_facts_and_pairs(dist, group, world, mine, packed)
     _lap("all_gather")
+    if _timing:
+      print(f"  [sharded] pairs per interface: {[int(p.numel()) for p in pair_lists]}", flush=True)
     facts = facts.numpy()
     sz_total = int(facts[:, 2].sum())
     voxels_total = sz_total * sy * sx
     epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
     # every rank solves the same small union-find over the labels that touch an interface
-    N_total, remaps = _global_numbering(facts[:, 0], [p.numpy() for p in pair_lists], [rank])
-    remap = torch.from_numpy(remaps[rank]).to(dev)
+    N_total, remap_np = _merge_native(facts[:, 0], [p.numpy() for p in pair_lists], rank)
+    remap = torch.from_numpy(remap_np).to(dev, non_blocking=True)
     _lap("host solve + remap")
     out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
     out = backend.write_remap(h, remap, N_total, out_dtype)
@@ -361,7 +377,9 @@ def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = F
                                   low[low.shape[0] - 1].contiguous(), backend.plane_labels(handles[r - 1], low.shape[0] - 1),
                                   kind, connectivity, delta_arr, binary_image)
       pair_lists.append(packed.cpu().numpy())
-    N_total, remaps = _global_numbering([h["N"] for h in handles], pair_lists, range(len(slabs)))
+    N_r = [h["N"] for h in handles]
+    merged = [_merge_native(N_r, pair_lists, r) for r in range(len(slabs))]
+    N_total, remaps = merged[0][0], {r: m[1] for r, m in enumerate(merged)}
     sz_total = sum(int(s.shape[0]) for s in slabs)
     voxels_total = sz_total * sy * sx
     epl_total = voxels_total if epl_skipped else sum(h["epl"] for h in handles)

@@ -712,3 +712,85 @@ int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int
   return 0;
 }
 
+
+// ---- sharded volumes: host side of the merge (no GPU work) ----
+// Slab r has local labels 1..n_labels[r]; pairs[r] holds n_pairs[r] packed equivalences
+// (label in slab r-1) << 32 | (label in slab r) across the interface below slab r (pairs[0] is unused).
+// A component is owned by the lowest slab it touches; owned components are numbered slab by slab in local
+// label order, which is the first-appearance order of the whole volume (cc3d/__init__.py:296-321, 425-468
+// do the same with a Python DisjointSet + renumber). Writes remap[0..n_labels[rank]] for slab `rank`
+// (remap[0] = 0) and the global component count.
+int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,
+                          int rank, int64_t* remap, int64_t* n_total) {
+  if (world <= 0 || rank < 0 || rank >= world || !n_labels || !remap || !n_total)
+    return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs: bad arguments");
+  std::vector<i64> off(world + 1, 0);
+  for (int r = 0; r < world; r++) off[r + 1] = off[r] + n_labels[r];
+  // edges between global ids (off[r] + label), nodes = ids that touch an interface
+  std::vector<std::pair<i64, i64>> edges;
+  for (int r = 1; r < world; r++) {
+    for (i64 k = 0; k < n_pairs[r]; k++) {
+      const u64 v = pairs[r][k];
+      const i64 lo = (i64)(v >> 32), up = (i64)(v & 0xFFFFFFFFull);
+      if (lo < 1 || lo > n_labels[r - 1] || up < 1 || up > n_labels[r])
+        return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs: pair label out of range");
+      edges.push_back({off[r - 1] + lo, off[r] + up});
+    }
+  }
+  std::sort(edges.begin(), edges.end());
+  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+  std::vector<i64> nodes;
+  nodes.reserve(edges.size() * 2);
+  for (auto& e : edges) { nodes.push_back(e.first); nodes.push_back(e.second); }
+  std::sort(nodes.begin(), nodes.end());
+  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+  const size_t nn = nodes.size();
+  std::vector<u32> parent(nn);
+  for (size_t i = 0; i < nn; i++) parent[i] = (u32)i;
+  auto find = [&](u32 i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+  auto index_of = [&](i64 id) { return (u32)(std::lower_bound(nodes.begin(), nodes.end(), id) - nodes.begin()); };
+  for (auto& e : edges) {
+    u32 a = find(index_of(e.first)), b = find(index_of(e.second));
+    if (a < b) parent[b] = a; else if (b < a) parent[a] = b;   // root = smallest id = first in raster order
+  }
+  // owned components per slab: all labels minus the interface nodes whose root lies elsewhere
+  std::vector<i64> owned(world);
+  for (int r = 0; r < world; r++) owned[r] = n_labels[r];
+  auto slab_of = [&](i64 id) { return (int)(std::upper_bound(off.begin(), off.end(), id - 1) - off.begin()) - 1; };
+  std::vector<char> nonowned(nn);
+  for (size_t i = 0; i < nn; i++) {
+    nonowned[i] = find((u32)i) != (u32)i;
+    if (nonowned[i]) owned[slab_of(nodes[i])]--;
+  }
+  std::vector<i64> base(world + 1, 0);
+  for (int r = 0; r < world; r++) base[r + 1] = base[r] + owned[r];
+  *n_total = base[world];
+  // final label of an owned node = base[slab] + local label - (non-owned labels of that slab below it)
+  std::vector<i64> final_of(nn, 0);
+  {
+    int cur = -1; i64 before = 0;
+    for (size_t i = 0; i < nn; i++) {
+      const int r = slab_of(nodes[i]);
+      if (r != cur) { cur = r; before = 0; }
+      if (nonowned[i]) before++;
+      else final_of[i] = base[r] + (nodes[i] - off[r]) - before;
+    }
+  }
+  // remap of this rank: labels in order, skipping the non-owned ones, then the interface nodes take their root's label
+  const i64 nl = n_labels[rank];
+  const size_t lo_i = std::lower_bound(nodes.begin(), nodes.end(), off[rank] + 1) - nodes.begin();
+  const size_t hi_i = std::upper_bound(nodes.begin(), nodes.end(), off[rank] + nl) - nodes.begin();
+  remap[0] = 0;
+  size_t j = lo_i;
+  i64 skipped = 0;
+  for (i64 l = 1; l <= nl; l++) {
+    if (j < hi_i && nodes[j] == off[rank] + l) {
+      if (nonowned[j]) { skipped++; remap[l] = final_of[find((u32)j)]; }
+      else remap[l] = final_of[j];
+      j++;
+    } else {
+      remap[l] = base[rank] + l - skipped;
+    }
+  }
+  return 0;
+}

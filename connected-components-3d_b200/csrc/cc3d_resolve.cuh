@@ -227,6 +227,9 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
       const u32 lp = lP[i];
       const bool left_same = x > 0 && lP[i - 1] == lp;
       const bool up_same = y > 0 && lP[i - sx] == lp;
+      // transitive predicates: when the straight neighbour joins p, every other matching q is its in-plane
+      // neighbour and already belongs to the same component of the lower slab
+      const bool straight = (MODE != MODE_DELTA) && E(p, vQ[i]);
 #pragma unroll
       for (int dy = -1; dy <= 1; dy++) {
 #pragma unroll
@@ -234,6 +237,7 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
           const int nz = (dx != 0) + (dy != 0);
           if (connectivity == 6 && nz > 0) continue;
           if (connectivity == 18 && nz > 1) continue;
+          if (straight && nz > 0) continue;
           const i64 xx = x + dx, yy = y + dy;
           if (xx < 0 || xx >= sx || yy < 0 || yy >= sy) continue;
           const i64 qi = yy * sx + xx;

@@ -116,6 +116,14 @@ int cc3d_b200_face_pairs(const void* values_upper, const uint32_t* labels_upper,
 int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, const uint32_t* b, int64_t n_pairs,
                           void* stream);
 
+/* Host side of the slab merge (no GPU work; replaces the Python DisjointSet + renumber of
+ * connected_components_stack, cc3d/__init__.py:296-321, 425-492). Slab r has local labels 1..n_labels[r];
+ * pairs[r][0..n_pairs[r]) are the packed face_pairs of the interface below slab r (pairs[0] unused).
+ * Writes remap[0..n_labels[rank]] (local label -> global label, remap[0] = 0) for slab `rank` and the
+ * global component count. Global numbering = first appearance in the whole volume. */
+int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,
+                          int rank, int64_t* remap, int64_t* n_total);
+
 /* Drops a session without writing. */
 void cc3d_b200_session_release(cc3d_b200_session* session);
 

@@ -183,3 +183,24 @@ def test_single_process_slabs_equal_monolithic_labelling():
       want, Nw = oracle.connected_components(vol, return_N=True, **kw)
       assert N == Nw
       assert np.array_equal(np.concatenate([o.numpy() for o in outs], 0), want.astype(np.int64)), (kw, nslab)
+
+
+def test_native_merge_equals_numpy_merge():
+  """cc3d_b200_merge_slabs (C++ host function in libcc3d_b200.so) against the numpy restatement in
+  cc3d_b200.sharded._global_numbering on random interface graphs."""
+  sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200"))
+  from cc3d_b200 import sharded
+  rng = np.random.default_rng(3)
+  for it in range(200):
+    world = int(rng.integers(1, 6))
+    N_r = rng.integers(0, 12, world)
+    pair_lists = [np.zeros(0, dtype=np.int64)]
+    for r in range(1, world):
+      n = int(rng.integers(0, 15)) if N_r[r - 1] > 0 and N_r[r] > 0 else 0
+      lo = rng.integers(1, N_r[r - 1] + 1, n) if n else np.zeros(0, dtype=np.int64)
+      up = rng.integers(1, N_r[r] + 1, n) if n else np.zeros(0, dtype=np.int64)
+      pair_lists.append(((lo.astype(np.int64) << 32) | up.astype(np.int64)))
+    Nw, remaps = sharded._global_numbering(N_r, pair_lists, range(world))
+    for r in range(world):
+      Ng, remap = sharded._merge_native(N_r, pair_lists, r)
+      assert Ng == Nw and np.array_equal(remap, remaps[r]), (it, r, N_r, pair_lists)
