@@ -237,9 +237,57 @@ def connected_components(
       int(periodic), space, stream, ctypes.byref(info), ctypes.byref(sess)))
     return info, sess
 
+  def dtype_rule(epl):
+    """The reference's out-dtype rule (fastcc3d.pyx:388-434) for an epl estimate."""
+    max_lab = min(epl, voxels)
+    uf_voxels = _even_ceil(shape3[0]) * _even_ceil(shape3[1]) * _even_ceil(shape3[2])
+    if binary_image:
+      if connectivity in (4, 6):
+        max_lab = min(max_lab, (uf_voxels // 2) + 1)
+      else:  # (sic) 8 and 18 take the 26-connected bound, fastcc3d.pyx:412
+        max_lab = min(max_lab, (uf_voxels // 8) + 1)
+    if out_dtype is not None:
+      odt = np.dtype(out_dtype)
+      if odt not in (np.uint16, np.uint32, np.uint64):
+        raise ValueError(
+          f"Explicitly defined out_dtype ({odt}) must be one of: np.uint16, np.uint32, np.uint64")
+      if np.iinfo(odt).max < max_lab:
+        raise ValueError(
+          f"Explicitly defined out_dtype ({odt}) is too small "
+          f"to contain the estimated maximum number of labels ({max_lab}).")
+      return odt
+    if max_lab < np.iinfo(np.uint16).max:
+      return np.dtype(np.uint16)
+    if max_lab < np.iinfo(np.uint32).max:
+      return np.dtype(np.uint32)
+    return np.dtype(np.uint64)
+
   if dev_guard is not None:
     dev_guard.__enter__()
   try:
+    # Device-resident fast path: the out dtype is guessed (uint32 unless the caller fixed it) so that both
+    # phases run back to back without a host round trip; the reference's rule is checked afterwards and the
+    # (small-volume) cases where it picks another width are converted.
+    if on_device and not (periodic_boundary and delta == 0):
+      import torch
+      guess = np.dtype(np.uint32)
+      if out_dtype is not None and np.dtype(out_dtype) in (np.uint16, np.uint32, np.uint64) and (
+          np.dtype(out_dtype) != np.uint16 or voxels < 65535):
+        guess = np.dtype(out_dtype)
+      out_flat = torch.empty((voxels,), dtype=_torch_dtype(guess), device=tensor.device)
+      info = _lib.ResolveInfo()
+      _lib.check(L.cc3d_b200_label_with_info(
+        in_ptr, kind, sx, sy, sz, int(connectivity), delta_arr.ctypes.data, int(binary_image), 0, out_flat.data_ptr(),
+        _OUT_KIND[guess], _lib.DEVICE, ctypes.byref(info), stream))
+      final = dtype_rule(voxels if epl_skipped else int(info.epl))
+      N = int(info.N)
+      if final != guess:
+        signed = {2: torch.int16, 4: torch.int32, 8: torch.int64}
+        out_flat = out_flat.view(signed[guess.itemsize]).to(signed[final.itemsize]).view(_torch_dtype(final))
+      out_labels = out_flat.reshape(shape_in) if order == "C" else \
+        out_flat.reshape(tuple(reversed(shape_in))).permute(*reversed(range(dims)))
+      return (out_labels, N) if return_N else out_labels
+
     info, sess = resolve(bool(periodic_boundary))
     try:
       if epl_skipped:

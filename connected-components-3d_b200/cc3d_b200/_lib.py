@@ -66,6 +66,8 @@ def lib():
   L.cc3d_b200_session_release.argtypes = [vp]
   L.cc3d_b200_label.restype = ci
   L.cc3d_b200_label.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, vp, ci, ci, p(u64), vp]
+  L.cc3d_b200_label_with_info.restype = ci
+  L.cc3d_b200_label_with_info.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, vp, ci, ci, p(ResolveInfo), vp]
   L.cc3d_b200_statistics.restype = ci
   L.cc3d_b200_statistics.argtypes = [vp, ci, i64, i64, i64, u64, vp, vp, vp, ci, vp]
   L.cc3d_b200_mask_by_label.restype = ci

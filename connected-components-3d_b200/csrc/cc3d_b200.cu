@@ -158,6 +158,7 @@ struct cc3d_b200_session {
   i64 voxels = 0;
   u32* L = nullptr;   // final label of every run, at the run's first voxel
   u32* M = nullptr;   // edge bitmaps (F and X planes are what the expansion needs)
+  Counters* ctr = nullptr;   // device-side counters of the resolve phase
   u64 N = 0;
 };
 
@@ -270,9 +271,49 @@ static void c8_edges_typed(const T* in, u32* M, const Geom& g, const void* delta
   g_launches += 1;
 }
 
+// Reads the counters of an enqueued resolve phase (one stream synchronisation).
+// pinned landing zone of the counters so that their copy is truly asynchronous (one per host thread)
+static Counters* pinned_counters() {
+  thread_local Counters* hpin = nullptr;
+  if (!hpin && cudaMallocHost((void**)&hpin, sizeof(Counters)) != cudaSuccess) hpin = nullptr;
+  return hpin;
+}
+static int resolve_finish(cc3d_b200_session* S, cudaStream_t s, cc3d_b200_resolve_info* info) {
+  if (S->voxels == 0) return 0;
+  Counters hloc;
+  Counters* h = pinned_counters();
+  cudaError_t e = cudaSuccess;
+  if (!h) { h = &hloc; e = cudaMemcpyAsync(h, S->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s); }   // else: enqueued by resolve_enqueue
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e));
+  S->N = h->N;
+  info->N = h->N;
+  info->epl = h->epl;
+  info->first_foreground_row = h->epl ? h->first_row : -1;
+  info->last_foreground_row = h->epl ? h->last_row : -1;
+  return 0;
+}
+
+static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                           const void* delta, int binary_image, int periodic_boundary, int mem_space,
+                           void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session);
+
 int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
                             const void* delta, int binary_image, int periodic_boundary, int mem_space,
                             void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session) {
+  int rc = resolve_enqueue(in, in_kind, sx, sy, sz, connectivity, delta, binary_image, periodic_boundary, mem_space,
+                           stream, info, session);
+  if (rc) return rc;
+  rc = resolve_finish(*session, (cudaStream_t)stream, info);
+  if (rc) { cc3d_b200_session_release(*session); *session = nullptr; return rc; }
+  marks_collect(false);
+  return 0;
+}
+
+static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                           const void* delta, int binary_image, int periodic_boundary, int mem_space,
+                           void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session) {
   if (!info || !session) return fail(CC3D_B200_ERR_ARGUMENT, "info/session must not be NULL");
   *session = nullptr;
   info->N = 0; info->epl = 0; info->first_foreground_row = -1; info->last_foreground_row = -1;
@@ -319,7 +360,7 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
 
   size_t need = 4096;
   auto add = [&](size_t b) { need += ((b + 255) & ~size_t(255)) + 256; };
-  if (mem_space == CC3D_B200_HOST) add((size_t)voxels * es);
+  if (mem_space == CC3D_B200_HOST) { add((size_t)voxels * es); add((size_t)voxels * 4 + 512); }   // staged input + (u16/u32) output
   add((size_t)maxruns * 4);                // L
   add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
@@ -421,21 +462,8 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
     g_launches += 1;
     mark("C3_assign", s);
   }
-  Counters h;
-  cudaError_t e = cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e)); }
-  marks_collect(false);
-#ifdef CC_STATS
-  { u32 hc[8]; cudaMemcpy(hc, gqctl, 32, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[cc3d stats] runs=%llu queued=%u ovf=%u hops=%u finds=%u nontrivial=%u\n", (unsigned long long)h.nruns, hc[0], hc[1], hc[2], hc[3], hc[4]); }
-#endif
-  S->N = h.N;
-  info->N = h.N;
-  info->epl = h.epl;
-  info->first_foreground_row = h.epl ? h.first_row : -1;
-  info->last_foreground_row = h.epl ? h.last_row : -1;
+  S->ctr = ctr;
+  if (Counters* h = pinned_counters()) cudaMemcpyAsync(h, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s);
   *session = S;
   return 0;
 }
@@ -461,7 +489,7 @@ static void launch_write(const cc3d_b200_session* S, OUT* dout, i64 row0, i64 nr
 
 // shared implementation of label_write / label_write_rows / label_write_remap
 static int write_impl(cc3d_b200_session* S, void* out, int out_kind, int mem_space, void* stream, i64 row0, i64 nrows,
-                      const void* remap, int remap_kind, u64 max_label, bool release) {
+                      const void* remap, int remap_kind, u64 max_label, bool release, bool collect_marks = true) {
   if (!S) return fail(CC3D_B200_ERR_ARGUMENT, "NULL session");
   auto done = [&](int rc) { if (release) cc3d_b200_session_release(S); return rc; };
   const size_t os = (out_kind == CC3D_B200_U16) ? 2 : (out_kind == CC3D_B200_U32 ? 4 : (out_kind == CC3D_B200_U64 ? 8 : 0));
@@ -506,7 +534,7 @@ static int write_impl(cc3d_b200_session* S, void* out, int out_kind, int mem_spa
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
-  marks_collect(true);
+  if (collect_marks) marks_collect(true);
   if (tmp_out) cudaFree(tmp_out);
   if (tmp_remap) cudaFree(tmp_remap);
   if (e != cudaSuccess) return done(fail(CC3D_B200_ERR_CUDA, std::string("label_write: ") + cudaGetErrorString(e)));
@@ -598,6 +626,29 @@ int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, 
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("solve_pairs: ") + cudaGetErrorString(e));
   return 0;
+}
+
+int cc3d_b200_label_with_info(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                              const void* delta, int binary_image, int periodic_boundary, void* out, int out_kind,
+                              int mem_space, cc3d_b200_resolve_info* info, void* stream) {
+  if (!info) return fail(CC3D_B200_ERR_ARGUMENT, "info must not be NULL");
+  // both phases are enqueued back to back; one synchronisation at the end
+  cc3d_b200_session* S = nullptr;
+  int rc = resolve_enqueue(in, in_kind, sx, sy, sz, connectivity, delta, binary_image, periodic_boundary,
+                           mem_space, stream, info, &S);
+  if (rc) return rc;
+  if (g_timing) {   // per-kernel timings need the two-phase path (events are collected per phase)
+    rc = resolve_finish(S, (cudaStream_t)stream, info);
+    if (rc) { cc3d_b200_session_release(S); return rc; }
+    marks_collect(false);
+    return cc3d_b200_label_write(S, out, out_kind, mem_space, stream);
+  }
+  rc = write_impl(S, out, out_kind, mem_space, stream, 0, S->g.sy * S->g.sz, nullptr, 0, 0, false, false);
+  if (rc == 0) rc = resolve_finish(S, (cudaStream_t)stream, info);
+  if (rc == 0 && ((out_kind == CC3D_B200_U16 && info->N > 0xFFFFull)))
+    rc = fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind");
+  cc3d_b200_session_release(S);
+  return rc;
 }
 
 int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,

@@ -132,6 +132,13 @@ int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t
                     const void* delta, int binary_image, int periodic_boundary, void* out,
                     int out_kind, int mem_space, uint64_t* N, void* stream);
 
+/* Same, and also returns what label_resolve reports (N, epl, foreground rows), so that a caller that guessed
+ * the out kind before the call (normally u32) can check the reference's out-dtype rule afterwards and only
+ * convert in the rare case the guess was wrong. No host round trip between the two phases. */
+int cc3d_b200_label_with_info(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                              const void* delta, int binary_image, int periodic_boundary, void* out,
+                              int out_kind, int mem_space, cc3d_b200_resolve_info* info, void* stream);
+
 /* Row a13: per-label statistics in MEMORY axes (x fastest). counts[N+1] (uint32, wraps like the
  * reference), bbox[(N+1)*6] uint32 as xmin,xmax,ymin,ymax,zmin,zmax (absent label: min=UINT32_MAX,
  * max=0), sums[(N+1)*3] uint64 coordinate sums (centroid = sum / count, exact below 2^53).
