@@ -365,7 +365,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
   add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
-  size_t gqcap = (size_t)std::min<i64>(4 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
+  size_t gqcap = (size_t)std::min<i64>(8 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
   if (g_queue_cap_override.load()) gqcap = (size_t)g_queue_cap_override.load();
   add(gqcap * 8); add(64);
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);

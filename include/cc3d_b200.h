@@ -157,7 +157,7 @@ size_t cc3d_b200_workspace_bytes(void);
 void cc3d_b200_release_workspace(void);
 
 /* Testing aid: capacity (entries) of the global edge queue between the tile kernel and the global union
- * kernel; 0 restores the default (4 per bitmap word). A tiny value forces the overflow fallback path. */
+ * kernel; 0 restores the default (8 per bitmap word). A tiny value forces the overflow fallback path. */
 void cc3d_b200_debug_set_queue_capacity(uint64_t entries);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
