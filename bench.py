@@ -296,7 +296,14 @@ def main():
       traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
     except Exception:
       traffic = None
+  # each dense kernel against its OWN compulsory traffic: A reads the input once, D writes the output once
+  own = {}
+  for kname, nbytes in (("A_faces", voxels * x.element_size()), ("D_expand", voxels * out_bytes)):
+    if kname in kavg:
+      gbs = nbytes / (kavg[kname] / 1e3) / 1e9
+      own[kname] = {"bytes": nbytes, "ms": kavg[kname], "GB/s": gbs, "frac": gbs / peak}
   roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "per_kernel_own_bytes": own,
               "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
               "note": "achieved = (sizeof(in)+sizeof(out)) * voxels / duration of the dominant kernel; pipeline_frac = same bytes / whole step",
               "kernel_ms": kavg, "kernel_share": {k: v / sum(kavg.values()) for k, v in kavg.items()},
