@@ -12,8 +12,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-OUT = os.path.join(HERE, "cc3d_b200", "libcc3d_b200.so")
+# CC3D_BUILD_TAG=<tag> builds an experimental variant next to the product library (A/B runs on the GPU box:
+# CC3D_NVCC_EXTRA="-DFOO=1" CC3D_BUILD_TAG=foo python build.py; CC3D_B200_LIB=.../libcc3d_b200_foo.so python ...)
+TAG = os.environ.get("CC3D_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+OUT = os.path.join(HERE, "cc3d_b200", "libcc3d_b200" + ("_" + TAG if TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("CC3D_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

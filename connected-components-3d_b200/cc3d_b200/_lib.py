@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcc3d_b200.so")
+LIB_PATH = os.environ.get("CC3D_B200_LIB") or os.path.join(_HERE, "libcc3d_b200.so")   # env: experimental builds only
 
 HOST, DEVICE = 0, 1
 U8, U16, U32, U64, F32, F64 = range(6)

@@ -140,10 +140,10 @@ size_t bitmap_words(const Geom& g, bool with_diagonals) {
 
 // exclusive scan of n counts (n on the host, or ceil(*n_dev / 2^shift) when n_dev is given; n_max bounds it)
 int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_dev, int shift, u64* total_dev,
-                u32* total32_dev, cudaStream_t s) {
+                u32* total32_dev, cudaStream_t s, Counters* track = nullptr, u32 W = 1) {
   const i64 nb = (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
   const unsigned grid = (unsigned)std::min<i64>(nb, CC_GRID_BLOCKS);
-  k_scan_reduce<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n_max, n_dev, shift);
+  k_scan_reduce<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n_max, n_dev, shift, track, W);
   k_scan_blocks<<<1, 1024, 0, s>>>(bsum, n_max, n_dev, shift, total_dev, total32_dev);
   k_scan_apply<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, prefix, n_max, n_dev, shift);
   g_launches += 3;
@@ -159,6 +159,7 @@ struct cc3d_b200_session {
   u32* L = nullptr;   // final label of every run, at the run's first voxel
   u32* M = nullptr;   // edge bitmaps (F and X planes are what the expansion needs)
   Counters* ctr = nullptr;   // device-side counters of the resolve phase
+  bool epl_is_runs = false;  // multilabel: epl (cc3d.hpp:287-315) = number of x-runs, counted by scan S
   u64 N = 0;
 };
 
@@ -289,9 +290,9 @@ static int resolve_finish(cc3d_b200_session* S, cudaStream_t s, cc3d_b200_resolv
   if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e));
   S->N = h->N;
   info->N = h->N;
-  info->epl = h->epl;
-  info->first_foreground_row = h->epl ? h->first_row : -1;
-  info->last_foreground_row = h->epl ? h->last_row : -1;
+  info->epl = S->epl_is_runs ? h->nruns : h->epl;
+  info->first_foreground_row = h->nruns ? h->first_row : -1;
+  info->last_foreground_row = h->nruns ? h->last_row : -1;
   return 0;
 }
 
@@ -393,6 +394,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   u64* gqbuf = (u64*)ar.take(gqcap * 8);
   u32* gqctl = (u32*)ar.take(64);   // [0] count, [1] overflow flag
   S->L = L; S->M = M;
+  S->epl_is_runs = (mode == MODE_EQ);
 
   k_init_counters<<<1, 1, 0, s>>>(ctr, gqctl);
   g_launches += 1;
@@ -423,7 +425,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   if (rc == 0) {
     // S: number the runs
     u32* RS = M + g.offRS;
-    scan_counts(RS, RS, bsum, nwords, nullptr, 0, &ctr->nruns, RS + nwords, s);
+    scan_counts(RS, RS, bsum, nwords, nullptr, 0, &ctr->nruns, RS + nwords, s, ctr, (u32)g.W);
     mark("S_scan_runs", s);
     // B: unions
     rc = -1;

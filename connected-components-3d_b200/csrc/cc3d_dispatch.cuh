@@ -34,11 +34,30 @@ static int launch_faces(const LabelArgs& a) {
   const bool two_d = a.connectivity == 4 || a.connectivity == 8;
   if (two_d && g.sz != 1) return -1;
   const unsigned nych = (unsigned)((g.sy + CC_FACE_YCH - 1) / CC_FACE_YCH);
-  const i64 ntasks = g.W * nych * g.sz;
+  const unsigned nwg = (unsigned)((g.W + CC_FACE_NW - 1) / CC_FACE_NW);
+  const i64 ntasks = (i64)nwg * nych * g.sz;
   const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
   const T* in = static_cast<const T*>(a.in);
-  if (two_d) k_faces<T, MODE, false><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, (unsigned)ntasks);
-  else k_faces<T, MODE, true><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, (unsigned)ntasks);
+  // staged (cp.async) variant: every group of CC_FACE_NW words lies inside the row and every row is 16-byte aligned
+  const bool staged = (g.sx % (32 * CC_FACE_NW)) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0
+#ifdef CC_FACES_NO_ASYNC
+                      && false
+#endif
+      ;
+  if (staged) {
+    constexpr size_t smem = faces_async_smem<T>();
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_faces_async<T, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_faces_async<T, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    if (two_d) k_faces_async<T, MODE, false><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+    else k_faces_async<T, MODE, true><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+  } else {
+    if (two_d) k_faces<T, MODE, false><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+    else k_faces<T, MODE, true><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+  }
   ++*a.launches;
   return 0;
 }

@@ -5,133 +5,248 @@
 
 #define CC_FACE_WARPS 8
 #define CC_FACE_YCH 32   // rows of one plane a warp walks through
-#define CC_FACE_UNR 4    // rows whose loads are issued back to back
+#define CC_FACE_NW 4     // bitmap words (of one row) a warp handles per row step
 
-template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(CC_FULL, v, 1); }
-template <> __device__ __forceinline__ uint8_t shfl_up1(uint8_t v) { return (uint8_t)__shfl_up_sync(CC_FULL, (unsigned)v, 1); }
-template <> __device__ __forceinline__ uint16_t shfl_up1(uint16_t v) { return (uint16_t)__shfl_up_sync(CC_FULL, (unsigned)v, 1); }
-template <> __device__ __forceinline__ uint64_t shfl_up1(uint64_t v) { return (uint64_t)__shfl_up_sync(CC_FULL, (unsigned long long)v, 1); }
+// Faces of one row of CC_FACE_NW words (c: voxels, l: -x neighbours, d: -z neighbours, up: -y neighbours);
+// lane 0 stores the group's four {F,X,Y,Z} and run-start counts.
+template <typename T, int MODE, bool HASZ>
+__device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T* c, const T* l, const T* d, const T* up,
+                                                 int lane, uint4* __restrict__ mq, u32* __restrict__ rs, bool rs_vec, u32& epl) {
+  constexpr int NW = CC_FACE_NW;
+  u32 F[NW], X[NW], Y[NW], Z[NW];
+#pragma unroll
+  for (int k = 0; k < NW; k++) {
+    const bool f = E.fg(c[k]);
+    F[k] = __ballot_sync(CC_FULL, f);
+    X[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
+    Y[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
+    Z[k] = HASZ ? __ballot_sync(CC_FULL, E(c[k], d[k])) : 0u;
+    // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
+    if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NW; k++) mq[k] = make_uint4(F[k], X[k], Y[k], Z[k]);
+    if (rs_vec) *reinterpret_cast<uint4*>(rs) = make_uint4(__popc(F[0] & ~X[0]), __popc(F[1] & ~X[1]), __popc(F[2] & ~X[2]), __popc(F[3] & ~X[3]));
+    else {
+#pragma unroll
+      for (int k = 0; k < NW; k++) rs[k] = __popc(F[k] & ~X[k]);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
-// Kernel A. One warp owns one bitmap-word column (32 voxels in x) of one z-plane and walks CC_FACE_YCH
-// rows down y, one voxel per lane. The row above stays in registers; the loads of CC_FACE_UNR rows
-// (this plane and plane z-1) are issued back to back before any of them is used. Per row: three
-// compares and four ballots (F, X, Y, Z); lane 0 stores the four words with one 16-byte store.
-// The row body is branch free (rows past the chunk end are predicated off). HASZ = 3D connectivity.
+// Kernel A. One warp owns CC_FACE_NW consecutive bitmap words (128 voxels in x) of one z-plane and walks
+// CC_FACE_YCH rows down y, one voxel per lane and word. Per word: the voxel c, its -x neighbour l (an
+// L1-resident reload of the same lines shifted by one element), its -z neighbour d; the row above stays
+// in registers. Three compares and four ballots (F, X, Y, Z) per word; lane 0 stores the four uint4
+// {F,X,Y,Z} of the group (64 contiguous bytes) and the four run-start counts. The loads of row r+1 are
+// issued before row r is evaluated (software pipeline), all addresses are one pointer + immediates.
+// The foreground row range and (MODE_EQ) epl = number of runs come out of scan S; the other predicates
+// count the reference's value transitions here (cc3d.hpp:300-303). HASZ = 3D connectivity.
+// Groups that do not lie fully inside the row (sx not a multiple of 128) take the bounds-checked path.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool HASZ>
 __global__ void __launch_bounds__(CC_FACE_WARPS * 32)
 k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
-        unsigned nych, unsigned ntasks) {
+        unsigned nych, unsigned nwg, unsigned ntasks) {
+  constexpr int NW = CC_FACE_NW;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const unsigned task = blockIdx.x * CC_FACE_WARPS + warp;
+  const unsigned task = blockIdx.x * CC_FACE_WARPS + (threadIdx.x >> 5);
+  if (task >= ntasks) return;
+  const u32 W = (u32)g.W, sx = (u32)g.sx, sy = (u32)g.sy;
+  const u32 wg = task % nwg;
+  const u32 t = task / nwg;
+  const u32 ych = t % nych, z = t / nych;
+  const u32 y0 = ych * CC_FACE_YCH;
+  const u32 nrow = min(sy, y0 + CC_FACE_YCH) - y0;
+  const u32 w0 = wg * NW;
+  const bool hasz = HASZ && z > 0;
+  const size_t plane = (size_t)sy * sx;
+  const u32 row0 = z * sy + y0;
+  uint4* __restrict__ mq = reinterpret_cast<uint4*>(M) + ((size_t)row0 * W + w0);
+  u32* __restrict__ rs = M + g.offRS + ((size_t)row0 * W + w0);
+  u32 epl = 0;
 
-  u32 epl = 0, rfirst = 0xFFFFFFFFu, rlast = 0, anyfg = 0;
-  if (task < ntasks) {
-    const u32 W = (u32)g.W, sx = (u32)g.sx, sy = (u32)g.sy;
-    const u32 w = task % W;
-    const u32 t = task / W;
-    const u32 ych = t % nych, z = t / nych;
-    const u32 y0 = ych * CC_FACE_YCH;
-    const u32 y1 = min(sy, y0 + CC_FACE_YCH);
-    const u32 x = (w << 5) + lane;
-    const bool inx = x < sx;
-    const bool edge = lane == 0 && x > 0;
-    const bool hasz = HASZ && z > 0;
-    const u32 plane = sy * sx;
-    const u32 row0 = z * sy + y0;
-    const u32 off0 = row0 * sx + (inx ? x : 0);   // voxel (x, y0, z); voxels < 2^32
-    u32 idx = row0 * W + w;
-    uint4* __restrict__ MQ = reinterpret_cast<uint4*>(M);
-    u32* __restrict__ RS = M + g.offRS;
-    const T* __restrict__ p = in + off0;           // walks down the column
-    T up = (T)0;
-    if (y0 > 0 && inx) up = *(p - sx);
-    u32 rowbits = 0;                               // bit k: row y0 + k has foreground
-
-    // one row: faces of the 32 voxels c (left neighbour l, -y neighbour up, -z neighbour d)
-    auto step = [&](const T c, const T pe, const T d, const u32 k, const bool store) {
-      T l = shfl_up1(c);
-      if (lane == 0) l = pe;
-      const bool f = E.fg(c);
-      const u32 F = __ballot_sync(CC_FULL, f);
-      const u32 X = __ballot_sync(CC_FULL, E(c, l));
-      const u32 Y = __ballot_sync(CC_FULL, E(c, up));
-      const u32 Z = HASZ ? __ballot_sync(CC_FULL, E(c, d)) : 0u;
-      const u32 ns = __popc(F & ~X);
-      // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
-      if constexpr (MODE == MODE_EQ) epl += ns;
-      else epl += __popc(__ballot_sync(CC_FULL, f && c != l));
-      if (F) rowbits |= 1u << k;
-      if (store && lane == 0) {
-        MQ[idx] = make_uint4(F, X, Y, Z);
-        RS[idx] = ns;
+  if ((w0 + NW) * 32 <= sx) {
+    // ---- fast path: NW full words ----
+    const T* __restrict__ p = in + ((size_t)row0 * sx + (w0 << 5) + lane);
+    const bool noleft = (w0 == 0 && lane == 0);      // voxel x == 0 has no -x neighbour
+    const bool rs_vec = (W & 3) == 0;
+    // three register sets rotate through the roles {row above, current row, row being loaded}
+    T c0[NW], l0[NW], d0[NW], c1[NW], l1[NW], d1[NW], c2[NW], l2[NW], d2[NW];
+    auto load_row = [&](T* cc, T* ll, T* dd, const T* q) {
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        cc[k] = q[32 * k];
+        if (k == 0) { ll[0] = (T)0; if (!noleft) ll[0] = *(q - 1); }
+        else ll[k] = q[32 * k - 1];
+        dd[k] = (T)0;
+        if (hasz) dd[k] = *(q + 32 * k - plane);
       }
-      up = c;
-      idx += W;
     };
-
-    u32 yb = y0;
-    if ((w << 5) + 32 <= sx && yb + CC_FACE_UNR <= y1) {   // warp-uniform: the whole word lies inside the row
-      // full groups of CC_FACE_UNR rows, software pipelined: the unpredicated loads of the next group are
-      // issued before the current group is evaluated
-      T pc[CC_FACE_UNR], pe[CC_FACE_UNR], dc[CC_FACE_UNR];
-      auto load_group = [&](T* a, T* b, T* c, const T* q) {
+    auto eval_row = [&](const T* c, const T* l, const T* d, const T* up) {
+      faces_eval_store<T, MODE, HASZ>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
+      mq += W; rs += W;
+    };
 #pragma unroll
-        for (int k = 0; k < CC_FACE_UNR; k++) {
-          a[k] = q[k * sx];
-          b[k] = (T)0;
-          if (edge) b[k] = *(q + k * sx - 1);
-          c[k] = (T)0;
-          if (hasz) c[k] = *(q + k * sx - plane);
+    for (int k = 0; k < NW; k++) { c2[k] = (T)0; if (y0 > 0) c2[k] = *(p + 32 * k - sx); }
+    load_row(c0, l0, d0, p);
+    u32 r = 0;
+    for (; r + 3 < nrow; r += 3) {
+      const T* p1 = p + sx; const T* p2 = p1 + sx; p = p2 + sx;
+      load_row(c1, l1, d1, p1); eval_row(c0, l0, d0, c2);
+      load_row(c2, l2, d2, p2); eval_row(c1, l1, d1, c0);
+      load_row(c0, l0, d0, p);  eval_row(c2, l2, d2, c1);
+    }
+    const u32 rem = nrow - r;   // 1..3 rows left, the first of them is loaded in set 0
+    if (rem >= 2) load_row(c1, l1, d1, p + sx);
+    eval_row(c0, l0, d0, c2);
+    if (rem >= 2) {
+      if (rem == 3) load_row(c2, l2, d2, p + 2 * (size_t)sx);
+      eval_row(c1, l1, d1, c0);
+      if (rem == 3) eval_row(c2, l2, d2, c1);
+    }
+  } else {
+    // ---- bounds-checked path: words of a group that crosses the end of the row ----
+    const u32 nw = min((u32)NW, W - w0);
+    for (u32 k = 0; k < nw; k++) {
+      const u32 x = ((w0 + k) << 5) + lane;
+      const bool inx = x < sx;
+      const T* __restrict__ p = in + ((size_t)row0 * sx + (inx ? x : 0));
+      T up = (T)0;
+      if (y0 > 0 && inx) up = *(p - sx);
+      for (u32 r = 0; r < nrow; r++) {
+        T c = (T)0, l = (T)0, d = (T)0;
+        if (inx) { c = *p; if (x > 0) l = *(p - 1); if (hasz) d = *(p - plane); }
+        const bool f = E.fg(c);
+        const u32 F = __ballot_sync(CC_FULL, f);
+        const u32 X = __ballot_sync(CC_FULL, E(c, l));
+        const u32 Y = __ballot_sync(CC_FULL, E(c, up));
+        const u32 Z = HASZ ? __ballot_sync(CC_FULL, E(c, d)) : 0u;
+        if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c != l));
+        if (lane == 0) {
+          mq[(size_t)r * W + k] = make_uint4(F, X, Y, Z);
+          rs[(size_t)r * W + k] = __popc(F & ~X);
         }
-      };
-      load_group(pc, pe, dc, p);
-      for (; yb + 2 * CC_FACE_UNR <= y1; yb += CC_FACE_UNR) {
-        T npc[CC_FACE_UNR], npe[CC_FACE_UNR], ndc[CC_FACE_UNR];
-        load_group(npc, npe, ndc, p + CC_FACE_UNR * sx);
-#pragma unroll
-        for (int k = 0; k < CC_FACE_UNR; k++) step(pc[k], pe[k], dc[k], yb - y0 + k, true);
-#pragma unroll
-        for (int k = 0; k < CC_FACE_UNR; k++) { pc[k] = npc[k]; pe[k] = npe[k]; dc[k] = ndc[k]; }
-        p += CC_FACE_UNR * sx;
+        up = c;
+        p += sx;
       }
-#pragma unroll
-      for (int k = 0; k < CC_FACE_UNR; k++) step(pc[k], pe[k], dc[k], yb - y0 + k, true);
-      p += CC_FACE_UNR * sx;
-      yb += CC_FACE_UNR;
-    }
-    // remaining rows, and every row of a partial last word (lanes past sx hold 0)
-    for (; yb < y1; yb++) {
-      T c = (T)0, e = (T)0, d = (T)0;
-      if (inx) { c = *p; if (hasz) d = *(p - plane); }
-      if (edge) e = *(p - 1);
-      step(c, e, d, yb - y0, true);
-      p += sx;
-    }
-    if (rowbits) {
-      anyfg = 1;
-      rfirst = row0 + __ffs(rowbits) - 1;
-      rlast = row0 + 31 - __clz(rowbits);
     }
   }
+  if constexpr (MODE != MODE_EQ) {
+    if (lane == 0 && epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)epl);
+  }
+}
 
-  // block-level reduction of epl and the foreground row range
-  __shared__ u32 s_epl, s_rmin, s_rmax, s_any;
-  if (threadIdx.x == 0) { s_epl = 0; s_rmin = 0xFFFFFFFFu; s_rmax = 0; s_any = 0; }
-  __syncthreads();
-  if (lane == 0 && anyfg) {
-    atomicAdd(&s_epl, epl);
-    atomicMin(&s_rmin, rfirst);
-    atomicMax(&s_rmax, rlast);
-    s_any = 1;
+// ---------------------------------------------------------------------------------------------
+// Kernel A, staged variant (the one that runs when rows are 16-byte aligned and sx is a multiple of 128).
+// Same task decomposition and arithmetic as k_faces, but the rows travel global -> shared memory with
+// cp.async (16 bytes per lane, no registers held while in flight) through a per-warp ring of
+// CC_FACE_STAGES row slots, so the bytes in flight per SM no longer depend on the register budget.
+// Slot layout: [16 B: the 16 bytes left of the group (-x neighbour of its first voxel)][row z][row z-1].
+// ---------------------------------------------------------------------------------------------
+#define CC_FACE_STAGES 4
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T> constexpr size_t faces_async_smem() {
+  return (size_t)CC_FACE_WARPS * CC_FACE_STAGES * (16 + 2 * CC_FACE_NW * 32 * sizeof(T));
+}
+
+template <typename T, int MODE, bool HASZ>
+__global__ void __launch_bounds__(CC_FACE_WARPS * 32)
+k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
+              unsigned nych, unsigned nwg, unsigned ntasks) {
+  constexpr int NW = CC_FACE_NW;
+  constexpr int RB = NW * 32 * (int)sizeof(T);       // bytes of one row of the group
+  constexpr int SLOT = 16 + 2 * RB;
+  extern __shared__ __align__(16) unsigned char face_smem[];
+  const int lane = threadIdx.x & 31;
+  const unsigned task = blockIdx.x * CC_FACE_WARPS + (threadIdx.x >> 5);
+  if (task >= ntasks) return;
+  unsigned char* ring = face_smem + (size_t)(threadIdx.x >> 5) * CC_FACE_STAGES * SLOT;
+  const u32 W = (u32)g.W, sx = (u32)g.sx, sy = (u32)g.sy;
+  const u32 wg = task % nwg;
+  const u32 t = task / nwg;
+  const u32 ych = t % nych, z = t / nych;
+  const u32 y0 = ych * CC_FACE_YCH;
+  const u32 nrow = min(sy, y0 + CC_FACE_YCH) - y0;
+  const u32 w0 = wg * NW;
+  const bool hasz = HASZ && z > 0;
+  const bool hasleft = w0 > 0;
+  const size_t rowbytes = (size_t)sx * sizeof(T);
+  const size_t planebytes = (size_t)sy * rowbytes;
+  const u32 row0 = z * sy + y0;
+  uint4* __restrict__ mq = reinterpret_cast<uint4*>(M) + ((size_t)row0 * W + w0);
+  u32* __restrict__ rs = M + g.offRS + ((size_t)row0 * W + w0);
+  const bool rs_vec = (W & 3) == 0;
+  u32 epl = 0;
+  const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(in + ((size_t)row0 * sx + (w0 << 5)));   // next row to issue
+  u32 issued = 0;
+  auto issue = [&](unsigned char* slot) {
+    if (issued < nrow) {
+#pragma unroll
+      for (int off = 0; off < RB; off += 512) {
+        const int o = off + lane * 16;
+        if (RB >= 512 || o < RB) {
+          cp_async16(slot + 16 + o, gsrc + o);
+          if (hasz) cp_async16(slot + 16 + RB + o, gsrc - planebytes + o);
+        }
+      }
+      if (lane == 0 && hasleft) cp_async16(slot, gsrc - 16);
+      gsrc += rowbytes;
+      issued++;
+    }
+    cp_async_commit();
+  };
+  T up[NW];
+  {
+    const T* p = in + ((size_t)row0 * sx + (w0 << 5) + lane);
+#pragma unroll
+    for (int k = 0; k < NW; k++) { up[k] = (T)0; if (y0 > 0) up[k] = *(p + 32 * k - sx); }
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && s_any) {
-    if (s_epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)s_epl);
-    atomicMin((long long*)&ctr->first_row, (long long)s_rmin);
-    atomicMax((long long*)&ctr->last_row, (long long)s_rmax);
+  // slots keep zeros where nothing is ever copied: the left pad of the first group, row z-1 of plane 0
+  if (!hasleft || (HASZ && !hasz)) {
+#pragma unroll
+    for (int s = 0; s < CC_FACE_STAGES; s++) {
+      if (!hasleft && lane == 0) *reinterpret_cast<uint4*>(ring + s * SLOT) = make_uint4(0u, 0u, 0u, 0u);
+      if (HASZ && !hasz)
+        for (int o = lane * 16; o < RB; o += 512) *reinterpret_cast<uint4*>(ring + s * SLOT + 16 + RB + o) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int s = 0; s < CC_FACE_STAGES - 1; s++) issue(ring + s * SLOT);
+  for (u32 r = 0; r < nrow; r += CC_FACE_STAGES) {
+#pragma unroll
+    for (int s = 0; s < CC_FACE_STAGES; s++) {
+      if (r + s < nrow) {
+        issue(ring + ((s + CC_FACE_STAGES - 1) % CC_FACE_STAGES) * SLOT);
+        cp_async_wait<CC_FACE_STAGES - 1>();
+        __syncwarp();
+        const T* sc = reinterpret_cast<const T*>(ring + s * SLOT + 16);
+        const T* sd = reinterpret_cast<const T*>(ring + s * SLOT + 16 + RB);
+        T c[NW], l[NW], d[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+          c[k] = sc[32 * k + lane];
+          l[k] = sc[32 * k + lane - 1];
+          d[k] = HASZ ? sd[32 * k + lane] : (T)0;
+        }
+        faces_eval_store<T, MODE, HASZ>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
+        mq += W; rs += W;
+#pragma unroll
+        for (int k = 0; k < NW; k++) up[k] = c[k];
+      }
+    }
+  }
+  if constexpr (MODE != MODE_EQ) {
+    if (lane == 0 && epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)epl);
   }
 }
 

@@ -37,21 +37,45 @@ k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, con
 // C2 / S: exclusive scan of u32 counts, three small kernels (block reduce, scan of block sums, apply).
 // The length is either a host value or derived from a device-side count (see dev_len); the kernels
 // loop over 4096-element chunks, so the grid does not depend on the length.
+// track != nullptr (scan S): also reduces the first / last row that has a run start (= any foreground)
+// into track->first_row / last_row; W = bitmap words per row.
 __global__ void __launch_bounds__(CC_SCAN_THREADS)
-k_scan_reduce(const u32* __restrict__ cnt, u64* __restrict__ bsum, i64 n_host, const u64* __restrict__ n_dev, int shift) {
+k_scan_reduce(const u32* __restrict__ cnt, u64* __restrict__ bsum, i64 n_host, const u64* __restrict__ n_dev, int shift,
+              Counters* __restrict__ track, u32 W) {
   const u32 n = dev_len(n_host, n_dev, shift);
   const u32 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  u32 imin = 0xFFFFFFFFu, imax = 0;
+  bool any = false;
   for (u32 blk = blockIdx.x; blk < nb; blk += gridDim.x) {
     const u32 base = blk * CC_SCAN_CHUNK;
     u32 s = 0;
 #pragma unroll
     for (int k = 0; k < CC_SCAN_ITEMS; k++) {
       const u32 i = base + k * CC_SCAN_THREADS + threadIdx.x;
-      if (i < n) s += cnt[i];
+      if (i < n) {
+        const u32 v = cnt[i];
+        s += v;
+        if (track && v) { imin = min(imin, i); imax = i; any = true; }
+      }
     }
     u32 tot;
     block_exclusive_scan(s, &tot);
     if (threadIdx.x == 0) bsum[blk] = tot;
+  }
+  if (track) {   // block-uniform; one pair of global atomics per block
+    __shared__ u32 s_min, s_max;
+    if (threadIdx.x == 0) { s_min = 0xFFFFFFFFu; s_max = 0; }
+    __syncthreads();
+    if (__ballot_sync(CC_FULL, any)) {
+      imin = __reduce_min_sync(CC_FULL, imin);
+      imax = __reduce_max_sync(CC_FULL, imax);
+      if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, imin); atomicMax(&s_max, imax); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_min != 0xFFFFFFFFu) {
+      atomicMin((long long*)&track->first_row, (long long)(s_min / W));
+      atomicMax((long long*)&track->last_row, (long long)(s_max / W));
+    }
   }
 }
 
