@@ -26,6 +26,24 @@ template <typename T> int run_union_stage(const LabelArgs& a);     // kernel B
 template <typename T> int run_periodic_stage(const LabelArgs& a);  // kernel P (after kernel B)
 
 #ifdef CC3D_INSTANTIATE
+template <typename T, int MODE, int NW>
+static void launch_faces_staged(const LabelArgs& a, const Edge<T, MODE>& E, bool two_d, unsigned nych) {
+  const Geom& g = a.g;
+  const unsigned nwg = (unsigned)(g.W / NW);
+  const i64 ntasks = (i64)nwg * nych * g.sz;
+  const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
+  const T* in = static_cast<const T*>(a.in);
+  constexpr size_t smem = faces_async_smem<T, NW>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_faces_async<T, MODE, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_faces_async<T, MODE, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  if (two_d) k_faces_async<T, MODE, false, NW><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+  else k_faces_async<T, MODE, true, NW><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+}
+
 template <typename T, int MODE>
 static int launch_faces(const LabelArgs& a) {
   Edge<T, MODE> E;
@@ -34,27 +52,21 @@ static int launch_faces(const LabelArgs& a) {
   const bool two_d = a.connectivity == 4 || a.connectivity == 8;
   if (two_d && g.sz != 1) return -1;
   const unsigned nych = (unsigned)((g.sy + CC_FACE_YCH - 1) / CC_FACE_YCH);
-  const unsigned nwg = (unsigned)((g.W + CC_FACE_NW - 1) / CC_FACE_NW);
-  const i64 ntasks = (i64)nwg * nych * g.sz;
-  const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
   const T* in = static_cast<const T*>(a.in);
-  // staged (cp.async) variant: every group of CC_FACE_NW words lies inside the row and every row is 16-byte aligned
-  const bool staged = (g.sx % (32 * CC_FACE_NW)) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0
+  // staged (cp.async) variants: every group of NW words lies inside the row and every row is 16-byte aligned
+  bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
 #ifdef CC_FACES_NO_ASYNC
-                      && false
+  aligned = false;
 #endif
-      ;
-  if (staged) {
-    constexpr size_t smem = faces_async_smem<T>();
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_faces_async<T, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_faces_async<T, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
-    }
-    if (two_d) k_faces_async<T, MODE, false><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
-    else k_faces_async<T, MODE, true><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
-  } else {
+#ifdef CC_FACES_NW8
+  if (aligned && g.sx % 256 == 0 && sizeof(T) <= 4) launch_faces_staged<T, MODE, 8>(a, E, two_d, nych);
+  else
+#endif
+  if (aligned && g.sx % 128 == 0) launch_faces_staged<T, MODE, 4>(a, E, two_d, nych);
+  else {
+    const unsigned nwg = (unsigned)((g.W + CC_FACE_NW - 1) / CC_FACE_NW);
+    const i64 ntasks = (i64)nwg * nych * g.sz;
+    const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
     if (two_d) k_faces<T, MODE, false><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
     else k_faces<T, MODE, true><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
   }

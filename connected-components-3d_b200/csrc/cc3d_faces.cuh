@@ -3,16 +3,19 @@
 #pragma once
 #include "cc3d_common.cuh"
 
+#ifndef CC_FACE_WARPS
 #define CC_FACE_WARPS 8
+#endif
+#ifndef CC_FACE_YCH
 #define CC_FACE_YCH 32   // rows of one plane a warp walks through
+#endif
 #define CC_FACE_NW 4     // bitmap words (of one row) a warp handles per row step
 
 // Faces of one row of CC_FACE_NW words (c: voxels, l: -x neighbours, d: -z neighbours, up: -y neighbours);
 // lane 0 stores the group's four {F,X,Y,Z} and run-start counts.
-template <typename T, int MODE, bool HASZ>
+template <typename T, int MODE, bool HASZ, int NW>
 __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T* c, const T* l, const T* d, const T* up,
                                                  int lane, uint4* __restrict__ mq, u32* __restrict__ rs, bool rs_vec, u32& epl) {
-  constexpr int NW = CC_FACE_NW;
   u32 F[NW], X[NW], Y[NW], Z[NW];
 #pragma unroll
   for (int k = 0; k < NW; k++) {
@@ -27,8 +30,11 @@ __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < NW; k++) mq[k] = make_uint4(F[k], X[k], Y[k], Z[k]);
-    if (rs_vec) *reinterpret_cast<uint4*>(rs) = make_uint4(__popc(F[0] & ~X[0]), __popc(F[1] & ~X[1]), __popc(F[2] & ~X[2]), __popc(F[3] & ~X[3]));
-    else {
+    if (rs_vec) {
+#pragma unroll
+      for (int k = 0; k < NW; k += 4)
+        reinterpret_cast<uint4*>(rs)[k >> 2] = make_uint4(__popc(F[k] & ~X[k]), __popc(F[k + 1] & ~X[k + 1]), __popc(F[k + 2] & ~X[k + 2]), __popc(F[k + 3] & ~X[k + 3]));
+    } else {
 #pragma unroll
       for (int k = 0; k < NW; k++) rs[k] = __popc(F[k] & ~X[k]);
     }
@@ -86,7 +92,7 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
       }
     };
     auto eval_row = [&](const T* c, const T* l, const T* d, const T* up) {
-      faces_eval_store<T, MODE, HASZ>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
+      faces_eval_store<T, MODE, HASZ, NW>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
       mq += W; rs += W;
     };
 #pragma unroll
@@ -146,7 +152,9 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
 // CC_FACE_STAGES row slots, so the bytes in flight per SM no longer depend on the register budget.
 // Slot layout: [16 B: the 16 bytes left of the group (-x neighbour of its first voxel)][row z][row z-1].
 // ---------------------------------------------------------------------------------------------
+#ifndef CC_FACE_STAGES
 #define CC_FACE_STAGES 4
+#endif
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
@@ -154,15 +162,14 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename T> constexpr size_t faces_async_smem() {
-  return (size_t)CC_FACE_WARPS * CC_FACE_STAGES * (16 + 2 * CC_FACE_NW * 32 * sizeof(T));
+template <typename T, int NW> constexpr size_t faces_async_smem() {
+  return (size_t)CC_FACE_WARPS * CC_FACE_STAGES * (16 + 2 * NW * 32 * sizeof(T));
 }
 
-template <typename T, int MODE, bool HASZ>
+template <typename T, int MODE, bool HASZ, int NW>
 __global__ void __launch_bounds__(CC_FACE_WARPS * 32)
 k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
               unsigned nych, unsigned nwg, unsigned ntasks) {
-  constexpr int NW = CC_FACE_NW;
   constexpr int RB = NW * 32 * (int)sizeof(T);       // bytes of one row of the group
   constexpr int SLOT = 16 + 2 * RB;
   extern __shared__ __align__(16) unsigned char face_smem[];
@@ -187,22 +194,17 @@ k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MOD
   const bool rs_vec = (W & 3) == 0;
   u32 epl = 0;
   const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(in + ((size_t)row0 * sx + (w0 << 5)));   // next row to issue
-  u32 issued = 0;
   auto issue = [&](unsigned char* slot) {
-    if (issued < nrow) {
 #pragma unroll
-      for (int off = 0; off < RB; off += 512) {
-        const int o = off + lane * 16;
-        if (RB >= 512 || o < RB) {
-          cp_async16(slot + 16 + o, gsrc + o);
-          if (hasz) cp_async16(slot + 16 + RB + o, gsrc - planebytes + o);
-        }
+    for (int off = 0; off < RB; off += 512) {
+      const int o = off + lane * 16;
+      if (RB >= 512 || o < RB) {
+        cp_async16(slot + 16 + o, gsrc + o);
+        if (hasz) cp_async16(slot + 16 + RB + o, gsrc - planebytes + o);
       }
-      if (lane == 0 && hasleft) cp_async16(slot, gsrc - 16);
-      gsrc += rowbytes;
-      issued++;
     }
-    cp_async_commit();
+    if (lane == 0 && hasleft) cp_async16(slot, gsrc - 16);
+    gsrc += rowbytes;
   };
   T up[NW];
   {
@@ -220,28 +222,49 @@ k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MOD
     }
     __syncwarp();
   }
+  auto eval_slot = [&](const unsigned char* slot) {
+    const T* sc = reinterpret_cast<const T*>(slot + 16);
+    const T* sd = reinterpret_cast<const T*>(slot + 16 + RB);
+    T c[NW], l[NW], d[NW];
 #pragma unroll
-  for (int s = 0; s < CC_FACE_STAGES - 1; s++) issue(ring + s * SLOT);
-  for (u32 r = 0; r < nrow; r += CC_FACE_STAGES) {
+    for (int k = 0; k < NW; k++) {
+      c[k] = sc[32 * k + lane];
+      l[k] = sc[32 * k + lane - 1];
+      d[k] = HASZ ? sd[32 * k + lane] : (T)0;
+    }
+    faces_eval_store<T, MODE, HASZ, NW>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
+    mq += W; rs += W;
+#pragma unroll
+    for (int k = 0; k < NW; k++) up[k] = c[k];
+  };
+  u32 issued = 0;
+#pragma unroll
+  for (int s = 0; s < CC_FACE_STAGES - 1; s++) {
+    if (issued < nrow) { issue(ring + s * SLOT); issued++; }
+    cp_async_commit();
+  }
+  u32 r = 0;
+  // full trips: every row of the trip exists and so does the row issued CC_FACE_STAGES-1 ahead of it
+  for (; r + 2 * CC_FACE_STAGES - 1 <= nrow; r += CC_FACE_STAGES) {
+#pragma unroll
+    for (int s = 0; s < CC_FACE_STAGES; s++) {
+      issue(ring + ((s + CC_FACE_STAGES - 1) % CC_FACE_STAGES) * SLOT);
+      cp_async_commit();
+      cp_async_wait<CC_FACE_STAGES - 1>();
+      __syncwarp();
+      eval_slot(ring + s * SLOT);
+    }
+  }
+  issued = r + CC_FACE_STAGES - 1;
+  for (; r < nrow; r += CC_FACE_STAGES) {
 #pragma unroll
     for (int s = 0; s < CC_FACE_STAGES; s++) {
       if (r + s < nrow) {
-        issue(ring + ((s + CC_FACE_STAGES - 1) % CC_FACE_STAGES) * SLOT);
+        if (issued < nrow) { issue(ring + ((s + CC_FACE_STAGES - 1) % CC_FACE_STAGES) * SLOT); issued++; }
+        cp_async_commit();
         cp_async_wait<CC_FACE_STAGES - 1>();
         __syncwarp();
-        const T* sc = reinterpret_cast<const T*>(ring + s * SLOT + 16);
-        const T* sd = reinterpret_cast<const T*>(ring + s * SLOT + 16 + RB);
-        T c[NW], l[NW], d[NW];
-#pragma unroll
-        for (int k = 0; k < NW; k++) {
-          c[k] = sc[32 * k + lane];
-          l[k] = sc[32 * k + lane - 1];
-          d[k] = HASZ ? sd[32 * k + lane] : (T)0;
-        }
-        faces_eval_store<T, MODE, HASZ>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
-        mq += W; rs += W;
-#pragma unroll
-        for (int k = 0; k < NW; k++) up[k] = c[k];
+        eval_slot(ring + s * SLOT);
       }
     }
   }
