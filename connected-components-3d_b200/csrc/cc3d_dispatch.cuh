@@ -90,10 +90,17 @@ static int launch_union(const LabelArgs& a) {
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
-  const size_t smem = (size_t)(CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * CC_TILE_GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2) * 4;
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+  if constexpr (MODE == MODE_DELTA) {
+    // continuous predicate: edge-parallel item lists (every word has candidates that need a value test)
+    const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
+    if (!attr_set) { cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_union_tile_items<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+  } else {
+    const size_t smem = (size_t)(CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * CC_TILE_GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2) * 4;
+    if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+  }
   if (a.mark) a.mark("B1_union_tile", a.stream);
   k_union_queue<<<CC_QUEUE_BLOCKS * 4, 256, 0, a.stream>>>(a.L, a.GQ);
   k_union_global<T, MODE, CONN><<<CC_QUEUE_BLOCKS, 256, 0, a.stream>>>(in, a.M, a.L, g, E, a.GQ.ovf);

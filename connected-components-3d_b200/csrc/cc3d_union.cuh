@@ -131,9 +131,12 @@ struct WordEdges {
     return any != 0;
   }
 
-  template <typename EMIT>
-  __device__ __forceinline__ void diagonals(EMIT&& emit) const {
-    if constexpr (!DIAG0) return;
+  // candidate masks of the diagonal directions: 0 A0, 1 C0, 2 A1, 3 C1, 4 B2, 5 A2, 6 C2, 7 B3, 8 A3, 9 C3
+  // (bit b: voxel b of this word may be joined to its neighbour in that direction); false = all empty
+  __device__ __forceinline__ bool diag_masks(u32* m) const {
+#pragma unroll
+    for (int t = 0; t < 10; t++) m[t] = 0;
+    if constexpr (!DIAG0) return false;
     const Q4 Z4 = {0u, 0u, 0u, 0u};
     auto sh3 = [](u32 c, u32 lw, u32 rw) -> S3 { S3 s; s.c = c; s.l = (c << 1) | (lw >> 31); s.r = (c >> 1) | (rw << 31); return s; };
     auto row3 = [&](u32 j) -> R3 {
@@ -144,16 +147,12 @@ struct WordEdges {
       o.F = sh3(c.F, l.F, r.F); o.X = sh3(c.X, l.X, r.X); o.Y = sh3(c.Y, l.Y, r.Y); o.Z = sh3(c.Z, l.Z, r.Z);
       return o;
     };
-    // candidate masks: 0 A0, 1 C0, 2 A1, 3 C1, 4 B2, 5 A2, 6 C2, 7 B3, 8 A3, 9 C3
-    u32 m[10];
-#pragma unroll
-    for (int t = 0; t < 10; t++) m[t] = 0;
     if constexpr (MODE == MODE_MASK) {
       if (hasU) { m[0] = __ldg(M + g.offA0 + i); m[1] = __ldg(M + g.offC0 + i); }
     } else {
       const bool want0 = hasU && (!TRANS || (P.F & ~P.Y));
       const bool wantz = DIAGZ && hasD && (!TRANS || (P.F & ~P.Z));
-      if (!want0 && !wantz) return;
+      if (!want0 && !wantz) return false;
       const Q4 Pr = hasR ? ldq(M, i + 1) : Z4;
       const S3 Xp = sh3(P.X, Pl.X, Pr.X), Yp = sh3(P.Y, Pl.Y, Pr.Y), Zp = sh3(P.Z, Pl.Z, Pr.Z);
       const u32 Fp = P.F;
@@ -224,6 +223,16 @@ struct WordEdges {
         }
       }
     }
+    u32 any = 0;
+#pragma unroll
+    for (int t = 0; t < 10; t++) any |= m[t];
+    return any != 0;
+  }
+
+  template <typename EMIT>
+  __device__ __forceinline__ void diagonals(EMIT&& emit) const {
+    u32 m[10];
+    if (!diag_masks(m)) return;
     // one loop over the voxels that have any candidate (instead of one divergent loop per direction)
     u32 any = 0;
 #pragma unroll
@@ -432,6 +441,232 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
     const int n = __popc(fx.x & ~fx.y);
     if (n == 0) continue;
     const u32 g0 = __ldg(RS + i);
+    if (!tile_ok) { for (int k = 0; k < n; k++) L[g0 + k] = g0 + k; continue; }
+    const u32 l0 = (r << capl) + (g0 - segRS[r]);
+    for (int k = 0; k < n; k++) {
+      u32 l = l0 + k, p;
+      while ((p = lab[l]) != l) l = p;
+      L[g0 + k] = segRS[l >> capl] + (l & ((1u << capl) - 1u));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel B1, item-list variant (used for the continuous predicate, where every word has diagonal candidates
+// whose value test is expensive and diverges inside a per-word loop). One CTA per union tile (2^tw words x 2^ty rows x 2^tz planes = CC_TILE_WORDS words).
+// A run belongs to the tile its first voxel lies in; an edge is tile-local when both of its runs belong
+// to the tile. The runs that start in a tile row segment (2^tw words of one row) have contiguous ids
+// from RS[first word] on, so local node = segment * cap + (run id - first id of the segment) keeps the
+// raster order of the runs (link-to-smaller stays valid) and converts back with one table lookup.
+//
+// Work is split into a word-parallel part and an edge-parallel part so that neither diverges:
+//   pre-pass : run starts and first run id of every word of the tile -> shared memory (wS, wR)
+//   enumerate: one thread per word computes edge MASKS with whole-word logic (round 0: the straight edges
+//              left by the x / square rules; round 1: diagonal candidates of the words flagged in round 0)
+//              and expands them into 18-bit work items (word, direction, bit) in a shared-memory list
+//              (slots reserved with one warp scan + one atomic per warp)
+//   resolve  : one thread per item: run ids of both ends from wS/wR (global bitmaps when the neighbour lies
+//              outside the tile), value test for EQ / DELTA candidates, then union in the 16-bit
+//              shared-memory forest, or - for edges that leave the tile - a staging buffer that is
+//              appended to the global edge queue GQ for kernel B2.
+// Finally every run of the tile gets L[run] = run id of its tile root.
+// A tile whose rows hold more than 16 runs per word (possible for multilabel input only) sends all its
+// edges to B2. If GQ overflows, *ovf is raised and kernel B2s redoes every edge on the global forest.
+// ---------------------------------------------------------------------------------------------
+#define CC_TILE_ITEMS 4096    // work items per enumerate step (256 words)
+#define CC_TILE_SMEM_WORDS (CC_TILE_NODES / 2 + CC_TILE_ITEMS + 2 * CC_TILE_GQ + 3 * CC_TILE_WORDS + CC_TILE_WORDS / 2)
+
+template <typename T, int MODE, int CONN>
+__global__ void __launch_bounds__(256)
+k_union_tile_items(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
+             u32 ntx, u32 nty, EdgeQueue GQ) {
+  extern __shared__ __align__(16) u32 smem_u32[];
+  uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [CC_TILE_NODES] 16-bit parents
+  u32* items = smem_u32 + CC_TILE_NODES / 2;               // [CC_TILE_ITEMS]
+  u64* gq = reinterpret_cast<u64*>(items + CC_TILE_ITEMS); // [CC_TILE_GQ] edges that leave the tile
+  u32* segRS = items + CC_TILE_ITEMS + 2 * CC_TILE_GQ;     // [CC_TILE_WORDS] first run id of every row segment
+  u32* wS = segRS + CC_TILE_WORDS;                         // [CC_TILE_WORDS] run starts of every word
+  u32* wR = wS + CC_TILE_WORDS;                            // [CC_TILE_WORDS] id of the first run that starts in the word, minus 1
+  uint16_t* todo = reinterpret_cast<uint16_t*>(wR + CC_TILE_WORDS);   // [CC_TILE_WORDS]
+  __shared__ u32 s_in[2], s_gn, s_gbase, s_tn, s_big;   // s_in: item counters of the current / next enumerate step
+  const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz, sx = (u32)g.sx;
+  const u32 TW = 1u << g.tw, TY = 1u << g.ty;
+  const u32 nseg = CC_TILE_WORDS >> g.tw;        // TY * TZ
+  const u32 capl = g.tw + 4;                     // log2(runs a segment can hold locally)
+  u32 t = blockIdx.x;
+  const u32 bx = t % ntx; t /= ntx;
+  const u32 by = t % nty;
+  const u32 bz = t / nty;
+  const u32 w0 = bx << g.tw, y0 = by << g.ty, z0 = bz << g.tz;
+  const u32 wend = min(w0 + TW, W);
+  const u32* __restrict__ RS = M + g.offRS;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) { s_in[0] = 0; s_in[1] = 0; s_gn = 0; s_tn = 0; s_big = 0; }
+  __syncthreads();
+  for (u32 r = threadIdx.x; r < nseg; r += blockDim.x) {
+    const u32 y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+    u32 first = 0xFFFFFFFFu;
+    if (y < sy && z < sz) {
+      const u32 j = (z * sy + y) * W;
+      first = __ldg(RS + j + w0);
+      if (__ldg(RS + j + wend) - first > (1u << capl)) s_big = 1;   // multilabel rows with > 16 runs per word
+    }
+    segRS[r] = first;
+  }
+  for (u32 q = threadIdx.x; q < CC_TILE_WORDS; q += blockDim.x) {
+    const u32 wx = q & (TW - 1), r = q >> g.tw;
+    const u32 w = w0 + wx, y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+    u32 st = 0, rid = 0;
+    if (w < W && y < sy && z < sz) {
+      const u32 i = (z * sy + y) * W + w;
+      const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)i);
+      st = fx.x & ~fx.y;
+      rid = __ldg(RS + i) - 1u;
+    }
+    wS[q] = st; wR[q] = rid;
+  }
+  for (u32 k = threadIdx.x; k < CC_TILE_NODES / 2; k += blockDim.x) smem_u32[k] = (2 * k) | ((2 * k + 1) << 16);
+  __syncthreads();
+  const bool tile_ok = s_big == 0;   // otherwise every edge of this tile goes to kernel B2
+
+  auto push_global = [&](u32 gp, u32 gq_) {
+    const u32 pos = atomicAdd(GQ.count, 1u);
+    if (pos < GQ.cap) GQ.q[pos] = (u64)gp | ((u64)gq_ << 32);
+    else *GQ.ovf = 1u;
+  };
+
+  // direction table: 0 Y (0,-1,0), 1 Z (0,0,-1), then the ten diagonal directions of WordEdges::diag_masks;
+  // two bits per direction: d + 1
+  constexpr u32 DXP = (1u << 0) | (1u << 2) | (0u << 4) | (2u << 6) | (0u << 8) | (2u << 10) | (1u << 12) | (0u << 14) | (2u << 16) | (1u << 18) | (0u << 20) | (2u << 22);
+  constexpr u32 DYP = (0u << 0) | (1u << 2) | (0u << 4) | (0u << 6) | (1u << 8) | (1u << 10) | (0u << 12) | (0u << 14) | (0u << 16) | (2u << 18) | (2u << 20) | (2u << 22);
+  constexpr u32 DZP = (1u << 0) | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (0u << 10) | (0u << 12) | (0u << 14) | (0u << 16) | (0u << 18) | (0u << 20) | (0u << 22);
+
+  // one edge: word q of the tile, direction t, voxel b of the word
+  auto resolve = [&](const u32 item) {
+    const u32 b = item & 31u, tdir = (item >> 5) & 15u, q = item >> 9;
+    const u32 wx = q & (TW - 1), r = q >> g.tw;
+    const int ly = (int)(r & (TY - 1)), lz = (int)(r >> g.ty);
+    const int dx = (int)((DXP >> (2 * tdir)) & 3u) - 1, dy = (int)((DYP >> (2 * tdir)) & 3u) - 1, dz = (int)((DZP >> (2 * tdir)) & 3u) - 1;
+    const u32 gp = wR[q] + __popc(wS[q] & (CC_FULL >> (31 - b)));
+    const int xl = (int)((wx << 5) + b) + dx;            // x of q relative to the tile
+    const int lyq = ly + dy, lzq = lz + dz;
+    const bool inside = xl >= 0 && xl < (int)(TW << 5) && lyq >= 0 && lyq < (int)TY && lzq >= 0;
+    const u32 rowP = (z0 + lz) * sy + y0 + ly;
+    const u32 rowQ = (u32)((int)rowP + dy + dz * (int)sy);
+    const u32 xq = (u32)((int)((w0 << 5)) + xl);
+    if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA) {
+      if (tdir >= 2) {   // diagonal candidate: test the predicate on the two voxel values
+        if (!E(in[(size_t)rowP * sx + ((w0 + wx) << 5) + b], in[(size_t)rowQ * sx + xq])) return;
+      }
+    }
+    u32 gq_, rq = 0;
+    if (inside) {
+      rq = ((u32)lzq << g.ty) + (u32)lyq;
+      const u32 qq = (rq << g.tw) + ((u32)xl >> 5);
+      gq_ = wR[qq] + __popc(wS[qq] & (CC_FULL >> (31 - (xl & 31))));
+    } else {
+      gq_ = run_id(M, g, rowQ * W, xq);
+    }
+    bool local = tile_ok && inside && gp >= segRS[r];
+    if (local) local = gq_ >= segRS[rq];
+    if (local) {
+      sm_union16(lab, (r << capl) + (gp - segRS[r]), (rq << capl) + (gq_ - segRS[rq]));
+    } else {
+      const u32 pos = atomicAdd(&s_gn, 1u);
+      if (pos < CC_TILE_GQ) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+      else push_global(gp, gq_);
+    }
+  };
+
+  WordEdges<T, MODE, CONN> we(in, M, g, E);
+  u32 par = 0;   // which item counter this step uses
+#pragma unroll 1
+  for (int round = 0; round < 2; round++) {
+    // ---- round 0 = straight edges of every word, round 1 = diagonals of the to-do words ----
+    const u32 nwords_round = round == 0 ? (u32)CC_TILE_WORDS : s_tn;
+#pragma unroll 1
+    for (u32 base = 0; base < nwords_round; base += blockDim.x, par ^= 1u) {
+      // -- enumerate: masks of one word per thread --
+      const u32 e = base + threadIdx.x;
+      u32 m[12];
+#pragma unroll
+      for (int k = 0; k < 12; k++) m[k] = 0;
+      u32 q = 0;
+      if (e < nwords_round) {
+        q = round == 0 ? e : (u32)todo[e];
+        const u32 wx = q & (TW - 1), r = q >> g.tw;
+        const u32 w = w0 + wx, y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+        if (w < W && y < sy && z < sz) {
+          const u32 row = z * sy + y;
+          if (we.load(row * W + w, row, w, y, z)) {
+            if (round == 0) {
+              m[0] = we.need_y();
+              m[1] = we.need_z();
+              if (we.may_have_diagonals()) todo[atomicAdd(&s_tn, 1u)] = (uint16_t)q;
+            } else {
+              we.diag_masks(m + 2);
+            }
+          }
+        }
+      }
+      // -- expand the masks into work items; slots: warp scan + one atomic per warp --
+      u32 n = 0;
+#pragma unroll
+      for (int k = 0; k < 12; k++) n += __popc(m[k]);
+      u32 inc = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(CC_FULL, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const u32 wtot = __shfl_sync(CC_FULL, inc, 31);
+      u32 wbase = 0;
+      if (wtot) {
+        if (lane == 31) wbase = atomicAdd(&s_in[par], wtot);
+        wbase = __shfl_sync(CC_FULL, wbase, 31);
+      }
+      u32 pos = wbase + inc - n;
+      if (n) {
+        const u32 qb = q << 9;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+          u32 mk = m[k];
+          while (mk) {
+            const u32 b = __ffs(mk) - 1; mk &= mk - 1;
+            const u32 item = qb | ((u32)k << 5) | b;
+            if (pos < CC_TILE_ITEMS) items[pos] = item;
+            else resolve(item);          // list full: resolve in place
+            pos++;
+          }
+        }
+      }
+      __syncthreads();
+      // -- resolve: one item per thread and step --
+      const u32 ni = min(s_in[par], (u32)CC_TILE_ITEMS);
+      if (threadIdx.x == 0) s_in[par ^ 1u] = 0;   // last read before the previous step's second barrier
+      for (u32 k = threadIdx.x; k < ni; k += blockDim.x) resolve(items[k]);
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+
+  // ---- staged edges -> global queue; runs -> tile roots ----
+  const u32 gn = min(s_gn, (u32)CC_TILE_GQ);
+  if (threadIdx.x == 0 && gn) s_gbase = atomicAdd(GQ.count, gn);
+  __syncthreads();
+  for (u32 e = threadIdx.x; e < gn; e += blockDim.x) {
+    const u32 pos = s_gbase + e;
+    if (pos < GQ.cap) GQ.q[pos] = gq[e];
+    else *GQ.ovf = 1u;
+  }
+#pragma unroll 1
+  for (u32 q = threadIdx.x; q < CC_TILE_WORDS; q += blockDim.x) {
+    u32 st = wS[q];
+    if (!st) continue;
+    const u32 r = q >> g.tw;
+    const u32 g0 = wR[q] + 1u;
+    const int n = __popc(st);
     if (!tile_ok) { for (int k = 0; k < n; k++) L[g0 + k] = g0 + k; continue; }
     const u32 l0 = (r << capl) + (g0 - segRS[r]);
     for (int k = 0; k < n; k++) {
