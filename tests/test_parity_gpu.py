@@ -38,7 +38,7 @@ def _truth(oracle_mod):
   return ref if ref is not None else oracle_mod
 
 
-def _fuzz(cc3d, truth, seed, ncase, maxdim):
+def _fuzz(cc3d, truth, seed, ncase, maxdim, wide=False):
   rng = np.random.default_rng(seed)
   dtypes = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64, np.float32, np.float64, bool]
   checked = 0
@@ -49,6 +49,13 @@ def _fuzz(cc3d, truth, seed, ncase, maxdim):
       shape = (int(rng.integers(1, 400)), int(rng.integers(1, 400)))
     dt = dtypes[rng.integers(len(dtypes))]
     order = "F" if rng.random() < 0.5 else "C"
+    if wide:
+      # long fast axis: full-width union tiles (16 words) with staged halos; multiples of 128 take the staged
+      # (cp.async) face kernel, the others its bounds-checked path
+      dims = int(rng.integers(2, 4))
+      fast = int(rng.choice([128, 256, 384, 512, 640, 500, 530, 700, int(rng.integers(130, 720))]))
+      rest = (int(rng.integers(1, 40)),) if dims == 2 else (int(rng.integers(1, 22)), int(rng.integers(1, 14)))
+      shape = (fast,) + rest if order == "F" else rest[::-1] + (fast,)
     nvals = int(rng.integers(2, 6))
     if dt == bool:
       x = rng.random(shape) < rng.random()
@@ -93,6 +100,11 @@ def test_differential_fuzz_small(cc3d, oracle_mod):
 def test_differential_fuzz_seams(cc3d, oracle_mod):
   """Shapes that cross several 64x8x8 tiles in every axis."""
   assert _fuzz(cc3d, _truth(oracle_mod), seed=202, ncase=150, maxdim=150) > 100
+
+
+def test_differential_fuzz_wide(cc3d, oracle_mod):
+  """Rows of 128..720 voxels: the staged face kernel, full-width union tiles with staged halos, partial last words."""
+  assert _fuzz(cc3d, _truth(oracle_mod), seed=505, ncase=160, maxdim=24, wide=True) > 120
 
 
 def test_c_oracle_agrees_too(cc3d, oracle_mod):
