@@ -56,6 +56,12 @@ def lib():
   L.cc3d_b200_label_write_rows.argtypes = [vp, i64, i64, vp, ci, vp]
   L.cc3d_b200_label_write_remap.restype = ci
   L.cc3d_b200_label_write_remap.argtypes = [vp, vp, ci, u64, vp, ci, ci, vp]
+  L.cc3d_b200_slab_begin.restype = ci
+  L.cc3d_b200_slab_begin.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, vp, p(vp), vp, vp, vp]
+  L.cc3d_b200_face_pairs_async.restype = ci
+  L.cc3d_b200_face_pairs_async.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ci, vp, u64, vp, vp]
+  L.cc3d_b200_slab_finish.restype = ci
+  L.cc3d_b200_slab_finish.argtypes = [vp, vp, ci, vp, ci, vp]
   L.cc3d_b200_face_pairs.restype = ci
   L.cc3d_b200_face_pairs.argtypes = [vp, vp, vp, vp, ci, i64, i64, ci, vp, ci, vp, u64, p(u64), vp]
   L.cc3d_b200_solve_pairs.restype = ci

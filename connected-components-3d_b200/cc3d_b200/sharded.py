@@ -274,6 +274,100 @@ def _out_dtype_rule(out_dtype, epl_total, voxels_total, shape_total, binary_imag
   return np.dtype(np.uint64)
 
 
+_FAST_PAIR_CAP = 8192   # face pairs per rank that travel with the single all-gather of the fast path
+_fast_cap_seen = {}     # (sy, sx, connectivity) -> capacity that was enough last time (avoids the retry on the next step)
+
+
+def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, out_dtype, group, rank, world):
+  """CUDA fast path of connected_components_slab: the whole step is enqueued on the current stream
+  (cc3d_b200_slab_begin / face_pairs_async / slab_finish, NCCL point-to-point + one all-gather) and the
+  host synchronises ONCE, to read the gathered facts and face pairs for the merge."""
+  import torch
+  import torch.distributed as dist
+  L = _lib.lib()
+  dev = slab.device
+  sz, sy, sx = slab.shape
+  stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  cap = _fast_cap_seen.get((sy, sx, connectivity), _FAST_PAIR_CAP)
+  import os, time
+  prof = os.environ.get("CC3D_SHARDED_TIMING") is not None
+  stamps, evs = [("start", time.perf_counter())], []
+  def lap(name):
+    if prof:
+      stamps.append((name, time.perf_counter()))
+      e = torch.cuda.Event(enable_timing=True); e.record(); evs.append((name, e))
+  lap("t0")
+  top_labs = torch.empty((sy, sx), dtype=torch.int32, device=dev) if rank + 1 < world else None
+  bot_labs = torch.empty((sy, sx), dtype=torch.int32, device=dev) if rank > 0 else None
+  sess = ctypes.c_void_p()
+  buf = torch.zeros((4 + cap,), dtype=torch.int64, device=dev)      # [N, epl, sz, n_pairs, pairs...]
+  with torch.cuda.device(dev):
+    _lib.check(L.cc3d_b200_slab_begin(
+      slab.data_ptr(), kind, sx, sy, sz, int(connectivity), delta_arr.ctypes.data, int(binary_image), stream,
+      ctypes.byref(sess), bot_labs.data_ptr() if bot_labs is not None else None,
+      top_labs.data_ptr() if top_labs is not None else None, buf.data_ptr()))
+  lap("begin")
+  try:
+    while True:
+      if world > 1:
+        top_vals = slab[sz - 1].view(torch.uint8)
+        recv = _exchange_planes(dist, group, rank, world, [top_vals, top_labs] if top_labs is not None else [],
+                                [top_vals, bot_labs])
+        if rank > 0:
+          with torch.cuda.device(dev):
+            _lib.check(L.cc3d_b200_face_pairs_async(
+              slab[0].data_ptr(), bot_labs.data_ptr(), recv[0].data_ptr(), recv[1].data_ptr(), kind, sx, sy,
+              int(connectivity), delta_arr.ctypes.data, int(binary_image), buf[4:].data_ptr(), cap,
+              buf[3:4].data_ptr(), stream))
+        lap("exchange+pairs")
+        gathered = torch.empty((world, 4 + cap), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+        lap("all_gather")
+      else:
+        gathered = buf[None]
+      host = torch.empty(gathered.shape, dtype=torch.int64, pin_memory=True)
+      host.copy_(gathered, non_blocking=True)
+      lap("d2h")
+      torch.cuda.current_stream(dev).synchronize()          # the one host synchronisation of the step
+      lap("sync")
+      facts = host.numpy()
+      counts = facts[:, 3]
+      if int(counts.max()) <= cap:
+        break
+      # rare: an interface has more pairs than fit; repeat the pair extraction with a larger buffer
+      cap = 1 << int(counts.max() - 1).bit_length()
+      _fast_cap_seen[(sy, sx, connectivity)] = cap
+      nbuf = torch.zeros((4 + cap,), dtype=torch.int64, device=dev)
+      nbuf[:3] = buf[:3]
+      buf = nbuf
+    sz_total = int(facts[:, 2].sum())
+    voxels_total = sz_total * sy * sx
+    epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
+    pair_lists = [facts[r, 4: 4 + int(counts[r])] for r in range(world)]
+    N_total, remap_np = _merge_native(facts[:, 0], pair_lists, rank)
+    lap("merge")
+    out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
+    if np.iinfo(out_dtype).max < N_total:
+      raise _lib.CC3DB200Error(-1, "N does not fit the requested output kind")
+    remap = torch.from_numpy(remap_np).pin_memory().to(dev, non_blocking=True)
+    tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}[out_dtype]
+    okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}[out_dtype]
+    out = torch.empty((sz, sy, sx), dtype=tdt, device=dev)
+    s2, sess = sess, None
+    with torch.cuda.device(dev):
+      _lib.check(L.cc3d_b200_slab_finish(s2, remap.data_ptr(), _lib.U64, out.data_ptr(), okind, stream))
+    lap("finish")
+    if prof and rank == int(os.environ.get("CC3D_SHARDED_TIMING") or 0):
+      torch.cuda.synchronize(dev)
+      host = " ".join(f"{n}={(t - stamps[i][1]) * 1e3:.3f}" for i, (n, t) in enumerate(stamps[1:]))
+      gpu = " ".join(f"{n}={evs[i][1].elapsed_time(e):.3f}" for i, (n, e) in enumerate(evs[1:]))
+      print(f"  [slab_fast rank {rank}] host ms: {host} | gpu ms: {gpu} | pairs {[int(c) for c in counts]}", flush=True)
+    return out, N_total
+  finally:
+    if sess is not None:
+      L.cc3d_b200_session_release(sess)
+
+
 def connected_components_slab(slab, connectivity: int = 26, return_N: bool = False, delta=0,
                               out_dtype: Optional[Any] = None, binary_image: bool = False, group=None,
                               backend=None):
@@ -301,6 +395,9 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
 
   sz, sy, sx = slab.shape
   import os, time
+  if isinstance(backend, CudaBackend) and dev.type == "cuda" and not os.environ.get("CC3D_SHARDED_STEPWISE"):
+    out, N_total = _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, out_dtype, group, rank, world)
+    return (out, N_total) if return_N else out
   _timing = os.environ.get("CC3D_SHARDED_TIMING") and rank == 0
   _t = [time.perf_counter()]
   def _lap(name):

@@ -41,6 +41,7 @@ struct Arena {
   size_t cap = 0;
   size_t off = 0;
   int device = -1;
+  cudaEvent_t pending = nullptr;   // set by a stream-ordered release: work that still uses the memory
   void* take(size_t bytes) {
     off = (off + 255) & ~size_t(255);
     void* p = base + off;
@@ -51,7 +52,15 @@ struct Arena {
 std::mutex g_pool_mu;
 Arena g_cached;  // at most one idle arena is kept
 
-int arena_acquire(size_t bytes, Arena* out) {
+// the work recorded by a stream-ordered release has to finish before the memory is reused (or freed)
+void arena_settle(Arena& a, cudaStream_t s, bool on_stream) {
+  if (!a.pending) return;
+  if (on_stream) cudaStreamWaitEvent(s, a.pending, 0);
+  else cudaEventSynchronize(a.pending);
+  cudaEventDestroy(a.pending);
+  a.pending = nullptr;
+}
+int arena_acquire(size_t bytes, Arena* out, cudaStream_t s = nullptr, bool on_stream = false) {
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
   {
@@ -59,9 +68,10 @@ int arena_acquire(size_t bytes, Arena* out) {
     if (g_cached.base && g_cached.device == dev && g_cached.cap >= bytes) {
       *out = g_cached; out->off = 0;
       g_cached = Arena();
+      arena_settle(*out, s, on_stream);
       return 0;
     }
-    if (g_cached.base) { cudaFree(g_cached.base); g_cached = Arena(); }
+    if (g_cached.base) { arena_settle(g_cached, nullptr, false); cudaFree(g_cached.base); g_cached = Arena(); }
   }
   Arena a;
   a.device = dev;
@@ -75,11 +85,19 @@ void arena_release(Arena& a) {
   if (!a.base) return;
   std::lock_guard<std::mutex> lk(g_pool_mu);
   if (g_cached.base) {
-    if (g_cached.cap >= a.cap) { cudaFree(a.base); a = Arena(); return; }
+    if (g_cached.cap >= a.cap) { arena_settle(a, nullptr, false); cudaFree(a.base); a = Arena(); return; }
+    arena_settle(g_cached, nullptr, false);
     cudaFree(g_cached.base);
   }
   g_cached = a; g_cached.off = 0;
   a = Arena();
+}
+// release while work enqueued on `s` still uses the arena: the next user waits for it (on its own stream)
+void arena_release_after(Arena& a, cudaStream_t s) {
+  if (!a.base) return;
+  if (cudaEventCreateWithFlags(&a.pending, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(a.pending, s);
+  else { a.pending = nullptr; cudaStreamSynchronize(s); }
+  arena_release(a);
 }
 
 std::atomic<unsigned long long> g_launches{0};
@@ -371,7 +389,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   add(gqcap * 8); add(64);
   add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
-  if (int rc = arena_acquire(need, &S->arena)) { delete S; return rc; }
+  if (int rc = arena_acquire(need, &S->arena, (cudaStream_t)stream, true)) { delete S; return rc; }
   Arena& ar = S->arena;
 
   marks_begin(s);
@@ -616,6 +634,75 @@ int cc3d_b200_face_pairs(const void* values_upper, const uint32_t* labels_upper,
   return 0;
 }
 
+// ---- sharded fast path: everything enqueued on the caller's stream, no host synchronisation ----
+__global__ void k_slab_facts(const Counters* __restrict__ ctr, int epl_is_runs, long long sz, long long* __restrict__ out) {
+  out[0] = (long long)ctr->N;
+  out[1] = (long long)(epl_is_runs ? ctr->nruns : ctr->epl);
+  out[2] = sz;
+}
+
+int cc3d_b200_slab_begin(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                         const void* delta, int binary_image, void* stream, cc3d_b200_session** session,
+                         uint32_t* labels_first_plane, uint32_t* labels_last_plane, int64_t* facts) {
+  if (!session || !facts) return fail(CC3D_B200_ERR_ARGUMENT, "session/facts must not be NULL");
+  if (connectivity != 6 && connectivity != 18 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "sharded volumes support 6, 18 and 26 connectivity");
+  if (sx <= 0 || sy <= 0 || sz <= 0) return fail(CC3D_B200_ERR_ARGUMENT, "empty slab");
+  cc3d_b200_resolve_info info;
+  cc3d_b200_session* S = nullptr;
+  int rc = resolve_enqueue(in, in_kind, sx, sy, sz, connectivity, delta, binary_image, 0, CC3D_B200_DEVICE, stream, &info, &S);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (labels_first_plane) launch_write<uint32_t>(S, labels_first_plane, 0, sy, nullptr, 0, s);
+  if (labels_last_plane) launch_write<uint32_t>(S, labels_last_plane, (sz - 1) * sy, sy, nullptr, 0, s);
+  k_slab_facts<<<1, 1, 0, s>>>(S->ctr, S->epl_is_runs ? 1 : 0, (long long)sz, (long long*)facts);
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)); }
+  *session = S;
+  return 0;
+}
+
+int cc3d_b200_slab_finish(cc3d_b200_session* S, const void* remap, int remap_kind, void* out, int out_kind, void* stream) {
+  if (!S) return fail(CC3D_B200_ERR_ARGUMENT, "NULL session");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = 0;
+  if (!remap || !out) rc = fail(CC3D_B200_ERR_ARGUMENT, "NULL remap table / output");
+  else if (remap_kind != CC3D_B200_U32 && remap_kind != CC3D_B200_U64) rc = fail(CC3D_B200_ERR_KIND, "remap kind must be u32 or u64");
+  else {
+    const i64 nrows = S->g.sy * S->g.sz;
+    if (out_kind == CC3D_B200_U16) launch_write<uint16_t>(S, (uint16_t*)out, 0, nrows, remap, remap_kind, s);
+    else if (out_kind == CC3D_B200_U32) launch_write<uint32_t>(S, (uint32_t*)out, 0, nrows, remap, remap_kind, s);
+    else if (out_kind == CC3D_B200_U64) launch_write<uint64_t>(S, (uint64_t*)out, 0, nrows, remap, remap_kind, s);
+    else rc = fail(CC3D_B200_ERR_KIND, "out kind must be u16, u32 or u64");
+    if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = fail(CC3D_B200_ERR_CUDA, "slab_finish: launch failed");
+  }
+  arena_release_after(S->arena, s);
+  delete S;
+  return rc;
+}
+
+int cc3d_b200_face_pairs_async(const void* values_upper, const uint32_t* labels_upper, const void* values_lower,
+                               const uint32_t* labels_lower, int in_kind, int64_t sx, int64_t sy, int connectivity,
+                               const void* delta, int binary_image, uint64_t* pairs, uint64_t capacity,
+                               uint64_t* count_dev, void* stream) {
+  const size_t es = kind_size(in_kind);
+  if (!es) return fail(CC3D_B200_ERR_KIND, "unsupported input kind");
+  if (connectivity != 6 && connectivity != 18 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "sharded volumes support 6, 18 and 26 connectivity");
+  if (!count_dev || !pairs) return fail(CC3D_B200_ERR_ARGUMENT, "pairs/count must not be NULL");
+  if (sx * sy == 0) return 0;
+  bool delta_zero = true;
+  if (delta) { for (size_t i = 0; i < es; i++) if (((const unsigned char*)delta)[i]) delta_zero = false; }
+  const int mode = binary_image ? MODE_NONZERO : (delta_zero ? MODE_EQ : MODE_DELTA);
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* dcount = (unsigned long long*)count_dev;   // caller zeroes it (stream ordered)
+  const u32 *lP = labels_upper, *lQ = labels_lower;
+  CC_KIND_SWITCH(in_kind, face_pairs_typed((const KT*)values_upper, lP, (const KT*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s));
+  if (cudaGetLastError() != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, "face_pairs_async: launch failed");
+  return 0;
+}
+
 int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, const uint32_t* b, int64_t n_pairs,
                           void* stream) {
   if (n_nodes <= 0) return 0;
@@ -777,73 +864,49 @@ int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* co
                           int rank, int64_t* remap, int64_t* n_total) {
   if (world <= 0 || rank < 0 || rank >= world || !n_labels || !remap || !n_total)
     return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs: bad arguments");
+  // global id of (slab r, local label l >= 1) = off[r] + l: id order = first-appearance order of the whole volume
   std::vector<i64> off(world + 1, 0);
   for (int r = 0; r < world; r++) off[r + 1] = off[r] + n_labels[r];
-  // edges between global ids (off[r] + label), nodes = ids that touch an interface
-  std::vector<std::pair<i64, i64>> edges;
-  for (int r = 1; r < world; r++) {
-    for (i64 k = 0; k < n_pairs[r]; k++) {
-      const u64 v = pairs[r][k];
-      const i64 lo = (i64)(v >> 32), up = (i64)(v & 0xFFFFFFFFull);
-      if (lo < 1 || lo > n_labels[r - 1] || up < 1 || up > n_labels[r])
-        return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs: pair label out of range");
-      edges.push_back({off[r - 1] + lo, off[r] + up});
-    }
-  }
-  std::sort(edges.begin(), edges.end());
-  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
-  std::vector<i64> nodes;
-  nodes.reserve(edges.size() * 2);
-  for (auto& e : edges) { nodes.push_back(e.first); nodes.push_back(e.second); }
-  std::sort(nodes.begin(), nodes.end());
-  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
-  const size_t nn = nodes.size();
-  std::vector<u32> parent(nn);
-  for (size_t i = 0; i < nn; i++) parent[i] = (u32)i;
+  const i64 total = off[world];
+  if (total >= 0xFFFFFFFFll) return fail(CC3D_B200_ERR_TOO_LARGE, "merge_slabs: more than 2^32-2 slab labels");
+  // union-find over the ids directly (no sorting, duplicates are harmless); root = smallest id of the set
+  static thread_local std::vector<u32> parent;
+  parent.resize((size_t)total + 1);
+  for (i64 i = 0; i <= total; i++) parent[(size_t)i] = (u32)i;
   auto find = [&](u32 i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
-  auto index_of = [&](i64 id) { return (u32)(std::lower_bound(nodes.begin(), nodes.end(), id) - nodes.begin()); };
-  for (auto& e : edges) {
-    u32 a = find(index_of(e.first)), b = find(index_of(e.second));
-    if (a < b) parent[b] = a; else if (b < a) parent[a] = b;   // root = smallest id = first in raster order
+  for (int r = 1; r < world; r++) {
+    const u64* pr = pairs[r];
+    const i64 nlo = n_labels[r - 1], nup = n_labels[r];
+    u64 last = ~0ull;
+    for (i64 k = 0; k < n_pairs[r]; k++) {
+      const u64 v = pr[k];
+      if (v == last) continue;
+      last = v;
+      const i64 lo = (i64)(v >> 32), up = (i64)(v & 0xFFFFFFFFull);
+      if (lo < 1 || lo > nlo || up < 1 || up > nup)
+        return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs: pair label out of range");
+      const u32 a = find((u32)(off[r - 1] + lo)), b = find((u32)(off[r] + up));
+      if (a < b) parent[b] = a; else if (b < a) parent[a] = b;
+    }
   }
-  // owned components per slab: all labels minus the interface nodes whose root lies elsewhere
-  std::vector<i64> owned(world);
-  for (int r = 0; r < world; r++) owned[r] = n_labels[r];
-  auto slab_of = [&](i64 id) { return (int)(std::upper_bound(off.begin(), off.end(), id - 1) - off.begin()) - 1; };
-  std::vector<char> nonowned(nn);
-  for (size_t i = 0; i < nn; i++) {
-    nonowned[i] = find((u32)i) != (u32)i;
-    if (nonowned[i]) owned[slab_of(nodes[i])]--;
-  }
+  // a component is owned by the slab of its root; owned components are numbered slab by slab in label order
   std::vector<i64> base(world + 1, 0);
-  for (int r = 0; r < world; r++) base[r + 1] = base[r] + owned[r];
+  for (int r = 0; r < world; r++) {
+    i64 owned = 0;
+    for (i64 id = off[r] + 1; id <= off[r + 1]; id++) owned += find((u32)id) == (u32)id;
+    base[r + 1] = base[r] + owned;
+  }
   *n_total = base[world];
-  // final label of an owned node = base[slab] + local label - (non-owned labels of that slab below it)
-  std::vector<i64> final_of(nn, 0);
-  {
-    int cur = -1; i64 before = 0;
-    for (size_t i = 0; i < nn; i++) {
-      const int r = slab_of(nodes[i]);
-      if (r != cur) { cur = r; before = 0; }
-      if (nonowned[i]) before++;
-      else final_of[i] = base[r] + (nodes[i] - off[r]) - before;
-    }
+  // final labels of the roots that the labels of slab `rank` point at: roots lie in slabs <= rank; number them
+  // lazily (final label of root id in slab r = base[r] + rank of id among the roots of slab r)
+  static thread_local std::vector<i64> final_of;
+  final_of.assign((size_t)off[rank + 1] + 1, 0);
+  for (int r = 0; r <= rank; r++) {
+    i64 next = base[r];
+    for (i64 id = off[r] + 1; id <= off[r + 1]; id++)
+      if (parent[(size_t)id] == (u32)id) final_of[(size_t)id] = ++next;
   }
-  // remap of this rank: labels in order, skipping the non-owned ones, then the interface nodes take their root's label
-  const i64 nl = n_labels[rank];
-  const size_t lo_i = std::lower_bound(nodes.begin(), nodes.end(), off[rank] + 1) - nodes.begin();
-  const size_t hi_i = std::upper_bound(nodes.begin(), nodes.end(), off[rank] + nl) - nodes.begin();
   remap[0] = 0;
-  size_t j = lo_i;
-  i64 skipped = 0;
-  for (i64 l = 1; l <= nl; l++) {
-    if (j < hi_i && nodes[j] == off[rank] + l) {
-      if (nonowned[j]) { skipped++; remap[l] = final_of[find((u32)j)]; }
-      else remap[l] = final_of[j];
-      j++;
-    } else {
-      remap[l] = base[rank] + l - skipped;
-    }
-  }
+  for (i64 l = 1; l <= n_labels[rank]; l++) remap[l] = final_of[find((u32)(off[rank] + l))];
   return 0;
 }

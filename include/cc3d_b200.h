@@ -124,6 +124,27 @@ int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, 
 int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,
                           int rank, int64_t* remap, int64_t* n_total);
 
+/* Sharded fast path (one process per GPU, small slabs): the three calls below only ENQUEUE work on `stream`;
+ * none of them synchronises, so a whole slab step needs one host synchronisation (after the all-gather of the
+ * facts and face pairs). Device memory only.
+ *   slab_begin : resolve phase of a slab + the resolved local labels of its first / last z-plane (uint32,
+ *                sy*sx each, either may be NULL) + facts[3] = {N_local, epl, sz} (int64, device), all on stream.
+ *   face_pairs_async : as cc3d_b200_face_pairs, count stays on the device (*count_dev must be zero on entry
+ *                in stream order; it may exceed `capacity`, pairs past the capacity are dropped).
+ *   slab_finish: final write through the local->global remap table (device), then the session's workspace is
+ *                returned to the cache behind an event (the next user waits for the write on its own stream).
+ * Together they replace the per-slab body of the reference's connected_components_stack loop
+ * (cc3d/__init__.py:399-470) for device-resident slabs. */
+int cc3d_b200_slab_begin(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                         const void* delta, int binary_image, void* stream, cc3d_b200_session** session,
+                         uint32_t* labels_first_plane, uint32_t* labels_last_plane, int64_t* facts);
+int cc3d_b200_face_pairs_async(const void* values_upper, const uint32_t* labels_upper, const void* values_lower,
+                               const uint32_t* labels_lower, int in_kind, int64_t sx, int64_t sy, int connectivity,
+                               const void* delta, int binary_image, uint64_t* pairs, uint64_t capacity,
+                               uint64_t* count_dev, void* stream);
+int cc3d_b200_slab_finish(cc3d_b200_session* session, const void* remap, int remap_kind, void* out, int out_kind,
+                          void* stream);
+
 /* Drops a session without writing. */
 void cc3d_b200_session_release(cc3d_b200_session* session);
 
