@@ -23,6 +23,7 @@ from ._lib import CC3DB200Error
 
 __all__ = [
   "connected_components", "statistics", "dust", "estimate_provisional_labels",
+  "largest_k", "voxel_connectivity_graph", "color_connectivity_graph",
   "DimensionError", "CC3DB200Error", "last_timings", "set_timing",
 ]
 
@@ -615,3 +616,157 @@ def _dust_device(img, threshold, connectivity, in_place, binary_image, precomput
       t.data_ptr(), t.element_size(), lab.data_ptr(), _kind_of(_torch_np_dtype(lab)), t.numel(),
       keep_d.data_ptr(), N, _lib.DEVICE, stream))
   return (t, dust_N) if return_N else t
+
+
+# ----------------------------------------------------------------------------------------------
+# Callers either side of the labelling path: largest_k, voxel / colour connectivity graphs
+# ----------------------------------------------------------------------------------------------
+def _remap(labels, table, N, out_dtype):
+  """out[i] = table[labels[i]] on the GPU; numpy in/out (same memory order) or CUDA tensor in/out."""
+  L = _lib.lib()
+  table = np.ascontiguousarray(table, dtype=np.uint32)
+  okind = _kind_of(np.dtype(np.uint8) if out_dtype == bool else np.dtype(out_dtype))
+  if _is_torch(labels) and labels.is_cuda:
+    import torch
+    t = labels.contiguous()
+    tdt = torch.bool if out_dtype == bool else _torch_dtype(np.dtype(out_dtype))
+    out = torch.empty(t.shape, dtype=torch.uint8 if out_dtype == bool else tdt, device=t.device)
+    tab = torch.from_numpy(table.view(np.int32)).to(t.device)
+    with torch.cuda.device(t.device):
+      _lib.check(L.cc3d_b200_remap_labels(t.data_ptr(), _kind_of(_torch_np_dtype(t)), t.numel(), tab.data_ptr(), int(N),
+                                          out.data_ptr(), okind, _lib.DEVICE,
+                                          ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+    return out.view(torch.bool) if out_dtype == bool else out
+  labels = np.asarray(labels)
+  order = "F" if (labels.flags.f_contiguous and not labels.flags.c_contiguous) else "C"
+  src = np.asarray(_view_as_unsigned(labels), order=order)
+  out = np.empty(labels.shape, dtype=np.uint8 if out_dtype == bool else out_dtype, order=order)
+  if src.size:
+    _lib.check(L.cc3d_b200_remap_labels(src.ctypes.data, _kind_of(src.dtype), src.size, table.ctypes.data, int(N),
+                                        out.ctypes.data, okind, _lib.HOST, None))
+  return out.view(bool) if out_dtype == bool else out
+
+
+def largest_k(img, k: int, connectivity: int = 26, delta=0, return_N: bool = False, binary_image: bool = False,
+              precomputed_ccl: bool = False):
+  """Returns the k largest connected components of the image; same contract as cc3d.largest_k
+  (cc3d/__init__.py:199-279, the path without fastremap: kept components are renumbered 1..k from the
+  smallest to the largest). Labelling, voxel counts and the relabelling run on the GPU."""
+  assert k >= 0
+  is_t = _is_torch(img)
+  if k == 0:
+    if is_t:
+      import torch
+      return torch.zeros(img.shape, dtype=torch.uint16, device=img.device)
+    order = "C" if img.flags.c_contiguous else "F"
+    return np.zeros(img.shape, dtype=np.uint16, order=order)
+
+  if precomputed_ccl:
+    cc_labels = img.clone() if is_t else np.copy(img, order="F")
+    N = _torch_max(cc_labels) if is_t else int(np.max(cc_labels))
+  else:
+    cc_labels, N = connected_components(img, connectivity=connectivity, return_N=True, delta=delta,
+                                        binary_image=bool(binary_image))
+  if N <= k:
+    return (cc_labels, N) if return_N else cc_labels
+
+  cts = statistics(cc_labels, no_slice_conversion=True)["voxel_counts"]
+  if k == 1:
+    table = np.zeros(N + 1, dtype=np.uint32)
+    table[int(np.argmax(cts[1:])) + 1] = 1
+    cc_out = _remap(cc_labels, table, N, bool)
+    return (cc_out, 1) if return_N else cc_out
+
+  preserve = np.argpartition(cts[1:], len(cts) - k - 1)[-k:]
+  preserve += 1
+  preserve_list = [int(l) for l in sorted(preserve, key=lambda label: cts[label])]
+  table = np.zeros(N + 1, dtype=np.uint32)
+  for i, label in enumerate(preserve_list):
+    table[label] = i + 1
+  cc_out = _remap(cc_labels, table, N, _torch_np_dtype(cc_labels) if is_t else cc_labels.dtype)
+  return (cc_out, len(preserve_list)) if return_N else cc_out
+
+
+def voxel_connectivity_graph(data, connectivity: int = 26):
+  """Voxel connectivity graph of a multi-label image; same contract and bit layout as
+  cc3d.voxel_connectivity_graph (fastcc3d.pyx:1021-1170): uint8 for connectivity 4, 8, 6 and uint32 for 18, 26,
+  array-index axes (x = axis 0), Fortran-ordered result."""
+  L = _lib.lib()
+  is_t = _is_torch(data)
+  dims = data.ndim
+  if dims not in (1, 2, 3):
+    raise DimensionError("Only 1D, 2D, and 3D arrays supported. Got: " + str(dims))
+  if dims == 2 and connectivity not in (4, 8, 6, 18, 26):
+    raise ValueError("Only 4, 8, and 6, 18, 26 connectivities are supported for 2D images. Got: " + str(connectivity))
+  elif dims != 2 and connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  out_dtype = np.uint8 if connectivity in (4, 8, 6) else np.uint32
+  if is_t and data.is_cuda:
+    import torch
+    if data.numel() == 0:
+      return torch.zeros((0,), dtype=_torch_dtype(np.dtype(out_dtype)), device=data.device)
+    ndt = _torch_np_dtype(data)
+    if ndt.kind not in "biu":
+      raise TypeError("Type {} not currently supported.".format(ndt))
+    shape = tuple(data.shape) + (1,) * (3 - dims)
+    t = data.reshape(shape).permute(2, 1, 0).contiguous()     # memory order: axis 0 fastest
+    g = torch.empty(t.shape, dtype=_torch_dtype(np.dtype(out_dtype)), device=t.device)
+    with torch.cuda.device(t.device):
+      _lib.check(L.cc3d_b200_voxel_connectivity_graph(
+        t.data_ptr(), _kind_of(ndt), shape[0], shape[1], shape[2], int(connectivity), g.data_ptr(), _lib.DEVICE,
+        ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+    return g.permute(2, 1, 0).reshape(tuple(data.shape))
+  if is_t:
+    data = data.numpy()
+  if data.size == 0:
+    return np.zeros(shape=(0,), dtype=out_dtype)
+  data = np.asfortranarray(data)
+  if data.dtype.kind not in "biu":
+    raise TypeError("Type {} not currently supported.".format(data.dtype))
+  src = _view_as_unsigned(data)
+  shape = tuple(src.shape) + (1,) * (3 - dims)
+  graph = np.zeros(src.shape, dtype=out_dtype, order="F")
+  _lib.check(L.cc3d_b200_voxel_connectivity_graph(
+    src.ctypes.data, _kind_of(src.dtype), shape[0], shape[1], shape[2], int(connectivity), graph.ctypes.data,
+    _lib.HOST, None))
+  return graph
+
+
+def color_connectivity_graph(vcg, connectivity: int = 26, return_N: bool = False):
+  """Labels the components of a voxel connectivity graph; same contract as cc3d.color_connectivity_graph
+  (fastcc3d.pyx:941-1018): uint32 labels, every voxel labelled, numbered by first appearance in Fortran order."""
+  L = _lib.lib()
+  if _is_torch(vcg):
+    dev = vcg.device
+    out = color_connectivity_graph(vcg.cpu().numpy(), connectivity, return_N)
+    import torch
+    if return_N:
+      return torch.from_numpy(out[0].view(np.int32)).to(dev).view(torch.uint32), out[1]
+    return torch.from_numpy(out.view(np.int32)).to(dev).view(torch.uint32)
+  dims = len(vcg.shape)
+  if dims not in (2, 3):
+    raise DimensionError("Only 2D, and 3D arrays supported. Got: " + str(dims))
+  if dims == 2 and connectivity not in [4, 8, 6, 26]:
+    raise ValueError(f"Only 4 and 8 connectivity is supported for 2D images. Got: {connectivity}")
+  elif dims != 2 and connectivity not in [6, 26]:
+    raise ValueError(f"Only 6 and 26 connectivity are supported for 3D images. Got: {connectivity}")
+  if vcg.dtype not in [np.uint8, np.uint32]:
+    raise ValueError(f"Only uint8 and uint32 are supported. Got: {vcg.dtype}")
+  if vcg.size == 0:
+    return np.zeros([0] * dims, dtype=np.uint32, order="F")
+  while vcg.ndim < 3:
+    vcg = vcg[..., np.newaxis]
+  vcg = np.asfortranarray(vcg)
+  sx, sy, sz = vcg.shape
+  if connectivity in [18, 26] and sz > 1 and vcg.dtype != np.uint32:
+    raise ValueError(f"Only uint32 is supported for 18 and 26 connected. Got: {vcg.dtype}")
+  out_labels = np.zeros((sx, sy, sz), dtype=np.uint32, order="F")
+  N = ctypes.c_uint64(0)
+  _lib.check(L.cc3d_b200_color_connectivity_graph(
+    vcg.ctypes.data, _kind_of(vcg.dtype), sx, sy, sz, int(connectivity), out_labels.ctypes.data, ctypes.byref(N),
+    _lib.HOST, None))
+  while out_labels.ndim > dims:
+    out_labels = out_labels[..., 0]
+  if return_N:
+    return (out_labels, int(N.value))
+  return out_labels

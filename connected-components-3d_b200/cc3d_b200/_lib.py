@@ -76,6 +76,12 @@ def lib():
   L.cc3d_b200_label_with_info.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, vp, ci, ci, p(ResolveInfo), vp]
   L.cc3d_b200_statistics.restype = ci
   L.cc3d_b200_statistics.argtypes = [vp, ci, i64, i64, i64, u64, vp, vp, vp, ci, vp]
+  L.cc3d_b200_voxel_connectivity_graph.restype = ci
+  L.cc3d_b200_voxel_connectivity_graph.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, vp]
+  L.cc3d_b200_color_connectivity_graph.restype = ci
+  L.cc3d_b200_color_connectivity_graph.argtypes = [vp, ci, i64, i64, i64, ci, vp, p(u64), ci, vp]
+  L.cc3d_b200_remap_labels.restype = ci
+  L.cc3d_b200_remap_labels.argtypes = [vp, ci, i64, vp, u64, vp, ci, ci, vp]
   L.cc3d_b200_mask_by_label.restype = ci
   L.cc3d_b200_mask_by_label.argtypes = [vp, ci, vp, ci, i64, vp, u64, ci, vp]
   L.cc3d_b200_workspace_bytes.restype = ctypes.c_size_t

@@ -11,6 +11,7 @@
 #include "../../include/cc3d_b200.h"
 #include "cc3d_dispatch.cuh"
 #include "cc3d_misc.cuh"
+#include "cc3d_graphs.cuh"
 #include "cc3d_resolve.cuh"
 
 namespace {
@@ -860,6 +861,185 @@ int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int
 // label order, which is the first-appearance order of the whole volume (cc3d/__init__.py:296-321, 425-468
 // do the same with a Python DisjointSet + renumber). Writes remap[0..n_labels[rank]] for slab `rank`
 // (remap[0] = 0) and the global component count.
+// ---- callers either side of the labelling path ----
+template <typename T>
+static int voxel_graph_typed(const T* in, void* graph, i64 sx, i64 sy, i64 sz, int connectivity, cudaStream_t s) {
+  const i64 voxels = sx * sy * sz;
+  const unsigned blocks = (unsigned)std::min<i64>((voxels + 255) / 256, 148 * 64);
+  switch (connectivity) {
+    case 4: k_voxel_graph<T, uint8_t, 4, true><<<blocks, 256, 0, s>>>(in, (uint8_t*)graph, sx, sy, sz); break;
+    case 8: k_voxel_graph<T, uint8_t, 8, true><<<blocks, 256, 0, s>>>(in, (uint8_t*)graph, sx, sy, sz); break;
+    case 6: k_voxel_graph<T, uint8_t, 6, false><<<blocks, 256, 0, s>>>(in, (uint8_t*)graph, sx, sy, sz); break;
+    case 18: k_voxel_graph<T, uint32_t, 18, false><<<blocks, 256, 0, s>>>(in, (uint32_t*)graph, sx, sy, sz); break;
+    case 26: k_voxel_graph<T, uint32_t, 26, false><<<blocks, 256, 0, s>>>(in, (uint32_t*)graph, sx, sy, sz); break;
+    default: return -1;
+  }
+  g_launches += 1;
+  return 0;
+}
+
+int cc3d_b200_voxel_connectivity_graph(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                                       void* graph, int mem_space, void* stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  const size_t es = kind_size(kind);
+  if (!es || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "labels must be u8/u16/u32/u64");
+  if (connectivity != 4 && connectivity != 8 && connectivity != 6 && connectivity != 18 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "Only 4 and 8 2D and 6, 18, and 26 3D connectivities are supported.");
+  if ((connectivity == 4 || connectivity == 8) && sz != 1)
+    return fail(CC3D_B200_ERR_2D_NEEDS_SZ1, "sz must be 1 for 2D connectivities.");
+  const i64 voxels = sx * sy * sz;
+  if (voxels == 0) return 0;
+  const size_t os = (connectivity == 18 || connectivity == 26) ? 4 : 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar;
+  const void* din = labels; void* dg = graph;
+  if (mem_space == CC3D_B200_HOST) {
+    if (int rc = arena_acquire((size_t)voxels * (es + os) + 4096, &ar)) return rc;
+    void* d = ar.take((size_t)voxels * es);
+    dg = ar.take((size_t)voxels * os);
+    cudaMemcpyAsync(d, labels, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+    din = d;
+  }
+  int rc = -1;
+  switch (kind) {
+    case CC3D_B200_U8: rc = voxel_graph_typed((const uint8_t*)din, dg, sx, sy, sz, connectivity, s); break;
+    case CC3D_B200_U16: rc = voxel_graph_typed((const uint16_t*)din, dg, sx, sy, sz, connectivity, s); break;
+    case CC3D_B200_U32: rc = voxel_graph_typed((const uint32_t*)din, dg, sx, sy, sz, connectivity, s); break;
+    case CC3D_B200_U64: rc = voxel_graph_typed((const uint64_t*)din, dg, sx, sy, sz, connectivity, s); break;
+  }
+  cudaError_t e = cudaSuccess;
+  if (rc == 0 && mem_space == CC3D_B200_HOST) e = cudaMemcpyAsync(graph, dg, (size_t)voxels * os, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (rc) return fail(CC3D_B200_ERR_ARGUMENT, "voxel_connectivity_graph: no kernel for this configuration");
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("voxel_connectivity_graph: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+__global__ void k_set_u64(u64* p, u64 v) { *p = v; }
+
+int cc3d_b200_color_connectivity_graph(const void* vcg, int vcg_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                                       uint32_t* out, uint64_t* N, int mem_space, void* stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  if (vcg_kind != CC3D_B200_U8 && vcg_kind != CC3D_B200_U32) return fail(CC3D_B200_ERR_KIND, "Only uint8 and uint32 are supported.");
+  if (connectivity != 4 && connectivity != 8 && connectivity != 6 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "Only 4, 8, 6 and 26 connectivities are supported.");
+  if (sz > 1 && connectivity != 6 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "Only 6 and 26 connectivity is supported in 3D.");
+  if (sz > 1 && connectivity == 26 && vcg_kind != CC3D_B200_U32)
+    return fail(CC3D_B200_ERR_KIND, "26-connectivity requires a 32-bit voxel graph.");
+  if (N) *N = 0;
+  const i64 voxels = sx * sy * sz;
+  if (voxels == 0) return 0;
+  if ((u64)voxels >= 0xFFFFFFFFull) return fail(CC3D_B200_ERR_TOO_LARGE, "graph has >= 2^32-1 voxels");
+  // backward directions the reference follows (cc3d_graphs.hpp:584-1106); 2D graphs come in two bit layouts
+  VcgDirs D;
+  D.n = 0;
+  auto add = [&](int dx, int dy, int dz, int bit_number) {
+    D.d[D.n][0] = (signed char)dx; D.d[D.n][1] = (signed char)dy; D.d[D.n][2] = (signed char)dz;
+    D.mask[D.n] = 1u << (bit_number - 1); D.n++;
+  };
+  add(-1, 0, 0, 2); add(0, -1, 0, 4);
+  if (sz == 1) {
+    if (connectivity == 8 || connectivity == 26) {
+      if (vcg_kind == CC3D_B200_U8) { add(-1, -1, 0, 8); add(1, -1, 0, 7); }
+      else { add(-1, -1, 0, 10); add(1, -1, 0, 9); }
+    }
+  } else {
+    add(0, 0, -1, 6);
+    if (connectivity == 26) {
+      add(-1, -1, 0, 10); add(1, -1, 0, 9);
+      add(-1, 0, -1, 16); add(1, 0, -1, 15); add(0, -1, -1, 18); add(0, 1, -1, 17);
+      add(-1, -1, -1, 26); add(1, -1, -1, 25); add(-1, 1, -1, 24); add(1, 1, -1, 23);
+    }
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t vs = kind_size(vcg_kind);
+  const i64 nwords2 = (voxels + 31) / 32;
+  const i64 nb2 = (nwords2 + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  size_t need = 4096 + (size_t)nwords2 * 12 + (size_t)(nb2 + 1) * 8 + 1024 + 4 * 256;
+  if (mem_space == CC3D_B200_HOST) need += (size_t)voxels * (vs + 4) + 512;
+  Arena ar;
+  if (int rc = arena_acquire(need, &ar, s, true)) return rc;
+  const void* dv = vcg; u32* dout = out;
+  if (mem_space == CC3D_B200_HOST) {
+    void* d = ar.take((size_t)voxels * vs);
+    dout = (u32*)ar.take((size_t)voxels * 4);
+    cudaMemcpyAsync(d, vcg, (size_t)voxels * vs, cudaMemcpyHostToDevice, s);
+    dv = d;
+  }
+  u32* GR = (u32*)ar.take((size_t)nwords2 * 4);
+  u32* cnt = (u32*)ar.take((size_t)nwords2 * 4);
+  u32* prefix = (u32*)ar.take((size_t)nwords2 * 4);
+  u64* bsum = (u64*)ar.take((size_t)(nb2 + 1) * 8);
+  u64* nvox = (u64*)ar.take(8);
+  u64* ntot = (u64*)ar.take(8);
+  const unsigned blocks = (unsigned)std::min<i64>((voxels + 255) / 256, 148 * 64);
+  k_set_u64<<<1, 1, 0, s>>>(nvox, (u64)voxels);
+  k_iota<<<(unsigned)((voxels + 255) / 256), 256, 0, s>>>(dout, voxels);
+  if (vcg_kind == CC3D_B200_U8) k_vcg_union<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)dv, dout, sx, sy, sz, D);
+  else k_vcg_union<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)dv, dout, sx, sy, sz, D);
+  k_compress<<<CC_GRID_BLOCKS, 256, 0, s>>>(dout, GR, cnt, nvox);
+  scan_counts(cnt, prefix, bsum, nwords2, nullptr, 0, ntot, nullptr, s);
+  k_assign<<<CC_GRID_BLOCKS, 256, 0, s>>>(dout, GR, prefix, nvox);
+  g_launches += 5;
+  u64 hN = 0;
+  cudaError_t e = cudaMemcpyAsync(&hN, ntot, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && mem_space == CC3D_B200_HOST) e = cudaMemcpyAsync(out, dout, (size_t)voxels * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("color_connectivity_graph: ") + cudaGetErrorString(e));
+  if (N) *N = hN;
+  return 0;
+}
+
+template <typename LT>
+static void remap_typed(const LT* labels, const u32* table, u64 N, void* out, int out_kind, i64 n, cudaStream_t s) {
+  const unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 32);
+  switch (out_kind) {
+    case CC3D_B200_U8: k_remap_labels<LT, uint8_t><<<blocks, 256, 0, s>>>(labels, table, N, (uint8_t*)out, n); break;
+    case CC3D_B200_U16: k_remap_labels<LT, uint16_t><<<blocks, 256, 0, s>>>(labels, table, N, (uint16_t*)out, n); break;
+    case CC3D_B200_U32: k_remap_labels<LT, uint32_t><<<blocks, 256, 0, s>>>(labels, table, N, (uint32_t*)out, n); break;
+    default: k_remap_labels<LT, uint64_t><<<blocks, 256, 0, s>>>(labels, table, N, (uint64_t*)out, n); break;
+  }
+}
+
+int cc3d_b200_remap_labels(const void* labels, int label_kind, int64_t voxels, const uint32_t* table, uint64_t N,
+                           void* out, int out_kind, int mem_space, void* stream) {
+  const size_t ls = kind_size(label_kind), os = kind_size(out_kind);
+  if (!ls || label_kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "labels must be u8/u16/u32/u64");
+  if (!os || out_kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "out must be u8/u16/u32/u64");
+  if (voxels <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena ar;
+  const void* dl = labels; const u32* dt = table; void* dout = out;
+  if (mem_space == CC3D_B200_HOST) {
+    if (int rc = arena_acquire((size_t)voxels * (ls + os) + (N + 1) * 4 + 4096, &ar)) return rc;
+    void* l = ar.take((size_t)voxels * ls);
+    dout = ar.take((size_t)voxels * os);
+    u32* t = (u32*)ar.take((N + 1) * 4);
+    cudaMemcpyAsync(l, labels, (size_t)voxels * ls, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(t, table, (N + 1) * 4, cudaMemcpyHostToDevice, s);
+    dl = l; dt = t;
+  }
+  switch (label_kind) {
+    case CC3D_B200_U8: remap_typed((const uint8_t*)dl, dt, N, dout, out_kind, voxels, s); break;
+    case CC3D_B200_U16: remap_typed((const uint16_t*)dl, dt, N, dout, out_kind, voxels, s); break;
+    case CC3D_B200_U32: remap_typed((const uint32_t*)dl, dt, N, dout, out_kind, voxels, s); break;
+    default: remap_typed((const uint64_t*)dl, dt, N, dout, out_kind, voxels, s); break;
+  }
+  g_launches += 1;
+  cudaError_t e = cudaSuccess;
+  if (mem_space == CC3D_B200_HOST) e = cudaMemcpyAsync(out, dout, (size_t)voxels * os, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("remap_labels: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,
                           int rank, int64_t* remap, int64_t* n_total) {
   if (world <= 0 || rank < 0 || rank >= world || !n_labels || !remap || !n_total)

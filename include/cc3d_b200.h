@@ -172,6 +172,26 @@ int cc3d_b200_statistics(const void* labels, int kind, int64_t sx, int64_t sy, i
 int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int label_kind,
                             int64_t voxels, const uint8_t* keep, uint64_t N, int mem_space, void* stream);
 
+/* ---- callers either side of the labelling path ---- */
+
+/* cc3d.voxel_connectivity_graph (fastcc3d.pyx:1021-1170 -> extract_voxel_connectivity_graph,
+ * cc3d_graphs.hpp:31-247): bit b of graph[p] is cleared iff the neighbour in direction b exists and holds a
+ * different value. graph is uint8 for connectivity 4, 8, 6 and uint32 for 18, 26 (the reference's bit order). */
+int cc3d_b200_voxel_connectivity_graph(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz,
+                                       int connectivity, void* graph, int mem_space, void* stream);
+
+/* cc3d.color_connectivity_graph (fastcc3d.pyx:941-1018 -> color_connectivity_graph_N, cc3d_graphs.hpp:1076-1106):
+ * labels the components of a voxel connectivity graph (uint8 or uint32; connectivity 4/8 for sz == 1, 6/26
+ * otherwise; 26 needs uint32) following the backward bits of every voxel, numbered by first appearance.
+ * out: uint32[voxels]; *N = number of components. */
+int cc3d_b200_color_connectivity_graph(const void* vcg, int vcg_kind, int64_t sx, int64_t sy, int64_t sz,
+                                       int connectivity, uint32_t* out, uint64_t* N, int mem_space, void* stream);
+
+/* out[i] = table[labels[i]] (labels above N give 0): the relabelling step of cc3d.largest_k
+ * (cc3d/__init__.py:262-276, fastremap.mask_except + renumber / runs + draw). out kind u8/u16/u32/u64. */
+int cc3d_b200_remap_labels(const void* labels, int label_kind, int64_t voxels, const uint32_t* table, uint64_t N,
+                           void* out, int out_kind, int mem_space, void* stream);
+
 /* Device-memory workspace currently cached by the library on the active device (bytes), and a
  * call that frees it. */
 size_t cc3d_b200_workspace_bytes(void);

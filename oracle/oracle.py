@@ -8,6 +8,9 @@ boundary logic, `statistics` and `dust`:
   estimate_provisional_labels <- fastcc3d.pyx:169-242 / cc3d.hpp:287-315
   statistics            <- fastcc3d.pyx:682-938
   dust                  <- cc3d/__init__.py:71-155
+  largest_k             <- cc3d/__init__.py:199-279 (the path without fastremap)
+  voxel_connectivity_graph <- fastcc3d.pyx:1021-1170 / cc3d_graphs.hpp:31-247 (numpy slicing)
+  color_connectivity_graph <- fastcc3d.pyx:941-1018 / cc3d_graphs.hpp:583-1106 (backward-bit graph, scipy components)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 Parity pin: tests/test_oracle.py checks it against the reference build (oracle/_ref) when that is
@@ -66,6 +69,31 @@ def reference_module():
     return fastcc3d
   except ImportError:
     return None
+
+
+def reference_package():
+  """The reference's Python layer (cc3d/__init__.py: dust, largest_k, ...) executed IN PLACE from
+  /root/reference on top of the built extension, or None when either is absent (e.g. on the GPU box).
+  Nothing is copied: the source is read where it lies and run as the package `cc3d_ref`."""
+  ext = reference_module()
+  src = "/root/reference/cc3d/__init__.py"
+  if ext is None or not os.path.isfile(src):
+    return None
+  if "cc3d_ref" in sys.modules:
+    return sys.modules["cc3d_ref"]
+  import types
+  pkg = types.ModuleType("cc3d_ref")
+  pkg.__path__ = []
+  pkg.__package__ = "cc3d_ref"
+  pkg.__file__ = src
+  sys.modules["cc3d_ref"] = pkg
+  sys.modules["cc3d_ref.fastcc3d"] = ext
+  try:
+    exec(compile(open(src).read(), src, "exec"), pkg.__dict__)
+  except Exception:
+    del sys.modules["cc3d_ref"], sys.modules["cc3d_ref.fastcc3d"]
+    return None
+  return pkg
 
 
 def _as_unsigned_or_float(data: np.ndarray) -> np.ndarray:
@@ -258,3 +286,125 @@ def dust(img, threshold, connectivity=26, in_place=False, binary_image=False, pr
   img[mask] = 0
   img = img.view(orig_dtype)
   return (img, dust_N) if return_N else img
+
+
+def largest_k(img, k, connectivity=26, delta=0, return_N=False, binary_image=False, precomputed_ccl=False):
+  """cc3d/__init__.py:199-279, fallback branch (no fastremap): kept labels are redrawn as 1..k, smallest first."""
+  assert k >= 0
+  order = "C" if img.flags.c_contiguous else "F"
+  if k == 0:
+    return np.zeros(img.shape, dtype=np.uint16, order=order)
+  if precomputed_ccl:
+    cc_labels = np.copy(img, order="F")
+    N = int(np.max(cc_labels))
+  else:
+    cc_labels, N = connected_components(img, connectivity=connectivity, return_N=True, delta=delta,
+                                        binary_image=bool(binary_image))
+  if N <= k:
+    return (cc_labels, N) if return_N else cc_labels
+  cts = statistics(cc_labels, no_slice_conversion=True)["voxel_counts"]
+  if k == 1:
+    cc_out = cc_labels == (np.argmax(cts[1:]) + 1)
+    return (cc_out, 1) if return_N else cc_out
+  preserve = np.argpartition(cts[1:], len(cts) - k - 1)[-k:]
+  preserve += 1
+  preserve_list = [int(l) for l in sorted(preserve, key=lambda label: cts[label])]
+  table = np.zeros(N + 1, dtype=cc_labels.dtype)
+  for i, label in enumerate(preserve_list):
+    table[label] = i + 1
+  cc_out = table[cc_labels]
+  cc_out = np.asarray(cc_out, order="C" if cc_labels.flags.c_contiguous else "F")
+  return (cc_out, len(preserve_list)) if return_N else cc_out
+
+
+# direction tables in the reference's bit order (cc3d_graphs.hpp:91-110 and :31-76)
+_VCG_DIR3 = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1),
+             (1, 1, 0), (-1, 1, 0), (1, -1, 0), (-1, -1, 0), (1, 0, 1), (-1, 0, 1), (0, 1, 1), (0, -1, 1),
+             (1, 0, -1), (-1, 0, -1), (0, 1, -1), (0, -1, -1),
+             (1, 1, 1), (-1, 1, 1), (1, -1, 1), (-1, -1, 1), (1, 1, -1), (-1, 1, -1), (1, -1, -1), (-1, -1, -1)]
+_VCG_DIR2 = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (1, 1, 0), (-1, 1, 0), (1, -1, 0), (-1, -1, 0)]
+
+
+def _shifted_pairs(shape, d):
+  """Slices (p, q) with q = p + d for every voxel p whose neighbour q lies inside the array."""
+  sp, sq = [], []
+  for n, k in zip(shape, d):
+    if k == 0:
+      sp.append(slice(0, n)); sq.append(slice(0, n))
+    elif k > 0:
+      sp.append(slice(0, n - 1)); sq.append(slice(1, n))
+    else:
+      sp.append(slice(1, n)); sq.append(slice(0, n - 1))
+  return tuple(sp), tuple(sq)
+
+
+def voxel_connectivity_graph(data, connectivity=26):
+  dims = data.ndim
+  if dims == 2 and connectivity not in (4, 8, 6, 18, 26):
+    raise ValueError("Only 4, 8, and 6, 18, 26 connectivities are supported for 2D images. Got: " + str(connectivity))
+  elif dims != 2 and connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  out_dtype = np.uint8 if connectivity in (4, 8, 6) else np.uint32
+  if data.size == 0:
+    return np.zeros(shape=(0,), dtype=out_dtype)
+  x = np.asfortranarray(data)
+  while x.ndim < 3:
+    x = x[..., np.newaxis]
+  if connectivity in (4, 8):
+    if x.shape[2] != 1:
+      raise RuntimeError("sz must be 1 for 2D connectivities.")
+    dirs = _VCG_DIR2[:connectivity]
+  else:
+    dirs = _VCG_DIR3[:connectivity]
+  graph = np.full(x.shape, (1 << len(dirs)) - 1, dtype=np.uint32, order="F")
+  for b, d in enumerate(dirs):
+    sp, sq = _shifted_pairs(x.shape, d)
+    graph[sp] &= np.where(x[sp] != x[sq], np.uint32(~(1 << b) & 0xFFFFFFFF), np.uint32(0xFFFFFFFF))
+  return np.asfortranarray(graph.astype(out_dtype)).reshape(data.shape, order="F")
+
+
+def color_connectivity_graph(vcg, connectivity=26, return_N=False):
+  from scipy.sparse import coo_matrix
+  from scipy.sparse.csgraph import connected_components as graph_cc
+  dims = vcg.ndim
+  if dims == 2 and connectivity not in [4, 8, 6, 26]:
+    raise ValueError(f"Only 4 and 8 connectivity is supported for 2D images. Got: {connectivity}")
+  elif dims != 2 and connectivity not in [6, 26]:
+    raise ValueError(f"Only 6 and 26 connectivity are supported for 3D images. Got: {connectivity}")
+  if vcg.dtype not in [np.uint8, np.uint32]:
+    raise ValueError(f"Only uint8 and uint32 are supported. Got: {vcg.dtype}")
+  if vcg.size == 0:
+    return np.zeros([0] * dims, dtype=np.uint32, order="F")
+  g = np.asfortranarray(vcg)
+  while g.ndim < 3:
+    g = g[..., np.newaxis]
+  sx, sy, sz = g.shape
+  # backward edges the reference follows: (direction, bit number); 2D graphs have two layouts
+  edges = [((-1, 0, 0), 2), ((0, -1, 0), 4)]
+  if sz == 1:
+    if connectivity in (8, 26):
+      edges += [((-1, -1, 0), 8), ((1, -1, 0), 7)] if g.dtype == np.uint8 else [((-1, -1, 0), 10), ((1, -1, 0), 9)]
+  else:
+    edges.append(((0, 0, -1), 6))
+    if connectivity == 26:
+      if g.dtype != np.uint32:
+        raise ValueError(f"Only uint32 is supported for 18 and 26 connected. Got: {g.dtype}")
+      edges += [((-1, -1, 0), 10), ((1, -1, 0), 9), ((-1, 0, -1), 16), ((1, 0, -1), 15), ((0, -1, -1), 18),
+                ((0, 1, -1), 17), ((-1, -1, -1), 26), ((1, -1, -1), 25), ((-1, 1, -1), 24), ((1, 1, -1), 23)]
+  idx = np.arange(g.size, dtype=np.int64).reshape(g.shape, order="F")
+  ia, ib = [], []
+  for d, bit in edges:
+    sp, sq = _shifted_pairs(g.shape, d)
+    m = (g[sp].astype(np.uint32) & np.uint32(1 << (bit - 1))) != 0
+    ia.append(idx[sp][m]); ib.append(idx[sq][m])
+  ia, ib = np.concatenate(ia), np.concatenate(ib)
+  n = g.size
+  _, lab = graph_cc(coo_matrix((np.ones(ia.size, dtype=np.int8), (ia, ib)), shape=(n, n)), directed=False)
+  # number by first appearance in Fortran (memory) order
+  _, first = np.unique(lab, return_index=True)
+  rank = np.empty(first.size, dtype=np.int64)
+  rank[np.argsort(first)] = np.arange(1, first.size + 1)
+  out = rank[lab].astype(np.uint32).reshape(g.shape, order="F")
+  while out.ndim > dims:
+    out = out[..., 0]
+  return (out, int(first.size)) if return_N else out

@@ -31,6 +31,10 @@ x = benchdata.voronoi_multilabel((n, n, n), cell=40, seed=2, device=dev, dtype=t
 run("voronoi u32 26", x, connectivity=26)
 run("voronoi u32 6", x, connectivity=6)
 run("voronoi u32 18", x, connectivity=18)
+if os.environ.get("U64"):
+    x64 = benchdata.voronoi_multilabel((256, 1024, 1024), cell=80, seed=2, device=dev, dtype=torch.int64, id_bits=62)
+    run("voronoi u64 256x1024x1024 26", x64, connectivity=26)
+    del x64
 xb = benchdata.random_binary((n, n, n), 0.5, 1, dev)
 run("random binary u8 26 (multilabel path)", xb, connectivity=26)
 run("random binary u8 26 (binary)", xb, connectivity=26, binary_image=True)

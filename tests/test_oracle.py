@@ -124,3 +124,56 @@ def test_oracle_dust_matches_reference(oracle_mod):
   assert dN == int(np.count_nonzero(keep))
   if ref is not None:
     assert np.array_equal(ref.statistics(lab, no_slice_conversion=True)["voxel_counts"], cnt)
+
+
+def _graph_cases(rng, n):
+  for it in range(n):
+    dims = int(rng.integers(2, 4))
+    shape = tuple(int(rng.integers(1, 11)) for _ in range(dims))
+    dt = [np.uint8, np.uint16, np.uint32, np.uint64, np.int32, bool][rng.integers(6)]
+    x = (rng.random(shape) < 0.5) if dt == bool else rng.integers(0, 3, shape).astype(dt)
+    x = np.asarray(x, order="F" if rng.random() < 0.5 else "C")
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    yield x, conns[rng.integers(len(conns))]
+
+
+def test_oracle_graph_rows_vs_reference(oracle_mod):
+  """voxel_connectivity_graph, color_connectivity_graph, largest_k against the reference build."""
+  ref = oracle_mod.reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built (needs /root/reference)")
+  rng = np.random.default_rng(17)
+  n = 0
+  for x, c in _graph_cases(rng, 150):
+    a, b = ref.voxel_connectivity_graph(x, connectivity=c), oracle_mod.voxel_connectivity_graph(x, connectivity=c)
+    assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (x.shape, x.dtype, c)
+    if c in (4, 8, 6, 26):
+      ca, Na = ref.color_connectivity_graph(a, connectivity=c, return_N=True)
+      cb, Nb = oracle_mod.color_connectivity_graph(a, connectivity=c, return_N=True)
+      assert Na == Nb and np.array_equal(ca, cb), (x.shape, x.dtype, c)
+      n += 1
+  assert n > 60
+
+
+def test_oracle_largest_k_vs_reference_python_layer(oracle_mod):
+  """largest_k lives in the reference's Python layer (cc3d/__init__.py:199-279); it is executed in place from
+  /root/reference (nothing copied) to pin the oracle's restatement."""
+  pkg = oracle_mod.reference_package()
+  if pkg is None:
+    pytest.skip("reference Python layer not available (needs /root/reference and oracle/_ref)")
+  rng = np.random.default_rng(18)
+  checked = 0
+  for it in range(80):
+    shape = tuple(int(rng.integers(2, 14)) for _ in range(3))
+    x = np.asarray(blobs(rng, shape, 6, 2).astype(np.uint32), order="F" if it % 2 else "C")
+    for k in (0, 1, 2, 3, 50):
+      a = pkg.largest_k(x, k, connectivity=26, return_N=True) if k else (pkg.largest_k(x, k), 0)
+      b = oracle_mod.largest_k(x, k, connectivity=26, return_N=True) if k else (oracle_mod.largest_k(x, k), 0)
+      assert a[1] == b[1] and a[0].dtype == b[0].dtype and a[0].shape == b[0].shape, (shape, k)
+      assert np.array_equal(a[0], b[0]), (shape, k)
+      assert a[0].flags.c_contiguous == b[0].flags.c_contiguous and a[0].flags.f_contiguous == b[0].flags.f_contiguous
+      checked += 1
+    d1, n1 = pkg.dust(x, threshold=5, return_N=True), None
+    d2 = oracle_mod.dust(x, threshold=5, return_N=True)
+    assert d1[1] == d2[1] and np.array_equal(d1[0], d2[0])
+  assert checked == 400

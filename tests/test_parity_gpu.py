@@ -348,3 +348,56 @@ def test_many_runs_per_word_tiles(cc3d, oracle_mod):
     a, Na = _truth(oracle_mod).connected_components(x, connectivity=conn, return_N=True)
     b, Nb = cc3d.connected_components(x, connectivity=conn, return_N=True)
     assert_same_labels(a, Na, b, Nb, f"dense runs conn={conn}")
+
+
+def test_voxel_and_color_connectivity_graph(cc3d, oracle_mod):
+  """voxel_connectivity_graph and color_connectivity_graph against the reference (bit-exact)."""
+  truth = _truth(oracle_mod)
+  rng = np.random.default_rng(21)
+  dts = [np.uint8, np.uint16, np.uint32, np.uint64, np.int16, np.int64, bool]
+  n = 0
+  for it in range(160):
+    dims = int(rng.integers(2, 4))
+    shape = tuple(int(rng.integers(1, 40)) for _ in range(dims)) if it % 8 else ((130, 70, 33) if dims == 3 else (300, 257))
+    dt = dts[rng.integers(len(dts))]
+    x = (rng.random(shape) < 0.5) if dt == bool else blobs(rng, shape, 4, int(rng.integers(1, 5))).astype(dt)
+    x = np.asarray(x, order="F" if rng.random() < 0.5 else "C")
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    c = conns[rng.integers(len(conns))]
+    a, b = truth.voxel_connectivity_graph(x, connectivity=c), cc3d.voxel_connectivity_graph(x, connectivity=c)
+    assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (shape, np.dtype(dt), c)
+    if c in (4, 8, 6, 26):
+      # knock a few links out so that the graph is not just the label image again
+      g = a.copy()
+      g[rng.random(g.shape) < 0.05] &= g.dtype.type(rng.integers(0, 1 << 26) & (0xFF if g.dtype == np.uint8 else 0x3FFFFFF))
+      ca, Na = truth.color_connectivity_graph(g, connectivity=c, return_N=True)
+      cb, Nb = cc3d.color_connectivity_graph(g, connectivity=c, return_N=True)
+      assert Na == Nb and ca.dtype == cb.dtype and np.array_equal(ca, cb), (shape, np.dtype(dt), c)
+      n += 1
+  assert n > 60
+  import torch
+  x = blobs(rng, (40, 50, 60), 5, 3).astype(np.int32)
+  for c in (6, 26):
+    want = truth.voxel_connectivity_graph(x, connectivity=c)
+    got = cc3d.voxel_connectivity_graph(torch.from_numpy(x).cuda(), connectivity=c)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy().view(want.dtype), want)
+
+
+def test_largest_k(cc3d, oracle_mod):
+  """largest_k (reference path without fastremap) on numpy arrays and CUDA tensors."""
+  import torch
+  truth = oracle_mod.reference_package() or oracle_mod   # the reference's Python layer when /root/reference is here
+  rng = np.random.default_rng(22)
+  for it in range(40):
+    shape = tuple(int(rng.integers(4, 60)) for _ in range(3))
+    x = np.asarray(blobs(rng, shape, 7, int(rng.integers(2, 5))).astype(np.uint32), order="F" if it % 2 else "C")
+    for k in (0, 1, 2, 5, 1000):
+      a = truth.largest_k(x, k, connectivity=26, return_N=True) if k else (truth.largest_k(x, k), 0)
+      b = cc3d.largest_k(x, k, connectivity=26, return_N=True) if k else (cc3d.largest_k(x, k), 0)
+      assert a[1] == b[1] and a[0].dtype == b[0].dtype and np.array_equal(a[0], b[0]), (shape, k)
+      assert a[0].flags.c_contiguous == b[0].flags.c_contiguous
+    if it % 8 == 0:
+      t = torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).cuda()
+      a = truth.largest_k(np.ascontiguousarray(x), 3, return_N=True)
+      b = cc3d.largest_k(t, 3, return_N=True)
+      assert a[1] == b[1] and np.array_equal(b[0].cpu().numpy().view(a[0].dtype), a[0])
