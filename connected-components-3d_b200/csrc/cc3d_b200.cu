@@ -51,7 +51,12 @@ struct Arena {
   }
 };
 std::mutex g_pool_mu;
-Arena g_cached;  // at most one idle arena is kept
+// Idle arenas. One is enough for back-to-back calls; the multi-slab path on ONE device (every slab's session is
+// alive until the merge) parks up to CC_ARENA_POOL of them so that the next volume does not pay cudaMalloc / cudaFree
+// (which synchronise the device) per slab.
+#define CC_ARENA_POOL 16
+std::vector<Arena> g_pool;
+int g_live = 0, g_peak_live = 0;   // arenas checked out now / at most at the same time
 
 // the work recorded by a stream-ordered release has to finish before the memory is reused (or freed)
 void arena_settle(Arena& a, cudaStream_t s, bool on_stream) {
@@ -61,37 +66,64 @@ void arena_settle(Arena& a, cudaStream_t s, bool on_stream) {
   cudaEventDestroy(a.pending);
   a.pending = nullptr;
 }
+void arena_free(Arena& a) {
+  arena_settle(a, nullptr, false);
+  if (a.base) cudaFree(a.base);
+  a = Arena();
+}
 int arena_acquire(size_t bytes, Arena* out, cudaStream_t s = nullptr, bool on_stream = false) {
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (g_cached.base && g_cached.device == dev && g_cached.cap >= bytes) {
-      *out = g_cached; out->off = 0;
-      g_cached = Arena();
+    // best fit among the idle arenas of this device
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); i++)
+      if (g_pool[i].device == dev && g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = i;
+    if (best >= 0) {
+      *out = g_pool[best]; out->off = 0;
+      g_pool.erase(g_pool.begin() + best);
       arena_settle(*out, s, on_stream);
+      g_peak_live = std::max(g_peak_live, ++g_live);
       return 0;
     }
-    if (g_cached.base) { arena_settle(g_cached, nullptr, false); cudaFree(g_cached.base); g_cached = Arena(); }
   }
   Arena a;
   a.device = dev;
   a.cap = bytes + (bytes >> 4) + (1 << 20);
   cudaError_t e = cudaMalloc((void**)&a.base, a.cap);
+  if (e != cudaSuccess) {
+    // out of memory: drop the idle arenas and try once more
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      for (auto& p : g_pool) arena_free(p);
+      g_pool.clear();
+    }
+    e = cudaMalloc((void**)&a.base, a.cap);
+  }
   if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
   *out = a;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_peak_live = std::max(g_peak_live, ++g_live);
+  }
   return 0;
 }
 void arena_release(Arena& a) {
   if (!a.base) return;
   std::lock_guard<std::mutex> lk(g_pool_mu);
-  if (g_cached.base) {
-    if (g_cached.cap >= a.cap) { arena_settle(a, nullptr, false); cudaFree(a.base); a = Arena(); return; }
-    arena_settle(g_cached, nullptr, false);
-    cudaFree(g_cached.base);
-  }
-  g_cached = a; g_cached.off = 0;
+  a.off = 0;
+  if (g_live > 0) g_live--;
+  g_pool.push_back(a);
   a = Arena();
+  // keep as many idle arenas as were ever checked out at the same time (1 for plain calls), the largest ones
+  while ((int)g_pool.size() > std::min(std::max(g_peak_live, 1), CC_ARENA_POOL)) {
+    int smallest = 0;
+    for (int i = 1; i < (int)g_pool.size(); i++) if (g_pool[i].cap < g_pool[smallest].cap) smallest = i;
+    arena_free(g_pool[smallest]);
+    g_pool.erase(g_pool.begin() + smallest);
+  }
 }
 // release while work enqueued on `s` still uses the arena: the next user waits for it (on its own stream)
 void arena_release_after(Arena& a, cudaStream_t s) {
@@ -194,11 +226,17 @@ int cc3d_b200_last_timings(const char** names, float* ms, int cap) {
 }
 unsigned long long cc3d_b200_launch_count(void) { return g_launches.load(); }
 void cc3d_b200_debug_set_queue_capacity(uint64_t entries) { g_queue_cap_override.store(entries); }
-size_t cc3d_b200_workspace_bytes(void) { std::lock_guard<std::mutex> lk(g_pool_mu); return g_cached.cap; }
+size_t cc3d_b200_workspace_bytes(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  size_t n = 0;
+  for (auto& p : g_pool) n += p.cap;
+  return n;
+}
 void cc3d_b200_release_workspace(void) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
-  if (g_cached.base) cudaFree(g_cached.base);
-  g_cached = Arena();
+  for (auto& p : g_pool) arena_free(p);
+  g_pool.clear();
+  g_peak_live = g_live;
 }
 
 static int check_shape(i64 sx, i64 sy, i64 sz) {
