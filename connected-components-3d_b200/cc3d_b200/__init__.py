@@ -433,9 +433,9 @@ def _torch_max(t) -> int:
     return 0
   if t.dtype in (getattr(torch, "uint16", None), getattr(torch, "uint32", None), getattr(torch, "uint64", None)):
     signed = {2: torch.int16, 4: torch.int32, 8: torch.int64}[t.element_size()]
-    v = t.view(signed)
-    if int(v.min()) >= 0:
-      return int(v.max())
+    lo, hi = torch.aminmax(t.view(signed))     # one pass
+    if int(lo) >= 0:
+      return int(hi)
     return int(t.cpu().numpy().max())
   return int(t.max())
 

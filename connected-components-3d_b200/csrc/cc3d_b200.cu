@@ -797,7 +797,7 @@ static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts,
   auto k = k_statistics<LT>;
   if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable)); attr = true; }
   k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
-  k<<<148 * 2, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums);
+  k<<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums);
   g_launches += 2;
   return 0;
 }

@@ -97,7 +97,7 @@ static int launch_union(const LabelArgs& a) {
     if (!attr_set) { cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     k_union_tile_items<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else {
-    const size_t smem = (size_t)(CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * CC_TILE_GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2) * 4;
+    const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
     if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   }

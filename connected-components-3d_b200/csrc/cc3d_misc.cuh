@@ -68,28 +68,31 @@ __global__ void k_minmax_final(const T* __restrict__ part_min, const T* __restri
   if (threadIdx.x == 0) { out2[0] = mn; out2[1] = mx; }
 }
 
-// ---- row a13: statistics (fastcc3d.pyx:771-938). Memory-axis coordinates. Runs of equal labels inside
-// a warp are aggregated, then merged in a per-CTA shared-memory table that is flushed with global
-// atomics once per CTA (persistent CTAs), so that a giant component costs O(#CTAs) global atomics. ----
+// ---- row a13: statistics (fastcc3d.pyx:771-938). Memory-axis coordinates.
+// One lane per voxel column: a warp owns a 32-voxel word column of one z-plane and walks CC_STAT_YCH rows down y;
+// every lane keeps the label of its current VERTICAL run in registers and only when the label changes adds the
+// finished run (count = rows, x fixed, y range, z) to a per-CTA shared-memory hash table. Label volumes have
+// vertical runs of tens to hundreds of voxels, so the table sees a few atomics per hundred voxels. The table
+// uses native 32-bit shared atomics only (64-bit sums are lo/hi pairs with an explicit carry; a 64-bit shared
+// atomicAdd compiles to a compare-and-swap spin loop) and is flushed with global atomics once per CTA
+// (persistent CTAs), so that a giant component costs O(#CTAs) global atomics. ----
 #define CC_STAT_SLOTS 1024
+#define CC_STAT_YCH 64
+#define CC_STAT_UNR 8
 struct StatTable {
   u32 key[CC_STAT_SLOTS];   // label + 1, 0 = empty
   u32 cnt[CC_STAT_SLOTS];
   u32 bb[CC_STAT_SLOTS][6];
-  unsigned long long sum[CC_STAT_SLOTS][3];
+  u32 sumlo[CC_STAT_SLOTS][3];
+  u32 sumhi[CC_STAT_SLOTS][3];
 };
 
-__device__ __forceinline__ void stat_global(u32 l, u32 len, u32 x0, u32 x1, u32 y, u32 z, unsigned long long sx_,
-                                            u32* counts, u32* bbox, unsigned long long* sums) {
-  atomicAdd(&counts[l], len);
-  u32* b = bbox + 6 * (size_t)l;
-  atomicMin(&b[0], x0); atomicMax(&b[1], x1);
-  atomicMin(&b[2], y); atomicMax(&b[3], y);
-  atomicMin(&b[4], z); atomicMax(&b[5], z);
-  unsigned long long* s = sums + 3 * (size_t)l;
-  atomicAdd(&s[0], sx_);
-  atomicAdd(&s[1], (unsigned long long)y * len);
-  atomicAdd(&s[2], (unsigned long long)z * len);
+// 64-bit add on a {lo, hi} pair of shared 32-bit words
+__device__ __forceinline__ void sm_add64(u32* lo, u32* hi, unsigned long long v) {
+  const u32 vl = (u32)v, vh = (u32)(v >> 32);
+  const u32 old = atomicAdd(lo, vl);
+  const u32 carry = (old + vl < old) ? 1u : 0u;
+  if (vh + carry) atomicAdd(hi, vh + carry);
 }
 
 template <typename LT>
@@ -102,54 +105,100 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
     tb.key[i] = 0; tb.cnt[i] = 0;
     tb.bb[i][0] = tb.bb[i][2] = tb.bb[i][4] = 0xFFFFFFFFu;
     tb.bb[i][1] = tb.bb[i][3] = tb.bb[i][5] = 0;
-    tb.sum[i][0] = tb.sum[i][1] = tb.sum[i][2] = 0;
+    tb.sumlo[i][0] = tb.sumlo[i][1] = tb.sumlo[i][2] = 0;
+    tb.sumhi[i][0] = tb.sumhi[i][1] = tb.sumhi[i][2] = 0;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const u32 sx = (u32)g.sx, sy = (u32)g.sy;
+  const i64 W = g.W;
+  const i64 nych = (g.sy + CC_STAT_YCH - 1) / CC_STAT_YCH;
+  const i64 ntasks = W * nych * g.sz;
   const i64 nwarps_total = ((i64)gridDim.x * blockDim.x) >> 5;
-  const i64 nseg_total = g.sy * g.sz * g.W;
-  for (i64 wid = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nseg_total; wid += nwarps_total) {
-    const i64 row = wid / g.W, seg = wid - row * g.W;
-    const i64 x = seg * 32 + lane;
-    const bool inx = x < g.sx;
-    const u64 l64 = inx ? (u64)labels[row * g.sx + x] : ~0ull;
-    const bool ok = inx && l64 <= N;
-    const u32 l = ok ? (u32)l64 : 0xFFFFFFFFu;
-    const u32 prev = __shfl_up_sync(CC_FULL, l, 1);
-    const bool head = lane == 0 || prev != l;
-    const u32 heads = __ballot_sync(CC_FULL, head);
-    if (head && ok) {
-      const u32 after = heads & ~((2u << lane) - 1u);  // heads strictly above this lane
-      const int end = after ? (__ffs(after) - 1) : 32;   // one past the run's last lane
-      const u32 len = end - lane;
-      const u32 x0 = (u32)x, x1 = (u32)(x + len - 1);
-      const unsigned long long sumx = (unsigned long long)len * x0 + (unsigned long long)len * (len - 1) / 2;
-      const u32 z = (u32)(row / g.sy), y = (u32)(row - (i64)z * g.sy);
-      // find / claim a slot
-      u32 h = (l * 2654435761u) >> 22;  // 10 bits
-      int slot = -1;
+  constexpr u32 NONE = 0xFFFFFFFFu;
+
+  // n finished vertical runs of label l that share their rows ya..yb in plane z: columns xmin..xmax, xs = sum of
+  // their x (lanes of a warp that finish the same label at the same row are added by one of them)
+  auto flush = [&](u32 l, u32 n, unsigned long long xs, u32 xmin, u32 xmax, u32 ya, u32 yb, u32 z) {
+    const u32 rows = yb - ya + 1;
+    const u32 cnt = n * rows;
+    const unsigned long long sumx = xs * rows;
+    const unsigned long long sumy = ((unsigned long long)ya + yb) * rows / 2 * n;   // (ya+yb)*rows is even
+    const unsigned long long sumz = (unsigned long long)z * cnt;
+    u32 h = (l * 2654435761u) >> 22;  // 10 bits
+    int slot = -1;
 #pragma unroll 1
-      for (int probe = 0; probe < 16; probe++) {
-        const u32 s = (h + probe) & (CC_STAT_SLOTS - 1);
-        const u32 k = tb.key[s];
-        if (k == l + 1) { slot = s; break; }
-        if (k == 0) {
-          const u32 old = atomicCAS(&tb.key[s], 0u, l + 1);
-          if (old == 0 || old == l + 1) { slot = s; break; }
-        }
-      }
-      if (slot >= 0) {
-        atomicAdd(&tb.cnt[slot], len);
-        atomicMin(&tb.bb[slot][0], x0); atomicMax(&tb.bb[slot][1], x1);
-        atomicMin(&tb.bb[slot][2], y); atomicMax(&tb.bb[slot][3], y);
-        atomicMin(&tb.bb[slot][4], z); atomicMax(&tb.bb[slot][5], z);
-        atomicAdd(&tb.sum[slot][0], sumx);
-        atomicAdd(&tb.sum[slot][1], (unsigned long long)y * len);
-        atomicAdd(&tb.sum[slot][2], (unsigned long long)z * len);
-      } else {
-        stat_global(l, len, x0, x1, y, z, sumx, counts, bbox, sums);
+    for (int probe = 0; probe < 16; probe++) {
+      const u32 s = (h + probe) & (CC_STAT_SLOTS - 1);
+      const u32 k = *(volatile u32*)&tb.key[s];
+      if (k == l + 1) { slot = s; break; }
+      if (k == 0) {
+        const u32 old = atomicCAS(&tb.key[s], 0u, l + 1);
+        if (old == 0 || old == l + 1) { slot = s; break; }
       }
     }
+    if (slot < 0) {   // table full: straight to global memory
+      atomicAdd(&counts[l], cnt);
+      u32* b = bbox + 6 * (size_t)l;
+      atomicMin(&b[0], xmin); atomicMax(&b[1], xmax);
+      atomicMin(&b[2], ya); atomicMax(&b[3], yb);
+      atomicMin(&b[4], z); atomicMax(&b[5], z);
+      unsigned long long* sg = sums + 3 * (size_t)l;
+      atomicAdd(&sg[0], sumx); atomicAdd(&sg[1], sumy); atomicAdd(&sg[2], sumz);
+      return;
+    }
+    atomicAdd(&tb.cnt[slot], cnt);
+    volatile u32* b = tb.bb[slot];   // most runs do not move the box: read before the atomic
+    if (xmin < b[0]) atomicMin(&tb.bb[slot][0], xmin);
+    if (xmax > b[1]) atomicMax(&tb.bb[slot][1], xmax);
+    if (ya < b[2]) atomicMin(&tb.bb[slot][2], ya);
+    if (yb > b[3]) atomicMax(&tb.bb[slot][3], yb);
+    if (z < b[4]) atomicMin(&tb.bb[slot][4], z);
+    if (z > b[5]) atomicMax(&tb.bb[slot][5], z);
+    sm_add64(&tb.sumlo[slot][0], &tb.sumhi[slot][0], sumx);
+    sm_add64(&tb.sumlo[slot][1], &tb.sumhi[slot][1], sumy);
+    sm_add64(&tb.sumlo[slot][2], &tb.sumhi[slot][2], sumz);
+  };
+  // warp step: lanes with need == true finish the run (cur, ystart .. yend); lanes that finish the same label
+  // with the same first row form a group and the group's lowest lane adds it
+  auto finish_runs = [&](bool need, u32 cur, u32 ystart, u32 yend, u32 xbase, u32 z) {
+    const u32 m = __ballot_sync(CC_FULL, need);
+    if (!need) return;
+    const u32 grp = __match_any_sync(m, ((unsigned long long)cur << 32) | ystart);
+    if (lane != __ffs(grp) - 1) return;
+    const u32 n = __popc(grp);
+    const u32 possum = __popc(grp & 0xAAAAAAAAu) + 2 * __popc(grp & 0xCCCCCCCCu) + 4 * __popc(grp & 0xF0F0F0F0u) +
+                       8 * __popc(grp & 0xFF00FF00u) + 16 * __popc(grp & 0xFFFF0000u);
+    flush(cur, n, (unsigned long long)n * xbase + possum, xbase + __ffs(grp) - 1, xbase + 31 - __clz(grp), ystart, yend, z);
+  };
+
+  for (i64 task = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < ntasks; task += nwarps_total) {
+    const i64 w = task % W, t = task / W;
+    const u32 ych = (u32)(t % nych), z = (u32)(t / nych);
+    const u32 xbase = (u32)(w * 32);
+    const u32 x = xbase + lane;
+    const bool inx = x < sx;
+    const u32 y0 = ych * CC_STAT_YCH, y1 = min(sy, y0 + CC_STAT_YCH);
+    const LT* __restrict__ p = labels + (((size_t)z * sy + y0) * sx + (inx ? x : 0));
+    u32 cur = NONE, ystart = y0;
+    for (u32 yb = y0; yb < y1; yb += CC_STAT_UNR) {
+      u64 v[CC_STAT_UNR];
+#pragma unroll
+      for (int k = 0; k < CC_STAT_UNR; k++) v[k] = (inx && yb + k < y1) ? (u64)p[(size_t)k * sx] : ~0ull;
+      p += (size_t)CC_STAT_UNR * sx;
+#pragma unroll
+      for (int k = 0; k < CC_STAT_UNR; k++) {
+        if (yb + k < y1) {   // warp-uniform
+          const u32 l = v[k] <= N ? (u32)v[k] : NONE;
+          const bool change = l != cur;
+          if (__any_sync(CC_FULL, change)) {
+            finish_runs(change && cur != NONE, cur, ystart, yb + k - 1, xbase, z);
+            if (change) { cur = l; ystart = yb + k; }
+          }
+        }
+      }
+    }
+    finish_runs(cur != NONE, cur, ystart, y1 - 1, xbase, z);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < CC_STAT_SLOTS; i += blockDim.x) {
@@ -161,7 +210,8 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
     atomicMin(&b[2], tb.bb[i][2]); atomicMax(&b[3], tb.bb[i][3]);
     atomicMin(&b[4], tb.bb[i][4]); atomicMax(&b[5], tb.bb[i][5]);
     unsigned long long* s = sums + 3 * (size_t)l;
-    atomicAdd(&s[0], tb.sum[i][0]); atomicAdd(&s[1], tb.sum[i][1]); atomicAdd(&s[2], tb.sum[i][2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) atomicAdd(&s[k], ((unsigned long long)tb.sumhi[i][k] << 32) | tb.sumlo[i][k]);
   }
 }
 

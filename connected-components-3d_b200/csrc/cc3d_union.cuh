@@ -275,15 +275,22 @@ struct WordEdges {
 // ---------------------------------------------------------------------------------------------
 struct EdgeQueue { u64* q; u32* count; u32* ovf; u32 cap; };
 
+// Label volumes (MODE_EQ) are latency / barrier bound in this kernel: six resident CTAs per SM (40 registers,
+// a 512-entry staging buffer) hide more of it; dense binary tiles need the registers and the larger buffers.
+template <int MODE> struct TileQueues {
+  static constexpr u32 GQ = MODE == MODE_EQ ? 512 : CC_TILE_GQ;
+  static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2;
+};
 template <typename T, int MODE, int CONN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MODE == MODE_EQ ? 6 : 0)
 k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
+  constexpr u32 GQN = TileQueues<MODE>::GQ;
   extern __shared__ __align__(16) u32 smem_u32[];
   uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [CC_TILE_NODES] 16-bit parents
   u32* lq = smem_u32 + CC_TILE_NODES / 2;                  // [CC_TILE_LQ]
-  u64* gq = reinterpret_cast<u64*>(lq + CC_TILE_LQ);       // [CC_TILE_GQ]
-  u32* segRS = lq + CC_TILE_LQ + 2 * CC_TILE_GQ;           // [CC_TILE_WORDS] first run id of every row segment
+  u64* gq = reinterpret_cast<u64*>(lq + CC_TILE_LQ);       // [GQN]
+  u32* segRS = lq + CC_TILE_LQ + 2 * GQN;           // [CC_TILE_WORDS] first run id of every row segment
   uint16_t* todo = reinterpret_cast<uint16_t*>(segRS + CC_TILE_WORDS);   // [CC_TILE_WORDS]
   __shared__ u32 s_ln[4], s_gn, s_gbase, s_tn, s_big, s_runs;
   const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
@@ -359,7 +366,7 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
           else sm_union16(lab, lp, lq_);
         } else {
           const u32 pos = atomicAdd(&s_gn, 1u);
-          if (pos < CC_TILE_GQ) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+          if (pos < GQN) gq[pos] = (u64)gp | ((u64)gq_ << 32);
           else push_global(gp, gq_);
         }
       };
@@ -387,7 +394,7 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
               else if (loc) sm_union16(lab, lp, lq_);
               if (!loc) {
                 const u32 gpos = atomicAdd(&s_gn, 1u);
-                if (gpos < CC_TILE_GQ) gq[gpos] = (u64)gp | ((u64)gq_ << 32);
+                if (gpos < GQN) gq[gpos] = (u64)gp | ((u64)gq_ << 32);
                 else push_global(gp, gq_);
               }
             }
@@ -399,7 +406,7 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
               const u32 below = CC_FULL >> (31 - b);
               const u32 gp = we.RSp + __popc(we.Sp & below), gq_ = RSq + __popc(Sq & below);
               const u32 pos = pos0 + k++;
-              if (pos < CC_TILE_GQ) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+              if (pos < GQN) gq[pos] = (u64)gp | ((u64)gq_ << 32);
               else push_global(gp, gq_);
             }
           }
@@ -423,7 +430,7 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
   }
 
   // ---- staged edges -> global queue; runs -> tile roots ----
-  const u32 gn = min(s_gn, (u32)CC_TILE_GQ);
+  const u32 gn = min(s_gn, GQN);
   if (threadIdx.x == 0 && gn) s_gbase = atomicAdd(GQ.count, gn);
   __syncthreads();
   for (u32 e = threadIdx.x; e < gn; e += blockDim.x) {
