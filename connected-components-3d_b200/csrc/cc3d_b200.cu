@@ -793,9 +793,9 @@ int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t
 
 template <typename LT>
 static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts, u32* bbox, u64* sums, cudaStream_t s) {
-  static bool attr = false;
+  static PerDeviceOnce once;
   auto k = k_statistics<LT>;
-  if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable)); attr = true; }
+  if (once.first()) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable));
   k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
   k<<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums);
   g_launches += 2;

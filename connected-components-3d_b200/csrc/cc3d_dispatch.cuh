@@ -21,6 +21,18 @@ struct LabelArgs {
 };
 #define CC_QUEUE_BLOCKS (148 * 8)
 
+// cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) whether it was done
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 template <typename T> int run_faces_stage(const LabelArgs& a);     // kernel A
 template <typename T> int run_union_stage(const LabelArgs& a);     // kernel B
 template <typename T> int run_periodic_stage(const LabelArgs& a);  // kernel P (after kernel B)
@@ -34,11 +46,10 @@ static void launch_faces_staged(const LabelArgs& a, const Edge<T, MODE>& E, bool
   const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
   const T* in = static_cast<const T*>(a.in);
   constexpr size_t smem = faces_async_smem<T, NW>();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(k_faces_async<T, MODE, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_faces_async<T, MODE, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
   }
   if (two_d) k_faces_async<T, MODE, false, NW><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
   else k_faces_async<T, MODE, true, NW><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
@@ -90,15 +101,16 @@ static int launch_union(const LabelArgs& a) {
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
+  const bool set_attr = once.first();
   if constexpr (MODE == MODE_DELTA) {
     // continuous predicate: edge-parallel item lists (every word has candidates that need a value test)
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
-    if (!attr_set) { cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_union_tile_items<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else {
     const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
-    if (!attr_set) { cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);

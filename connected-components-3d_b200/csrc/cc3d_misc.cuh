@@ -69,22 +69,34 @@ __global__ void k_minmax_final(const T* __restrict__ part_min, const T* __restri
 }
 
 // ---- row a13: statistics (fastcc3d.pyx:771-938). Memory-axis coordinates.
-// One lane per voxel column: a warp owns a 32-voxel word column of one z-plane and walks CC_STAT_YCH rows down y;
-// every lane keeps the label of its current VERTICAL run in registers and only when the label changes adds the
-// finished run (count = rows, x fixed, y range, z) to a per-CTA shared-memory hash table. Label volumes have
-// vertical runs of tens to hundreds of voxels, so the table sees a few atomics per hundred voxels. The table
-// uses native 32-bit shared atomics only (64-bit sums are lo/hi pairs with an explicit carry; a 64-bit shared
-// atomicAdd compiles to a compare-and-swap spin loop) and is flushed with global atomics once per CTA
-// (persistent CTAs), so that a giant component costs O(#CTAs) global atomics. ----
-#define CC_STAT_SLOTS 1024
+// Three levels of accumulation, each fed by the one below only when a label ends:
+//   lane  : one lane per voxel column. A warp owns a 32-voxel word column of one z-plane and walks
+//           CC_STAT_YCH rows down y; a lane keeps the label and first row of its current VERTICAL run in
+//           registers (label volumes have vertical runs of tens to hundreds of voxels).
+//   warp  : when lanes finish runs, the lanes that finish the same label are reduced (redux.sync) and added to a
+//           per-warp table of 8 labels in shared memory. Its fields are relative to the warp's task (x - xbase,
+//           y - y0, at most 2048 voxels), so everything is 32-bit and the update is a plain read-modify-write by one
+//           lane: no atomics, no hashing.
+//   CTA   : at the end of a task (or when the warp table is full) its entries go to a per-CTA hash table with
+//           absolute coordinates, native 32-bit shared atomics only (64-bit sums are lo/hi pairs with an explicit
+//           carry; a 64-bit shared atomicAdd compiles to a compare-and-swap spin loop). Persistent CTAs flush the
+//           table with global atomics once, so a giant component costs O(#CTAs) global atomics. ----
+#define CC_STAT_SLOTS 512
 #define CC_STAT_YCH 64
 #define CC_STAT_UNR 8
+#define CC_STAT_WSLOTS 8
 struct StatTable {
   u32 key[CC_STAT_SLOTS];   // label + 1, 0 = empty
   u32 cnt[CC_STAT_SLOTS];
   u32 bb[CC_STAT_SLOTS][6];
   u32 sumlo[CC_STAT_SLOTS][3];
   u32 sumhi[CC_STAT_SLOTS][3];
+  // per-warp tables (8 warps): task-relative
+  u32 wkey[8][CC_STAT_WSLOTS];   // label + 1, 0 = empty
+  u32 wcnt[8][CC_STAT_WSLOTS];
+  u32 wsx[8][CC_STAT_WSLOTS];    // sum of (x - xbase)
+  u32 wsy[8][CC_STAT_WSLOTS];    // sum of 2 * (y - y0)
+  u32 wbb[8][CC_STAT_WSLOTS];    // xmin | xmax << 8 | ymin << 16 | ymax << 24 (relative)
 };
 
 // 64-bit add on a {lo, hi} pair of shared 32-bit words
@@ -108,24 +120,21 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
     tb.sumlo[i][0] = tb.sumlo[i][1] = tb.sumlo[i][2] = 0;
     tb.sumhi[i][0] = tb.sumhi[i][1] = tb.sumhi[i][2] = 0;
   }
+  if (threadIdx.x < 8 * CC_STAT_WSLOTS) (&tb.wkey[0][0])[threadIdx.x] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 sx = (u32)g.sx, sy = (u32)g.sy;
   const i64 W = g.W;
   const i64 nych = (g.sy + CC_STAT_YCH - 1) / CC_STAT_YCH;
   const i64 ntasks = W * nych * g.sz;
-  const i64 nwarps_total = ((i64)gridDim.x * blockDim.x) >> 5;
   constexpr u32 NONE = 0xFFFFFFFFu;
+  const LT nmax = (u64)(LT)~(LT)0 <= N ? (LT)~(LT)0 : (LT)N;   // labels above N are ignored
+  u32* wkey = tb.wkey[warp]; u32* wcnt = tb.wcnt[warp]; u32* wsx = tb.wsx[warp]; u32* wsy = tb.wsy[warp]; u32* wbb = tb.wbb[warp];
 
-  // n finished vertical runs of label l that share their rows ya..yb in plane z: columns xmin..xmax, xs = sum of
-  // their x (lanes of a warp that finish the same label at the same row are added by one of them)
-  auto flush = [&](u32 l, u32 n, unsigned long long xs, u32 xmin, u32 xmax, u32 ya, u32 yb, u32 z) {
-    const u32 rows = yb - ya + 1;
-    const u32 cnt = n * rows;
-    const unsigned long long sumx = xs * rows;
-    const unsigned long long sumy = ((unsigned long long)ya + yb) * rows / 2 * n;   // (ya+yb)*rows is even
-    const unsigned long long sumz = (unsigned long long)z * cnt;
-    u32 h = (l * 2654435761u) >> 22;  // 10 bits
+  // CTA table: cnt voxels of label l with absolute sums and box
+  auto cta_add = [&](u32 l, u32 cnt, unsigned long long sumx, unsigned long long sumy, unsigned long long sumz,
+                     u32 xmin, u32 xmax, u32 ymin, u32 ymax, u32 z) {
+    u32 h = (l * 2654435761u) >> 23;  // 9 bits
     int slot = -1;
 #pragma unroll 1
     for (int probe = 0; probe < 16; probe++) {
@@ -141,64 +150,116 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
       atomicAdd(&counts[l], cnt);
       u32* b = bbox + 6 * (size_t)l;
       atomicMin(&b[0], xmin); atomicMax(&b[1], xmax);
-      atomicMin(&b[2], ya); atomicMax(&b[3], yb);
+      atomicMin(&b[2], ymin); atomicMax(&b[3], ymax);
       atomicMin(&b[4], z); atomicMax(&b[5], z);
       unsigned long long* sg = sums + 3 * (size_t)l;
       atomicAdd(&sg[0], sumx); atomicAdd(&sg[1], sumy); atomicAdd(&sg[2], sumz);
       return;
     }
     atomicAdd(&tb.cnt[slot], cnt);
-    volatile u32* b = tb.bb[slot];   // most runs do not move the box: read before the atomic
+    volatile u32* b = tb.bb[slot];   // most additions do not move the box: read before the atomic
     if (xmin < b[0]) atomicMin(&tb.bb[slot][0], xmin);
     if (xmax > b[1]) atomicMax(&tb.bb[slot][1], xmax);
-    if (ya < b[2]) atomicMin(&tb.bb[slot][2], ya);
-    if (yb > b[3]) atomicMax(&tb.bb[slot][3], yb);
+    if (ymin < b[2]) atomicMin(&tb.bb[slot][2], ymin);
+    if (ymax > b[3]) atomicMax(&tb.bb[slot][3], ymax);
     if (z < b[4]) atomicMin(&tb.bb[slot][4], z);
     if (z > b[5]) atomicMax(&tb.bb[slot][5], z);
     sm_add64(&tb.sumlo[slot][0], &tb.sumhi[slot][0], sumx);
     sm_add64(&tb.sumlo[slot][1], &tb.sumhi[slot][1], sumy);
     sm_add64(&tb.sumlo[slot][2], &tb.sumhi[slot][2], sumz);
   };
-  // warp step: lanes with need == true finish the run (cur, ystart .. yend); lanes that finish the same label
-  // with the same first row form a group and the group's lowest lane adds it
-  auto finish_runs = [&](bool need, u32 cur, u32 ystart, u32 yend, u32 xbase, u32 z) {
-    const u32 m = __ballot_sync(CC_FULL, need);
-    if (!need) return;
-    const u32 grp = __match_any_sync(m, ((unsigned long long)cur << 32) | ystart);
-    if (lane != __ffs(grp) - 1) return;
-    const u32 n = __popc(grp);
-    const u32 possum = __popc(grp & 0xAAAAAAAAu) + 2 * __popc(grp & 0xCCCCCCCCu) + 4 * __popc(grp & 0xF0F0F0F0u) +
-                       8 * __popc(grp & 0xFF00FF00u) + 16 * __popc(grp & 0xFFFF0000u);
-    flush(cur, n, (unsigned long long)n * xbase + possum, xbase + __ffs(grp) - 1, xbase + 31 - __clz(grp), ystart, yend, z);
+  // entry e of this warp's table -> CTA table (absolute coordinates of the task: xbase, y0, z)
+  auto spill = [&](int e, u32 xbase, u32 y0, u32 z) {
+    const u32 k = wkey[e];
+    if (!k) return;
+    const u32 cnt = wcnt[e], bb = wbb[e];
+    cta_add(k - 1, cnt, (unsigned long long)xbase * cnt + wsx[e], (unsigned long long)y0 * cnt + (wsy[e] >> 1),
+            (unsigned long long)z * cnt, xbase + (bb & 0xFFu), xbase + ((bb >> 8) & 0xFFu), y0 + ((bb >> 16) & 0xFFu),
+            y0 + (bb >> 24), z);
+    wkey[e] = 0;
+  };
+  // warp step (convergent): lanes with need == true finish the run of label cur over rows ystart..yend (relative
+  // to y0); one label per iteration of the loop
+  auto finish_runs = [&](bool need, u32 cur, u32 ystart, u32 yend, u32 xbase, u32 y0, u32 z) {
+    u32 m = __ballot_sync(CC_FULL, need);
+    while (m) {
+      const int leader = __ffs(m) - 1;
+      const u32 lab = __shfl_sync(CC_FULL, cur, leader);
+      const bool mine = need && cur == lab;
+      const u32 grp = __ballot_sync(CC_FULL, mine);
+      m &= ~grp;
+      u32 R = 0, SX = 0, SY = 0, YMIN = 0;
+      if (mine) {
+        const u32 rows = yend - ystart + 1;
+        R = __reduce_add_sync(grp, rows);
+        SX = __reduce_add_sync(grp, (u32)lane * rows);
+        SY = __reduce_add_sync(grp, (ystart + yend) * rows);       // = 2 * sum of (y - y0) over the runs
+        YMIN = __reduce_min_sync(grp, ystart);
+      }
+      // slot of the label in the warp table (lanes 0..7 look at one entry each)
+      const u32 k = lane < CC_STAT_WSLOTS ? wkey[lane] : 0xFFFFFFFFu;
+      const u32 hit = __ballot_sync(CC_FULL, k == lab + 1);
+      int slot;
+      if (hit) slot = __ffs(hit) - 1;
+      else {
+        const u32 empty = __ballot_sync(CC_FULL, k == 0);
+        if (empty) slot = __ffs(empty) - 1;
+        else {   // full: make room (round robin over the entries by label)
+          slot = (int)(lab & (CC_STAT_WSLOTS - 1));
+          if (lane == leader) spill(slot, xbase, y0, z);
+        }
+        __syncwarp();
+      }
+      if (lane == leader) {
+        const u32 xmin = (u32)(__ffs(grp) - 1), xmax = (u32)(31 - __clz(grp));
+        if (hit) {
+          const u32 bb = wbb[slot];
+          wcnt[slot] += R; wsx[slot] += SX; wsy[slot] += SY;
+          wbb[slot] = min(bb & 0xFFu, xmin) | (max((bb >> 8) & 0xFFu, xmax) << 8) | (min((bb >> 16) & 0xFFu, YMIN) << 16) |
+                      (max(bb >> 24, yend) << 24);
+        } else {
+          wkey[slot] = lab + 1; wcnt[slot] = R; wsx[slot] = SX; wsy[slot] = SY;
+          wbb[slot] = xmin | (xmax << 8) | (YMIN << 16) | (yend << 24);
+        }
+      }
+      __syncwarp();
+    }
   };
 
-  for (i64 task = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < ntasks; task += nwarps_total) {
+  // every CTA walks a contiguous range of tasks (a compact region of the volume: few labels in its table)
+  const i64 per_cta = (ntasks + gridDim.x - 1) / gridDim.x;
+  const i64 task_end = min(ntasks, (i64)(blockIdx.x + 1) * per_cta);
+  for (i64 task = (i64)blockIdx.x * per_cta + warp; task < task_end; task += blockDim.x >> 5) {
     const i64 w = task % W, t = task / W;
     const u32 ych = (u32)(t % nych), z = (u32)(t / nych);
     const u32 xbase = (u32)(w * 32);
     const u32 x = xbase + lane;
     const bool inx = x < sx;
-    const u32 y0 = ych * CC_STAT_YCH, y1 = min(sy, y0 + CC_STAT_YCH);
+    const u32 y0 = ych * CC_STAT_YCH;
+    const u32 nrow = min(sy, y0 + CC_STAT_YCH) - y0;
     const LT* __restrict__ p = labels + (((size_t)z * sy + y0) * sx + (inx ? x : 0));
-    u32 cur = NONE, ystart = y0;
-    for (u32 yb = y0; yb < y1; yb += CC_STAT_UNR) {
-      u64 v[CC_STAT_UNR];
+    u32 cur = NONE, ystart = 0;
+    auto row_step = [&](LT v, u32 r) {
+      const u32 l = (inx && v <= nmax) ? (u32)v : NONE;
+      const bool change = l != cur;
+      if (__any_sync(CC_FULL, change)) {
+        finish_runs(change && cur != NONE, cur, ystart, r - 1, xbase, y0, z);
+        if (change) { cur = l; ystart = r; }
+      }
+    };
+    u32 r = 0;
+    for (; r + CC_STAT_UNR <= nrow; r += CC_STAT_UNR) {   // full groups of rows: loads issued back to back
+      LT v[CC_STAT_UNR];
 #pragma unroll
-      for (int k = 0; k < CC_STAT_UNR; k++) v[k] = (inx && yb + k < y1) ? (u64)p[(size_t)k * sx] : ~0ull;
+      for (int k = 0; k < CC_STAT_UNR; k++) v[k] = p[(size_t)k * sx];
       p += (size_t)CC_STAT_UNR * sx;
 #pragma unroll
-      for (int k = 0; k < CC_STAT_UNR; k++) {
-        if (yb + k < y1) {   // warp-uniform
-          const u32 l = v[k] <= N ? (u32)v[k] : NONE;
-          const bool change = l != cur;
-          if (__any_sync(CC_FULL, change)) {
-            finish_runs(change && cur != NONE, cur, ystart, yb + k - 1, xbase, z);
-            if (change) { cur = l; ystart = yb + k; }
-          }
-        }
-      }
+      for (int k = 0; k < CC_STAT_UNR; k++) row_step(v[k], r + k);
     }
-    finish_runs(cur != NONE, cur, ystart, y1 - 1, xbase, z);
+    for (; r < nrow; r++) { row_step(*p, r); p += sx; }
+    finish_runs(cur != NONE, cur, ystart, nrow - 1, xbase, y0, z);
+    if (lane < CC_STAT_WSLOTS) spill(lane, xbase, y0, z);
+    __syncwarp();
   }
   __syncthreads();
   for (int i = threadIdx.x; i < CC_STAT_SLOTS; i += blockDim.x) {
