@@ -192,12 +192,20 @@ size_t bitmap_words(const Geom& g, bool with_diagonals) {
 // exclusive scan of n counts (n on the host, or ceil(*n_dev / 2^shift) when n_dev is given; n_max bounds it)
 int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_dev, int shift, u64* total_dev,
                 u32* total32_dev, cudaStream_t s, Counters* track = nullptr, u32 W = 1) {
-  const i64 nb = (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  const i64 nb = std::max<i64>(1, (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK);
+#ifdef CC_SCAN_THREE_KERNELS
   const unsigned grid = (unsigned)std::min<i64>(nb, CC_GRID_BLOCKS);
   k_scan_reduce<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n_max, n_dev, shift, track, W);
   k_scan_blocks<<<1, 1024, 0, s>>>(bsum, n_max, n_dev, shift, total_dev, total32_dev);
   k_scan_apply<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, prefix, n_max, n_dev, shift);
   g_launches += 3;
+#else
+  // bsum holds nb chunk states + the ticket counter (callers size it (nb + 1) * 8 bytes)
+  cudaMemsetAsync(bsum, 0, (size_t)(nb + 1) * 8, s);
+  k_scan_onepass<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, prefix, (unsigned long long*)bsum, (u32)nb, n_max, n_dev, shift,
+                                                           total_dev, total32_dev, track, W);
+  g_launches += 1;
+#endif
   return 0;
 }
 
@@ -505,7 +513,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
     u32* BK = (u32*)ar.take((size_t)nbwords * 4);
     u32* bcnt = (u32*)ar.take((size_t)nbwords * 4);
     u32* bprefix = (u32*)ar.take((size_t)nbwords * 4);
-    u64* bsum3 = (u64*)ar.take(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8);
+    u64* bsum3 = (u64*)ar.take(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 2) * 8);
     u64* dummyN = (u64*)ar.take(8);
     cudaMemsetAsync(BK, 0, (size_t)nbwords * 4, s);
     k_fill_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(K, CC_BG, &ctr->nruns);

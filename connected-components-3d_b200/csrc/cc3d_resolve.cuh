@@ -159,6 +159,96 @@ k_scan_apply(const u32* cnt, const u64* __restrict__ bsum, u32* prefix, i64 n_ho
   }
 }
 
+// One-pass exclusive scan (decoupled look-back): chunks of 4096 counts are handed out in order by a ticket, a
+// chunk publishes its aggregate, then its inclusive prefix as soon as the chunks before it are known. status[c] =
+// flag << 32 | value (flag 1 = aggregate, 2 = inclusive prefix; values < 2^32), status[nb_max] = ticket counter;
+// both must be zero on entry. Replaces the reduce / scan-of-sums / apply triple (one launch instead of three).
+// track != nullptr (scan S): also reduces the first / last row that has a run start into track->first_row/last_row.
+#define CC_SCAN_FLAG_A (1ull << 32)
+#define CC_SCAN_FLAG_P (2ull << 32)
+__global__ void __launch_bounds__(CC_SCAN_THREADS)
+k_scan_onepass(const u32* cnt, u32* prefix, unsigned long long* __restrict__ status, u32 nb_max, i64 n_host,
+               const u64* __restrict__ n_dev, int shift, u64* __restrict__ total, u32* __restrict__ total32,
+               Counters* __restrict__ track, u32 W) {
+  __shared__ u32 s_chunk, s_prev, s_min, s_max;
+  const u32 n = dev_len(n_host, n_dev, shift);
+  const u32 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  if (threadIdx.x == 0) { s_chunk = (u32)atomicAdd(&status[nb_max], 1ull); s_min = 0xFFFFFFFFu; s_max = 0; }
+  __syncthreads();
+  const u32 chunk = s_chunk;
+  if (chunk >= nb) {
+    if (nb == 0 && chunk == 0 && threadIdx.x == 0) { *total = 0; if (total32) *total32 = 0; }
+    return;
+  }
+  const u32 base = chunk * CC_SCAN_CHUNK + threadIdx.x * CC_SCAN_ITEMS;
+  u32 v[CC_SCAN_ITEMS];
+  if (base + CC_SCAN_ITEMS <= n) {
+    const uint4* p = reinterpret_cast<const uint4*>(cnt + base);
+#pragma unroll
+    for (int k = 0; k < CC_SCAN_ITEMS / 4; k++) {
+      const uint4 t = p[k];
+      v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CC_SCAN_ITEMS; k++) v[k] = (base + k < n) ? cnt[base + k] : 0;
+  }
+  u32 sum = 0;
+#pragma unroll
+  for (int k = 0; k < CC_SCAN_ITEMS; k++) sum += v[k];
+  if (track && sum) {
+    u32 lo = CC_SCAN_ITEMS, hi = 0;
+#pragma unroll
+    for (int k = 0; k < CC_SCAN_ITEMS; k++) if (v[k]) { lo = min(lo, (u32)k); hi = k; }
+    atomicMin(&s_min, base + lo); atomicMax(&s_max, base + hi);
+  }
+  u32 tot;
+  u32 ex = block_exclusive_scan(sum, &tot);
+  if (threadIdx.x < 32) {   // warp 0: publish the aggregate, look back, publish the inclusive prefix
+    const int lane = threadIdx.x;
+    u32 prev = 0;
+    if (chunk > 0) {
+      if (lane == 0) { __threadfence(); atomicExch(&status[chunk], CC_SCAN_FLAG_A | tot); }
+      i64 idx = (i64)chunk - 1;
+      while (true) {
+        const i64 j = idx - lane;
+        unsigned long long st = CC_SCAN_FLAG_P;   // before chunk 0: prefix 0
+        if (j >= 0) { do { st = *(volatile unsigned long long*)&status[j]; } while ((st >> 32) == 0); }
+        const u32 isp = __ballot_sync(CC_FULL, (st >> 32) == 2);
+        const int stop = isp ? (__ffs(isp) - 1) : 32;            // nearest predecessor with a full prefix
+        const u32 part = lane <= stop ? (u32)st : 0u;
+        prev += __reduce_add_sync(CC_FULL, part);
+        if (isp) break;
+        idx -= 32;
+      }
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&status[chunk], CC_SCAN_FLAG_P | (unsigned long long)(prev + tot));
+      s_prev = prev;
+      if (chunk == nb - 1) { *total = (u64)prev + tot; if (total32) *total32 = prev + tot; }
+    }
+  }
+  __syncthreads();
+  ex += s_prev;
+  if (base + CC_SCAN_ITEMS <= n) {
+    uint4* q = reinterpret_cast<uint4*>(prefix + base);
+#pragma unroll
+    for (int k = 0; k < CC_SCAN_ITEMS / 4; k++) {
+      uint4 t;
+      t.x = ex; ex += v[4 * k]; t.y = ex; ex += v[4 * k + 1]; t.z = ex; ex += v[4 * k + 2]; t.w = ex; ex += v[4 * k + 3];
+      q[k] = t;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CC_SCAN_ITEMS; k++) { if (base + k < n) prefix[base + k] = ex; ex += v[k]; }
+  }
+  if (track && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) {
+    atomicMin((long long*)&track->first_row, (long long)(s_min / W));
+    atomicMax((long long*)&track->last_row, (long long)(s_max / W));
+  }
+}
+
 __device__ __forceinline__ u32 rank_in_bitmap(const u32* __restrict__ bm, const u32* __restrict__ prefix, i64 word, int bit) {
   return prefix[word] + __popc(bm[word] & ((1u << bit) - 1u));
 }
