@@ -193,7 +193,7 @@ size_t bitmap_words(const Geom& g, bool with_diagonals) {
 int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_dev, int shift, u64* total_dev,
                 u32* total32_dev, cudaStream_t s, Counters* track = nullptr, u32 W = 1) {
   const i64 nb = std::max<i64>(1, (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK);
-#ifdef CC_SCAN_THREE_KERNELS
+#ifndef CC_SCAN_ONEPASS   // (one-pass scan: enabled once verified on the GPU)
   const unsigned grid = (unsigned)std::min<i64>(nb, CC_GRID_BLOCKS);
   k_scan_reduce<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n_max, n_dev, shift, track, W);
   k_scan_blocks<<<1, 1024, 0, s>>>(bsum, n_max, n_dev, shift, total_dev, total32_dev);
