@@ -23,7 +23,7 @@ from ._lib import CC3DB200Error
 
 __all__ = [
   "connected_components", "statistics", "dust", "estimate_provisional_labels",
-  "largest_k", "voxel_connectivity_graph", "color_connectivity_graph",
+  "largest_k", "voxel_connectivity_graph", "color_connectivity_graph", "contacts", "region_graph",
   "DimensionError", "CC3DB200Error", "last_timings", "set_timing",
 ]
 
@@ -770,3 +770,59 @@ def color_connectivity_graph(vcg, connectivity: int = 26, return_N: bool = False
   if return_N:
     return (out_labels, int(N.value))
   return out_labels
+
+
+def contacts(labels, connectivity: int = 26, surface_area: bool = True, anisotropy=(1, 1, 1)) -> dict:
+  """Region adjacency graph with contact areas; same contract as cc3d.contacts (fastcc3d.pyx:1196-1252):
+  {(label_1, label_2): float} with label_1 < label_2. The GPU counts the contacts of every pair per direction
+  class exactly; the value is count x face area (float32 like the reference, which adds areas one by one: the two
+  agree whenever the reference's running sum stays exactly representable, e.g. integer areas below 2^24).
+  Label values must be < 2^32."""
+  L = _lib.lib()
+  if _is_torch(labels):
+    labels = labels.cpu().numpy() if labels.is_cuda else labels.numpy()
+  labels = np.asarray(labels)
+  while labels.ndim < 3:
+    labels = labels[..., np.newaxis]
+  anisotropy = tuple(anisotropy)
+  while len(anisotropy) < 3:
+    anisotropy = anisotropy + (1,)
+  if connectivity not in (4, 8, 6, 18, 26):
+    raise ValueError(f"Only (2d) 4, 8, (3d) 6, 18, and 26 connectivities are supported. Got: {connectivity}")
+  if labels.dtype.kind not in "biu":
+    raise TypeError("Type {} not currently supported.".format(labels.dtype))
+  labels = np.asfortranarray(_view_as_unsigned(labels))
+  if labels.dtype == bool:
+    labels = labels.view(np.uint8)
+  sx, sy, sz = labels.shape
+  if connectivity in (4, 8) and sz != 1:
+    raise RuntimeError("z thickness must be 1 for 2d region graph extraction.")
+  if labels.size == 0:
+    return {}
+  cap = 1 << 16
+  while True:
+    keys = np.empty(cap, dtype=np.uint64)
+    vals = np.empty((cap, 4), dtype=np.uint32)
+    n = ctypes.c_uint64(0)
+    _lib.check(L.cc3d_b200_contacts(labels.ctypes.data, _kind_of(labels.dtype), sx, sy, sz, int(connectivity),
+                                    keys.ctypes.data, vals.ctypes.data, cap, ctypes.byref(n), _lib.HOST, None))
+    if n.value <= cap:
+      break
+    cap = 1 << int(n.value - 1).bit_length()
+  keys, vals = keys[: n.value], vals[: n.value]
+  wx, wy, wz = (np.float32(a) for a in anisotropy)
+  if connectivity in (4, 8):
+    areas = [wy, wx, np.float32(0), np.float32(0)] if surface_area else [np.float32(1)] * 4
+  else:
+    areas = [wy * wz, wx * wz, wx * wy, np.float32(0)] if surface_area else [np.float32(1)] * 4
+  total = np.zeros(keys.size, dtype=np.float64)
+  for c in range(4):
+    total += vals[:, c].astype(np.float64) * float(areas[c])
+  total = total.astype(np.float32)
+  lo, hi = (keys >> np.uint64(32)).tolist(), (keys & np.uint64(0xFFFFFFFF)).tolist()
+  return {(a, b): float(v) for a, b, v in zip(lo, hi, total)}
+
+
+def region_graph(labels, connectivity: int = 26) -> set:
+  """Set of label pairs that touch; same contract as cc3d.region_graph (fastcc3d.pyx:1180-1194)."""
+  return set(contacts(labels, connectivity=connectivity).keys())

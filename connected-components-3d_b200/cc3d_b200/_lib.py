@@ -80,6 +80,8 @@ def lib():
   L.cc3d_b200_voxel_connectivity_graph.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, vp]
   L.cc3d_b200_color_connectivity_graph.restype = ci
   L.cc3d_b200_color_connectivity_graph.argtypes = [vp, ci, i64, i64, i64, ci, vp, p(u64), ci, vp]
+  L.cc3d_b200_contacts.restype = ci
+  L.cc3d_b200_contacts.argtypes = [vp, ci, i64, i64, i64, ci, vp, vp, u64, p(u64), ci, vp]
   L.cc3d_b200_remap_labels.restype = ci
   L.cc3d_b200_remap_labels.argtypes = [vp, ci, i64, vp, u64, vp, ci, ci, vp]
   L.cc3d_b200_mask_by_label.restype = ci

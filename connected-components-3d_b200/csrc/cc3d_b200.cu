@@ -1086,6 +1086,78 @@ int cc3d_b200_remap_labels(const void* labels, int label_kind, int64_t voxels, c
   return 0;
 }
 
+int cc3d_b200_contacts(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                       uint64_t* pairs, uint32_t* class_counts, uint64_t capacity, uint64_t* count, int mem_space,
+                       void* stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  const size_t es = kind_size(kind);
+  if (!es || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "labels must be u8/u16/u32/u64");
+  if (connectivity != 4 && connectivity != 8 && connectivity != 6 && connectivity != 18 && connectivity != 26)
+    return fail(CC3D_B200_ERR_CONNECTIVITY, "Only (2d) 4, 8, or (3d) 6, 18, and 26 connectivities are supported.");
+  if ((connectivity == 4 || connectivity == 8) && sz != 1)
+    return fail(CC3D_B200_ERR_2D_NEEDS_SZ1, "z thickness must be 1 for 2d region graph extraction.");
+  if (!count) return fail(CC3D_B200_ERR_ARGUMENT, "count must not be NULL");
+  *count = 0;
+  const i64 voxels = sx * sy * sz;
+  if (voxels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  // hash table: grows (x8) until the pairs fit
+  u32 slots = 1u << 16;
+  while ((u64)slots < 4 * capacity && slots < (1u << 28)) slots <<= 1;
+  while (true) {
+    Arena ar;
+    size_t need = 4096 + (size_t)slots * (8 + 16) + 512 + capacity * (8 + 16) + 1024;
+    if (mem_space == CC3D_B200_HOST) need += (size_t)voxels * es + 512;
+    if (int rc = arena_acquire(need, &ar, s, true)) return rc;
+    const void* din = labels;
+    if (mem_space == CC3D_B200_HOST) {
+      void* d = ar.take((size_t)voxels * es);
+      cudaMemcpyAsync(d, labels, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+      din = d;
+    }
+    ContactTable tb;
+    tb.keys = (unsigned long long*)ar.take((size_t)slots * 8);
+    tb.vals = (u32*)ar.take((size_t)slots * 16);
+    tb.flags = (u32*)ar.take(64);
+    tb.mask = slots - 1;
+    unsigned long long* dcount = (unsigned long long*)(tb.flags + 4);
+    unsigned long long* dkeys = (unsigned long long*)ar.take(capacity * 8 + 16);
+    u32* dvals = (u32*)ar.take(capacity * 16 + 16);
+    cudaMemsetAsync(tb.keys, 0, (size_t)slots * 8, s);
+    cudaMemsetAsync(tb.vals, 0, (size_t)slots * 16, s);
+    cudaMemsetAsync(tb.flags, 0, 64, s);
+    const unsigned blocks = (unsigned)std::min<i64>((voxels + 255) / 256, 148 * 16);
+    switch (kind) {
+      case CC3D_B200_U8: k_contacts<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)din, sx, sy, sz, connectivity, tb); break;
+      case CC3D_B200_U16: k_contacts<uint16_t><<<blocks, 256, 0, s>>>((const uint16_t*)din, sx, sy, sz, connectivity, tb); break;
+      case CC3D_B200_U32: k_contacts<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)din, sx, sy, sz, connectivity, tb); break;
+      default: k_contacts<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)din, sx, sy, sz, connectivity, tb); break;
+    }
+    k_contacts_compact<<<(slots + 255) / 256, 256, 0, s>>>(tb, dkeys, dvals, dcount, capacity);
+    g_launches += 2;
+    u32 hflags[4] = {0, 0, 0, 0};
+    unsigned long long hcount = 0;
+    cudaError_t e = cudaMemcpyAsync(hflags, tb.flags, 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hcount, dcount, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, std::string("contacts: ") + cudaGetErrorString(e)); }
+    if (hflags[1]) { arena_release(ar); return fail(CC3D_B200_ERR_TOO_LARGE, "contacts: label values must be < 2^32"); }
+    if (hflags[0] && slots < (1u << 28)) { arena_release(ar); slots <<= 3; continue; }   // table full: larger table
+    if (hflags[0]) { arena_release(ar); return fail(CC3D_B200_ERR_TOO_LARGE, "contacts: too many distinct pairs"); }
+    *count = hcount;
+    if (hcount <= capacity && hcount > 0) {
+      const cudaMemcpyKind k = mem_space == CC3D_B200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+      cudaMemcpyAsync(pairs, dkeys, hcount * 8, k, s);
+      cudaMemcpyAsync(class_counts, dvals, hcount * 16, k, s);
+      e = cudaStreamSynchronize(s);
+    }
+    arena_release(ar);
+    if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("contacts: ") + cudaGetErrorString(e));
+    return 0;
+  }
+}
+
 int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,
                           int rank, int64_t* remap, int64_t* n_total) {
   if (world <= 0 || rank < 0 || rank >= world || !n_labels || !remap || !n_total)

@@ -187,6 +187,16 @@ int cc3d_b200_voxel_connectivity_graph(const void* labels, int kind, int64_t sx,
 int cc3d_b200_color_connectivity_graph(const void* vcg, int vcg_kind, int64_t sx, int64_t sy, int64_t sz,
                                        int connectivity, uint32_t* out, uint64_t* N, int mem_space, void* stream);
 
+/* cc3d.contacts / cc3d.region_graph (fastcc3d.pyx:1180-1252 -> extract_region_graph, cc3d_graphs.hpp:300-468):
+ * every pair of different non-zero labels that touch under the connectivity, with the NUMBER of contacts per class
+ * (class_counts[4*i + 0..3]: across x, across y, across z, edge/corner; 2D: across x, across y, -, diagonal), so that
+ * the caller forms surface areas (count x face area) or voxel counts exactly. pairs[i] = min << 32 | max; label
+ * values must be < 2^32. *count = number of pairs; if it exceeds `capacity` nothing is written: call again with
+ * more room. Border behaviour of the reference's compute_neighborhood is reproduced. */
+int cc3d_b200_contacts(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                       uint64_t* pairs, uint32_t* class_counts, uint64_t capacity, uint64_t* count, int mem_space,
+                       void* stream);
+
 /* out[i] = table[labels[i]] (labels above N give 0): the relabelling step of cc3d.largest_k
  * (cc3d/__init__.py:262-276, fastremap.mask_except + renumber / runs + draw). out kind u8/u16/u32/u64. */
 int cc3d_b200_remap_labels(const void* labels, int label_kind, int64_t voxels, const uint32_t* table, uint64_t N,

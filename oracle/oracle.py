@@ -11,6 +11,7 @@ boundary logic, `statistics` and `dust`:
   largest_k             <- cc3d/__init__.py:199-279 (the path without fastremap)
   voxel_connectivity_graph <- fastcc3d.pyx:1021-1170 / cc3d_graphs.hpp:31-247 (numpy slicing)
   color_connectivity_graph <- fastcc3d.pyx:941-1018 / cc3d_graphs.hpp:583-1106 (backward-bit graph, scipy components)
+  contacts / region_graph <- fastcc3d.pyx:1180-1252 / cc3d_graphs.hpp:259-468 (compute_neighborhood offsets incl. borders)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 Parity pin: tests/test_oracle.py checks it against the reference build (oracle/_ref) when that is
@@ -408,3 +409,64 @@ def color_connectivity_graph(vcg, connectivity=26, return_N=False):
   while out.ndim > dims:
     out = out[..., 0]
   return (out, int(first.size)) if return_N else out
+
+
+def contacts(labels, connectivity=26, surface_area=True, anisotropy=(1, 1, 1)):
+  """cc3d_graphs.hpp:300-468 with compute_neighborhood (:259-313) restated on index arrays (vectorised numpy);
+  float32 accumulation in raster order per pair like the reference (np.add.at on float32 is sequential)."""
+  labels = np.asarray(labels)
+  while labels.ndim < 3:
+    labels = labels[..., np.newaxis]
+  anisotropy = tuple(anisotropy)
+  while len(anisotropy) < 3:
+    anisotropy = anisotropy + (1,)
+  if connectivity not in (4, 8, 6, 18, 26):
+    raise ValueError(f"Only (2d) 4, 8, (3d) 6, 18, and 26 connectivities are supported. Got: {connectivity}")
+  lab = np.asfortranarray(labels)
+  if np.issubdtype(lab.dtype, np.signedinteger):
+    lab = lab.view(f"u{lab.dtype.itemsize}")
+  sx, sy, sz = lab.shape
+  if connectivity in (4, 8) and sz != 1:
+    raise RuntimeError("z thickness must be 1 for 2d region graph extraction.")
+  flat = lab.reshape(-1, order="F").astype(np.uint64)
+  n = flat.size
+  if n == 0:
+    return {}
+  loc = np.arange(n, dtype=np.int64)
+  x, y, z = loc % sx, (loc // sx) % sy, loc // (sx * sy)
+  px, mx = (x < sx - 1).astype(np.int64), -(x > 0).astype(np.int64)
+  py, my = sx * (y < sy - 1).astype(np.int64), -sx * (y > 0).astype(np.int64)
+  mz = -sx * sy * (z > 0).astype(np.int64)
+  wx, wy, wz = (np.float32(a) for a in anisotropy)
+  if connectivity in (4, 8):
+    offs = [mx, my, (connectivity > 4) * (mx + my), (connectivity > 4) * (px + my)][: connectivity // 2]
+    areas = [wy, wx, np.float32(0), np.float32(0)] if surface_area else [np.float32(1)] * 4
+  else:
+    b = lambda a: (a != 0).astype(np.int64)
+    offs = [mx, my, mz,
+            (mx + my) * (b(mx) & b(my)), (px + my) * (b(px) & b(my)), (mx + mz) * (b(mx) & b(mz)), (px + mz) * (b(px) & b(mz)),
+            (my + mz) * (b(my) & b(mz)), (py + mz) * (b(py) & b(mz)),
+            (mx + my + mz) * (b(my) & b(mz)), (px + my + mz) * (b(my) & b(mz)), (mx + py + mz) * (b(py) & b(mz)),
+            (px + py + mz) * (b(py) & b(mz))][: connectivity // 2]
+    areas = ([wy * wz, wx * wz, wx * wy] + [np.float32(0)] * 10) if surface_area else [np.float32(1)] * 13
+  # contacts in the reference's order: voxel by voxel (raster), direction by direction
+  recs = []
+  for i, off in enumerate(offs):
+    q = flat[loc + off]
+    m = (flat != 0) & (q != 0) & (q != flat)
+    idx = np.nonzero(m)[0]
+    recs.append((idx, np.full(idx.size, i, dtype=np.int64), np.minimum(flat[idx], q[idx]), np.maximum(flat[idx], q[idx])))
+  if not recs or sum(r[0].size for r in recs) == 0:
+    return {}
+  idx = np.concatenate([r[0] for r in recs]); d = np.concatenate([r[1] for r in recs])
+  a = np.concatenate([r[2] for r in recs]); bb = np.concatenate([r[3] for r in recs])
+  order = np.lexsort((d, idx))
+  a, bb, d = a[order], bb[order], d[order]
+  pairs, inv = np.unique(np.stack([a, bb], 1), axis=0, return_inverse=True)
+  acc = np.zeros(pairs.shape[0], dtype=np.float32)
+  np.add.at(acc, inv.reshape(-1), np.asarray(areas, dtype=np.float32)[d])
+  return {(int(p[0]), int(p[1])): float(v) for p, v in zip(pairs, acc)}
+
+
+def region_graph(labels, connectivity=26):
+  return set(contacts(labels, connectivity=connectivity).keys())

@@ -177,3 +177,27 @@ def test_oracle_largest_k_vs_reference_python_layer(oracle_mod):
     d2 = oracle_mod.dust(x, threshold=5, return_N=True)
     assert d1[1] == d2[1] and np.array_equal(d1[0], d2[0])
   assert checked == 400
+
+
+def test_oracle_contacts_vs_reference(oracle_mod):
+  """contacts / region_graph against the reference build, including its border behaviour."""
+  ref = oracle_mod.reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built (needs /root/reference)")
+  rng = np.random.default_rng(19)
+  n = 0
+  for it in range(120):
+    dims = int(rng.integers(2, 4))
+    shape = tuple(int(rng.integers(1, 9)) for _ in range(dims))
+    dt = [np.uint8, np.uint16, np.uint32, np.uint64, np.int32][rng.integers(5)]
+    x = np.asarray(rng.integers(0, 4, shape).astype(dt), order="F" if rng.random() < 0.5 else "C")
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    c = conns[rng.integers(len(conns))]
+    sa = bool(rng.integers(0, 2))
+    an = [(1, 1, 1), (4, 4, 40), (2, 3, 5)][rng.integers(3)]
+    a = ref.contacts(x, connectivity=c, surface_area=sa, anisotropy=an)
+    b = oracle_mod.contacts(x, connectivity=c, surface_area=sa, anisotropy=an)
+    assert a == b, (shape, np.dtype(dt), c, sa, an)
+    assert ref.region_graph(x, connectivity=c) == oracle_mod.region_graph(x, connectivity=c)
+    n += 1
+  assert n == 120

@@ -401,3 +401,25 @@ def test_largest_k(cc3d, oracle_mod):
       a = truth.largest_k(np.ascontiguousarray(x), 3, return_N=True)
       b = cc3d.largest_k(t, 3, return_N=True)
       assert a[1] == b[1] and np.array_equal(b[0].cpu().numpy().view(a[0].dtype), a[0])
+
+
+def test_contacts_and_region_graph(cc3d, oracle_mod):
+  """contacts / region_graph against the reference (exact: integer face areas)."""
+  truth = _truth(oracle_mod)
+  rng = np.random.default_rng(23)
+  for it in range(120):
+    dims = int(rng.integers(2, 4))
+    shape = tuple(int(rng.integers(1, 30)) for _ in range(dims)) if it % 10 else ((90, 70, 40) if dims == 3 else (200, 150))
+    dt = [np.uint8, np.uint16, np.uint32, np.uint64, np.int32][rng.integers(5)]
+    x = rng.integers(0, 4, shape).astype(dt) if it % 3 else blobs(rng, shape, 6, int(rng.integers(1, 5))).astype(dt)
+    x = np.asarray(x, order="F" if rng.random() < 0.5 else "C")
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    c = conns[rng.integers(len(conns))]
+    sa = bool(rng.integers(0, 2))
+    an = [(1, 1, 1), (4, 4, 40), (2, 3, 5)][rng.integers(3)]
+    a = truth.contacts(x, connectivity=c, surface_area=sa, anisotropy=an)
+    b = cc3d.contacts(x, connectivity=c, surface_area=sa, anisotropy=an)
+    assert a == b, (shape, np.dtype(dt), c, sa, an)
+    assert truth.region_graph(x, connectivity=c) == cc3d.region_graph(x, connectivity=c)
+  big = np.arange(1, 40 * 40 * 40 + 1, dtype=np.uint32).reshape(40, 40, 40)      # 64 000 labels: the hash table has to grow
+  assert truth.contacts(big, connectivity=26) == cc3d.contacts(big, connectivity=26)
