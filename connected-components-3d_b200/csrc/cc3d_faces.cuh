@@ -236,6 +236,7 @@ k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MOD
     mq += W; rs += W;
 #pragma unroll
     for (int k = 0; k < NW; k++) up[k] = c[k];
+    __syncwarp();   // every lane has read the slot before the copy of a later row is issued into it
   };
   u32 issued = 0;
 #pragma unroll
