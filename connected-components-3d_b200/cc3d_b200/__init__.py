@@ -524,11 +524,86 @@ def _view_as_unsigned(img):
   return img
 
 
+def _validate_connectivity(dims, connectivity):
+  """Same checks and messages as connected_components (fastcc3d.pyx:313-320)."""
+  if dims not in (1, 2, 3):
+    raise DimensionError("Only 1D, 2D, and 3D arrays supported. Got: " + str(dims))
+  if dims == 2 and connectivity not in (4, 8, 6, 18, 26):
+    raise ValueError("Only 4, 8, and 6, 18, 26 connectivities are supported for 2D images. Got: " + str(connectivity))
+  elif dims != 2 and connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+
+
+def _dust_bounds(threshold):
+  """[lo, hi) of the component sizes that stay (cc3d/__init__.py:117-127); sizes are integers."""
+  import math
+  big = (1 << 62)
+  if isinstance(threshold, (tuple, list)):
+    lo, hi = threshold[0], threshold[1]
+  else:
+    lo, hi = threshold, big
+  lo = max(-big, min(big, int(math.ceil(lo))))
+  hi = max(-big, min(big, int(math.ceil(hi)) if hi != big else big))
+  return lo, hi
+
+
+def _dust_fused(img, threshold, connectivity, in_place, binary_image, invert, return_N):
+  """dust without a label volume: cc3d_b200_dust labels the image, takes the component sizes from the run table
+  and masks the image while expanding (numpy arrays and CUDA tensors; integer images, contiguous)."""
+  L = _lib.lib()
+  lo, hi = _dust_bounds(threshold)
+  N, nm = ctypes.c_uint64(0), ctypes.c_uint64(0)
+  if _is_torch(img):
+    import torch
+    t, order = _torch_order(img.detach())
+    out = t if (in_place and t.data_ptr() == img.data_ptr()) else torch.empty_like(t, memory_format=torch.preserve_format)
+    shape3 = list(t.shape) + [1] * (3 - t.ndim) if order == "F" else [1] * (3 - t.ndim) + list(t.shape)
+    sx, sy, sz = shape3 if order == "F" else shape3[::-1]
+    if t.numel():
+      with torch.cuda.device(t.device):
+        _lib.check(L.cc3d_b200_dust(
+          t.data_ptr(), out.data_ptr(), _kind_of(_torch_np_dtype(t)), sx, sy, sz, int(connectivity), int(bool(binary_image)),
+          lo, hi, int(bool(invert)), _lib.DEVICE, ctypes.byref(N), ctypes.byref(nm),
+          ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+    elif out is not t:
+      out.copy_(t)
+    n_total, n_mask = int(N.value), int(nm.value)
+    dust_N = n_mask if invert else n_total - n_mask
+    return (out, dust_N) if return_N else out
+  orig_dtype = img.dtype
+  src = _view_as_unsigned(img)
+  if src.dtype == bool:
+    src = src.view(np.uint8)
+  order = "F" if (src.flags.f_contiguous and not src.flags.c_contiguous) else "C"
+  out = src if in_place else np.empty(src.shape, dtype=src.dtype, order=order)
+  shape3 = list(src.shape)
+  while len(shape3) < 3:
+    shape3 = [1] + shape3 if order == "C" else shape3 + [1]
+  sx, sy, sz = (shape3[::-1] if order == "C" else shape3)
+  if src.size:
+    _lib.check(L.cc3d_b200_dust(
+      src.ctypes.data, out.ctypes.data, _kind_of(src.dtype), sx, sy, sz, int(connectivity), int(bool(binary_image)),
+      lo, hi, int(bool(invert)), _lib.HOST, ctypes.byref(N), ctypes.byref(nm), None))
+  n_total, n_mask = int(N.value), int(nm.value)
+  dust_N = n_mask if invert else n_total - n_mask
+  if n_mask == 0 and invert:
+    out = np.zeros(img.shape, dtype=src.dtype, order="F")   # (sic) cc3d/__init__.py:139-146
+  out = out.view(orig_dtype)
+  return (out, dust_N) if return_N else out
+
+
 def dust(img, threshold, connectivity: int = 26, in_place: bool = False, binary_image: bool = False,
          precomputed_ccl: bool = False, invert: bool = False, return_N: bool = False):
   """Remove connected components smaller than threshold (or outside [lo, hi)); same contract as cc3d.dust.
   A CUDA tensor is processed entirely on its device (labelling, statistics and masking) and a tensor is returned."""
   L = _lib.lib()
+  if not precomputed_ccl:
+    if _is_torch(img) and img.is_cuda and _torch_np_dtype(img).kind in "biu":
+      return _dust_fused(img, threshold, connectivity, in_place, binary_image, invert, return_N)
+    if isinstance(img, np.ndarray) and img.dtype.kind in "biu" and img.ndim in (1, 2, 3) and (
+        img.flags.c_contiguous or img.flags.f_contiguous) and (img.ndim == 3 or connectivity in (4, 8, 6, 18, 26)):
+      _validate_connectivity(img.ndim, connectivity)
+      return _dust_fused(img, threshold, connectivity, in_place, binary_image, invert, return_N)
   if _is_torch(img) and img.is_cuda:
     return _dust_device(img, threshold, connectivity, in_place, binary_image, precomputed_ccl, invert, return_N)
   orig_dtype = img.dtype

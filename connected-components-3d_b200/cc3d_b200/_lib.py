@@ -84,6 +84,8 @@ def lib():
   L.cc3d_b200_contacts.argtypes = [vp, ci, i64, i64, i64, ci, vp, vp, u64, p(u64), ci, vp]
   L.cc3d_b200_remap_labels.restype = ci
   L.cc3d_b200_remap_labels.argtypes = [vp, ci, i64, vp, u64, vp, ci, ci, vp]
+  L.cc3d_b200_dust.restype = ci
+  L.cc3d_b200_dust.argtypes = [vp, vp, ci, i64, i64, i64, ci, ci, i64, i64, ci, ci, p(u64), p(u64), vp]
   L.cc3d_b200_mask_by_label.restype = ci
   L.cc3d_b200_mask_by_label.argtypes = [vp, ci, vp, ci, i64, vp, u64, ci, vp]
   L.cc3d_b200_workspace_bytes.restype = ctypes.c_size_t

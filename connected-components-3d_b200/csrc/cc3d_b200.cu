@@ -219,6 +219,7 @@ struct cc3d_b200_session {
   u32* M = nullptr;   // edge bitmaps (F and X planes are what the expansion needs)
   Counters* ctr = nullptr;   // device-side counters of the resolve phase
   bool epl_is_runs = false;  // multilabel: epl (cc3d.hpp:287-315) = number of x-runs, counted by scan S
+  const void* din = nullptr; // device copy of the input (the caller's buffer, or the staged copy of a host buffer)
   u64 N = 0;
 };
 
@@ -458,7 +459,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   Counters* ctr = (Counters*)ar.take(sizeof(Counters));
   u64* gqbuf = (u64*)ar.take(gqcap * 8);
   u32* gqctl = (u32*)ar.take(64);   // [0] count, [1] overflow flag
-  S->L = L; S->M = M;
+  S->L = L; S->M = M; S->din = din;
   S->epl_is_runs = (mode == MODE_EQ);
 
   k_init_counters<<<1, 1, 0, s>>>(ctr, gqctl);
@@ -1156,6 +1157,64 @@ int cc3d_b200_contacts(const void* labels, int kind, int64_t sx, int64_t sy, int
     if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("contacts: ") + cudaGetErrorString(e));
     return 0;
   }
+}
+
+template <typename IT>
+static void expand_mask_typed(const cc3d_b200_session* S, const IT* img, IT* out, const unsigned char* keep, cudaStream_t s) {
+  const Geom& g = S->g;
+  const unsigned nchunks = (unsigned)((g.W + 31) / 32);
+  const i64 nwarps = g.sy * g.sz * nchunks;
+  k_expand_mask<IT><<<(unsigned)((nwarps + 7) / 8), 256, 0, s>>>(S->L, S->M, img, out, g, nchunks, (u32)nwarps, keep);
+}
+
+int cc3d_b200_dust(const void* img, void* out, int kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                   int binary_image, int64_t lo, int64_t hi, int invert, int mem_space, uint64_t* N,
+                   uint64_t* n_masked, void* stream) {
+  if (kind < CC3D_B200_U8 || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "dust: img must be u8/u16/u32/u64");
+  if (!out || !N || !n_masked) return fail(CC3D_B200_ERR_ARGUMENT, "dust: out / N / n_masked must not be NULL");
+  *N = 0; *n_masked = 0;
+  const size_t es = kind_size(kind);
+  const i64 voxels = sx * sy * sz;
+  if (voxels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char zero_delta[8] = {0};
+  cc3d_b200_resolve_info info;
+  cc3d_b200_session* S = nullptr;
+  int rc = resolve_enqueue(img, kind, sx, sy, sz, connectivity, zero_delta, binary_image, 0, mem_space, stream, &info, &S);
+  if (rc) return rc;
+  rc = resolve_finish(S, s, &info);          // N decides the size of the count / keep tables
+  if (rc) { cc3d_b200_session_release(S); return rc; }
+  marks_collect(false);
+  const u64 n = info.N;
+  Arena ar;
+  if (int rc2 = arena_acquire((size_t)(n + 1) * 5 + 4096, &ar, s, true)) { cc3d_b200_session_release(S); return rc2; }
+  u32* counts = (u32*)ar.take((size_t)(n + 1) * 4);
+  unsigned char* keep = (unsigned char*)ar.take((size_t)(n + 1));
+  unsigned long long* dmasked = (unsigned long long*)ar.take(8);
+  cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s);
+  cudaMemsetAsync(dmasked, 0, 8, s);
+  k_run_counts<<<148 * 4, 256, 0, s>>>(S->L, S->M, S->g, counts);
+  k_dust_keep<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(counts, keep, n, (long long)lo, (long long)hi, invert, dmasked);
+  // host images are masked in place in their staged copy; device images go straight to `out` (which may be `img`)
+  void* dout = mem_space == CC3D_B200_HOST ? const_cast<void*>(S->din) : out;
+  switch (kind) {
+    case CC3D_B200_U8: expand_mask_typed(S, (const uint8_t*)S->din, (uint8_t*)dout, keep, s); break;
+    case CC3D_B200_U16: expand_mask_typed(S, (const uint16_t*)S->din, (uint16_t*)dout, keep, s); break;
+    case CC3D_B200_U32: expand_mask_typed(S, (const uint32_t*)S->din, (uint32_t*)dout, keep, s); break;
+    default: expand_mask_typed(S, (const uint64_t*)S->din, (uint64_t*)dout, keep, s); break;
+  }
+  g_launches += 3;
+  unsigned long long hmasked = 0;
+  cudaError_t e = cudaMemcpyAsync(&hmasked, dmasked, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && mem_space == CC3D_B200_HOST) e = cudaMemcpyAsync(out, dout, (size_t)voxels * es, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  cc3d_b200_session_release(S);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("dust: ") + cudaGetErrorString(e));
+  *N = n;
+  *n_masked = hmasked;
+  return 0;
 }
 
 int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,

@@ -108,10 +108,14 @@ static int launch_union(const LabelArgs& a) {
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_union_tile_items<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
-  } else {
+  } else if constexpr (MODE == MODE_NONZERO) {
     const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+  } else {
+    const size_t smem = (size_t)HybridQueues<MODE>::SMEM_WORDS * 4;
+    if (set_attr) cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_union_tile_hybrid<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);
   k_union_queue<<<CC_QUEUE_BLOCKS * 4, 256, 0, a.stream>>>(a.L, a.GQ);

@@ -27,24 +27,6 @@ __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T
     // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
     if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
   }
-#ifdef CC_FACE_LANE_STORES
-  if (NW == 4 && rs_vec) {
-    // lanes 0..3 store one word each (one store instruction for the 64 bytes), lane 4 the four run-start counts
-    const int k = lane & 3;
-    const u32 f = k == 0 ? F[0] : (k == 1 ? F[1] : (k == 2 ? F[2] : F[3]));
-    const u32 x = k == 0 ? X[0] : (k == 1 ? X[1] : (k == 2 ? X[2] : X[3]));
-    const u32 y = k == 0 ? Y[0] : (k == 1 ? Y[1] : (k == 2 ? Y[2] : Y[3]));
-    const u32 z = k == 0 ? Z[0] : (k == 1 ? Z[1] : (k == 2 ? Z[2] : Z[3]));
-    uint4 v = make_uint4(f, x, y, z);
-    uint4* dst = mq + k;
-    if (lane == 4) {
-      v = make_uint4(__popc(F[0] & ~X[0]), __popc(F[1] & ~X[1]), __popc(F[2] & ~X[2]), __popc(F[3] & ~X[3]));
-      dst = reinterpret_cast<uint4*>(rs);
-    }
-    if (lane < 5) *dst = v;
-    return;
-  }
-#endif
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < NW; k++) mq[k] = make_uint4(F[k], X[k], Y[k], Z[k]);

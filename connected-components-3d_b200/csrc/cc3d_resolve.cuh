@@ -320,6 +320,109 @@ k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__
   }
 }
 
+// ---- fused dust (cc3d/__init__.py:71-155): component sizes straight from the run table, then the image is
+// masked while it is expanded - the label volume is never written or read. ----
+#define CC_CNT_SLOTS 2048
+// One thread per bitmap word: every piece of a run inside the word adds its length to its component's count
+// (per-CTA shared-memory hash table first, one global atomic per label and CTA).
+__global__ void __launch_bounds__(256)
+k_run_counts(const u32* __restrict__ L, const u32* __restrict__ M, Geom g, u32* __restrict__ counts) {
+  __shared__ u32 s_key[CC_CNT_SLOTS], s_cnt[CC_CNT_SLOTS];
+  for (int i = threadIdx.x; i < CC_CNT_SLOTS; i += blockDim.x) { s_key[i] = 0; s_cnt[i] = 0; }
+  __syncthreads();
+  const u32 nwords = (u32)g.nwords;
+  const u32 per_cta = (nwords + gridDim.x - 1) / gridDim.x;
+  const u32 end = min(nwords, (blockIdx.x + 1) * per_cta);
+  for (u32 j = blockIdx.x * per_cta + threadIdx.x; j < end; j += blockDim.x) {
+    const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)j);
+    const u32 F = fx.x;
+    if (!F) continue;
+    const u32 runstarts = F & ~fx.y;
+    u32 starts = F & (~fx.y | 1u);            // pieces: a run start, or bit 0 of a run that enters the word
+    const u32 stops = ~F | starts;            // a piece ends before the next piece or the next background voxel
+    const u32 rid0 = __ldg(M + g.offRS + j) - 1u;
+    while (starts) {
+      const int b = __ffs(starts) - 1; starts &= starts - 1;
+      const u32 rest = b == 31 ? 0u : (stops >> (b + 1));
+      const u32 len = rest ? (u32)__ffs(rest) : (u32)(32 - b);
+      const u32 lab = L[rid0 + __popc(runstarts & (CC_FULL >> (31 - b)))];
+      u32 h = (lab * 2654435761u) >> 21;   // 11 bits
+      bool done = false;
+#pragma unroll 1
+      for (int probe = 0; probe < 8 && !done; probe++) {
+        const u32 s = (h + probe) & (CC_CNT_SLOTS - 1);
+        u32 k = *(volatile u32*)&s_key[s];
+        if (k == 0) k = atomicCAS(&s_key[s], 0u, lab + 1);
+        if (k == 0 || k == lab + 1) { atomicAdd(&s_cnt[s], len); done = true; }
+      }
+      if (!done) atomicAdd(&counts[lab], len);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CC_CNT_SLOTS; i += blockDim.x)
+    if (s_key[i]) atomicAdd(&counts[s_key[i] - 1], s_cnt[i]);
+}
+
+// keep[l] for l in 0..N: components with lo <= size < hi stay (invert: the others stay); *n_masked = number of
+// components outside [lo, hi)
+__global__ void __launch_bounds__(256)
+k_dust_keep(const u32* __restrict__ counts, unsigned char* __restrict__ keep, u64 N, long long lo, long long hi, int invert,
+            unsigned long long* __restrict__ n_masked) {
+  const u64 l = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  bool masked = false;
+  if (l <= N) {
+    if (l == 0) keep[0] = invert ? 0 : 1;
+    else {
+      const long long c = (long long)counts[l];
+      masked = !(lo <= c && c < hi);
+      keep[l] = (masked != (invert != 0)) ? 0 : 1;
+    }
+  }
+  const u32 m = __ballot_sync(CC_FULL, masked);
+  if (m && (threadIdx.x & 31) == 0) atomicAdd(n_masked, (unsigned long long)__popc(m));
+}
+
+// out[v] = keep[label of v] ? img[v] : 0 (same walk as k_expand; out may alias img)
+template <typename IT>
+__global__ void __launch_bounds__(256)
+k_expand_mask(const u32* __restrict__ L, const u32* __restrict__ M, const IT* img, IT* out, Geom g, unsigned nchunks,
+              u32 nwarps_total, const unsigned char* __restrict__ keep) {
+  __shared__ uint4 s_words[8][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= nwarps_total) return;
+  const u32 row = wid / nchunks;
+  const u32 chunk = wid - row * nchunks;
+  const u32 W = (u32)g.W, sx = (u32)g.sx;
+  const u32 wl = (chunk << 5) + lane;
+  {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (wl < W) {
+      const u32 j = row * W + wl;
+      const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)j);
+      v.x = fx.x;
+      v.y = fx.x & ~fx.y;
+      v.z = __ldg(M + g.offRS + j) - 1u;
+    }
+    s_words[warp][lane] = v;
+  }
+  __syncwarp();
+  const u32 nwd = min(32u, W - (chunk << 5));
+  const u32 below = CC_FULL >> (31 - lane);
+  const u32 bit = 1u << lane;
+  const u32 x = (chunk << 10) + lane;
+  const size_t base = (size_t)row * sx + x;
+  for (u32 j = 0; j < nwd; j++) {
+    if (x + (j << 5) >= sx) break;
+    const uint4 wv = s_words[warp][j];
+    const IT v = img[base + (j << 5)];
+    bool k = false;
+    if (wv.x & bit) k = keep[L[wv.z + __popc(wv.y & below)]] != 0;
+    out[base + (j << 5)] = k ? v : (IT)0;
+  }
+}
+
 // ---- sharded volumes (z-slabs): equivalences across one slab interface ----
 // P = first plane of the upper slab (later in raster order), Q = last plane of the lower slab.
 // Emits (label in Q's slab, label in P's slab) for every edge of the chosen predicate/neighbourhood

@@ -275,8 +275,7 @@ struct WordEdges {
 // ---------------------------------------------------------------------------------------------
 struct EdgeQueue { u64* q; u32* count; u32* ovf; u32 cap; };
 
-// Label volumes (MODE_EQ) are latency / barrier bound in this kernel: six resident CTAs per SM (40 registers,
-// a 512-entry staging buffer) hide more of it; dense binary tiles need the registers and the larger buffers.
+// (binary volumes; multilabel volumes run k_union_tile_hybrid below)
 template <int MODE> struct TileQueues {
   static constexpr u32 GQ = MODE == MODE_EQ ? 512 : CC_TILE_GQ;
   static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2;
@@ -426,6 +425,322 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
       sm_union16(lab, v & 0xFFFFu, v >> 16);
     }
     __syncthreads();
+    }
+  }
+
+  // ---- staged edges -> global queue; runs -> tile roots ----
+  const u32 gn = min(s_gn, GQN);
+  if (threadIdx.x == 0 && gn) s_gbase = atomicAdd(GQ.count, gn);
+  __syncthreads();
+  for (u32 e = threadIdx.x; e < gn; e += blockDim.x) {
+    const u32 pos = s_gbase + e;
+    if (pos < GQ.cap) GQ.q[pos] = gq[e];
+    else *GQ.ovf = 1u;
+  }
+#pragma unroll 1
+  for (u32 q = threadIdx.x; q < CC_TILE_WORDS; q += blockDim.x) {
+    const u32 wx = q & (TW - 1), r = q >> g.tw;
+    const u32 w = w0 + wx, y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+    if (w >= W || y >= sy || z >= sz) continue;
+    const u32 i = (z * sy + y) * W + w;
+    const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)i);
+    const int n = __popc(fx.x & ~fx.y);
+    if (n == 0) continue;
+    const u32 g0 = __ldg(RS + i);
+    if (!tile_ok) { for (int k = 0; k < n; k++) L[g0 + k] = g0 + k; continue; }
+    const u32 l0 = (r << capl) + (g0 - segRS[r]);
+    for (int k = 0; k < n; k++) {
+      u32 l = l0 + k, p;
+      while ((p = lab[l]) != l) l = p;
+      L[g0 + k] = segRS[l >> capl] + (l & ((1u << capl) - 1u));
+    }
+  }
+}
+
+// Kernel B1 for multilabel volumes (EQ, and the explicit-diagonal planes of continuous 2D-8): round 0 as in
+// k_union_tile; round 1 expands the diagonal candidate masks of the to-do words into (word, direction, bit) work
+// items and resolves one item per thread from a shared-memory stash of run starts / first run ids (wS, wR) instead
+// of running the candidate loop per word. Tiles with many runs (dense noise) keep the per-word loop: their item
+// lists would overflow. Label volumes are latency / barrier bound here: six resident CTAs per SM (40 registers, a
+// 512-entry staging buffer) hide more of it.
+template <int MODE> struct HybridQueues {
+  static constexpr u32 GQ = MODE == MODE_EQ ? 512 : CC_TILE_GQ;
+  static constexpr bool ITEMS = true;
+  static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2 + (ITEMS ? 2 * CC_TILE_WORDS : 0);
+};
+template <typename T, int MODE, int CONN>
+__global__ void __launch_bounds__(256, MODE == MODE_EQ ? 6 : 0)
+k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
+             u32 ntx, u32 nty, EdgeQueue GQ) {
+  constexpr u32 GQN = HybridQueues<MODE>::GQ;
+  constexpr bool ITEMS = HybridQueues<MODE>::ITEMS;   // round 1 through item lists (needs the wS / wR stash)
+  extern __shared__ __align__(16) u32 smem_u32[];
+  uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [CC_TILE_NODES] 16-bit parents
+  u32* lq = smem_u32 + CC_TILE_NODES / 2;                  // [CC_TILE_LQ]
+  u64* gq = reinterpret_cast<u64*>(lq + CC_TILE_LQ);       // [GQN]
+  u32* segRS = lq + CC_TILE_LQ + 2 * GQN;           // [CC_TILE_WORDS] first run id of every row segment
+  uint16_t* todo = reinterpret_cast<uint16_t*>(segRS + CC_TILE_WORDS);   // [CC_TILE_WORDS]
+  u32* wS = segRS + CC_TILE_WORDS + CC_TILE_WORDS / 2;     // [CC_TILE_WORDS] run starts of every word (round 0 -> round 1)
+  u32* wR = wS + CC_TILE_WORDS;                            // [CC_TILE_WORDS] id of the first run that starts in the word, minus 1
+  __shared__ u32 s_ln[4], s_in[2], s_gn, s_gbase, s_tn, s_big, s_runs;
+  const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
+  const u32 TW = 1u << g.tw, TY = 1u << g.ty;
+  const u32 nseg = CC_TILE_WORDS >> g.tw;        // TY * TZ
+  const u32 capl = g.tw + 4;                     // log2(runs a segment can hold locally)
+  u32 t = blockIdx.x;
+  const u32 bx = t % ntx; t /= ntx;
+  const u32 by = t % nty;
+  const u32 bz = t / nty;
+  const u32 w0 = bx << g.tw, y0 = by << g.ty, z0 = bz << g.tz;
+  const u32 wend = min(w0 + TW, W);
+  const u32* __restrict__ RS = M + g.offRS;
+
+  if (threadIdx.x < 4) s_ln[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_gn = 0; s_tn = 0; s_big = 0; s_runs = 0; s_in[0] = 0; s_in[1] = 0; }
+  __syncthreads();
+  for (u32 r = threadIdx.x; r < nseg; r += blockDim.x) {
+    const u32 y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+    u32 first = 0xFFFFFFFFu;
+    if (y < sy && z < sz) {
+      const u32 j = (z * sy + y) * W;
+      first = __ldg(RS + j + w0);
+      const u32 cnt = __ldg(RS + j + wend) - first;
+      if (cnt > (1u << capl)) s_big = 1;   // multilabel rows with > 16 runs per word
+      atomicAdd(&s_runs, cnt);
+    }
+    segRS[r] = first;
+  }
+  for (u32 k = threadIdx.x; k < CC_TILE_NODES / 2; k += blockDim.x) smem_u32[k] = (2 * k) | ((2 * k + 1) << 16);
+  __syncthreads();
+  const bool tile_ok = s_big == 0;   // otherwise every edge of this tile goes to kernel B2
+  // dense tiles enumerate 256 words at a time so that the edge queue is drained before it overflows
+  const u32 step = s_runs > CC_TILE_LQ / 2 ? 256u : (u32)CC_TILE_WORDS;
+
+  auto push_global = [&](u32 gp, u32 gq_) {
+    const u32 pos = atomicAdd(GQ.count, 1u);
+    if (pos < GQ.cap) GQ.q[pos] = (u64)gp | ((u64)gq_ << 32);
+    else *GQ.ovf = 1u;
+  };
+
+  WordEdges<T, MODE, CONN> we(in, M, g, E);
+  int sub = 0;
+#pragma unroll 1
+  for (int round = 0; round < 1; round++) {
+    // ---- round 0: straight edges of every word, enumerated and classified per word; words that may have
+    //      diagonal candidates are put on the to-do list of round 1 ----
+    const u32 nitems = (u32)CC_TILE_WORDS;
+#pragma unroll 1
+    for (u32 base = 0; base < nitems; base += step, sub++) {
+    const u32 iend = min(nitems, base + step);
+#pragma unroll 1
+    for (u32 e = base + threadIdx.x; e < iend; e += blockDim.x) {
+      const u32 q = e;
+      const u32 wx = q & (TW - 1), r = q >> g.tw;
+      const int ly = (int)(r & (TY - 1)), lz = (int)(r >> g.ty);
+      const u32 w = w0 + wx, y = y0 + ly, z = z0 + lz;
+      if constexpr (ITEMS) wS[q] = 0;
+      if (w >= W || y >= sy || z >= sz) continue;
+      const u32 row = z * sy + y;
+      if (!we.load(row * W + w, row, w, y, z)) continue;
+      if constexpr (ITEMS) { wS[q] = we.Sp; wR[q] = we.RSp; }
+      const u32 baseP = segRS[r];
+      if (round == 0) {
+        // straight edges: q is the same x in the row above / the plane below, so whether the edge stays in
+        // the tile is decided per word (row inside the tile) except for runs that entered the tile from the
+        // left. One queue reservation per word; slots of edges that turn out to leave the tile get a no-op.
+        auto straight_fast = [&](u32 need, const Q4& Qf, const u32 jq, const bool rowlocal, const u32 rq) {
+          if (!need) return;
+          const u32 Sq = Qf.F & ~Qf.X;
+          const u32 RSq = __ldg(RS + jq) - 1u;
+          const u32 n = __popc(need);
+          if (rowlocal) {
+            const u32 baseQ = segRS[rq];
+            const u32 pos0 = atomicAdd(&s_ln[sub], n);
+            u32 k = 0;
+            while (need) {
+              const int b = __ffs(need) - 1; need &= need - 1;
+              const u32 below = CC_FULL >> (31 - b);
+              const u32 gp = we.RSp + __popc(we.Sp & below), gq_ = RSq + __popc(Sq & below);
+              const bool loc = gp >= baseP && gq_ >= baseQ;
+              const u32 lp = (r << capl) + (gp - baseP), lq_ = (rq << capl) + (gq_ - baseQ);
+              const u32 pos = pos0 + k++;
+              if (pos < CC_TILE_LQ) lq[pos] = loc ? (lp | (lq_ << 16)) : 0u;
+              else if (loc) sm_union16(lab, lp, lq_);
+              if (!loc) {
+                const u32 gpos = atomicAdd(&s_gn, 1u);
+                if (gpos < GQN) gq[gpos] = (u64)gp | ((u64)gq_ << 32);
+                else push_global(gp, gq_);
+              }
+            }
+          } else {
+            const u32 pos0 = atomicAdd(&s_gn, n);
+            u32 k = 0;
+            while (need) {
+              const int b = __ffs(need) - 1; need &= need - 1;
+              const u32 below = CC_FULL >> (31 - b);
+              const u32 gp = we.RSp + __popc(we.Sp & below), gq_ = RSq + __popc(Sq & below);
+              const u32 pos = pos0 + k++;
+              if (pos < GQN) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+              else push_global(gp, gq_);
+            }
+          }
+        };
+        straight_fast(we.need_y(), we.U, we.i - W, tile_ok && ly > 0, r - 1);
+        straight_fast(we.need_z(), we.D, we.i - W * sy, tile_ok && lz > 0, r - TY);
+        if (we.may_have_diagonals()) todo[atomicAdd(&s_tn, 1u)] = (uint16_t)q;
+      }
+    }
+    __syncthreads();
+    // ---- tile-local unions, one queued edge per thread and step ----
+    const u32 ln = min(s_ln[sub], (u32)CC_TILE_LQ);
+    for (u32 e = threadIdx.x; e < ln; e += blockDim.x) {
+      const u32 v = lq[e];
+      sm_union16(lab, v & 0xFFFFu, v >> 16);
+    }
+    __syncthreads();
+    }
+  }
+
+  // ---- round 1: diagonal candidates of the to-do words. Word-parallel masks, expanded into work items
+  //      (word, direction, bit) in the edge-queue buffer, then one item per thread: run ids of both ends from the
+  //      shared-memory stash (wS / wR), value test for EQ / DELTA, union or staging. ----
+  // Dense tiles (random binary volumes: a dozen candidates per word) keep the per-word candidate loop with the
+  // balanced union queue - their item lists would overflow; label volumes take the item lists.
+  const bool dense_tile = !ITEMS || s_runs > CC_TILE_LQ / 2;
+  if (WordEdges<T, MODE, CONN>::DIAG0 && dense_tile) {
+    const u32 ntodo = s_tn;
+#pragma unroll 1
+    for (u32 base = 0; base < ntodo; base += step, sub++) {
+      const u32 iend = min(ntodo, base + step);
+#pragma unroll 1
+      for (u32 e = base + threadIdx.x; e < iend; e += blockDim.x) {
+        const u32 q = (u32)todo[e];
+        const u32 wx = q & (TW - 1), r = q >> g.tw;
+        const int ly = (int)(r & (TY - 1)), lz = (int)(r >> g.ty);
+        const u32 w = w0 + wx, y = y0 + ly, z = z0 + lz;
+        const u32 row = z * sy + y;
+        if (!we.load(row * W + w, row, w, y, z)) continue;
+        const u32 baseP = segRS[r];
+        auto classify = [&](u32 gp, u32 gq_, int dy, int dz, u32 xq) {
+          bool local = tile_ok && gp >= baseP;
+          u32 rq = 0;
+          if (local) {
+            const int lyq = ly + dy, lzq = lz + dz;
+            local = ((xq >> 5) >> g.tw) == bx && lyq >= 0 && lyq < (int)TY && lzq >= 0;
+            if (local) { rq = ((u32)lzq << g.ty) + (u32)lyq; local = gq_ >= segRS[rq]; }
+          }
+          if (local) {
+            const u32 lp = (r << capl) + (gp - baseP), lq_ = (rq << capl) + (gq_ - segRS[rq]);
+            const u32 pos = atomicAdd(&s_ln[sub & 3], 1u);
+            if (pos < CC_TILE_LQ) lq[pos] = lp | (lq_ << 16);
+            else sm_union16(lab, lp, lq_);
+          } else {
+            const u32 pos = atomicAdd(&s_gn, 1u);
+            if (pos < GQN) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+            else push_global(gp, gq_);
+          }
+        };
+        we.diagonals(classify);
+      }
+      __syncthreads();
+      const u32 ln = min(s_ln[sub & 3], (u32)CC_TILE_LQ);
+      for (u32 e = threadIdx.x; e < ln; e += blockDim.x) {
+        const u32 v = lq[e];
+        sm_union16(lab, v & 0xFFFFu, v >> 16);
+      }
+      __syncthreads();
+    }
+  } else if constexpr (WordEdges<T, MODE, CONN>::DIAG0 && ITEMS) {
+    // two bits per diagonal direction of WordEdges::diag_masks: d + 1
+    constexpr u32 DXP = (0u << 0) | (2u << 2) | (0u << 4) | (2u << 6) | (1u << 8) | (0u << 10) | (2u << 12) | (1u << 14) | (0u << 16) | (2u << 18);
+    constexpr u32 DYP = (0u << 0) | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (0u << 10) | (0u << 12) | (2u << 14) | (2u << 16) | (2u << 18);
+    constexpr u32 DZP = (1u << 0) | (1u << 2) | (0u << 4) | (0u << 6) | (0u << 8) | (0u << 10) | (0u << 12) | (0u << 14) | (0u << 16) | (0u << 18);
+    const u32 sx = (u32)g.sx;
+    const int lane = threadIdx.x & 31;
+    auto resolve = [&](const u32 item) {
+      const u32 b = item & 31u, tdir = (item >> 5) & 15u, q = item >> 9;
+      const u32 wx = q & (TW - 1), r = q >> g.tw;
+      const int ly = (int)(r & (TY - 1)), lz = (int)(r >> g.ty);
+      const int dx = (int)((DXP >> (2 * tdir)) & 3u) - 1, dy = (int)((DYP >> (2 * tdir)) & 3u) - 1, dz = (int)((DZP >> (2 * tdir)) & 3u) - 1;
+      const u32 gp = wR[q] + __popc(wS[q] & (CC_FULL >> (31 - b)));
+      const int xl = (int)((wx << 5) + b) + dx;            // x of q relative to the tile
+      const int lyq = ly + dy, lzq = lz + dz;
+      const bool inside = xl >= 0 && xl < (int)(TW << 5) && lyq >= 0 && lyq < (int)TY && lzq >= 0;
+      const u32 rowP = (z0 + lz) * sy + y0 + ly;
+      const u32 rowQ = (u32)((int)rowP + dy + dz * (int)sy);
+      const u32 xq = (u32)((int)(w0 << 5) + xl);
+      if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA) {
+        if (!E(in[(size_t)rowP * sx + ((w0 + wx) << 5) + b], in[(size_t)rowQ * sx + xq])) return;
+      }
+      u32 gq_, rq = 0;
+      if (inside) {
+        rq = ((u32)lzq << g.ty) + (u32)lyq;
+        const u32 qq = (rq << g.tw) + ((u32)xl >> 5);
+        gq_ = wR[qq] + __popc(wS[qq] & (CC_FULL >> (31 - (xl & 31))));
+      } else {
+        gq_ = run_id(M, g, rowQ * W, xq);
+      }
+      bool local = tile_ok && inside && gp >= segRS[r];
+      if (local) local = gq_ >= segRS[rq];
+      if (local) {
+        sm_union16(lab, (r << capl) + (gp - segRS[r]), (rq << capl) + (gq_ - segRS[rq]));
+      } else {
+        const u32 pos = atomicAdd(&s_gn, 1u);
+        if (pos < GQN) gq[pos] = (u64)gp | ((u64)gq_ << 32);
+        else push_global(gp, gq_);
+      }
+    };
+    const u32 ntodo = s_tn;
+    u32 par = 0;
+#pragma unroll 1
+    for (u32 base = 0; base < ntodo; base += blockDim.x, par ^= 1u) {
+      const u32 e = base + threadIdx.x;
+      u32 m[10];
+#pragma unroll
+      for (int t = 0; t < 10; t++) m[t] = 0;
+      u32 q = 0;
+      if (e < ntodo) {
+        q = (u32)todo[e];
+        const u32 wx = q & (TW - 1), r = q >> g.tw;
+        const u32 w = w0 + wx, y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
+        const u32 row = z * sy + y;
+        if (we.load(row * W + w, row, w, y, z)) we.diag_masks(m);
+      }
+      u32 n = 0;
+#pragma unroll
+      for (int t = 0; t < 10; t++) n += __popc(m[t]);
+      u32 inc = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(CC_FULL, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const u32 wtot = __shfl_sync(CC_FULL, inc, 31);
+      u32 wbase = 0;
+      if (wtot) {
+        if (lane == 31) wbase = atomicAdd(&s_in[par], wtot);
+        wbase = __shfl_sync(CC_FULL, wbase, 31);
+      }
+      u32 pos = wbase + inc - n;
+      if (n) {
+        const u32 qb = q << 9;
+#pragma unroll
+        for (int t = 0; t < 10; t++) {
+          u32 mk = m[t];
+          while (mk) {
+            const u32 bb = __ffs(mk) - 1; mk &= mk - 1;
+            const u32 item = qb | ((u32)t << 5) | bb;
+            if (pos < CC_TILE_LQ) lq[pos] = item;
+            else resolve(item);          // list full: resolve in place
+            pos++;
+          }
+        }
+      }
+      __syncthreads();
+      const u32 ni = min(s_in[par], (u32)CC_TILE_LQ);
+      if (threadIdx.x == 0) s_in[par ^ 1u] = 0;
+      for (u32 kk = threadIdx.x; kk < ni; kk += blockDim.x) resolve(lq[kk]);
+      __syncthreads();
     }
   }
 

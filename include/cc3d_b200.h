@@ -202,6 +202,16 @@ int cc3d_b200_contacts(const void* labels, int kind, int64_t sx, int64_t sy, int
 int cc3d_b200_remap_labels(const void* labels, int label_kind, int64_t voxels, const uint32_t* table, uint64_t N,
                            void* out, int out_kind, int mem_space, void* stream);
 
+/* Row a14 fused: cc3d.dust (cc3d/__init__.py:71-155) without materialising the label volume. The image is
+ * labelled (connectivity, binary_image as in cc3d_b200_label, delta = 0), component sizes come from the run table,
+ * components with lo <= size < hi stay (a scalar threshold t is lo = t, hi = INT64_MAX; invert swaps which side
+ * stays and, like np.isin(..., invert=True), also clears the background), and out[v] = stays ? img[v] : 0 is
+ * written in the same pass that would expand the labels. out may be img (in place). *N = number of components,
+ * *n_masked = number of components outside [lo, hi) (dust_N = N - n_masked, or n_masked when inverted). */
+int cc3d_b200_dust(const void* img, void* out, int kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
+                   int binary_image, int64_t lo, int64_t hi, int invert, int mem_space, uint64_t* N,
+                   uint64_t* n_masked, void* stream);
+
 /* Device-memory workspace currently cached by the library on the active device (bytes), and a
  * call that frees it. */
 size_t cc3d_b200_workspace_bytes(void);
