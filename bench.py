@@ -363,6 +363,30 @@ def main():
                    "compulsory_roofline_frac": w["alg_bytes"] * v.numel() / (m / steps_ / 1e3) / 1e9 / peak})
       del v, o_
 
+  # ---- rows a13 / a14 on the headline volume: statistics of its labelling, dust(threshold=100) of the volume ----
+  if world == 1 and not args.no_extra:
+    lab_t, n_lab = cc3d_b200.connected_components(x, return_N=True, **kw)
+    def timed_call(fn, steps_=10):
+      for _ in range(3):
+        fn()
+      torch.cuda.synchronize()
+      a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a0.record()
+      for _ in range(steps_):
+        fn()
+      a1.record()
+      torch.cuda.synchronize()
+      return a0.elapsed_time(a1) / steps_
+    m_st = timed_call(lambda: cc3d_b200.statistics(lab_t, no_slice_conversion=True))
+    also.append({"workload": "statistics_of_" + args.workload, "value": voxels / (m_st / 1e3) / 1e9, "unit": UNIT, "ms_per_step": m_st,
+                 "N": int(n_lab), "compulsory_roofline_frac": out_bytes * voxels / (m_st / 1e3) / 1e9 / peak,
+                 "note": "public call on the CUDA label tensor: label max + statistics kernel + D2H of the per-label arrays + host finalisation"})
+    m_du = timed_call(lambda: cc3d_b200.dust(x, threshold=100, connectivity=kw.get("connectivity", 26)))
+    also.append({"workload": "dust100_of_" + args.workload, "value": voxels / (m_du / 1e3) / 1e9, "unit": UNIT, "ms_per_step": m_du,
+                 "compulsory_roofline_frac": 3 * x.element_size() * voxels / (m_du / 1e3) / 1e9 / peak,
+                 "note": "fused dust: image read twice and written once, no label volume"})
+    del lab_t
+
   # ---- configs[2]: ONE 2048^3 uint64 Voronoi volume, z-slabs over the ranks (strong scaling; needs slabs < 2^32 voxels) ----
   if world >= 4 and not args.no_extra:
     import benchdata

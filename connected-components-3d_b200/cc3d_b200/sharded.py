@@ -103,6 +103,11 @@ class CudaBackend:
                                                     okind, _lib.DEVICE, self._stream(out)))
     return out
 
+  def partial_statistics(self, labels, N):
+    """(counts u32[N+1], bbox u32[N+1, 6], sums u64[N+1, 3]) of one slab in ARRAY axes, slab-local coordinates."""
+    from . import _statistics_arrays_device
+    return _statistics_arrays_device(labels, int(N))
+
   def release(self, h):
     if h.get("sess") is not None:
       self.L.cc3d_b200_session_release(h["sess"])
@@ -487,3 +492,55 @@ def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = F
     for h in handles:
       backend.release(h)
   return (outs, N_total) if return_N else outs
+
+
+def statistics_slab(labels_slab, N: int, no_slice_conversion: bool = False, group=None, backend=None):
+  """cc3d.statistics of a volume whose labelling is sharded as z-slabs over the ranks of `group`
+  (labels_slab = this rank's (sz_local, sy, sx) block of connected_components_slab's result, N = the global
+  component count). Every rank computes the partial sums of its slab (the statistics kernel), shifts them to
+  volume coordinates and ONE all-reduce pair (sum for counts / coordinate sums, max for the boxes) combines them;
+  every rank returns the statistics of the whole volume: same arrays and dtypes as
+  cc3d_b200.statistics(whole_labels) (fastcc3d.pyx:682-938)."""
+  import torch
+  import torch.distributed as dist
+  from . import _finish_statistics
+  if labels_slab.ndim != 3:
+    raise ValueError("labels_slab must be a 3-D (sz_local, sy, sx) tensor")
+  if backend is None:
+    backend = CudaBackend()
+  distributed = dist.is_available() and dist.is_initialized()
+  rank = dist.get_rank(group) if distributed else 0
+  world = dist.get_world_size(group) if distributed else 1
+  dev = labels_slab.device
+  sz, sy, sx = (int(v) for v in labels_slab.shape)
+  N = int(N)
+  counts, bbox, sums = backend.partial_statistics(labels_slab.contiguous(), N)     # array axes: (z, y, x)
+  counts = np.asarray(counts).astype(np.int64)
+  bbox = np.asarray(bbox).astype(np.int64).reshape(N + 1, 3, 2)
+  sums = np.asarray(sums).astype(np.int64)
+  # depth of every slab -> z offset of this one
+  depths = torch.zeros((world,), dtype=torch.int64, device=dev)
+  depths[rank] = sz
+  if world > 1:
+    dist.all_reduce(depths, op=dist.ReduceOp.SUM, group=group)
+  depths = depths.cpu().numpy()
+  z0 = int(depths[:rank].sum())
+  sz_total = int(depths.sum())
+  present = counts > 0
+  sums[:, 0] += z0 * counts
+  absent = np.iinfo(np.uint32).max
+  # boxes as (-min, max) so that one MAX all-reduce combines both; absent labels: (-(2^32-1), 0)
+  lo = np.where(present[:, None], bbox[:, :, 0] + np.array([z0, 0, 0]), absent)
+  hi = np.where(present[:, None], bbox[:, :, 1] + np.array([z0, 0, 0]), 0)
+  add = torch.from_numpy(np.concatenate([counts[:, None], sums], 1)).to(dev)
+  mx = torch.from_numpy(np.concatenate([-lo, hi], 1)).to(dev)
+  if world > 1:
+    dist.all_reduce(add, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+  add, mx = add.cpu().numpy(), mx.cpu().numpy()
+  counts_g = (add[:, 0] & 0xFFFFFFFF).astype(np.uint32)        # uint32 counts wrap like the reference's
+  sums_g = add[:, 1:].astype(np.uint64)
+  bbox_g = np.stack([-mx[:, :3], mx[:, 3:]], 2).reshape(N + 1, 6).astype(np.uint32)
+  voxels = sz_total * sy * sx
+  bdtype = np.uint32 if max(sz_total, sy, sx) > np.iinfo(np.uint16).max else np.uint16
+  return _finish_statistics(counts_g, bbox_g, sums_g, bdtype, voxels, no_slice_conversion)

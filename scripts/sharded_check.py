@@ -58,12 +58,15 @@ for name, conn, kw in cases:
             dist.gather(slab, vparts, dst=0)
         else:
             parts, vparts = [out], [slab]
+        st = sharded.statistics_slab(out, N, no_slice_conversion=True)      # every rank: statistics of the whole volume
         if rank == 0:
             whole = torch.cat(vparts, 0)
             ref, Nr = cc3d_b200.connected_components(whole, connectivity=conn, return_N=True, **kw)
             got = torch.cat(parts, 0)
             ok = (Nr == N) and ref.element_size() == got.element_size() and bool(torch.equal(ref.view(got.dtype), got))
-        check = f"identical_to_single_gpu={ok}"
+            rs = cc3d_b200.statistics(ref, no_slice_conversion=True)
+            st_ok = all(np.array_equal(st[k], rs[k], equal_nan=(k == "centroids")) for k in rs)
+        check = f"identical_to_single_gpu={ok}" + (f" sharded_statistics_equal={st_ok}" if rank == 0 else "")
     else:
         # interface property: my first plane vs the previous rank's last plane (straight neighbours, equal values)
         good = torch.ones(1, dtype=torch.int64, device=dev)

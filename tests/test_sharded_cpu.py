@@ -48,6 +48,20 @@ class OracleBackend:
   def plane_labels(self, h, z):
     return self.torch.from_numpy(h["labels"][z].astype(np.int32))
 
+  def partial_statistics(self, labels, N):
+    """Per-slab partial sums in array axes (numpy restatement of the statistics kernel's outputs)."""
+    lab = labels.numpy().astype(np.int64)
+    counts = np.bincount(lab.ravel(), minlength=N + 1)[: N + 1].astype(np.uint32)
+    bbox = np.zeros((N + 1, 3, 2), dtype=np.uint32)
+    bbox[:, :, 0] = np.iinfo(np.uint32).max
+    sums = np.zeros((N + 1, 3), dtype=np.uint64)
+    idx = np.indices(lab.shape)
+    for ax in range(3):
+      np.minimum.at(bbox[:, ax, 0], lab.ravel(), idx[ax].ravel().astype(np.uint32))
+      np.maximum.at(bbox[:, ax, 1], lab.ravel(), idx[ax].ravel().astype(np.uint32))
+      sums[:, ax] = np.bincount(lab.ravel(), weights=idx[ax].ravel(), minlength=N + 1)[: N + 1].astype(np.uint64)
+    return counts, bbox.reshape(N + 1, 6), sums
+
   def face_pairs(self, vals_upper, labs_upper, vals_lower, labs_lower, kind, connectivity, delta_arr, binary_image):
     P, Q = vals_upper.numpy(), vals_lower.numpy()
     lP, lQ = labs_upper.numpy().astype(np.int64), labs_lower.numpy().astype(np.int64)
@@ -116,7 +130,8 @@ def _worker(rank, world, port, cases, results):
       bounds = np.linspace(0, vol.shape[0], world + 1).astype(int)
       slab = torch.from_numpy(np.ascontiguousarray(vol[bounds[rank]:bounds[rank + 1]]))
       out, N = sharded.connected_components_slab(slab, return_N=True, backend=backend, **kw)
-      results.put((ci, rank, out.numpy(), N))
+      st = sharded.statistics_slab(out.to(torch.int64), N, no_slice_conversion=True, backend=backend)
+      results.put((ci, rank, out.numpy(), N, st))
   finally:
     dist.destroy_process_group()
 
@@ -153,8 +168,8 @@ def test_slabs_equal_monolithic_labelling(world):
     p.start()
   got = {}
   for _ in range(world * len(cases)):
-    ci, rank, out, N = results.get(timeout=120)
-    got[(ci, rank)] = (out, N)
+    ci, rank, out, N, st = results.get(timeout=120)
+    got[(ci, rank)] = (out, N, st)
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
@@ -165,6 +180,14 @@ def test_slabs_equal_monolithic_labelling(world):
       assert got[(ci, r)][1] == Nw, f"case {ci} rank {r}: N {got[(ci, r)][1]} != {Nw}"
     whole = np.concatenate(parts, axis=0)
     assert np.array_equal(whole, want.astype(np.int64)), f"case {ci} ({kw}) differs from the monolithic labelling"
+    # statistics_slab: every rank holds the statistics of the whole volume
+    ref_st = oracle.statistics(want, no_slice_conversion=True)
+    for r in range(world):
+      st = got[(ci, r)][2]
+      assert np.array_equal(st["voxel_counts"], ref_st["voxel_counts"]), f"case {ci} rank {r}: counts"
+      assert st["bounding_boxes"].dtype == ref_st["bounding_boxes"].dtype
+      assert np.array_equal(st["bounding_boxes"], ref_st["bounding_boxes"]), f"case {ci} rank {r}: boxes"
+      assert np.array_equal(st["centroids"], ref_st["centroids"], equal_nan=True), f"case {ci} rank {r}: centroids"
 
 
 def test_single_process_slabs_equal_monolithic_labelling():
