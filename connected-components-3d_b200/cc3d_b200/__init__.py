@@ -410,17 +410,19 @@ def _statistics_arrays_device(t, N: int):
   ndim = t.ndim
   shape3 = list(t.shape) + [1] * (3 - ndim)
   mem = shape3 if order == "F" else shape3[::-1]
-  counts = torch.empty((N + 1,), dtype=torch.int32, device=t.device)
-  bbox = torch.empty((N + 1, 6), dtype=torch.int32, device=t.device)
-  sums = torch.empty((N + 1, 3), dtype=torch.int64, device=t.device)
+  # one device buffer for the three per-label arrays (sums | boxes | counts): one copy back, one synchronisation
+  n1 = N + 1
+  buf = torch.empty((n1 * 52,), dtype=torch.uint8, device=t.device)
+  p_sums, p_bbox, p_counts = buf.data_ptr(), buf.data_ptr() + n1 * 24, buf.data_ptr() + n1 * 48
   stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
   with torch.cuda.device(t.device):
     _lib.check(L.cc3d_b200_statistics(
       t.data_ptr(), _kind_of(_torch_np_dtype(t)), mem[0], mem[1], mem[2], N,
-      counts.data_ptr(), bbox.data_ptr(), sums.data_ptr(), _lib.DEVICE, stream))
-  counts = counts.cpu().numpy().view(np.uint32)
-  bbox = bbox.cpu().numpy().view(np.uint32)
-  sums = sums.cpu().numpy().view(np.uint64)
+      p_counts, p_bbox, p_sums, _lib.DEVICE, stream))
+  host = buf.cpu().numpy()
+  sums = host[: n1 * 24].view(np.uint64).reshape(n1, 3)
+  bbox = host[n1 * 24: n1 * 48].view(np.uint32).reshape(n1, 6)
+  counts = host[n1 * 48:].view(np.uint32)
   if order != "F":  # memory axes (x fastest) -> array axes
     sums = sums[:, ::-1]
     bbox = bbox.reshape(N + 1, 3, 2)[:, ::-1, :].reshape(N + 1, 6)
@@ -433,9 +435,9 @@ def _torch_max(t) -> int:
     return 0
   if t.dtype in (getattr(torch, "uint16", None), getattr(torch, "uint32", None), getattr(torch, "uint64", None)):
     signed = {2: torch.int16, 4: torch.int32, 8: torch.int64}[t.element_size()]
-    lo, hi = torch.aminmax(t.view(signed))     # one pass
-    if int(lo) >= 0:
-      return int(hi)
+    lo, hi = (int(v) for v in torch.stack(torch.aminmax(t.view(signed))).cpu())     # one pass, one copy back
+    if lo >= 0:
+      return hi
     return int(t.cpu().numpy().max())
   return int(t.max())
 
