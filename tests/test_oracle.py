@@ -201,3 +201,26 @@ def test_oracle_contacts_vs_reference(oracle_mod):
     assert ref.region_graph(x, connectivity=c) == oracle_mod.region_graph(x, connectivity=c)
     n += 1
   assert n == 120
+
+
+def _graph_goldens():
+  import glob, os
+  return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graphs_*.npz")))
+
+
+@pytest.mark.parametrize("path", _graph_goldens(), ids=[p.split("/")[-1][:-4] for p in _graph_goldens()])
+def test_oracle_matches_graph_goldens(oracle_mod, path):
+  """SURVEY 8(f) rows against fixtures generated from the reference (tests/golden/make_golden_graphs.py)."""
+  z = np.load(path)
+  x, c = z["x"], int(z["connectivity"])
+  assert np.array_equal(oracle_mod.voxel_connectivity_graph(x, connectivity=c), z["vcg"])
+  if "colors" in z:
+    col, N = oracle_mod.color_connectivity_graph(z["vcg_cut"], connectivity=c, return_N=True)
+    assert N == int(z["colors_N"]) and np.array_equal(col, z["colors"])
+  ct = oracle_mod.contacts(x, connectivity=c, surface_area=True, anisotropy=(4, 4, 40))
+  want = {(int(a), int(b)): float(v) for (a, b), v in zip(z["contact_pairs"], z["contact_areas"])}
+  assert ct == want
+  for k in (1, 3):
+    if f"largest_{k}" in z:
+      got, N = oracle_mod.largest_k(x, k, connectivity=c, return_N=True)
+      assert N == int(z[f"largest_{k}_N"]) and got.dtype == z[f"largest_{k}"].dtype and np.array_equal(got, z[f"largest_{k}"])

@@ -423,3 +423,27 @@ def test_contacts_and_region_graph(cc3d, oracle_mod):
     assert truth.region_graph(x, connectivity=c) == cc3d.region_graph(x, connectivity=c)
   big = np.arange(1, 40 * 40 * 40 + 1, dtype=np.uint32).reshape(40, 40, 40)      # 64 000 labels: the hash table has to grow
   assert truth.contacts(big, connectivity=26) == cc3d.contacts(big, connectivity=26)
+
+
+def _graph_goldens():
+  import glob, os
+  return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graphs_*.npz")))
+
+
+@pytest.mark.parametrize("path", _graph_goldens(), ids=[p.split("/")[-1][:-4] for p in _graph_goldens()])
+def test_graph_goldens(cc3d, path):
+  """SURVEY 8(f) rows against fixtures generated from the reference (incl. largest_k from its Python layer)."""
+  z = np.load(path)
+  x, c = z["x"], int(z["connectivity"])
+  g = cc3d.voxel_connectivity_graph(x, connectivity=c)
+  assert g.dtype == z["vcg"].dtype and np.array_equal(g, z["vcg"])
+  if "colors" in z:
+    col, N = cc3d.color_connectivity_graph(z["vcg_cut"], connectivity=c, return_N=True)
+    assert N == int(z["colors_N"]) and col.dtype == z["colors"].dtype and np.array_equal(col, z["colors"])
+  ct = cc3d.contacts(x, connectivity=c, surface_area=True, anisotropy=(4, 4, 40))
+  assert ct == {(int(a), int(b)): float(v) for (a, b), v in zip(z["contact_pairs"], z["contact_areas"])}
+  for k in (1, 3):
+    if f"largest_{k}" in z:
+      got, N = cc3d.largest_k(x, k, connectivity=c, return_N=True)
+      assert N == int(z[f"largest_{k}_N"]) and got.dtype == z[f"largest_{k}"].dtype and np.array_equal(got, z[f"largest_{k}"])
+      assert got.flags.c_contiguous == z[f"largest_{k}"].flags.c_contiguous or got.ndim < 2
