@@ -166,8 +166,11 @@ template <typename T, int NW> constexpr size_t faces_async_smem() {
   return (size_t)CC_FACE_WARPS * CC_FACE_STAGES * (16 + 2 * NW * 32 * sizeof(T));
 }
 
+#ifndef CC_FACE_MINB
+#define CC_FACE_MINB 0
+#endif
 template <typename T, int MODE, bool HASZ, int NW>
-__global__ void __launch_bounds__(CC_FACE_WARPS * 32)
+__global__ void __launch_bounds__(CC_FACE_WARPS * 32, CC_FACE_MINB)
 k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
               unsigned nych, unsigned nwg, unsigned ntasks) {
   constexpr int RB = NW * 32 * (int)sizeof(T);       // bytes of one row of the group
