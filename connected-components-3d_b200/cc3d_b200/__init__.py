@@ -24,6 +24,7 @@ from ._lib import CC3DB200Error
 __all__ = [
   "connected_components", "statistics", "dust", "estimate_provisional_labels",
   "largest_k", "voxel_connectivity_graph", "color_connectivity_graph", "contacts", "region_graph",
+  "runs", "draw", "erase", "each",
   "DimensionError", "CC3DB200Error", "last_timings", "set_timing",
 ]
 
@@ -903,3 +904,287 @@ def contacts(labels, connectivity: int = 26, surface_area: bool = True, anisotro
 def region_graph(labels, connectivity: int = 26) -> set:
   """Set of label pairs that touch; same contract as cc3d.region_graph (fastcc3d.pyx:1180-1194)."""
   return set(contacts(labels, connectivity=connectivity).keys())
+
+
+# ----------------------------------------------------------------------------------------------
+# runs / draw / erase / each (SURVEY.md 8(f)4; fastcc3d.pyx:1258-1372, cc3d_graphs.hpp:470-523)
+# ----------------------------------------------------------------------------------------------
+_RUN_KINDS = (np.dtype(np.uint8), np.dtype(np.uint16), np.dtype(np.uint32), np.dtype(np.uint64))
+
+
+def _flat_memory_order(arr: np.ndarray) -> np.ndarray:
+  """1-D view of the array in memory order (reference `_reshape(arr, (arr.size,))`, fastcc3d.pyx:129-161):
+  Fortran or C contiguous arrays are viewed in place, anything else is copied to C order."""
+  if arr.flags.f_contiguous:
+    return arr.reshape(-1, order="F")
+  if arr.flags.c_contiguous:
+    return arr.reshape(-1)
+  return arr.reshape((arr.size,))
+
+
+def _run_dtype(dtype) -> np.dtype:
+  dtype = np.dtype(dtype)
+  if dtype == np.bool_:
+    return np.dtype(np.uint8)
+  if dtype not in _RUN_KINDS:
+    raise TypeError("Unsupported type: " + str(dtype))
+  return dtype
+
+
+def _torch_flat(t):
+  """(dense 1-D tensor in memory order, order) of a CUDA tensor."""
+  t, order = _torch_order(t)
+  if order == "F":
+    return t.permute(*reversed(range(t.ndim))).reshape(-1), order
+  return t.reshape(-1), order
+
+
+def _run_table_device(flat_t, np_dtype):
+  """(values, starts, ends) int64 CUDA tensors (bit patterns of uint64) of the runs of a flat CUDA tensor, in
+  position order; two calls at most: the first one with a guessed capacity."""
+  import torch
+  L = _lib.lib()
+  n = flat_t.numel()
+  kind = _kind_of(_run_dtype(np_dtype))
+  count = ctypes.c_uint64(0)
+  cap = int(min(n, max(1 << 16, n // 16)))
+  with torch.cuda.device(flat_t.device):
+    stream = ctypes.c_void_p(torch.cuda.current_stream(flat_t.device).cuda_stream)
+    while True:
+      tab = torch.empty((3, max(cap, 1)), dtype=torch.int64, device=flat_t.device)
+      _lib.check(L.cc3d_b200_runs(flat_t.data_ptr(), kind, n, tab[0].data_ptr(), tab[1].data_ptr(), tab[2].data_ptr(),
+                                  cap, ctypes.byref(count), _lib.DEVICE, stream))
+      if count.value <= cap:
+        break
+      cap = int(count.value)
+  k = int(count.value)
+  return tab[0, :k], tab[1, :k], tab[2, :k]
+
+
+def _group_runs(values: np.ndarray, starts: np.ndarray, ends: np.ndarray):
+  """Run table in position order -> (labels ascending, offsets, starts, ends grouped by label, position order kept):
+  the iteration order of the reference's std::map<T, vector<pair>> (cc3d_graphs.hpp:472-474)."""
+  order = np.argsort(values, kind="stable")
+  v = values[order]
+  labels, first = np.unique(v, return_index=True)
+  offsets = np.append(first, v.size).astype(np.int64)
+  return labels, offsets, starts[order], ends[order]
+
+
+def _runs_table(labels):
+  """Grouped run table of a numpy array or CUDA tensor: (label values, offsets, starts, ends) as numpy uint64 /
+  int64 arrays. The extraction runs on the GPU (cc3d_b200_runs); grouping by label is host bookkeeping."""
+  L = _lib.lib()
+  if _is_torch(labels) and labels.is_cuda:
+    flat, _ = _torch_flat(labels)
+    if flat.numel() == 0:
+      raise IndexError("Out of bounds on buffer access (axis 0)")   # the reference indexes labels[0] (fastcc3d.pyx:1269)
+    v, s, e = _run_table_device(flat, _torch_np_dtype(labels))
+    values, starts, ends = (x.cpu().numpy().view(np.uint64) for x in (v, s, e))
+    n, first = flat.numel(), (int(flat[0].item()) if flat.numel() == 1 else None)
+  else:
+    labels = np.asarray(labels.cpu().numpy() if _is_torch(labels) else labels)
+    dt = _run_dtype(labels.dtype)
+    flat = _flat_memory_order(labels)
+    if flat.dtype != dt:
+      flat = flat.view(dt)
+    n = flat.size
+    if n == 0:
+      raise IndexError("Out of bounds on buffer access (axis 0)")   # the reference indexes labels[0] (fastcc3d.pyx:1269)
+    first = int(flat[0]) if n == 1 else None
+    flat = np.ascontiguousarray(flat)
+    count = ctypes.c_uint64(0)
+    cap = int(min(n, max(1 << 16, n // 16)))
+    while True:
+      tab = np.empty((3, max(cap, 1)), dtype=np.uint64)
+      _lib.check(L.cc3d_b200_runs(flat.ctypes.data, _kind_of(dt), n, tab[0].ctypes.data, tab[1].ctypes.data,
+                                  tab[2].ctypes.data, cap, ctypes.byref(count), _lib.HOST, None))
+      if count.value <= cap:
+        break
+      cap = int(count.value)
+    k = int(count.value)
+    values, starts, ends = tab[0, :k], tab[1, :k], tab[2, :k]
+  if n == 1 and first == 0:
+    # a single-voxel array reports its run even when it is background (cc3d_graphs.hpp:481-484)
+    values, starts, ends = np.zeros(1, np.uint64), np.zeros(1, np.uint64), np.ones(1, np.uint64)
+  return _group_runs(values, starts, ends)
+
+
+def runs(labels) -> dict:
+  """Returns a dictionary describing where each label is located: {label: [(start, end), ...]} over the
+  flattened (memory order) array, half-open voxel ranges; same contract as cc3d.fastcc3d.runs
+  (fastcc3d.pyx:1258-1279 -> extract_runs, cc3d_graphs.hpp:470-503). Keys ascend, runs ascend by position."""
+  lab, off, starts, ends = _runs_table(labels)
+  s, e = starts.tolist(), ends.tolist()
+  return {int(l): list(zip(s[off[i]:off[i + 1]], e[off[i]:off[i + 1]])) for i, l in enumerate(lab.tolist())}
+
+
+def _label_for_image(label, np_dtype) -> int:
+  np_dtype = np.dtype(np_dtype)
+  if np_dtype == np.bool_:
+    return int(label != 0)
+  v = int(label)
+  if v < 0 or v > int(np.iinfo(np_dtype).max):
+    raise OverflowError(f"value {v} does not fit {np_dtype}")   # Cython's conversion to the image type raises too
+  return v
+
+
+def _runs_as_arrays(rns):
+  arr = np.asarray(rns, dtype=np.uint64) if len(rns) else np.zeros((0, 2), np.uint64)
+  arr = arr.reshape(-1, 2)
+  return np.ascontiguousarray(arr[:, 0]), np.ascontiguousarray(arr[:, 1])
+
+
+def draw(label, runs, image):
+  """Draws label onto the provided image according to runs (fastcc3d.pyx:1281-1314 -> set_run_voxels,
+  cc3d_graphs.hpp:505-523). Returns the flattened (memory order) image like the reference. numpy images are staged
+  through the device (only the window the runs span); CUDA tensors are drawn in place. An invalid run raises
+  RuntimeError("Invalid run.") and leaves the image untouched."""
+  L = _lib.lib()
+  starts, ends = _runs_as_arrays(runs)
+  if _is_torch(image) and image.is_cuda:
+    import torch
+    np_dt = _torch_np_dtype(image)
+    flat, _ = _torch_flat(image)
+    if flat.data_ptr() != image.data_ptr() and image.numel():
+      raise ValueError("draw: CUDA image must be dense in memory (C or Fortran contiguous)")
+    value = _label_for_image(label, np_dt)
+    if starts.size:
+      dev = image.device
+      st = torch.from_numpy(starts.view(np.int64)).to(dev)
+      en = torch.from_numpy(ends.view(np.int64)).to(dev)
+      with torch.cuda.device(dev):
+        _lib.check(L.cc3d_b200_draw(flat.data_ptr(), _kind_of(_run_dtype(np_dt)), flat.numel(), value, st.data_ptr(),
+                                    en.data_ptr(), starts.size, _lib.DEVICE,
+                                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return flat
+  dt = _run_dtype(image.dtype)
+  flat = _flat_memory_order(image)
+  value = _label_for_image(label, image.dtype)
+  if starts.size:
+    target = flat if flat.flags.c_contiguous else np.ascontiguousarray(flat)
+    _lib.check(L.cc3d_b200_draw(target.view(dt).ctypes.data, _kind_of(dt), target.size, value, starts.ctypes.data,
+                                ends.ctypes.data, starts.size, _lib.HOST, None))
+    if target is not flat:
+      flat[...] = target
+  return flat
+
+
+def erase(runs, image):
+  """Erases (sets to 0) part of the provided image according to runs (fastcc3d.pyx:1316-1326)."""
+  return draw(0, runs, image)
+
+
+_erase = erase
+
+
+def each(labels, binary: bool = False, in_place: bool = False):
+  """Returns an iterator that extracts each label from a dense labeling; same contract as cc3d.each
+  (fastcc3d.pyx:1328-1372): yields (label, image) for every non-zero label in ascending order, image = the label's
+  mask (bool when `binary`, else the label value in the labels' dtype) with the labels' shape and memory order.
+  in_place: one image is reused (read-only while it is out). The run table is extracted once on the GPU and stays
+  there; every image is rendered by the draw kernels. CUDA tensors give CUDA tensors (no host traffic); for numpy
+  input only the window of the image that the label's runs span crosses PCIe."""
+  import torch
+  is_t = _is_torch(labels) and labels.is_cuda
+  if not is_t:
+    labels = np.asarray(labels.cpu().numpy() if _is_torch(labels) else labels)
+    np_dt = labels.dtype
+    order = "F" if labels.flags.f_contiguous else "C"
+    shape = labels.shape
+  else:
+    np_dt = _torch_np_dtype(labels)
+    _, order = _torch_flat(labels)
+    shape = tuple(labels.shape)
+  _run_dtype(np_dt)
+  lab, off, starts, ends = _runs_table(labels)
+  img_dt = np.dtype(np.bool_) if binary else np.dtype(np_dt)
+  kind = _kind_of(_run_dtype(img_dt))
+  n_vox = int(np.prod(shape)) if len(shape) else 1
+  nonzero = [i for i, l in enumerate(lab.tolist()) if l != 0]
+  L = _lib.lib()
+  dev = labels.device if is_t else torch.device("cuda", torch.cuda.current_device())
+  state = {}
+
+  def table():
+    if "st" not in state:   # grouped run table, uploaded once
+      state["st"] = torch.from_numpy(starts.view(np.int64)).to(dev)
+      state["en"] = torch.from_numpy(ends.view(np.int64)).to(dev)
+    return state["st"], state["en"]
+
+  def device_image():
+    # zero-filled through the signed type of the same width (fill kernels exist for every signed type)
+    tdt = torch.uint8 if binary else (labels.dtype if is_t else _torch_dtype(_run_dtype(np_dt)))
+    signed = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[img_dt.itemsize]
+    z = torch.zeros(n_vox, dtype=signed, device=dev)
+    return z if z.dtype == tdt else z.view(tdt)
+
+  def render(flat_img, i, value):
+    st, en = table()
+    a, b = int(off[i]), int(off[i + 1])
+    with torch.cuda.device(dev):
+      _lib.check(L.cc3d_b200_draw(flat_img.data_ptr(), kind, n_vox, value, st[a:b].data_ptr(), en[a:b].data_ptr(),
+                                  b - a, _lib.DEVICE, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
+  def shaped(flat_img):
+    t = flat_img.view(torch.bool) if binary else flat_img
+    if order == "F" and len(shape) > 1:
+      return t.view(*reversed(shape)).permute(*reversed(range(len(shape))))
+    return t.view(*shape)
+
+  def window(i):
+    a, b = int(off[i]), int(off[i + 1])
+    return int(starts[a:b].min()), int(ends[a:b].max())
+
+  def host_flat(img):
+    f = img.reshape(-1, order=order)
+    return f.view(np.uint8) if binary else f.view(_run_dtype(np_dt))
+
+  def fetch(flat_img, host_img, lo, hi):   # device window -> the same window of the numpy image
+    src = flat_img[lo:hi]
+    dst = torch.from_numpy(host_flat(host_img)[lo:hi])
+    if dst.dtype != src.dtype:
+      src = src.view(dst.dtype)
+    dst.copy_(src)
+
+  class ImageIterator:
+    def __len__(self):
+      return len(nonzero)
+
+    def __iter__(self):
+      for i in nonzero:
+        key = int(lab[i])
+        value = _label_for_image(key, img_dt)
+        dimg = device_image()
+        render(dimg, i, value)
+        if is_t:
+          yield key, shaped(dimg)
+        else:
+          img = np.zeros(shape, dtype=img_dt, order=order)
+          lo, hi = window(i)
+          fetch(dimg, img, lo, hi)
+          yield key, img
+
+  class InPlaceImageIterator(ImageIterator):
+    def __iter__(self):
+      dimg = device_image()
+      img = None if is_t else np.zeros(shape, dtype=img_dt, order=order)
+      for i in nonzero:
+        key = int(lab[i])
+        render(dimg, i, _label_for_image(key, img_dt))
+        if is_t:
+          yield key, shaped(dimg)
+          render(dimg, i, 0)
+        else:
+          lo, hi = window(i)
+          fetch(dimg, img, lo, hi)
+          img.setflags(write=0)
+          yield key, img
+          img.setflags(write=1)
+          render(dimg, i, 0)
+          fetch(dimg, img, lo, hi)
+
+  return InPlaceImageIterator() if in_place else ImageIterator()
+
+
+from . import fastcc3d  # noqa: E402  (namespace alias: the reference exposes runs / draw as cc3d.fastcc3d.*)

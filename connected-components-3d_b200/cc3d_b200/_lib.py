@@ -84,6 +84,10 @@ def lib():
   L.cc3d_b200_contacts.argtypes = [vp, ci, i64, i64, i64, ci, vp, vp, u64, p(u64), ci, vp]
   L.cc3d_b200_remap_labels.restype = ci
   L.cc3d_b200_remap_labels.argtypes = [vp, ci, i64, vp, u64, vp, ci, ci, vp]
+  L.cc3d_b200_runs.restype = ci
+  L.cc3d_b200_runs.argtypes = [vp, ci, i64, vp, vp, vp, u64, p(u64), ci, vp]
+  L.cc3d_b200_draw.restype = ci
+  L.cc3d_b200_draw.argtypes = [vp, ci, i64, u64, vp, vp, u64, ci, vp]
   L.cc3d_b200_dust.restype = ci
   L.cc3d_b200_dust.argtypes = [vp, vp, ci, i64, i64, i64, ci, ci, i64, i64, ci, ci, p(u64), p(u64), vp]
   L.cc3d_b200_mask_by_label.restype = ci

@@ -13,6 +13,7 @@
 #include "cc3d_misc.cuh"
 #include "cc3d_graphs.cuh"
 #include "cc3d_resolve.cuh"
+#include "cc3d_runs.cuh"
 
 namespace {
 
@@ -1265,5 +1266,174 @@ int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* co
   }
   remap[0] = 0;
   for (i64 l = 1; l <= n_labels[rank]; l++) remap[l] = final_of[find((u32)(off[rank] + l))];
+  return 0;
+}
+
+// ---- runs / draw (reference cc3d_graphs.hpp:470-523, fastcc3d.pyx:1258-1314) ----
+
+template <typename T>
+static void runs_count_typed(const T* lab, i64 n, u32* cnt, i64 nchunks, cudaStream_t s) {
+  const unsigned blocks = (unsigned)std::min<i64>(nchunks, 148 * 32);
+  k_runs_count<T><<<blocks, 256, 0, s>>>(lab, n, cnt, nchunks);
+}
+template <typename T>
+static void runs_emit_typed(const T* lab, i64 n, const u32* prefix, i64 nchunks, u64* values, u64* starts, u64* ends,
+                            cudaStream_t s) {
+  const unsigned blocks = (unsigned)std::min<i64>(nchunks, 148 * 32);
+  k_runs_emit<T><<<blocks, 256, 0, s>>>(lab, n, prefix, nchunks, values, starts, ends);
+}
+
+int cc3d_b200_runs(const void* labels, int kind, int64_t voxels, uint64_t* values, uint64_t* starts, uint64_t* ends,
+                   uint64_t capacity, uint64_t* count, int mem_space, void* stream) {
+  const size_t es = kind_size(kind);
+  if (!es || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "Unsupported type: labels must be u8/u16/u32/u64");
+  if (!count) return fail(CC3D_B200_ERR_ARGUMENT, "count must not be NULL");
+  if (voxels < 0) return fail(CC3D_B200_ERR_ARGUMENT, "negative size");
+  if (voxels >= (1ll << 43)) return fail(CC3D_B200_ERR_TOO_LARGE, "runs: more than 2^43 voxels");
+  *count = 0;
+  if (voxels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool host = mem_space == CC3D_B200_HOST;
+  const i64 nchunks = (voxels + CC_RUN_CHUNK - 1) / CC_RUN_CHUNK;
+  const i64 nb = std::max<i64>(1, (nchunks + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK);
+  size_t need = 4096 + (size_t)(nchunks + 4) * 4 + (size_t)(nb + 1) * 8 + 1024;
+  if (host) need += (size_t)voxels * es + 512 + (size_t)capacity * 24 + 1024;
+  Arena ar;
+  if (int rc = arena_acquire(need, &ar, s, true)) return rc;
+  const void* dl = labels;
+  if (host) {
+    void* d = ar.take((size_t)voxels * es);
+    cudaError_t e = cudaMemcpyAsync(d, labels, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    dl = d;
+  }
+  u32* cnt = (u32*)ar.take((size_t)(nchunks + 4) * 4);
+  u64* bsum = (u64*)ar.take((size_t)(nb + 1) * 8);
+  u64* total_dev = (u64*)ar.take(16);
+  switch (kind) {
+    case CC3D_B200_U8: runs_count_typed((const uint8_t*)dl, voxels, cnt, nchunks, s); break;
+    case CC3D_B200_U16: runs_count_typed((const uint16_t*)dl, voxels, cnt, nchunks, s); break;
+    case CC3D_B200_U32: runs_count_typed((const uint32_t*)dl, voxels, cnt, nchunks, s); break;
+    default: runs_count_typed((const uint64_t*)dl, voxels, cnt, nchunks, s); break;
+  }
+  g_launches += 1;
+  scan_counts(cnt, cnt, bsum, nchunks, nullptr, 0, total_dev, nullptr, s);
+  u64 total = 0;
+  cudaError_t e = cudaMemcpyAsync(&total, total_dev, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, std::string("runs: ") + cudaGetErrorString(e)); }
+  *count = total;
+  if (total >= (1ull << 32)) { arena_release(ar); return fail(CC3D_B200_ERR_TOO_LARGE, "runs: more than 2^32 runs"); }
+  if (total == 0 || total > capacity) { arena_release(ar); return 0; }
+  if (!values || !starts || !ends) { arena_release(ar); return fail(CC3D_B200_ERR_ARGUMENT, "runs: output arrays must not be NULL"); }
+  u64 *dv = values, *ds = starts, *de = ends;
+  if (host) {
+    dv = (u64*)ar.take((size_t)total * 8); ds = (u64*)ar.take((size_t)total * 8); de = (u64*)ar.take((size_t)total * 8);
+  }
+  switch (kind) {
+    case CC3D_B200_U8: runs_emit_typed((const uint8_t*)dl, voxels, cnt, nchunks, dv, ds, de, s); break;
+    case CC3D_B200_U16: runs_emit_typed((const uint16_t*)dl, voxels, cnt, nchunks, dv, ds, de, s); break;
+    case CC3D_B200_U32: runs_emit_typed((const uint32_t*)dl, voxels, cnt, nchunks, dv, ds, de, s); break;
+    default: runs_emit_typed((const uint64_t*)dl, voxels, cnt, nchunks, dv, ds, de, s); break;
+  }
+  g_launches += 1;
+  if (host) {
+    cudaMemcpyAsync(values, dv, (size_t)total * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(starts, ds, (size_t)total * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(ends, de, (size_t)total * 8, cudaMemcpyDeviceToHost, s);
+  }
+  e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("runs: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+template <typename T>
+static void draw_typed(T* img, u64 value, const u64* starts, const u64* ends, u64 n_runs, u64 origin, u64* long_runs,
+                       unsigned long long* n_long, bool any_long, cudaStream_t s) {
+  const u64 warps_needed = n_runs;
+  const unsigned blocks = (unsigned)std::min<u64>((warps_needed + 7) / 8, 148 * 32);
+  k_draw_short<T><<<std::max(1u, blocks), 256, 0, s>>>(img, (T)value, starts, ends, n_runs, origin, long_runs, n_long);
+  g_launches += 1;
+  if (any_long) {
+    k_draw_long<T><<<148 * 8, 256, 0, s>>>(img, (T)value, long_runs, n_long);
+    g_launches += 1;
+  }
+}
+static void draw_kind(void* img, int kind, u64 value, const u64* starts, const u64* ends, u64 n_runs, u64 origin,
+                      u64* long_runs, unsigned long long* n_long, bool any_long, cudaStream_t s) {
+  switch (kind) {
+    case CC3D_B200_U8: draw_typed((uint8_t*)img, value, starts, ends, n_runs, origin, long_runs, n_long, any_long, s); break;
+    case CC3D_B200_U16: draw_typed((uint16_t*)img, value, starts, ends, n_runs, origin, long_runs, n_long, any_long, s); break;
+    case CC3D_B200_U32: draw_typed((uint32_t*)img, value, starts, ends, n_runs, origin, long_runs, n_long, any_long, s); break;
+    default: draw_typed((uint64_t*)img, value, starts, ends, n_runs, origin, long_runs, n_long, any_long, s); break;
+  }
+}
+
+int cc3d_b200_draw(void* image, int kind, int64_t voxels, uint64_t value, const uint64_t* starts, const uint64_t* ends,
+                   uint64_t n_runs, int mem_space, void* stream) {
+  const size_t es = kind_size(kind);
+  if (!es || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "Unsupported type: image must be u8/u16/u32/u64");
+  if (voxels < 0) return fail(CC3D_B200_ERR_ARGUMENT, "negative size");
+  if (n_runs == 0) return 0;
+  if (!image || !starts || !ends) return fail(CC3D_B200_ERR_ARGUMENT, "draw: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mem_space == CC3D_B200_HOST) {
+    // the run list is on the host: validate it here, stage only the window of the image the runs span
+    u64 lo = ~0ull, hi = 0, n_long = 0;
+    for (u64 r = 0; r < n_runs; r++) {
+      const u64 a = starts[r], b = ends[r];
+      if (a >= b || b > (u64)voxels) return fail(CC3D_B200_ERR_ARGUMENT, "Invalid run.");
+      lo = std::min(lo, a); hi = std::max(hi, b);
+      n_long += (b - a > CC_RUN_LONG);
+    }
+    const size_t window = (size_t)(hi - lo);
+    Arena ar;
+    if (int rc = arena_acquire(window * es + (size_t)n_runs * 16 + (size_t)n_long * 16 + 4096, &ar, s, true)) return rc;
+    void* dimg = ar.take(window * es);
+    u64* dst = (u64*)ar.take((size_t)n_runs * 8);
+    u64* den = (u64*)ar.take((size_t)n_runs * 8);
+    u64* dlong = (u64*)ar.take((size_t)n_long * 16 + 16);
+    unsigned long long* dn = (unsigned long long*)ar.take(16);
+    char* himg = (char*)image + (size_t)lo * es;
+    cudaMemcpyAsync(dimg, himg, window * es, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(dst, starts, (size_t)n_runs * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(den, ends, (size_t)n_runs * 8, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(dn, 0, 16, s);
+    draw_kind(dimg, kind, value, dst, den, n_runs, lo, dlong, dn, n_long > 0, s);
+    cudaError_t e = cudaMemcpyAsync(himg, dimg, window * es, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    arena_release(ar);
+    if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("draw: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  // device run list: validate with a kernel (one small read back), then draw
+  Arena ar;
+  if (int rc = arena_acquire(4096, &ar, s, true)) return rc;
+  unsigned long long* flags = (unsigned long long*)ar.take(32);   // [0] invalid, [1] long runs, [2] long-list cursor
+  cudaMemsetAsync(flags, 0, 32, s);
+  k_draw_check<<<(unsigned)std::min<u64>((n_runs + 255) / 256, 148 * 8), 256, 0, s>>>(starts, ends, n_runs, (u64)voxels, flags);
+  g_launches += 1;
+  unsigned long long hflags[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, std::string("draw: ") + cudaGetErrorString(e)); }
+  if (hflags[0]) { arena_release(ar); return fail(CC3D_B200_ERR_ARGUMENT, "Invalid run."); }
+  Arena ar2;
+  u64* dlong = nullptr;
+  if (hflags[1]) {
+    if (int rc = arena_acquire((size_t)hflags[1] * 16 + 4096, &ar2, s, true)) { arena_release(ar); return rc; }
+    dlong = (u64*)ar2.take((size_t)hflags[1] * 16);
+  }
+  draw_kind(image, kind, value, starts, ends, n_runs, 0, dlong, flags + 2, hflags[1] > 0, s);
+  e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar2);
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("draw: ") + cudaGetErrorString(e));
   return 0;
 }

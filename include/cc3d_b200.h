@@ -212,6 +212,23 @@ int cc3d_b200_dust(const void* img, void* out, int kind, int64_t sx, int64_t sy,
                    int binary_image, int64_t lo, int64_t hi, int invert, int mem_space, uint64_t* N,
                    uint64_t* n_masked, void* stream);
 
+/* cc3d.runs (fastcc3d.pyx:1258-1279 -> extract_runs, cc3d_graphs.hpp:470-503): the maximal runs of equal non-zero
+ * values of the FLATTENED label array (memory order; runs continue across row ends), in position order:
+ * values[k], starts[k], ends[k] (half open). *count = number of runs. When count > capacity nothing is written:
+ * call again with more room (capacity 0 = count only; the arrays may then be NULL). Output arrays live in the
+ * same mem_space as `labels`. The caller groups the table by value (the reference returns a std::map) and adds the
+ * reference's single-voxel quirk (a 1-voxel array reports its run even when it is background, cc3d_graphs.hpp:481-484). */
+int cc3d_b200_runs(const void* labels, int kind, int64_t voxels, uint64_t* values, uint64_t* starts, uint64_t* ends,
+                   uint64_t capacity, uint64_t* count, int mem_space, void* stream);
+
+/* cc3d.draw / erase (fastcc3d.pyx:1281-1326 -> set_run_voxels, cc3d_graphs.hpp:505-523): image[starts[k]..ends[k]) =
+ * value for every run (value is truncated to the image kind; bool images are u8 with value 0/1). The run list is
+ * validated first: a run with start >= end or end > voxels gives CC3D_B200_ERR_ARGUMENT "Invalid run." and leaves
+ * the image untouched (the reference throws at the first bad run, after drawing the ones before it). image, starts
+ * and ends share mem_space; for host images only the window the runs span is staged through the device. */
+int cc3d_b200_draw(void* image, int kind, int64_t voxels, uint64_t value, const uint64_t* starts, const uint64_t* ends,
+                   uint64_t n_runs, int mem_space, void* stream);
+
 /* Device-memory workspace currently cached by the library on the active device (bytes), and a
  * call that frees it. */
 size_t cc3d_b200_workspace_bytes(void);

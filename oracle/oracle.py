@@ -12,6 +12,7 @@ boundary logic, `statistics` and `dust`:
   voxel_connectivity_graph <- fastcc3d.pyx:1021-1170 / cc3d_graphs.hpp:31-247 (numpy slicing)
   color_connectivity_graph <- fastcc3d.pyx:941-1018 / cc3d_graphs.hpp:583-1106 (backward-bit graph, scipy components)
   contacts / region_graph <- fastcc3d.pyx:1180-1252 / cc3d_graphs.hpp:259-468 (compute_neighborhood offsets incl. borders)
+  runs / draw / erase / each <- fastcc3d.pyx:1258-1372 / cc3d_graphs.hpp:470-523 (numpy change-point restatement)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 Parity pin: tests/test_oracle.py checks it against the reference build (oracle/_ref) when that is
@@ -470,3 +471,81 @@ def contacts(labels, connectivity=26, surface_area=True, anisotropy=(1, 1, 1)):
 
 def region_graph(labels, connectivity=26):
   return set(contacts(labels, connectivity=connectivity).keys())
+
+
+# ---- runs / draw / erase / each (fastcc3d.pyx:1258-1372; cc3d_graphs.hpp:470-523) ----
+def _flat_memory_order(arr: np.ndarray) -> np.ndarray:
+  """reference `_reshape(arr, (arr.size,))` (fastcc3d.pyx:129-161)."""
+  if arr.flags.f_contiguous:
+    return arr.reshape(-1, order="F")
+  if arr.flags.c_contiguous:
+    return arr.reshape(-1)
+  return arr.reshape((arr.size,))
+
+
+def runs(labels: np.ndarray) -> dict:
+  """extract_runs (cc3d_graphs.hpp:470-503): maximal runs of equal non-zero values of the flattened array, keyed by
+  label in ascending order (std::map), each list in position order. A one-voxel array reports (0, 1) even for
+  background (:481-484)."""
+  labels = np.asarray(labels)
+  if labels.dtype != np.bool_ and labels.dtype not in (np.uint8, np.uint16, np.uint32, np.uint64):
+    raise TypeError("Unsupported type: " + str(labels.dtype))
+  flat = _flat_memory_order(labels)
+  if flat.dtype == np.bool_:
+    flat = flat.view(np.uint8)
+  n = flat.size
+  if n == 0:
+    raise IndexError("Out of bounds on buffer access (axis 0)")   # `&labels[0]` is bounds checked (fastcc3d.pyx:1269)
+  if n == 1:
+    return {int(flat[0]): [(0, 1)]}
+  change = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+  starts = np.concatenate(([0], change))
+  ends = np.concatenate((change, [n]))
+  vals = flat[starts]
+  keep = vals != 0
+  starts, ends, vals = starts[keep], ends[keep], vals[keep]
+  out = {}
+  for v in np.unique(vals).tolist():
+    m = vals == v
+    out[int(v)] = list(zip(starts[m].tolist(), ends[m].tolist()))
+  return out
+
+
+def draw(label, runs, image: np.ndarray) -> np.ndarray:
+  """set_run_voxels (cc3d_graphs.hpp:505-523) through fastcc3d.pyx:1281-1314: runs are drawn one after the other and
+  the first invalid one raises (the ones before it stay drawn). Returns the flattened image."""
+  if image.dtype != np.bool_ and image.dtype not in (np.uint8, np.uint16, np.uint32, np.uint64):
+    raise TypeError("Unsupported type: " + str(image.dtype))
+  flat = _flat_memory_order(image)
+  value = (label != 0) if image.dtype == np.bool_ else label
+  for a, b in runs:
+    if b > flat.size or a >= b:
+      raise RuntimeError("Invalid run.")
+    flat[a:b] = value
+  return flat
+
+
+def erase(runs, image: np.ndarray) -> np.ndarray:
+  return draw(0, runs, image)
+
+
+def each(labels: np.ndarray, binary: bool = False, in_place: bool = False):
+  """fastcc3d.pyx:1328-1372 as a plain generator of (label, image) (the in_place image is reused and read-only
+  while it is out; callers compare before advancing)."""
+  all_runs = runs(labels)
+  order = "F" if labels.flags.f_contiguous else "C"
+  dtype = np.bool_ if binary else labels.dtype
+  img = np.zeros(labels.shape, dtype=dtype, order=order) if in_place else None
+  for key, rns in all_runs.items():
+    if key == 0:
+      continue
+    if in_place:
+      draw(key, rns, img)
+      img.setflags(write=0)
+      yield key, img
+      img.setflags(write=1)
+      erase(rns, img)
+    else:
+      one = np.zeros(labels.shape, dtype=dtype, order=order)
+      draw(key, rns, one)
+      yield key, one

@@ -224,3 +224,92 @@ def test_oracle_matches_graph_goldens(oracle_mod, path):
     if f"largest_{k}" in z:
       got, N = oracle_mod.largest_k(x, k, connectivity=c, return_N=True)
       assert N == int(z[f"largest_{k}_N"]) and got.dtype == z[f"largest_{k}"].dtype and np.array_equal(got, z[f"largest_{k}"])
+
+
+def _run_cases(rng, n):
+  for it in range(n):
+    dims = int(rng.integers(1, 4))
+    shape = tuple(int(rng.integers(1, 12)) for _ in range(dims))
+    dt = [np.uint8, np.uint16, np.uint32, np.uint64, bool][rng.integers(5)]
+    x = (rng.random(shape) < 0.5) if dt == bool else blobs(rng, shape, 4, int(rng.integers(1, 4))).astype(dt)
+    if it % 7 == 0:
+      x = (np.zeros(shape, dtype=np.uint8) + (it % 2)).astype(dt)   # constant volumes: all background / one run
+    yield np.asarray(x, order="F" if rng.random() < 0.5 else "C")
+
+
+def test_oracle_runs_draw_each_vs_reference(oracle_mod):
+  """SURVEY 8(f)4 (runs / draw / each) against the reference build, incl. the one-voxel quirk and invalid runs."""
+  ref = oracle_mod.reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built (needs /root/reference)")
+  rng = np.random.default_rng(23)
+  n = 0
+  for x in _run_cases(rng, 200):
+    a, b = ref.runs(x), oracle_mod.runs(x)
+    assert a == b and list(a.keys()) == list(b.keys()), (x.shape, x.dtype)
+    for binary in (False, True):
+      for in_place in (False, True):
+        got = [(k, im.copy()) for k, im in oracle_mod.each(x, binary=binary, in_place=in_place)]
+        want = [(k, im.copy()) for k, im in ref.each(x, binary=binary, in_place=in_place)]
+        assert len(got) == len(want)
+        for (ka, ia), (kb, ib) in zip(got, want):
+          assert ka == kb and ia.dtype == ib.dtype and ia.shape == ib.shape and np.array_equal(ia, ib)
+          assert ia.flags.f_contiguous == ib.flags.f_contiguous and ia.flags.c_contiguous == ib.flags.c_contiguous
+    if a:
+      k = list(a.keys())[-1]
+      c1 = np.full(x.shape, 1, dtype=x.dtype, order="F" if x.flags.f_contiguous else "C")
+      c2 = c1.copy(order="K")
+      r1, r2 = ref.draw(0, a[k], c1), oracle_mod.draw(0, a[k], c2)
+      assert np.array_equal(c1, c2) and r1.shape == r2.shape and np.array_equal(r1, r2)
+    n += 1
+  assert n == 200
+  one = np.zeros((1, 1, 1), np.uint16)
+  assert ref.runs(one) == oracle_mod.runs(one) == {0: [(0, 1)]}
+  for f in (ref.runs, oracle_mod.runs):
+    with pytest.raises(IndexError):
+      f(np.zeros((0,), np.uint8))
+  for bad in ([(3, 3)], [(5, 2)], [(0, 65)], [(0, 4), (70, 71)]):
+    for f in (ref.draw, oracle_mod.draw):
+      with pytest.raises(RuntimeError, match="Invalid run"):
+        f(1, bad, np.zeros((8, 8), np.uint8))
+  with pytest.raises(TypeError):
+    oracle_mod.runs(np.zeros((3, 3), np.float32))
+  with pytest.raises(TypeError):
+    ref.runs(np.zeros((3, 3), np.float32))
+
+
+def _run_goldens():
+  import glob, os
+  return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runs_*.npz")))
+
+
+def load_run_golden(path):
+  z = np.load(path)
+  x = np.asarray(z["x"], order="F" if bool(z["f_order"]) else "C")
+  keys, off, tab = z["keys"].tolist(), z["offsets"].tolist(), z["table"].tolist()
+  want = {int(k): [tuple(p) for p in tab[off[i]:off[i + 1]]] for i, k in enumerate(keys)}
+  return z, x, want
+
+
+def each_checksums(it, order):
+  rows = []
+  for label, img in it:
+    f = np.asarray(img).reshape(-1, order=order)
+    nz = np.flatnonzero(f)
+    rows.append((label, nz.size, int(nz.sum() % (1 << 61)), int(f[nz[0]]) if nz.size else 0))
+  return np.array(rows, dtype=np.uint64).reshape(-1, 4)
+
+
+@pytest.mark.parametrize("path", _run_goldens(), ids=[p.split("/")[-1][:-4] for p in _run_goldens()])
+def test_oracle_matches_run_goldens(oracle_mod, path):
+  """runs / draw / each against fixtures generated from the reference (tests/golden/make_golden_runs.py)."""
+  z, x, want = load_run_golden(path)
+  order = "F" if bool(z["f_order"]) else "C"
+  got = oracle_mod.runs(x)
+  assert got == want and list(got.keys()) == list(want.keys())
+  canvas = np.full(x.shape, 7 if x.dtype != np.bool_ else 0, dtype=x.dtype, order=order)
+  oracle_mod.draw(int(z["draw_value"]), want[int(z["draw_key"])], canvas)
+  assert np.array_equal(canvas, z["drawn"])
+  for binary in (False, True):
+    for in_place in (False, True):
+      assert np.array_equal(each_checksums(oracle_mod.each(x, binary=binary, in_place=in_place), order), z[f"each_{int(binary)}"])
