@@ -24,7 +24,7 @@ from ._lib import CC3DB200Error
 __all__ = [
   "connected_components", "statistics", "dust", "estimate_provisional_labels",
   "largest_k", "voxel_connectivity_graph", "color_connectivity_graph", "contacts", "region_graph",
-  "runs", "draw", "erase", "each",
+  "runs", "draw", "erase", "each", "connected_components_stack",
   "DimensionError", "CC3DB200Error", "last_timings", "set_timing",
 ]
 
@@ -961,12 +961,28 @@ def _run_table_device(flat_t, np_dtype):
   return tab[0, :k], tab[1, :k], tab[2, :k]
 
 
+def _stable_argsort_u64(values: np.ndarray) -> np.ndarray:
+  """Stable argsort of uint64 label values. numpy radix-sorts 16-bit keys only, so values that fit 16 (32) bits -
+  the usual case: labels 1..N - are sorted in one (two) least-significant-digit passes over uint16 digits."""
+  if values.size == 0:
+    return np.zeros(0, np.int64)
+  vmax = int(values.max())
+  if vmax < (1 << 16):
+    return np.argsort(values.astype(np.uint16), kind="stable")
+  if vmax < (1 << 32):
+    o1 = np.argsort(values.astype(np.uint16), kind="stable")   # astype keeps the low 16 bits
+    hi = (values >> np.uint64(16)).astype(np.uint16)[o1]
+    return o1[np.argsort(hi, kind="stable")]
+  return np.argsort(values, kind="stable")
+
+
 def _group_runs(values: np.ndarray, starts: np.ndarray, ends: np.ndarray):
   """Run table in position order -> (labels ascending, offsets, starts, ends grouped by label, position order kept):
   the iteration order of the reference's std::map<T, vector<pair>> (cc3d_graphs.hpp:472-474)."""
-  order = np.argsort(values, kind="stable")
+  order = _stable_argsort_u64(values)
   v = values[order]
-  labels, first = np.unique(v, return_index=True)
+  first = np.concatenate(([0], np.flatnonzero(v[1:] != v[:-1]) + 1)) if v.size else np.zeros(0, np.int64)
+  labels = v[first]
   offsets = np.append(first, v.size).astype(np.int64)
   return labels, offsets, starts[order], ends[order]
 
@@ -1014,9 +1030,18 @@ def runs(labels) -> dict:
   """Returns a dictionary describing where each label is located: {label: [(start, end), ...]} over the
   flattened (memory order) array, half-open voxel ranges; same contract as cc3d.fastcc3d.runs
   (fastcc3d.pyx:1258-1279 -> extract_runs, cc3d_graphs.hpp:470-503). Keys ascend, runs ascend by position."""
+  import gc
   lab, off, starts, ends = _runs_table(labels)
-  s, e = starts.tolist(), ends.tolist()
-  return {int(l): list(zip(s[off[i]:off[i + 1]], e[off[i]:off[i + 1]])) for i, l in enumerate(lab.tolist())}
+  off = off.tolist()
+  # millions of small tuples: the cyclic collector would rescan them over and over while they are being built
+  gc_was_on = gc.isenabled()
+  gc.disable()
+  try:
+    pairs = list(zip(starts.tolist(), ends.tolist()))
+    return {l: pairs[off[i]:off[i + 1]] for i, l in enumerate(lab.tolist())}
+  finally:
+    if gc_was_on:
+      gc.enable()
 
 
 def _label_for_image(label, np_dtype) -> int:
@@ -1185,6 +1210,17 @@ def each(labels, binary: bool = False, in_place: bool = False):
           fetch(dimg, img, lo, hi)
 
   return InPlaceImageIterator() if in_place else ImageIterator()
+
+
+
+
+def connected_components_stack(stacked_images, connectivity: int = 26, return_N: bool = False,
+                               binary_image: bool = False, out_dtype=None, out=None):
+  """Streaming (out-of-GPU-memory) labelling of an iterable of z-slabs; see sharded.connected_components_stack
+  (counterpart of cc3d.connected_components_stack, cc3d/__init__.py:353-501)."""
+  from .sharded import connected_components_stack as _stack
+  return _stack(stacked_images, connectivity=connectivity, return_N=return_N, binary_image=binary_image,
+                out_dtype=out_dtype, out=out)
 
 
 from . import fastcc3d  # noqa: E402  (namespace alias: the reference exposes runs / draw as cc3d.fastcc3d.*)

@@ -108,6 +108,28 @@ class CudaBackend:
     from . import _statistics_arrays_device
     return _statistics_arrays_device(labels, int(N))
 
+  def to_device(self, slab_np):
+    """numpy (sz, sy, sx) C-contiguous slab -> device tensor (streaming front end)."""
+    return self.torch.from_numpy(slab_np).cuda()
+
+  def local_labels_host(self, h):
+    """Local labels 1..N of a resolved slab as a host uint32 array (sz, sy, sx); releases the session."""
+    torch = self.torch
+    sz, sy, sx = h["shape"]
+    out = torch.empty((sz, sy, sx), dtype=torch.int32, device=h["device"])
+    sess, h["sess"] = h["sess"], None
+    with torch.cuda.device(h["device"]):
+      _lib.check(self.L.cc3d_b200_label_write(sess, out.data_ptr(), _lib.U32, _lib.DEVICE, self._stream(out)))
+    return out.cpu().numpy().view(np.uint32)
+
+  def remap_host(self, local, table, out):
+    """out[i] = table[local[i]] through the GPU (cc3d_b200_remap_labels on host buffers); local: uint32, table:
+    uint32[N + 1], out: C-contiguous uint16/32/64 array of local's shape."""
+    okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}[out.dtype]
+    if local.size:
+      _lib.check(self.L.cc3d_b200_remap_labels(local.ctypes.data, _lib.U32, local.size, table.ctypes.data,
+                                               table.size - 1, out.ctypes.data, okind, _lib.HOST, None))
+
   def release(self, h):
     if h.get("sess") is not None:
       self.L.cc3d_b200_session_release(h["sess"])
@@ -492,6 +514,89 @@ def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = F
     for h in handles:
       backend.release(h)
   return (outs, N_total) if return_N else outs
+
+
+def connected_components_stack(stacked_images, connectivity: int = 26, return_N: bool = False,
+                               binary_image: bool = False, out_dtype: Optional[Any] = None, out=None, backend=None):
+  """Streaming front end for volumes larger than GPU memory: the counterpart of the reference's
+  connected_components_stack (cc3d/__init__.py:353-501). `stacked_images` is an iterable of 3-D images of equal
+  width and height (x, y) and arbitrary depth, sequenced from z = 0 upwards; only ONE slab (plus the previous
+  slab's last plane) is on the GPU at a time.
+
+  Pass 1, per slab: upload, label + resolve on the GPU, extract the cross-face equivalences with the previous
+  slab's last plane on the GPU (the reference loops over the two faces in Python, :425-468), bring the slab's local
+  labels back. Then the host merge of the interface graph (cc3d_b200_merge_slabs, replaces the Python DisjointSet
+  :296-321), and pass 2: every slab is renumbered through its remap table on the GPU into the result.
+
+  Differences from the reference: the result is a plain Fortran-ordered numpy array (sx, sy, sz_total) - or `out`,
+  e.g. an np.memmap of that shape - instead of a CrackleArray (crackle is not a dependency), connectivity 18 is
+  accepted, and the numbering is the first-appearance numbering of the whole volume: bit-identical to
+  connected_components(np.concatenate(images, axis=2)), where the reference only promises equality up to
+  renumbering (automated_test.py:1628-1641). The out-dtype rule is the monolithic one applied to the totals."""
+  from . import DimensionError
+  if connectivity not in (6, 18, 26):
+    raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
+  if backend is None:
+    backend = CudaBackend()
+  locals_, N_r, epl_r, depths = [], [], [], []
+  pair_lists = [np.zeros(0, dtype=np.int64)]
+  prev = None          # (last-plane values, last-plane local labels) of the previous slab, on the device
+  sx = sy = None
+  kind = delta_arr = None
+  epl_skipped = False
+  for image in stacked_images:
+    image = np.asarray(image)
+    if image.ndim == 2:
+      image = image[:, :, np.newaxis]
+    if image.ndim != 3:
+      raise DimensionError("Only 3D images are supported in a stack. Got: " + str(image.ndim))
+    if sx is None:
+      sx, sy = image.shape[:2]
+      kind, binary_image, epl_skipped, delta_arr = _normalise(image.dtype, 0, binary_image)
+    elif image.shape[:2] != (sx, sy):
+      raise ValueError(f"All images of a stack must share width and height: {image.shape[:2]} vs {(sx, sy)}")
+    if image.shape[2] == 0:
+      continue
+    slab_np = np.asfortranarray(image).T          # (sz, sy, sx) C-contiguous view: z is the slowest memory axis
+    if slab_np.dtype == np.float16:
+      slab_np = slab_np.view(np.uint16)
+    elif slab_np.dtype == np.bool_:
+      slab_np = slab_np.view(np.uint8)
+    slab = backend.to_device(slab_np)
+    h = backend.resolve(slab, kind, connectivity, delta_arr, binary_image)
+    try:
+      sz = slab.shape[0]
+      if prev is not None:
+        packed = backend.face_pairs(slab[0].contiguous(), backend.plane_labels(h, 0), prev[0], prev[1],
+                                    kind, connectivity, delta_arr, binary_image)
+        pair_lists.append(packed.cpu().numpy())
+      prev = (slab[sz - 1].contiguous(), backend.plane_labels(h, sz - 1))
+      N_r.append(h["N"]); epl_r.append(h["epl"]); depths.append(int(sz))
+      locals_.append(backend.local_labels_host(h))
+    finally:
+      backend.release(h)
+    del slab
+  if sx is None:
+    raise ValueError("connected_components_stack: no images")
+  sz_total = sum(depths)
+  voxels_total = sz_total * sy * sx
+  epl_total = voxels_total if epl_skipped else sum(epl_r)
+  out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
+  if out is None:
+    out = np.zeros((sx, sy, sz_total), dtype=out_dtype, order="F")
+  elif tuple(out.shape) != (sx, sy, sz_total) or out.dtype != out_dtype or not out.flags.f_contiguous:
+    raise ValueError(f"out must be a Fortran-ordered {out_dtype} array of shape {(sx, sy, sz_total)}")
+  N_total = 0
+  z0 = 0
+  for r, local in enumerate(locals_):
+    N_total, remap = _merge_native(N_r, pair_lists, r)
+    if N_total > np.iinfo(np.uint32).max:
+      raise ValueError("connected_components_stack: more than 2^32 - 1 components")
+    dst = out[:, :, z0:z0 + depths[r]].T         # (sz, sy, sx) C-contiguous view of the result
+    backend.remap_host(local, np.ascontiguousarray(remap, dtype=np.uint32), dst)
+    locals_[r] = None
+    z0 += depths[r]
+  return (out, int(N_total)) if return_N else out
 
 
 def statistics_slab(labels_slab, N: int, no_slice_conversion: bool = False, group=None, backend=None):

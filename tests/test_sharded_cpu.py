@@ -105,6 +105,16 @@ class OracleBackend:
   def release(self, h):
     pass
 
+  # streaming front end (connected_components_stack)
+  def to_device(self, slab_np):
+    return self.torch.from_numpy(np.ascontiguousarray(slab_np))
+
+  def local_labels_host(self, h):
+    return np.ascontiguousarray(h["labels"].astype(np.uint32))
+
+  def remap_host(self, local, table, out):
+    out[...] = table[local.astype(np.int64)].astype(out.dtype)
+
 
 def _free_port():
   s = socket.socket()
@@ -227,3 +237,53 @@ def test_native_merge_equals_numpy_merge():
     for r in range(world):
       Ng, remap = sharded._merge_native(N_r, pair_lists, r)
       assert Ng == Nw and np.array_equal(remap, remaps[r]), (it, r, N_r, pair_lists)
+
+
+def _stack_cases():
+  rng = np.random.default_rng(11)
+  for it, conn in enumerate((26, 6, 18, 26, 6, 26)):
+    sx, sy = int(rng.integers(3, 20)), int(rng.integers(3, 16))
+    depths = [int(d) for d in rng.integers(1, 7, int(rng.integers(1, 6)))]
+    sz = sum(depths)
+    coarse = rng.integers(0, 4, ((sx + 2) // 3, (sy + 2) // 3, (sz + 2) // 3))
+    vol = np.repeat(np.repeat(np.repeat(coarse, 3, 0), 3, 1), 3, 2)[:sx, :sy, :sz]
+    kw = dict(connectivity=conn)
+    if it == 3:
+      vol = rng.random((sx, sy, sz)) < 0.45
+      kw["binary_image"] = True
+    vol = vol.astype([np.uint32, np.uint8, np.int64, np.bool_, np.uint16, np.uint64][it])
+    cuts = np.cumsum([0] + depths)
+    images = [np.asarray(vol[:, :, a:b], order="C" if (i + it) % 2 else "F") for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]
+    if it == 4:
+      images.insert(1, np.zeros((sx, sy, 0), vol.dtype))          # empty image: skipped
+      images.append(vol[:, :, -1].copy() * 0 + vol[:, :, -1])     # a 2-D image is a slab of depth 1
+      vol = np.concatenate([vol, vol[:, :, -1:]], axis=2)
+    yield vol, images, kw
+
+
+def test_stack_streaming_equals_monolithic_labelling():
+  """connected_components_stack (streaming front end): the host logic (slab bookkeeping, face
+  interfaces, merge, remap, out-dtype rule) with the oracle backend; equals the monolithic labelling of the
+  Fortran-ordered concatenation bit for bit."""
+  sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200"))
+  sys.path.insert(0, ROOT)
+  from cc3d_b200 import sharded
+  from oracle import oracle
+  backend = OracleBackend()
+  n = 0
+  for vol, images, kw in _stack_cases():
+    want, Nw = oracle.connected_components(np.asfortranarray(vol), return_N=True, **kw)
+    got, N = sharded.connected_components_stack(iter(images), return_N=True, backend=backend, **kw)
+    assert N == Nw and got.dtype == want.dtype and got.shape == want.shape and got.flags.f_contiguous, kw
+    assert np.array_equal(got, want), kw
+    mm = np.zeros(want.shape, dtype=np.uint64, order="F")
+    res = sharded.connected_components_stack(images, out_dtype=np.uint64, out=mm, backend=backend, **kw)
+    assert res is mm and np.array_equal(mm, want)
+    n += 1
+  assert n == 6
+  with pytest.raises(ValueError):
+    sharded.connected_components_stack([np.zeros((3, 3, 2), np.uint8), np.zeros((3, 4, 2), np.uint8)], backend=backend)
+  with pytest.raises(ValueError):
+    sharded.connected_components_stack([np.zeros((3, 3, 2), np.uint8)], connectivity=8, backend=backend)
+  with pytest.raises(ValueError):
+    sharded.connected_components_stack([], backend=backend)
