@@ -194,7 +194,7 @@ size_t bitmap_words(const Geom& g, bool with_diagonals) {
 int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_dev, int shift, u64* total_dev,
                 u32* total32_dev, cudaStream_t s, Counters* track = nullptr, u32 W = 1) {
   const i64 nb = std::max<i64>(1, (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK);
-#ifndef CC_SCAN_ONEPASS   // (one-pass scan: enabled once verified on the GPU)
+#ifdef CC_SCAN_THREEPASS   // reduce / scan-of-sums / apply triple; the default is the one-pass look-back scan (verified on B200: 145 parity tests, 512^3 step 0.6945 -> 0.6908 ms, 256^3 0.2243 -> 0.2189 ms)
   const unsigned grid = (unsigned)std::min<i64>(nb, CC_GRID_BLOCKS);
   k_scan_reduce<<<grid, CC_SCAN_THREADS, 0, s>>>(cnt, bsum, n_max, n_dev, shift, track, W);
   k_scan_blocks<<<1, 1024, 0, s>>>(bsum, n_max, n_dev, shift, total_dev, total32_dev);
@@ -1274,13 +1274,15 @@ int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* co
 template <typename T>
 static void runs_count_typed(const T* lab, i64 n, u32* cnt, i64 nchunks, cudaStream_t s) {
   const unsigned blocks = (unsigned)std::min<i64>(nchunks, 148 * 32);
-  k_runs_count<T><<<blocks, 256, 0, s>>>(lab, n, cnt, nchunks);
+  if (((uintptr_t)lab & 15) == 0) k_runs_count_vec<T><<<blocks, 256, 0, s>>>(lab, n, cnt, nchunks);
+  else k_runs_count<T><<<blocks, 256, 0, s>>>(lab, n, cnt, nchunks);
 }
 template <typename T>
 static void runs_emit_typed(const T* lab, i64 n, const u32* prefix, i64 nchunks, u64* values, u64* starts, u64* ends,
                             cudaStream_t s) {
   const unsigned blocks = (unsigned)std::min<i64>(nchunks, 148 * 32);
-  k_runs_emit<T><<<blocks, 256, 0, s>>>(lab, n, prefix, nchunks, values, starts, ends);
+  if (((uintptr_t)lab & 15) == 0) k_runs_emit_vec<T><<<blocks, 256, 0, s>>>(lab, n, prefix, nchunks, values, starts, ends);
+  else k_runs_emit<T><<<blocks, 256, 0, s>>>(lab, n, prefix, nchunks, values, starts, ends);
 }
 
 int cc3d_b200_runs(const void* labels, int kind, int64_t voxels, uint64_t* values, uint64_t* starts, uint64_t* ends,

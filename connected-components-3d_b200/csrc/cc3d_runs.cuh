@@ -1,7 +1,8 @@
 // cc3d_runs.cuh — SURVEY 8(f)4: run-length index of a label volume and per-label rendering.
-//   R1 k_runs_count : run starts per 4096-voxel chunk            (reads the labels once)
+//   R1 k_runs_count(_vec) : run starts per 4096-voxel chunk      (reads the labels once)
 //   (scan of the chunk counts: scan_counts, cc3d_b200.cu)
-//   R2 k_runs_emit  : (value, start, end) of every non-zero run   (reads the labels once, writes 24 B per run)
+//   R2 k_runs_emit(_vec)  : (value, start, end) of every non-zero run (reads the labels once, writes 24 B per run)
+//   The _vec kernels (128-bit loads) need 16-byte aligned labels; the scalar ones serve unaligned views.
 //   W1 k_draw_check : validates a run list on the device
 //   W2 k_draw_short / k_draw_long : image[start..end) = value
 // Replaces extract_runs / set_run_voxels (reference cc3d_graphs.hpp:470-523). A run is a maximal stretch of equal
@@ -90,6 +91,129 @@ k_runs_emit(const T* __restrict__ lab, i64 n, const u32* __restrict__ prefix, i6
       if (st) { values[ex] = (u64)v; starts[ex] = (u64)j; }
       if (en) ends[ex + (st ? 1u : 0u) - 1u] = (u64)j + 1ull;
       rank += __popc(sb[k]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- 128-bit variants (labels 16-byte aligned): every lane holds 16 / sizeof(T) consecutive voxels per step, a warp
+// covers its 512-voxel segment in sizeof(T) steps, so the neighbour exchange costs two shuffles per 16 bytes and the
+// chunk is read ONCE (R2 keeps its 16 voxels per lane in registers between the count and the emission). ----
+template <typename T> __device__ __forceinline__ T shfl_up1(T v) {
+  if constexpr (sizeof(T) < 4) return (T)__shfl_up_sync(CC_FULL, (unsigned)v, 1);
+  else return __shfl_up_sync(CC_FULL, v, 1);
+}
+template <typename T> __device__ __forceinline__ T shfl_down1(T v) {
+  if constexpr (sizeof(T) < 4) return (T)__shfl_down_sync(CC_FULL, (unsigned)v, 1);
+  else return __shfl_down_sync(CC_FULL, v, 1);
+}
+
+template <typename T>
+__device__ __forceinline__ void run_load_vec(const T* __restrict__ lab, i64 j0, i64 n, T (&v)[16 / sizeof(T)]) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (j0 + VEC <= n) {
+    union { uint4 q; T e[VEC]; } u;
+    u.q = *reinterpret_cast<const uint4*>(lab + j0);
+#pragma unroll
+    for (int i = 0; i < VEC; i++) v[i] = u.e[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; i++) v[i] = (j0 + i < n) ? lab[j0 + i] : T(0);
+  }
+}
+
+// bit i of sm / em: voxel j0 + i starts / ends a run (voxels past the end hold 0 and never flag)
+template <typename T>
+__device__ __forceinline__ void run_masks_vec(const T* __restrict__ lab, i64 j0, i64 n, int lane,
+                                              const T (&v)[16 / sizeof(T)], u32& sm, u32& em) {
+  constexpr int VEC = 16 / sizeof(T);
+  T prev = shfl_up1(v[VEC - 1]);
+  T next = shfl_down1(v[0]);
+  if (lane == 0) prev = (j0 > 0 && j0 - 1 < n) ? lab[j0 - 1] : T(0);
+  if (lane == 31) next = (j0 + VEC < n) ? lab[j0 + VEC] : T(0);
+  sm = 0; em = 0;
+#pragma unroll
+  for (int i = 0; i < VEC; i++) {
+    const T p = i ? v[i ? i - 1 : 0] : prev;
+    const T q = (i + 1 < VEC) ? v[(i + 1 < VEC) ? i + 1 : i] : next;
+    if (v[i] != T(0) && p != v[i]) sm |= 1u << i;
+    if (v[i] != T(0) && q != v[i]) em |= 1u << i;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_runs_count_vec(const T* __restrict__ lab, i64 n, u32* __restrict__ cnt, i64 nchunks) {
+  constexpr int VEC = 16 / sizeof(T), STEPS = 16 / VEC;
+  __shared__ u32 s_w[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (i64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const i64 base = c * CC_RUN_CHUNK + (i64)warp * 512;
+    T v[STEPS][VEC];
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) run_load_vec(lab, base + (i64)(k * 32 + lane) * VEC, n, v[k]);
+    u32 total = 0;
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      u32 sm, em;
+      run_masks_vec(lab, base + (i64)(k * 32 + lane) * VEC, n, lane, v[k], sm, em);
+      total += __popc(sm);
+    }
+    total = __reduce_add_sync(CC_FULL, total);
+    if (lane == 0) s_w[warp] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 t = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) t += s_w[w];
+      cnt[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_runs_emit_vec(const T* __restrict__ lab, i64 n, const u32* __restrict__ prefix, i64 nchunks, u64* __restrict__ values,
+                u64* __restrict__ starts, u64* __restrict__ ends) {
+  constexpr int VEC = 16 / sizeof(T), STEPS = 16 / VEC;
+  __shared__ u32 s_w[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (i64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const i64 base = c * CC_RUN_CHUNK + (i64)warp * 512;
+    T v[STEPS][VEC];
+    u32 sm[STEPS], em[STEPS], ex[STEPS];   // ex: start rank of the lane's first voxel within the warp segment
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) run_load_vec(lab, base + (i64)(k * 32 + lane) * VEC, n, v[k]);
+    u32 seg = 0;   // starts of the steps before k (warp-uniform)
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      run_masks_vec(lab, base + (i64)(k * 32 + lane) * VEC, n, lane, v[k], sm[k], em[k]);
+      const u32 cnt_lane = __popc(sm[k]);
+      u32 inc = cnt_lane;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(CC_FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      ex[k] = seg + inc - cnt_lane;
+      seg += __shfl_sync(CC_FULL, inc, 31);
+    }
+    if (lane == 0) s_w[warp] = seg;
+    __syncthreads();
+    u32 rank = prefix[c];
+    for (int w = 0; w < warp; w++) rank += s_w[w];
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const i64 j0 = base + (i64)(k * 32 + lane) * VEC;
+      const u32 r0 = rank + ex[k];
+      if (sm[k] | em[k]) {
+#pragma unroll
+        for (int i = 0; i < VEC; i++) {
+          const u32 before = r0 + __popc(sm[k] & ((1u << i) - 1u));
+          if (sm[k] >> i & 1u) { values[before] = (u64)v[k][i]; starts[before] = (u64)(j0 + i); }
+          if (em[k] >> i & 1u) ends[before + (sm[k] >> i & 1u) - 1u] = (u64)(j0 + i) + 1ull;
+        }
+      }
     }
     __syncthreads();
   }
