@@ -191,8 +191,10 @@ size_t bitmap_words(const Geom& g, bool with_diagonals) {
 }
 
 // exclusive scan of n counts (n on the host, or ceil(*n_dev / 2^shift) when n_dev is given; n_max bounds it)
+// cleared: the caller has already zeroed bsum[0 .. nb] earlier in the stream (keeps the kernels of the label pipeline
+// back to back, see CC_PDL)
 int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_dev, int shift, u64* total_dev,
-                u32* total32_dev, cudaStream_t s, Counters* track = nullptr, u32 W = 1) {
+                u32* total32_dev, cudaStream_t s, Counters* track = nullptr, u32 W = 1, bool cleared = false) {
   const i64 nb = std::max<i64>(1, (n_max + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK);
 #ifdef CC_SCAN_THREEPASS   // reduce / scan-of-sums / apply triple; the default is the one-pass look-back scan (verified on B200: 145 parity tests, 512^3 step 0.6945 -> 0.6908 ms, 256^3 0.2243 -> 0.2189 ms)
   const unsigned grid = (unsigned)std::min<i64>(nb, CC_GRID_BLOCKS);
@@ -202,9 +204,14 @@ int scan_counts(const u32* cnt, u32* prefix, u64* bsum, i64 n_max, const u64* n_
   g_launches += 3;
 #else
   // bsum holds nb chunk states + the ticket counter (callers size it (nb + 1) * 8 bytes)
-  cudaMemsetAsync(bsum, 0, (size_t)(nb + 1) * 8, s);
-  k_scan_onepass<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, prefix, (unsigned long long*)bsum, (u32)nb, n_max, n_dev, shift,
-                                                           total_dev, total32_dev, track, W);
+  if (!cleared) {
+    cudaMemsetAsync(bsum, 0, (size_t)(nb + 1) * 8, s);
+    k_scan_onepass<<<(unsigned)nb, CC_SCAN_THREADS, 0, s>>>(cnt, prefix, (unsigned long long*)bsum, (u32)nb, n_max, n_dev, shift,
+                                                             total_dev, total32_dev, track, W);
+  } else {
+    cc_launch(k_scan_onepass, dim3((unsigned)nb), dim3(CC_SCAN_THREADS), 0, s, cnt, prefix, (unsigned long long*)bsum, (u32)nb,
+              n_max, n_dev, shift, total_dev, total32_dev, track, W);
+  }
   g_launches += 1;
 #endif
   return 0;
@@ -463,6 +470,13 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   S->L = L; S->M = M; S->din = din;
   S->epl_is_runs = (mode == MODE_EQ);
 
+  bool scans_cleared = false;
+#if defined(CC_PDL) && !defined(CC_SCAN_THREEPASS)
+  // the look-back status words of both scans are zeroed up front so that no memset sits between the kernels
+  cudaMemsetAsync(bsum, 0, (size_t)(std::max<i64>(nb, 1) + 1) * 8, s);
+  cudaMemsetAsync(bsum2, 0, (size_t)(std::max<i64>(nb2, 1) + 1) * 8, s);
+  scans_cleared = true;
+#endif
   k_init_counters<<<1, 1, 0, s>>>(ctr, gqctl);
   g_launches += 1;
 
@@ -492,7 +506,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   if (rc == 0) {
     // S: number the runs
     u32* RS = M + g.offRS;
-    scan_counts(RS, RS, bsum, nwords, nullptr, 0, &ctr->nruns, RS + nwords, s, ctr, (u32)g.W);
+    scan_counts(RS, RS, bsum, nwords, nullptr, 0, &ctr->nruns, RS + nwords, s, ctr, (u32)g.W, scans_cleared);
     mark("S_scan_runs", s);
     // B: unions
     rc = -1;
@@ -505,10 +519,10 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
 
   g_launches += stage_launches;
-  k_compress<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, GR, cnt, &ctr->nruns);
+  cc_launch(k_compress, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, cnt, &ctr->nruns);
   g_launches += 1;
   mark("C1_compress", s);
-  scan_counts(cnt, prefix, bsum2, nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s);
+  scan_counts(cnt, prefix, bsum2, nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s, nullptr, 1, scans_cleared);
   mark("C2_scan", s);
   if (block_order) {
     u32* K = (u32*)ar.take((size_t)maxruns * 4);
@@ -527,7 +541,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
     g_launches += 5;
     mark("C3_assign_blockorder", s);
   } else {
-    k_assign<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, GR, prefix, &ctr->nruns);
+    cc_launch(k_assign, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, prefix, &ctr->nruns);
     g_launches += 1;
     mark("C3_assign", s);
   }

@@ -51,8 +51,8 @@ static void launch_faces_staged(const LabelArgs& a, const Edge<T, MODE>& E, bool
     cudaFuncSetAttribute(k_faces_async<T, MODE, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_faces_async<T, MODE, true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  if (two_d) k_faces_async<T, MODE, false, NW><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
-  else k_faces_async<T, MODE, true, NW><<<blocks, CC_FACE_WARPS * 32, smem, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+  if (two_d) cc_launch(k_faces_async<T, MODE, false, NW>, dim3(blocks), dim3(CC_FACE_WARPS * 32), (size_t)(smem), a.stream, in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+  else cc_launch(k_faces_async<T, MODE, true, NW>, dim3(blocks), dim3(CC_FACE_WARPS * 32), (size_t)(smem), a.stream, in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
 }
 
 template <typename T, int MODE>
@@ -78,8 +78,8 @@ static int launch_faces(const LabelArgs& a) {
     const unsigned nwg = (unsigned)((g.W + CC_FACE_NW - 1) / CC_FACE_NW);
     const i64 ntasks = (i64)nwg * nych * g.sz;
     const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
-    if (two_d) k_faces<T, MODE, false><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
-    else k_faces<T, MODE, true><<<blocks, CC_FACE_WARPS * 32, 0, a.stream>>>(in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+    if (two_d) cc_launch(k_faces<T, MODE, false>, dim3(blocks), dim3(CC_FACE_WARPS * 32), (size_t)(0), a.stream, in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
+    else cc_launch(k_faces<T, MODE, true>, dim3(blocks), dim3(CC_FACE_WARPS * 32), (size_t)(0), a.stream, in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
   }
   ++*a.launches;
   return 0;
@@ -107,19 +107,19 @@ static int launch_union(const LabelArgs& a) {
     // continuous predicate: edge-parallel item lists (every word has candidates that need a value test)
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_union_tile_items<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    cc_launch(k_union_tile_items<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(256), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else if constexpr (MODE == MODE_NONZERO) {
     const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_union_tile<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(256), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else {
     const size_t smem = (size_t)HybridQueues<MODE>::SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_union_tile_hybrid<T, MODE, CONN><<<(unsigned)(ntx * nty * ntz), 256, smem, a.stream>>>(in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    cc_launch(k_union_tile_hybrid<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(256), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);
-  k_union_queue<<<CC_QUEUE_BLOCKS * 4, 256, 0, a.stream>>>(a.L, a.GQ);
-  k_union_global<T, MODE, CONN><<<CC_QUEUE_BLOCKS, 256, 0, a.stream>>>(in, a.M, a.L, g, E, a.GQ.ovf);
+  cc_launch(k_union_queue, dim3(CC_QUEUE_BLOCKS * 4), dim3(256), (size_t)(0), a.stream, a.L, a.GQ);
+  cc_launch(k_union_global<T, MODE, CONN>, dim3(CC_QUEUE_BLOCKS), dim3(256), (size_t)(0), a.stream, in, a.M, a.L, g, E, a.GQ.ovf);
   if (a.mark) a.mark("B2_union_queue", a.stream);
   *a.launches += 3;
   return 0;

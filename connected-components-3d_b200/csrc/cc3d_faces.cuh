@@ -56,6 +56,7 @@ template <typename T, int MODE, bool HASZ>
 __global__ void __launch_bounds__(CC_FACE_WARPS * 32)
 k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
         unsigned nych, unsigned nwg, unsigned ntasks) {
+  CC_PDL_WAIT();
   constexpr int NW = CC_FACE_NW;
   const int lane = threadIdx.x & 31;
   const unsigned task = blockIdx.x * CC_FACE_WARPS + (threadIdx.x >> 5);
@@ -173,6 +174,7 @@ template <typename T, int MODE, bool HASZ, int NW>
 __global__ void __launch_bounds__(CC_FACE_WARPS * 32, CC_FACE_MINB)
 k_faces_async(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
               unsigned nych, unsigned nwg, unsigned ntasks) {
+  CC_PDL_WAIT();
   constexpr int RB = NW * 32 * (int)sizeof(T);       // bytes of one row of the group
   constexpr int SLOT = 16 + 2 * RB;
   extern __shared__ __align__(16) unsigned char face_smem[];

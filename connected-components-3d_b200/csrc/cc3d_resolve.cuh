@@ -15,6 +15,7 @@ __device__ __forceinline__ u32 dev_len(i64 n_host, const u64* __restrict__ n_dev
 // the word's popcount are emitted for the scan.
 __global__ void __launch_bounds__(256)
 k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restrict__ n_dev) {
+  CC_PDL_WAIT();
   const u32 n = (u32)*n_dev;
   const u32 nwords2 = (n + 31) >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(CC_SCAN_THREADS)
 k_scan_onepass(const u32* cnt, u32* prefix, unsigned long long* __restrict__ status, u32 nb_max, i64 n_host,
                const u64* __restrict__ n_dev, int shift, u64* __restrict__ total, u32* __restrict__ total32,
                Counters* __restrict__ track, u32 W) {
+  CC_PDL_WAIT();
   __shared__ u32 s_chunk, s_prev, s_min, s_max;
   const u32 n = dev_len(n_host, n_dev, shift);
   const u32 nb = (n + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
@@ -256,6 +258,7 @@ __device__ __forceinline__ u32 rank_in_bitmap(const u32* __restrict__ bm, const 
 // C3: every run gets its component's final label (1-based rank of its root).
 __global__ void __launch_bounds__(256)
 k_assign(u32* __restrict__ L, const u32* __restrict__ GR, const u32* __restrict__ prefix, const u64* __restrict__ n_dev) {
+  CC_PDL_WAIT();
   const u32 n = (u32)*n_dev;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const bool isroot = (GR[i >> 5] >> (i & 31)) & 1u;

@@ -284,6 +284,7 @@ template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256, MODE == MODE_EQ ? 6 : 0)
 k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
+  CC_PDL_WAIT();
   constexpr u32 GQN = TileQueues<MODE>::GQ;
   extern __shared__ __align__(16) u32 smem_u32[];
   uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [CC_TILE_NODES] 16-bit parents
@@ -472,6 +473,7 @@ template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256, MODE == MODE_EQ ? 6 : 0)
 k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
+  CC_PDL_WAIT();
   constexpr u32 GQN = HybridQueues<MODE>::GQ;
   constexpr bool ITEMS = HybridQueues<MODE>::ITEMS;   // round 1 through item lists (needs the wS / wR stash)
   extern __shared__ __align__(16) u32 smem_u32[];
@@ -802,6 +804,7 @@ template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256)
 k_union_tile_items(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
+  CC_PDL_WAIT();
   extern __shared__ __align__(16) u32 smem_u32[];
   uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [CC_TILE_NODES] 16-bit parents
   u32* items = smem_u32 + CC_TILE_NODES / 2;               // [CC_TILE_ITEMS]
@@ -1002,6 +1005,7 @@ k_union_tile_items(const T* __restrict__ in, const u32* __restrict__ M, u32* __r
 // Kernel B2. One thread per queued edge: union on the global forest L (atomicMin link-to-smaller with
 // path halving). Tile roots are at most one hop away, so the finds are short.
 static __global__ void __launch_bounds__(256) k_union_queue(u32* __restrict__ L, EdgeQueue GQ) {
+  CC_PDL_WAIT();
   const u32 n = min(*GQ.count, GQ.cap);
   for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const u64 v = GQ.q[e];
@@ -1015,6 +1019,7 @@ template <typename T, int MODE, int CONN>
 __global__ void __launch_bounds__(256)
 k_union_global(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
                const u32* __restrict__ ovf) {
+  CC_PDL_WAIT();
   if (*ovf == 0) return;
   const u32 W = (u32)g.W, sy = (u32)g.sy;
   WordEdges<T, MODE, CONN> we(in, M, g, E);
