@@ -270,12 +270,31 @@ def _merge_native(N_r, pair_lists, rank):
   """cc3d_b200_merge_slabs (C++): same result as _global_numbering for one slab, without the Python overhead."""
   world = len(N_r)
   n_labels = np.ascontiguousarray(N_r, dtype=np.int64)
-  arrs = [np.ascontiguousarray(p, dtype=np.uint64) for p in pair_lists]
+  # packed pairs arrive as int64 rows of the gathered buffer: reinterpret, do not convert (no copy)
+  arrs = [p.view(np.uint64) if (isinstance(p, np.ndarray) and p.dtype == np.int64 and p.flags.c_contiguous)
+          else np.ascontiguousarray(p, dtype=np.uint64) for p in pair_lists]
   ptrs = (ctypes.c_void_p * world)(*[a.ctypes.data if a.size else None for a in arrs])
   n_pairs = np.array([a.size for a in arrs], dtype=np.int64)
   remap = np.empty(int(n_labels[rank]) + 1, dtype=np.int64)
   n_total = ctypes.c_int64(0)
   _lib.check(_lib.lib().cc3d_b200_merge_slabs(world, n_labels.ctypes.data, ctypes.cast(ptrs, ctypes.c_void_p), n_pairs.ctypes.data,
+                                              int(rank), remap.ctypes.data, ctypes.byref(n_total)))
+  return int(n_total.value), remap
+
+
+def _merge_gathered(facts, rank):
+  """_merge_native on the gathered buffer of the fast path without building per-slab views: facts is the
+  C-contiguous int64 array (world, 4 + cap) whose row r holds [N_r, epl_r, sz_r, n_pairs_r, pairs...]; the pair
+  pointers are computed from the base address."""
+  assert facts.dtype == np.int64 and facts.flags.c_contiguous and facts.ndim == 2 and facts.shape[1] >= 4
+  world = facts.shape[0]
+  n_labels = np.ascontiguousarray(facts[:, 0])
+  n_pairs = np.ascontiguousarray(facts[:, 3])
+  base = facts.__array_interface__["data"][0]
+  ptrs = (base + 32 + np.arange(world, dtype=np.uint64) * np.uint64(facts.strides[0])).astype(np.uint64)
+  remap = np.empty(int(n_labels[rank]) + 1, dtype=np.int64)
+  n_total = ctypes.c_int64(0)
+  _lib.check(_lib.lib().cc3d_b200_merge_slabs(world, n_labels.ctypes.data, ptrs.ctypes.data, n_pairs.ctypes.data,
                                               int(rank), remap.ctypes.data, ctypes.byref(n_total)))
   return int(n_total.value), remap
 
@@ -370,8 +389,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
     sz_total = int(facts[:, 2].sum())
     voxels_total = sz_total * sy * sx
     epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
-    pair_lists = [facts[r, 4: 4 + int(counts[r])] for r in range(world)]
-    N_total, remap_np = _merge_native(facts[:, 0], pair_lists, rank)
+    N_total, remap_np = _merge_gathered(facts, rank)
     lap("merge")
     out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
     if np.iinfo(out_dtype).max < N_total:

@@ -1241,45 +1241,59 @@ int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* co
   for (int r = 0; r < world; r++) off[r + 1] = off[r] + n_labels[r];
   const i64 total = off[world];
   if (total >= 0xFFFFFFFFll) return fail(CC3D_B200_ERR_TOO_LARGE, "merge_slabs: more than 2^32-2 slab labels");
-  // union-find over the ids directly (no sorting, duplicates are harmless); root = smallest id of the set
-  static thread_local std::vector<u32> parent;
-  parent.resize((size_t)total + 1);
-  for (i64 i = 0; i <= total; i++) parent[(size_t)i] = (u32)i;
-  auto find = [&](u32 i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+  // union-find over the ids directly (no sorting, duplicates are harmless); root = smallest id of the set.
+  // The buffers are thread-local vectors; the loops work on raw pointers (a thread_local access inside a shared
+  // library is a __tls_get_addr call, which the per-element form paid several times per pair).
+  static thread_local std::vector<u32> parent_tl;
+  static thread_local std::vector<i64> final_tl;
+  parent_tl.resize((size_t)total + 1);
+  u32* const parent = parent_tl.data();
+  for (i64 i = 0; i <= total; i++) parent[i] = (u32)i;
+  auto find = [parent](u32 i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
   for (int r = 1; r < world; r++) {
     const u64* pr = pairs[r];
     const i64 nlo = n_labels[r - 1], nup = n_labels[r];
-    u64 last = ~0ull;
+    const i64 off_lo = off[r - 1], off_up = off[r];
+    // the face kernel reports a pair once per touching voxel pair (a few hundred distinct pairs among thousands):
+    // a small direct-mapped cache of the pairs already united skips the repeats without touching the forest
+    constexpr int CACHE_BITS = 12;
+    u64 seen[1 << CACHE_BITS];
+    for (int i = 0; i < (1 << CACHE_BITS); i++) seen[i] = ~0ull;   // lo = up = 2^32-1 is never a valid pair
     for (i64 k = 0; k < n_pairs[r]; k++) {
       const u64 v = pr[k];
-      if (v == last) continue;
-      last = v;
+      u64& slot = seen[(v * 0x9E3779B97F4A7C15ull) >> (64 - CACHE_BITS)];
+      if (slot == v) continue;
+      slot = v;
       const i64 lo = (i64)(v >> 32), up = (i64)(v & 0xFFFFFFFFull);
       if (lo < 1 || lo > nlo || up < 1 || up > nup)
         return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs: pair label out of range");
-      const u32 a = find((u32)(off[r - 1] + lo)), b = find((u32)(off[r] + up));
+      const u32 a = find((u32)(off_lo + lo)), b = find((u32)(off_up + up));
       if (a < b) parent[b] = a; else if (b < a) parent[a] = b;
     }
   }
-  // a component is owned by the slab of its root; owned components are numbered slab by slab in label order
+  // flatten once (ids ascend, roots are minima: a parent is final when its child is visited), then every later
+  // question is a single load. A component is owned by the slab of its root; owned components are numbered slab by
+  // slab in label order.
+  for (i64 id = 1; id <= total; id++) parent[id] = parent[parent[id]];
   std::vector<i64> base(world + 1, 0);
   for (int r = 0; r < world; r++) {
     i64 owned = 0;
-    for (i64 id = off[r] + 1; id <= off[r + 1]; id++) owned += find((u32)id) == (u32)id;
+    for (i64 id = off[r] + 1; id <= off[r + 1]; id++) owned += parent[id] == (u32)id;
     base[r + 1] = base[r] + owned;
   }
   *n_total = base[world];
-  // final labels of the roots that the labels of slab `rank` point at: roots lie in slabs <= rank; number them
-  // lazily (final label of root id in slab r = base[r] + rank of id among the roots of slab r)
-  static thread_local std::vector<i64> final_of;
-  final_of.assign((size_t)off[rank + 1] + 1, 0);
+  // final labels of the roots that the labels of slab `rank` point at: roots lie in slabs <= rank
+  // (final label of root id in slab r = base[r] + rank of id among the roots of slab r)
+  final_tl.resize((size_t)off[rank + 1] + 1);
+  i64* const final_of = final_tl.data();
   for (int r = 0; r <= rank; r++) {
     i64 next = base[r];
     for (i64 id = off[r] + 1; id <= off[r + 1]; id++)
-      if (parent[(size_t)id] == (u32)id) final_of[(size_t)id] = ++next;
+      final_of[id] = parent[id] == (u32)id ? ++next : 0;
   }
   remap[0] = 0;
-  for (i64 l = 1; l <= n_labels[rank]; l++) remap[l] = final_of[find((u32)(off[rank] + l))];
+  const i64 off_me = off[rank];
+  for (i64 l = 1; l <= n_labels[rank]; l++) remap[l] = final_of[parent[off_me + l]];
   return 0;
 }
 

@@ -287,3 +287,34 @@ def test_stack_streaming_equals_monolithic_labelling():
     sharded.connected_components_stack([np.zeros((3, 3, 2), np.uint8)], connectivity=8, backend=backend)
   with pytest.raises(ValueError):
     sharded.connected_components_stack([], backend=backend)
+
+
+def test_merge_on_the_gathered_buffer_equals_native_merge():
+  """_merge_gathered (pointer arithmetic on the all-gathered [N, epl, sz, n_pairs, pairs...] rows of the CUDA fast
+  path) against _merge_native on per-slab views and the numpy merge; heavy duplication exercises the pair cache of
+  cc3d_b200_merge_slabs."""
+  sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200"))
+  import torch
+  from cc3d_b200 import sharded
+  rng = np.random.default_rng(5)
+  for it in range(120):
+    world = int(rng.integers(1, 7))
+    cap = int(rng.choice([0, 8, 64, 9000]))
+    facts = torch.zeros((world, 4 + cap), dtype=torch.int64).numpy()
+    facts[:, 0] = rng.integers(0, 40 if cap < 9000 else 3000, world)
+    facts[:, 1] = rng.integers(0, 1000, world)
+    facts[:, 2] = rng.integers(1, 9, world)
+    for r in range(1, world):
+      n = int(rng.integers(0, cap + 1)) if facts[r, 0] and facts[r - 1, 0] else 0
+      if n:
+        distinct = max(1, n // int(rng.choice([1, 3, 30])))
+        lo, up = rng.integers(1, facts[r - 1, 0] + 1, distinct), rng.integers(1, facts[r, 0] + 1, distinct)
+        idx = rng.integers(0, distinct, n)
+        facts[r, 3] = n
+        facts[r, 4:4 + n] = (lo[idx] << 32) | up[idx]
+    lists = [facts[r, 4:4 + int(facts[r, 3])] for r in range(world)]
+    Nw, remaps = sharded._global_numbering(facts[:, 0], lists, range(world))
+    for rank in range(world):
+      a = sharded._merge_native(facts[:, 0], lists, rank)
+      b = sharded._merge_gathered(facts, rank)
+      assert a[0] == b[0] == Nw and np.array_equal(a[1], b[1]) and np.array_equal(a[1], remaps[rank]), (it, rank)
