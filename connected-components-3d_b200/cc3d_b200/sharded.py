@@ -299,6 +299,30 @@ def _merge_gathered(facts, rank):
   return int(n_total.value), remap
 
 
+_gathered_merge_state = {"checked": False, "ok": True}
+
+
+def _merge_fast_path(facts, counts, rank, world):
+  """Merge of the CUDA fast path: _merge_gathered, cross-checked once per process against the per-slab-view call
+  (same C function, different argument marshalling); a disagreement or an exception switches this process to the
+  per-slab-view call for good."""
+  st = _gathered_merge_state
+  if st["ok"]:
+    try:
+      got = _merge_gathered(facts, rank)
+      if st["checked"]:
+        return got
+      want = _merge_native(facts[:, 0], [facts[r, 4: 4 + int(counts[r])] for r in range(world)], rank)
+      st["checked"] = True
+      if got[0] == want[0] and np.array_equal(got[1], want[1]):
+        return got
+      st["ok"] = False
+      return want
+    except Exception:   # noqa: BLE001 - any marshalling problem: take the plain path
+      st["ok"] = False
+  return _merge_native(facts[:, 0], [facts[r, 4: 4 + int(counts[r])] for r in range(world)], rank)
+
+
 def _out_dtype_rule(out_dtype, epl_total, voxels_total, shape_total, binary_image, connectivity):
   """Out-dtype rule of the monolithic call (fastcc3d.pyx:388-434)."""
   max_lab = min(epl_total, voxels_total)
@@ -389,7 +413,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
     sz_total = int(facts[:, 2].sum())
     voxels_total = sz_total * sy * sx
     epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
-    N_total, remap_np = _merge_gathered(facts, rank)
+    N_total, remap_np = _merge_fast_path(facts, counts, rank, world)
     lap("merge")
     out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
     if np.iinfo(out_dtype).max < N_total:

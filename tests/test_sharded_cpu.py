@@ -318,3 +318,6 @@ def test_merge_on_the_gathered_buffer_equals_native_merge():
       a = sharded._merge_native(facts[:, 0], lists, rank)
       b = sharded._merge_gathered(facts, rank)
       assert a[0] == b[0] == Nw and np.array_equal(a[1], b[1]) and np.array_equal(a[1], remaps[rank]), (it, rank)
+      c = sharded._merge_fast_path(facts, facts[:, 3], rank, world)
+      assert c[0] == Nw and np.array_equal(c[1], remaps[rank])
+  assert sharded._gathered_merge_state == {"checked": True, "ok": True}
