@@ -385,6 +385,26 @@ def main():
     also.append({"workload": "dust100_of_" + args.workload, "value": voxels / (m_du / 1e3) / 1e9, "unit": UNIT, "ms_per_step": m_du,
                  "compulsory_roofline_frac": 3 * x.element_size() * voxels / (m_du / 1e3) / 1e9 / peak,
                  "note": "fused dust: image read twice and written once, no label volume"})
+    # ---- SURVEY 8(f)4 on the same labelling: run table through the C-ABI on device buffers (R1 + scan + R2) ----
+    try:
+      import ctypes
+      from cc3d_b200 import _lib as _cl
+      Lc = _cl.lib()
+      flat = lab_t.reshape(-1)
+      kind_l = {1: _cl.U8, 2: _cl.U16, 4: _cl.U32, 8: _cl.U64}[flat.element_size()]
+      st_ = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+      cnt_ = ctypes.c_uint64(0)
+      _cl.check(Lc.cc3d_b200_runs(flat.data_ptr(), kind_l, flat.numel(), None, None, None, 0, ctypes.byref(cnt_), _cl.DEVICE, st_))
+      k_runs = int(cnt_.value)
+      tab = torch.empty((3, max(k_runs, 1)), dtype=torch.int64, device=flat.device)
+      m_rn = timed_call(lambda: _cl.check(Lc.cc3d_b200_runs(flat.data_ptr(), kind_l, flat.numel(), tab[0].data_ptr(), tab[1].data_ptr(),
+                                                             tab[2].data_ptr(), k_runs, ctypes.byref(cnt_), _cl.DEVICE, st_)))
+      also.append({"workload": "runs_of_" + args.workload, "value": voxels / (m_rn / 1e3) / 1e9, "unit": UNIT, "ms_per_step": m_rn,
+                   "runs": k_runs, "compulsory_roofline_frac": (flat.element_size() * voxels + 24 * k_runs) / (m_rn / 1e3) / 1e9 / peak,
+                   "note": "cc3d_b200_runs on the CUDA label tensor: count sweep + scan + emit sweep (labels read twice, 24 B per run written), one 8-byte read back"})
+      del tab
+    except Exception as e:   # the extra line must never cost the headline
+      also.append({"workload": "runs_of_" + args.workload, "error": repr(e)[:200]})
     del lab_t
 
   # ---- configs[2]: ONE 2048^3 uint64 Voronoi volume, z-slabs over the ranks (strong scaling; needs slabs < 2^32 voxels) ----
