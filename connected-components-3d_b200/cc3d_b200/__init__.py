@@ -68,6 +68,22 @@ def _is_torch(x) -> bool:
   return hasattr(x, "cpu") and hasattr(x, "data_ptr")
 
 
+def _adopt_device_array(x):
+  """Arrays that are neither numpy arrays nor torch tensors but expose their buffer - `__cuda_array_interface__`
+  (CuPy, Numba device arrays) or DLPack (`__dlpack__`) - are wrapped zero copy as torch tensors, so that device
+  buffers of other libraries take the same zero-copy path as CUDA torch tensors (the result is a torch tensor on
+  the same device; hand it back with `cupy.from_dlpack(out)` or the like). Anything else is returned unchanged."""
+  if isinstance(x, np.ndarray) or _is_torch(x):
+    return x
+  if hasattr(x, "__cuda_array_interface__"):
+    import torch
+    return torch.as_tensor(x, device="cuda")
+  if hasattr(x, "__dlpack__") and hasattr(x, "__dlpack_device__"):
+    import torch
+    return torch.from_dlpack(x)
+  return x
+
+
 def _torch_np_dtype(t):
   import torch
   table = {
@@ -139,6 +155,7 @@ def connected_components(
   accepted and ignored, as in the reference (fastcc3d.pyx:263-268, 388).
   """
   L = _lib.lib()
+  data = _adopt_device_array(data)
   is_torch = _is_torch(data)
   on_device = False
   tensor = None
@@ -447,6 +464,7 @@ def statistics(out_labels, no_slice_conversion: bool = False) -> dict:
   """Voxel counts, bounding boxes and centroids per label; same contract as cc3d.statistics.
   CUDA tensors are processed in place on their device."""
   device_labels = None
+  out_labels = _adopt_device_array(out_labels)
   if _is_torch(out_labels):
     if out_labels.is_cuda and out_labels.ndim >= 2 and out_labels.dtype != __import__("torch").bool:
       device_labels = out_labels

@@ -87,3 +87,30 @@ def test_runs_and_draw_fail_loudly_without_gpu(cc3d):
     list(cc3d.each(x))
   with pytest.raises(RuntimeError):   # the upload of the first slab already fails (torch), nothing is computed on the CPU
     cc3d.connected_components_stack([np.ones((4, 4, 2), np.uint8)])
+
+
+class _DLPackOnly:
+  """An array type of another library: nothing but the DLPack protocol."""
+
+  def __init__(self, t):
+    self._t = t
+
+  def __dlpack__(self, *args, **kwargs):
+    return self._t.__dlpack__(*args, **kwargs)
+
+  def __dlpack_device__(self):
+    return self._t.__dlpack_device__()
+
+
+def test_foreign_arrays_are_adopted_through_dlpack(cc3d):
+  import torch
+  t = torch.arange(24, dtype=torch.int32).reshape(2, 3, 4)
+  got = cc3d._adopt_device_array(_DLPackOnly(t))
+  assert isinstance(got, torch.Tensor) and got.data_ptr() == t.data_ptr() and torch.equal(got, t)   # zero copy
+  x = np.zeros((3, 3), np.uint8)
+  assert cc3d._adopt_device_array(x) is x and cc3d._adopt_device_array(t) is t
+  assert cc3d._adopt_device_array([1, 2]) == [1, 2]
+  if not torch.cuda.is_available():
+    # the adopted tensor takes the normal path: on a box without a GPU that is the loud failure, not an AttributeError
+    with pytest.raises(cc3d.CC3DB200Error):
+      cc3d.connected_components(_DLPackOnly(torch.ones((4, 4, 4), dtype=torch.uint8)))
