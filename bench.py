@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py — gigavoxels/s of 26-connected CCL on a 512^3 volume (BASELINE.json metric) on B200.
+Headline workload = BASELINE.json configs[0]: the reference's own connectomics.npy.ckl.gz fixture (512^3 uint32).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-A "step" is one full labelling call (resolve + write) on one synthetic volume.
+A "step" is one full labelling call (resolve + write) on the whole volume.
   value      device-resident input/output, CUDA events around K steps, max over ranks.
   e2e        same call through the public API on pinned HOST buffers (H2D + kernels + D2H per step).
   roofline   dominant kernel (tile labelling) against the measured HBM peak (MEASURED_PEAKS.json).
-  cpu_baseline  the unmodified reference (oracle/_ref) on this box's host, 1 core, bounded sample.
-`--impl reference` times the reference's own CPU implementation instead (same metric/config).
+  cpu_baseline  the unmodified reference (oracle/_ref) on this box's host, 1 core, on the SAME whole volume.
+`--impl reference` times the reference's own CPU implementation instead (same metric/config/volume).
+--gpus 1 also reports BASELINE configs[1..3] and configs[2] (2048^3 uint64, 8 virtual slabs on one GPU) under `also`;
+--gpus N > 1 first checks the sharded labelling bit for bit against the monolithic call (`parity_checked`).
 Under torchrun (N > 1) the ranks label ONE volume of N 512^3 z-slabs (cc3d_b200.sharded: per-slab labelling,
 NVLink face exchange, allgather of the face equivalences, global renumbering) - "weak" scaling, fixed work per GPU.
 """
@@ -44,11 +47,18 @@ WORKLOADS = {
   "continuous_512_f32_conn26": dict(kind="tone", shape=(512, 512, 512), kw=dict(connectivity=26, delta=10), in_bytes=4, alg_bytes=8,
                                     desc="configs[3] at 512^3: three-tone float32 + noise, delta=10, 26-connected"),
 }
-DEFAULT_WORKLOAD = "multilabel_512_u32_conn26"
+DEFAULT_WORKLOAD = "connectomics_512_u32_conn26"
+
+
+def fixture_available():
+  from oracle import decode_connectomics
+  return os.path.exists(decode_connectomics.DST)
 
 
 def make_volume(wl, device, rank=0, world=1):
-  """One rank's volume. world > 1: rank r holds z-slab r of ONE volume of shape (world*sz, sy, sx)."""
+  """One rank's volume. world > 1: rank r holds z-slab r of ONE volume of shape (world*sz, sy, sx).
+  connectomics: the volume of N ranks is N copies of the fixture stacked along z (every interface joins plane 511 of
+  one copy to plane 0 of the next, so the face merge has real work)."""
   import torch
   import benchdata
   sz, sy, sx = wl["shape"]
@@ -140,22 +150,11 @@ def reference_labeller():
   return oracle.connected_components, "port"
 
 
-def cpu_sample(wl, depth):
-  """Bounded sample of the workload for the CPU arm: the first `depth` z-planes, generated like the GPU input."""
+def cpu_volume(wl):
+  """The WHOLE single-GPU workload volume as a host array for the CPU arms (same generator, same seed as rank 0)."""
   import torch
-  import benchdata
-  sz, sy, sx = wl["shape"]
-  shape = (min(depth, sz), sy, sx)
   dev = "cuda" if torch.cuda.is_available() else "cpu"
-  if wl["kind"] == "binary":
-    full = benchdata.random_binary(shape, 0.5, 1, dev)
-  elif wl["kind"] == "voronoi":
-    full = benchdata.voronoi_multilabel(shape, cell=40, seed=2, device=dev, dtype=torch.int32)
-  elif wl["kind"] == "tone":
-    full = benchdata.three_tone_noise(shape, cell=64, seed=3, device=dev)
-  else:
-    full = make_volume(wl, dev)[: shape[0]]
-  return np.ascontiguousarray(full.cpu().numpy())
+  return np.ascontiguousarray(make_volume(wl, dev).cpu().numpy())
 
 
 def time_cpu(fn, x, kw, repeats):
@@ -168,24 +167,40 @@ def time_cpu(fn, x, kw, repeats):
 
 
 def run_reference_arm(args, wl):
+  """The reference's own CPU implementation (oracle/_ref, unmodified cc3d) on the SAME full volume the GPU arm labels at
+  N=1 (under torchrun only rank 0 works; cc3d is single threaded, so one slab of the N-slab volume is the bounded
+  sample of the N > 1 workload and is named as such)."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   fn, kind = reference_labeller()
-  x = cpu_sample(wl, depth=128)
-  for _ in range(args.warmup):
+  x = cpu_volume(wl)
+  steps, warmup = args.steps, args.warmup
+  # bounded: a whole-volume step is 0.6 s (multilabel) to 5 s (random binary); keep the arm within a few minutes
+  t0 = time.perf_counter()
+  fn(x, return_N=True, **wl["kw"])
+  t_one = time.perf_counter() - t0
+  budget = 150.0
+  if (steps + warmup) * t_one > budget:
+    warmup = min(warmup, 1)
+    steps = max(1, min(steps, int(budget / t_one) - warmup))
+  for _ in range(max(0, warmup - 1)):
     fn(x, return_N=True, **wl["kw"])
   t0 = time.perf_counter()
-  for _ in range(args.steps):
-    fn(x, return_N=True, **wl["kw"])
+  for _ in range(steps):
+    out, N = fn(x, return_N=True, **wl["kw"])
   dt = time.perf_counter() - t0
-  value = x.size * args.steps / dt / 1e9
-  sample = f"first {x.shape[0]} z-planes of the {args.workload} volume ({x.size} voxels) per step"
+  value = x.size * steps / dt / 1e9
+  sample = (f"the whole {'x'.join(str(v) for v in x.shape)} {args.workload} volume ({x.size} voxels) per step, "
+            f"{steps} timed steps" + (f" (requested {args.steps}; bounded to ~{int(budget)} s of CPU work)" if steps != args.steps else "")
+            + (f"; N={args.gpus} workload = {args.gpus} such slabs, cc3d is single threaded" if args.gpus > 1 else ""))
   line = {
-    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-    "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"),
-    "data": "synthetic", "config": {"workload": args.workload, "description": wl["desc"], "sample": sample},
+    "data": "fixture" if wl["kind"] == "connectomics" else "synthetic",
+    "config": {"workload": args.workload, "description": wl["desc"], "sample": sample, "N": int(N),
+               "same_volume_as_gpu_arm": True},
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                      "host_cores": os.cpu_count()},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,8 +218,13 @@ def main():
   ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-extra", action="store_true", help="skip the additional workloads reported under 'also'")
+  ap.add_argument("--no-big", action="store_true", help="skip the 1-GPU configs[2] leg (2048^3 uint64, 96 GiB)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+  if WORKLOADS[args.workload]["kind"] == "connectomics" and not fixture_available():
+    print("bench.py: oracle/_ref/connectomics_512_u32.npz is missing (python oracle/decode_connectomics.py builds it "
+          "where /root/reference exists); falling back to the synthetic Voronoi volume of the same shape", file=sys.stderr)
+    args.workload = "multilabel_512_u32_conn26"
   wl = WORKLOADS[args.workload]
 
   if args.impl == "reference":
@@ -265,6 +285,35 @@ def main():
     barrier()
     return max_over_ranks(e0.elapsed_time(e1)), N, out
 
+  # ---- N > 1: the sharded labelling must equal the monolithic labelling of the whole volume, bit for bit ----
+  parity = None
+  if world > 1:
+    import hashlib
+    out_s, N_s = label(x, **kw)
+    full_in = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=dev)
+    dist.all_gather_into_tensor(full_in, x)
+    signed = {2: torch.int16, 4: torch.int32, 8: torch.int64}[out_s.element_size()]
+    out_s = out_s.contiguous().view(signed)                  # NCCL has no unsigned 16/32/64-bit types in every build
+    full_out = torch.empty((world,) + tuple(out_s.shape), dtype=signed, device=dev)
+    dist.all_gather_into_tensor(full_out, out_s)
+    torch.cuda.synchronize()
+    if rank == 0:
+      whole = full_in.reshape((-1,) + tuple(x.shape[1:]))
+      mono, N_m = cc3d_b200.connected_components(whole, return_N=True, **kw)
+      same = bool(N_m == N_s and mono.element_size() == full_out.element_size()
+                  and torch.equal(mono.reshape(-1).view(signed), full_out.reshape(-1)))
+      sha = hashlib.sha256(mono.reshape(-1).cpu().numpy().tobytes()).hexdigest()
+      parity = {"parity_checked": same, "N_sharded": int(N_s), "N_monolithic": int(N_m), "labels_sha256": sha,
+                "how": f"rank 0 labelled the whole {tuple(whole.shape)} volume with the single-GPU call and compared it bit for bit "
+                       "with the all-gathered sharded result before the timed region"}
+      if not same:
+        print("bench.py: SHARDED RESULT DIFFERS FROM THE MONOLITHIC LABELLING", file=sys.stderr)
+      del mono, whole
+    del full_in, full_out, out_s
+    L.cc3d_b200_release_workspace()
+    torch.cuda.empty_cache()
+    barrier()
+
   # ---- value: device-resident ----
   launches0 = L.cc3d_b200_launch_count()
   with ClockSampler(local_rank) as clk:
@@ -306,10 +355,21 @@ def main():
     if kname in kavg:
       gbs = nbytes / (kavg[kname] / 1e3) / 1e9
       own[kname] = {"bytes": nbytes, "ms": kavg[kname], "GB/s": gbs, "frac": gbs / peak}
+  # the same kernel against the DRAM bytes it really moves (ncu dram__bytes_read + write per launch, profiles/traffic.json)
+  dram_frac = (traffic / (kavg[dom] / 1e3) / 1e9 / peak) if traffic else None
+  all_traffic = {}
+  try:
+    all_traffic = {k: v for k, v in json.load(open(tpath)).get(args.workload, {}).items() if k in kavg}
+  except Exception:
+    pass
   roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+              "dram_frac": dram_frac,
+              "per_kernel_dram_frac": {k: v / (kavg[k] / 1e3) / 1e9 / peak for k, v in all_traffic.items()},
               "per_kernel_own_bytes": own,
               "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-              "note": "achieved = (sizeof(in)+sizeof(out)) * voxels / duration of the dominant kernel; pipeline_frac = same bytes / whole step",
+              "note": "achieved = (sizeof(in)+sizeof(out)) * voxels / duration of the dominant kernel (the prescribed formula; it credits that "
+                      "kernel with bytes it does not move); dram_frac = that kernel's measured DRAM traffic / its duration / peak; "
+                      "pipeline_frac = compulsory bytes / whole step / peak (the honest end-to-end figure)",
               "kernel_ms": kavg, "kernel_share": {k: v / sum(kavg.values()) for k, v in kavg.items()},
               "pipeline_frac": alg_bytes / (ms / args.steps / 1e3) / 1e9 / peak}
 
@@ -425,24 +485,68 @@ def main():
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     fn, kind = reference_labeller()
-    xs = cpu_sample(wl, depth=256)
+    xs = np.ascontiguousarray(x.cpu().numpy())
     t = time_cpu(fn, xs, kw, repeats=3)
     cpu = {"value": xs.size / t / 1e9, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
-           "sample": f"first {xs.shape[0]} z-planes of the same volume ({xs.size} voxels), best of 3"}
+           "sample": f"the whole {'x'.join(str(v) for v in xs.shape)} volume the GPU arm labels ({xs.size} voxels), best of 3"}
+
+  # ---- configs[2] on ONE GPU: the 2048^3 uint64 Voronoi volume as 8 virtual z-slabs (64 GiB in, 32 GiB out) - the
+  #      1-GPU denominator of the 1 -> 8 GPU scaling figure, measured by the same driver run ----
+  if world == 1 and not args.no_extra and not args.no_big:
+    try:
+      import benchdata
+      from cc3d_b200 import sharded
+      del x, xh, oh
+      if "x_np" in dir():
+        del x_np, out_np
+      L.cc3d_b200_release_workspace()
+      torch.cuda.empty_cache()
+      free_b, _tot = torch.cuda.mem_get_info()
+      n3, ns = 2048, 8
+      if free_b < 150 * 2**30:
+        also.append({"workload": "voronoi_2048_u64_conn26_1gpu", "skipped": f"only {free_b / 2**30:.0f} GiB free"})
+      else:
+        szr = n3 // ns
+        slabs = [benchdata.voronoi_multilabel((n3, n3, n3), cell=160, seed=2, device=dev, dtype=torch.int64, id_bits=62,
+                                              z_range=(r * szr, (r + 1) * szr)) for r in range(ns)]
+        outs, n_ = sharded.connected_components_slabs(slabs, connectivity=26, return_N=True)
+        del outs
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(3):
+          outs, n_ = sharded.connected_components_slabs(slabs, connectivity=26, return_N=True)
+          del outs
+        b1.record()
+        torch.cuda.synchronize()
+        m = b0.elapsed_time(b1) / 3
+        also.append({"workload": "voronoi_2048_u64_conn26_1gpu", "description": "configs[2]: 2048^3 uint64 Voronoi, 26-connected, ONE GPU, "
+                     f"{ns} virtual z-slabs of {szr} planes through cc3d_b200.sharded.connected_components_slabs (a single call is limited "
+                     "to < 2^32-1 voxels); the N >= 4 runs report the same volume sharded over the GPUs",
+                     "value": float(n3) ** 3 / (m / 1e3) / 1e9, "unit": UNIT, "ms_per_step": m, "N": int(n_),
+                     "compulsory_roofline_frac": 12 * float(n3) ** 3 / (m / 1e3) / 1e9 / peak})
+        del slabs
+      L.cc3d_b200_release_workspace()
+      torch.cuda.empty_cache()
+    except Exception as e:   # never lose the headline line to the 96 GiB leg
+      also.append({"workload": "voronoi_2048_u64_conn26_1gpu", "error": repr(e)[:300]})
 
   if rank == 0:
     line = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-      "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"), "data": "synthetic",
+      "dtype": "u8" if wl["in_bytes"] == 1 else ("f32" if wl["kind"] == "tone" else "u32"),
+      "data": "fixture (the reference's benchmarks/connectomics.npy.ckl.gz, decoded)" if wl["kind"] == "connectomics" else "synthetic",
       "config": {"workload": args.workload, "description": wl["desc"], "out_dtype": out_dtype, "N": int(N),
                  "l2": "input + output of one step (>= 640 MB) are larger than the 126 MB L2",
-                 "parallelism": (f"one ({world}*512)x512x512 volume, one 512^3 z-slab per GPU (NVLink plane exchange + one all-gather, one host sync per step)"
+                 "parallelism": (f"one ({world}*512)x512x512 volume, one 512^3 z-slab per GPU (NVLink plane exchange + one all-gather of the face equivalences)"
                                  if world > 1 else "single GPU")},
       "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(per_step_launches) * args.steps,
       "gpu_launches_per_step": int(per_step_launches),
       "roofline": roofline, "cpu_baseline": cpu, "also": also,
     }
+    if parity is not None:
+      line.update(parity)
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
