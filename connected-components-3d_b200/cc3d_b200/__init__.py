@@ -214,6 +214,12 @@ def connected_components(
   sx, sy, sz = (shape3[::-1] if order == "C" else shape3)  # x = fastest memory axis
   voxels = sx * sy * sz
   kind = _kind_of(dtype)
+  if voxels >= _MAX_CALL_VOXELS:
+    # One C-ABI call handles < 2^32-1 voxels (32-bit voxel / run indices on the device). The reference has no such
+    # limit (int64 counts, uint64 labels), so larger volumes are split into z-slabs here and merged by the
+    # sharded machinery - same labels, same numbering, same dtype rule as one monolithic call would give.
+    return _connected_components_split(tensor if on_device else data, on_device, is_torch, order, shape_in, (sx, sy, sz),
+                                       connectivity, return_N, delta, out_dtype, periodic_boundary, binary_image, out_file)
   orig_dtype = np.dtype(dtype)
   binary_image = bool(binary_image) or orig_dtype == bool
 
@@ -392,6 +398,61 @@ def connected_components(
   return out_labels
 
 
+_MAX_CALL_VOXELS = 0xFFFFFFFF   # tests lower this to exercise the split path on small volumes
+
+
+def _connected_components_split(src, on_device, is_torch, order, shape_in, sxyz, connectivity, return_N, delta, out_dtype,
+                                periodic_boundary, binary_image, out_file):
+  """connected_components for volumes with >= 2^32-1 voxels: consecutive z-slabs (z = slowest memory axis) through
+  cc3d_b200.sharded.connected_components_slabs on the current device. Needs torch (device buffers) and enough device
+  memory for the input, the output and the per-slab workspaces; beyond that use connected_components_stack."""
+  import torch
+  from . import sharded
+  sx, sy, sz = sxyz
+  if connectivity not in (6, 18, 26) or sz < 2 or periodic_boundary:
+    raise ValueError(
+      f"A volume of {sx * sy * sz} voxels (>= 2^32-1) can only be labelled in z-slabs, which needs a 3D volume, "
+      f"connectivity 6/18/26 and no periodic_boundary (got shape {shape_in}, connectivity {connectivity}).")
+  planes = (_MAX_CALL_VOXELS - 1) // (sx * sy)
+  if planes < 1:
+    raise ValueError(f"A single z-plane of {sx * sy} voxels exceeds the per-call limit of 2^32-2 voxels.")
+  dims = len(shape_in)
+  if on_device:
+    zyx = (src if order == "C" else src.permute(*reversed(range(dims)))).reshape(sz, sy, sx)
+    dev = src.device
+  else:
+    zyx = (src if order == "C" else src.T).reshape(sz, sy, sx)   # views: the array is dense in this order
+    dev = torch.device("cuda", torch.cuda.current_device())
+  cuts = list(range(0, sz, planes)) + [sz]
+  with torch.cuda.device(dev):
+    if on_device:
+      slabs = [zyx[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    else:
+      slabs = [torch.from_numpy(np.ascontiguousarray(zyx[a:b])).to(dev) for a, b in zip(cuts[:-1], cuts[1:])]
+    outs, N = sharded.connected_components_slabs(slabs, connectivity=connectivity, return_N=True, delta=delta,
+                                                 out_dtype=out_dtype, binary_image=binary_image, whole=on_device)
+  if on_device:
+    full = outs
+    out_labels = full.reshape(shape_in) if order == "C" else \
+      full.reshape(tuple(reversed(shape_in))).permute(*reversed(range(dims)))
+    return (out_labels, N) if return_N else out_labels
+  np_dt = {2: np.uint16, 4: np.uint32, 8: np.uint64}[outs[0].element_size()]
+  if out_file is None:
+    flat = np.empty((sz, sy, sx), dtype=np_dt)
+  else:
+    import os
+    if isinstance(out_file, str):
+      with open(out_file, "wb") as f:
+        os.ftruncate(f.fileno(), sx * sy * sz * np.dtype(np_dt).itemsize)
+    flat = np.memmap(out_file, order="F", dtype=np_dt, shape=(sx * sy * sz,)).reshape(sz, sy, sx)
+  for (a, b), o in zip(zip(cuts[:-1], cuts[1:]), outs):
+    flat[a:b] = o.cpu().numpy().view(np_dt)
+  out_labels = flat.reshape(-1).reshape(shape_in, order=order)
+  if is_torch:
+    out_labels = torch.from_numpy(out_labels)
+  return (out_labels, N) if return_N else out_labels
+
+
 # ----------------------------------------------------------------------------------------------
 # statistics (fastcc3d.pyx:682-938)
 # ----------------------------------------------------------------------------------------------
@@ -556,15 +617,32 @@ def _validate_connectivity(dims, connectivity):
 
 
 def _dust_bounds(threshold):
-  """[lo, hi) of the component sizes that stay (cc3d/__init__.py:117-127); sizes are integers."""
+  """[lo, hi) of the component sizes that stay (cc3d/__init__.py:117-127); sizes are integers, so a real bound b is
+  equivalent to ceil(b). Non-finite bounds are legal in the reference (it compares sizes with the threshold
+  directly): +inf / -inf clamp to the ends of the range, NaN compares false with everything (nothing stays)."""
   import math
   big = (1 << 62)
+
+  def as_int(b, default):
+    if b is None:
+      return default
+    if isinstance(b, (float, np.floating)):
+      b = float(b)
+      if math.isnan(b):
+        return None
+      if math.isinf(b):
+        return big if b > 0 else -big
+      b = math.ceil(b)
+    return max(-big, min(big, int(b)))
+
   if isinstance(threshold, (tuple, list)):
-    lo, hi = threshold[0], threshold[1]
+    lo, hi = as_int(threshold[0], -big), as_int(threshold[1], big)
   else:
-    lo, hi = threshold, big
-  lo = max(-big, min(big, int(math.ceil(lo))))
-  hi = max(-big, min(big, int(math.ceil(hi)) if hi != big else big))
+    lo, hi = as_int(threshold, -big), big
+    if lo is None:            # scalar NaN: `size < nan` is false, nothing is dust
+      return -big, big
+  if lo is None or hi is None:
+    return big, -big          # empty range: `lo <= size < hi` is false for every size, as with a NaN bound
   return lo, hi
 
 
@@ -1128,7 +1206,6 @@ def each(labels, binary: bool = False, in_place: bool = False):
   in_place: one image is reused (read-only while it is out). The run table is extracted once on the GPU and stays
   there; every image is rendered by the draw kernels. CUDA tensors give CUDA tensors (no host traffic); for numpy
   input only the window of the image that the label's runs span crosses PCIe."""
-  import torch
   is_t = _is_torch(labels) and labels.is_cuda
   if not is_t:
     labels = np.asarray(labels.cpu().numpy() if _is_torch(labels) else labels)
@@ -1136,6 +1213,7 @@ def each(labels, binary: bool = False, in_place: bool = False):
     order = "F" if labels.flags.f_contiguous else "C"
     shape = labels.shape
   else:
+    import torch
     np_dt = _torch_np_dtype(labels)
     _, order = _torch_flat(labels)
     shape = tuple(labels.shape)
@@ -1146,7 +1224,43 @@ def each(labels, binary: bool = False, in_place: bool = False):
   n_vox = int(np.prod(shape)) if len(shape) else 1
   nonzero = [i for i, l in enumerate(lab.tolist()) if l != 0]
   L = _lib.lib()
-  dev = labels.device if is_t else torch.device("cuda", torch.cuda.current_device())
+  if not is_t:
+    # numpy input: torch is not needed. Every image is a zeroed numpy array drawn by cc3d_b200_draw on HOST buffers
+    # (the library stages only the window that the label's runs span).
+    hdt = _run_dtype(img_dt)
+    hkind = _kind_of(hdt)
+
+    def host_draw(img, i, value):
+      a, b = int(off[i]), int(off[i + 1])
+      flat = img.reshape(-1, order=order).view(hdt)
+      _lib.check(L.cc3d_b200_draw(flat.ctypes.data, hkind, n_vox, value, starts[a:b].ctypes.data, ends[a:b].ctypes.data,
+                                  b - a, _lib.HOST, None))
+
+    class HostImageIterator:
+      def __len__(self):
+        return len(nonzero)
+
+      def __iter__(self):
+        for i in nonzero:
+          key = int(lab[i])
+          img = np.zeros(shape, dtype=img_dt, order=order)
+          host_draw(img, i, _label_for_image(key, img_dt))
+          yield key, img
+
+    class HostInPlaceImageIterator(HostImageIterator):
+      def __iter__(self):
+        img = np.zeros(shape, dtype=img_dt, order=order)
+        for i in nonzero:
+          key = int(lab[i])
+          host_draw(img, i, _label_for_image(key, img_dt))
+          img.setflags(write=0)
+          yield key, img
+          img.setflags(write=1)
+          host_draw(img, i, 0)
+
+    return HostInPlaceImageIterator() if in_place else HostImageIterator()
+
+  dev = labels.device
   state = {}
 
   def table():
@@ -1233,12 +1347,12 @@ def each(labels, binary: bool = False, in_place: bool = False):
 
 
 def connected_components_stack(stacked_images, connectivity: int = 26, return_N: bool = False,
-                               binary_image: bool = False, out_dtype=None, out=None):
+                               binary_image: bool = False, out_dtype=None, out=None, scratch_dir=None):
   """Streaming (out-of-GPU-memory) labelling of an iterable of z-slabs; see sharded.connected_components_stack
   (counterpart of cc3d.connected_components_stack, cc3d/__init__.py:353-501)."""
   from .sharded import connected_components_stack as _stack
   return _stack(stacked_images, connectivity=connectivity, return_N=return_N, binary_image=binary_image,
-                out_dtype=out_dtype, out=out)
+                out_dtype=out_dtype, out=out, scratch_dir=scratch_dir)
 
 
 from . import fastcc3d  # noqa: E402  (namespace alias: the reference exposes runs / draw as cc3d.fastcc3d.*)

@@ -90,12 +90,15 @@ class CudaBackend:
                                               self._stream(parent)))
     return parent.to(torch.int64)
 
-  def write_remap(self, h, remap, max_label, out_dtype):
+  def write_remap(self, h, remap, max_label, out_dtype, out=None):
     torch = self.torch
     sz, sy, sx = h["shape"]
     tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}[out_dtype]
     okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}[out_dtype]
-    out = torch.empty((sz, sy, sx), dtype=tdt, device=h["device"])
+    if out is None:
+      out = torch.empty((sz, sy, sx), dtype=tdt, device=h["device"])
+    elif tuple(out.shape) != (sz, sy, sx) or out.dtype != tdt or not out.is_contiguous():
+      raise ValueError("write_remap: out must be a contiguous (sz, sy, sx) tensor of the output dtype")
     remap = remap.contiguous()
     sess, h["sess"] = h["sess"], None
     with torch.cuda.device(h["device"]):
@@ -518,11 +521,13 @@ def connected_components_slab(slab, connectivity: int = 26, return_N: bool = Fal
 
 
 def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = False, delta=0,
-                               out_dtype: Optional[Any] = None, binary_image: bool = False, backend=None):
+                               out_dtype: Optional[Any] = None, binary_image: bool = False, backend=None,
+                               whole: bool = False):
   """Single-process variant: `slabs` is a list of consecutive z-slabs (sz_i, sy, sx) of ONE volume, all on
   this process's device(s). Same merge as connected_components_slab without any collective; this is the
   way to label a volume with more than 2^32-2 voxels on one GPU (each slab must stay below that).
-  Returns the list of labelled slabs (and the global N)."""
+  Returns the list of labelled slabs (and the global N). whole=True: the slabs are written into ONE
+  (sum sz_i, sy, sx) tensor (allocated once the output dtype is known), which is returned instead of the list."""
   import torch
   from . import _torch_np_dtype
   if connectivity not in (6, 18, 26):
@@ -550,16 +555,28 @@ def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = F
     voxels_total = sz_total * sy * sx
     epl_total = voxels_total if epl_skipped else sum(h["epl"] for h in handles)
     out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
-    outs = [backend.write_remap(h, torch.from_numpy(remaps[r]).to(slabs[r].device), N_total, out_dtype)
+    dst = [None] * len(slabs)
+    if whole:
+      tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}[np.dtype(out_dtype)]
+      full = torch.empty((sz_total, sy, sx), dtype=tdt, device=slabs[0].device)
+      z0 = 0
+      for r, s_ in enumerate(slabs):
+        dst[r] = full[z0:z0 + int(s_.shape[0])]
+        z0 += int(s_.shape[0])
+    outs = [backend.write_remap(h, torch.from_numpy(remaps[r]).to(slabs[r].device), N_total, out_dtype,
+                                **({"out": dst[r]} if whole else {}))
             for r, h in enumerate(handles)]
   finally:
     for h in handles:
       backend.release(h)
+  if whole:
+    outs = full
   return (outs, N_total) if return_N else outs
 
 
 def connected_components_stack(stacked_images, connectivity: int = 26, return_N: bool = False,
-                               binary_image: bool = False, out_dtype: Optional[Any] = None, out=None, backend=None):
+                               binary_image: bool = False, out_dtype: Optional[Any] = None, out=None, backend=None,
+                               scratch_dir: Optional[str] = None):
   """Streaming front end for volumes larger than GPU memory: the counterpart of the reference's
   connected_components_stack (cc3d/__init__.py:353-501). `stacked_images` is an iterable of 3-D images of equal
   width and height (x, y) and arbitrary depth, sequenced from z = 0 upwards; only ONE slab (plus the previous
@@ -574,13 +591,18 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
   e.g. an np.memmap of that shape - instead of a CrackleArray (crackle is not a dependency), connectivity 18 is
   accepted, and the numbering is the first-appearance numbering of the whole volume: bit-identical to
   connected_components(np.concatenate(images, axis=2)), where the reference only promises equality up to
-  renumbering (automated_test.py:1628-1641). The out-dtype rule is the monolithic one applied to the totals."""
+  renumbering (automated_test.py:1628-1641). The out-dtype rule is the monolithic one applied to the totals.
+
+  Host memory: between the two passes every slab's LOCAL labels (uint32, 4 bytes per voxel) are kept; by default in
+  RAM, with `scratch_dir=` in memory-mapped files under that directory (deleted afterwards), so that together with
+  `out=` as an np.memmap the host footprint is one slab - the out-of-core use the reference's CrackleArray serves."""
   from . import DimensionError
   if connectivity not in (6, 18, 26):
     raise ValueError("Only 6, 18, and 26 connectivities are supported for 3D images. Got: " + str(connectivity))
   if backend is None:
     backend = CudaBackend()
   locals_, N_r, epl_r, depths = [], [], [], []
+  scratch_files = []
   pair_lists = [np.zeros(0, dtype=np.int64)]
   prev = None          # (last-plane values, last-plane local labels) of the previous slab, on the device
   sx = sy = None
@@ -614,7 +636,17 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
         pair_lists.append(packed.cpu().numpy())
       prev = (slab[sz - 1].contiguous(), backend.plane_labels(h, sz - 1))
       N_r.append(h["N"]); epl_r.append(h["epl"]); depths.append(int(sz))
-      locals_.append(backend.local_labels_host(h))
+      loc = backend.local_labels_host(h)
+      if scratch_dir is not None:
+        import os, tempfile
+        fd, path = tempfile.mkstemp(prefix="cc3d_b200_local_", suffix=".u32", dir=scratch_dir)
+        os.close(fd)
+        mm = np.memmap(path, dtype=np.uint32, mode="w+", shape=loc.shape)
+        mm[...] = loc
+        mm.flush()
+        scratch_files.append(path)
+        loc = mm
+      locals_.append(loc)
     finally:
       backend.release(h)
     del slab
@@ -635,9 +667,16 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
     if N_total > np.iinfo(np.uint32).max:
       raise ValueError("connected_components_stack: more than 2^32 - 1 components")
     dst = out[:, :, z0:z0 + depths[r]].T         # (sz, sy, sx) C-contiguous view of the result
-    backend.remap_host(local, np.ascontiguousarray(remap, dtype=np.uint32), dst)
+    backend.remap_host(np.ascontiguousarray(local), np.ascontiguousarray(remap, dtype=np.uint32), dst)
     locals_[r] = None
+    del local
     z0 += depths[r]
+  for path in scratch_files:
+    try:
+      import os
+      os.unlink(path)
+    except OSError:
+      pass
   return (out, int(N_total)) if return_N else out
 
 

@@ -10,6 +10,8 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 PY=${PYTHON:-python3}
 SUFFIX=$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')
+# the reference's own test file travels with the build (git-ignored): tests/test_reference_suite.py runs it against the drop-in
+if [ -f "$REF/automated_test.py" ]; then cp "$REF/automated_test.py" "$OUT/automated_test.py"; fi
 if [ -f "$OUT/fastcc3d$SUFFIX" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "oracle/_ref/fastcc3d$SUFFIX already built"; exit 0
 fi

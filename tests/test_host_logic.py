@@ -114,3 +114,17 @@ def test_foreign_arrays_are_adopted_through_dlpack(cc3d):
     # the adopted tensor takes the normal path: on a box without a GPU that is the loud failure, not an AttributeError
     with pytest.raises(cc3d.CC3DB200Error):
       cc3d.connected_components(_DLPackOnly(torch.ones((4, 4, 4), dtype=torch.uint8)))
+
+
+def test_dust_bounds_accept_non_finite_thresholds():
+  """the reference compares sizes with the threshold directly, so inf / nan bounds are legal."""
+  import numpy as np
+  from cc3d_b200 import _dust_bounds
+  big = 1 << 62
+  assert _dust_bounds(100) == (100, big)
+  assert _dust_bounds((10, np.inf)) == (10, big) and _dust_bounds((10.5, float("inf"))) == (11, big)
+  assert _dust_bounds((-np.inf, 5)) == (-big, 5)
+  assert _dust_bounds(np.float32(3.2)) == (4, big)
+  lo, hi = _dust_bounds((np.nan, 5))
+  assert lo > hi                       # empty range: every component is outside it
+  assert _dust_bounds(float("nan")) == (-big, big)   # `size < nan` is false: nothing is dust
