@@ -647,9 +647,9 @@ static void face_pairs_typed(const T* vP, const u32* lP, const T* vQ, const u32*
                              cudaStream_t s) {
   const i64 n = sx * sy;
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  if (mode == MODE_EQ) { Edge<T, MODE_EQ> E; E.delta = (T)0; k_face_pairs<T, MODE_EQ><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
-  else if (mode == MODE_NONZERO) { Edge<T, MODE_NONZERO> E; E.delta = (T)0; k_face_pairs<T, MODE_NONZERO><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
-  else { Edge<T, MODE_DELTA> E; memcpy(&E.delta, delta, sizeof(T)); k_face_pairs<T, MODE_DELTA><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
+  if (mode == MODE_EQ) { Edge<T, MODE_EQ> E; E.delta = (T)0; E.zeq = 0; k_face_pairs<T, MODE_EQ><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
+  else if (mode == MODE_NONZERO) { Edge<T, MODE_NONZERO> E; E.delta = (T)0; E.zeq = 0; k_face_pairs<T, MODE_NONZERO><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
+  else { Edge<T, MODE_DELTA> E; memcpy(&E.delta, delta, sizeof(T)); E.zeq = connectivity == 26 ? 1 : 0; k_face_pairs<T, MODE_DELTA><<<blocks, 256, 0, s>>>(vP, lP, vQ, lQ, sx, sy, connectivity, E, pairs, cap, count); }
   g_launches += 1;
 }
 

@@ -103,7 +103,15 @@ template <> struct is_float_t<double> { static constexpr bool value = true; };
 //   DELTA   : both non-zero and |v[p]-v[q]| <= delta in T arithmetic (cc3d_continuous.hpp:79-88)
 template <typename T, int MODE> struct Edge {
   T delta;
+  // DELTA, 3D 26-connected only: the reference copies the label of an EQUAL voxel at z-1 before it evaluates match()
+  // (cc3d_continuous.hpp:147-150); for finite values equality implies a match, but +-inf == +-inf joins two voxels whose
+  // difference is NaN. zeq = 1 reproduces that on the straight -z edge.
+  int zeq;
   __device__ __forceinline__ bool fg(T v) const { return v != (T)0; }
+  __device__ __forceinline__ bool zedge(T p, T q) const {
+    if constexpr (MODE == MODE_DELTA && is_float_t<T>::value) { if (zeq && p == q && p != (T)0) return true; }
+    return (*this)(p, q);
+  }
   __device__ __forceinline__ bool operator()(T p, T q) const {
     if constexpr (MODE == MODE_EQ) { return p == q && p != (T)0; }
     else if constexpr (MODE == MODE_NONZERO) { return p != (T)0 && q != (T)0; }

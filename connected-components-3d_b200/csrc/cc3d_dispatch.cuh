@@ -59,6 +59,7 @@ template <typename T, int MODE>
 static int launch_faces(const LabelArgs& a) {
   Edge<T, MODE> E;
   memcpy(&E.delta, a.delta, sizeof(T));
+  E.zeq = (MODE == MODE_DELTA && a.connectivity == 26) ? 1 : 0;
   const Geom& g = a.g;
   const bool two_d = a.connectivity == 4 || a.connectivity == 8;
   if (two_d && g.sz != 1) return -1;
@@ -98,6 +99,7 @@ template <typename T, int MODE, int CONN>
 static int launch_union(const LabelArgs& a) {
   Edge<T, MODE> E;
   memcpy(&E.delta, a.delta, sizeof(T));
+  E.zeq = 0;
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
@@ -153,6 +155,7 @@ template <typename T, int MODE, int CONN>
 static int launch_periodic(const LabelArgs& a) {
   Edge<T, MODE> E;
   memcpy(&E.delta, a.delta, sizeof(T));
+  E.zeq = 0;
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
   const i64 n0 = 2 * g.sy * g.sz, n1 = g.sx * g.sz, n2 = g.sx * g.sy;

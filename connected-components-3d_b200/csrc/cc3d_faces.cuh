@@ -23,7 +23,7 @@ __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T
     F[k] = __ballot_sync(CC_FULL, f);
     X[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
     Y[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
-    Z[k] = HASZ ? __ballot_sync(CC_FULL, E(c[k], d[k])) : 0u;
+    Z[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], d[k])) : 0u;
     // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
     if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
   }
@@ -130,7 +130,7 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
         const u32 F = __ballot_sync(CC_FULL, f);
         const u32 X = __ballot_sync(CC_FULL, E(c, l));
         const u32 Y = __ballot_sync(CC_FULL, E(c, up));
-        const u32 Z = HASZ ? __ballot_sync(CC_FULL, E(c, d)) : 0u;
+        const u32 Z = HASZ ? __ballot_sync(CC_FULL, E.zedge(c, d)) : 0u;
         if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c != l));
         if (lane == 0) {
           mq[(size_t)r * W + k] = make_uint4(F, X, Y, Z);

@@ -450,6 +450,7 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
       // transitive predicates: when the straight neighbour joins p, every other matching q is its in-plane
       // neighbour and already belongs to the same component of the lower slab
       const bool straight = (MODE != MODE_DELTA) && E(p, vQ[i]);
+      const bool zeq_join = (MODE == MODE_DELTA) && connectivity == 26 && E.zedge(p, vQ[i]) && !E(p, vQ[i]);   // +-inf == +-inf below
 #pragma unroll
       for (int dy = -1; dy <= 1; dy++) {
 #pragma unroll
@@ -462,7 +463,7 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
           if (xx < 0 || xx >= sx || yy < 0 || yy >= sy) continue;
           const i64 qi = yy * sx + xx;
           const T q = vQ[qi];
-          if (!E(p, q)) continue;
+          if (!E(p, q) && !(zeq_join && nz == 0)) continue;
           const u32 lq = lQ[qi];
           // the voxel to the left emits the same (lq, lp) through the same direction
           if (left_same && xx > 0 && lQ[qi - 1] == lq && E(vP[i - 1], vQ[qi - 1])) continue;
