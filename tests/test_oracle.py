@@ -313,3 +313,30 @@ def test_oracle_matches_run_goldens(oracle_mod, path):
   for binary in (False, True):
     for in_place in (False, True):
       assert np.array_equal(each_checksums(oracle_mod.each(x, binary=binary, in_place=in_place), order), z[f"each_{int(binary)}"])
+
+
+def test_oracle_float_special_values_vs_reference(oracle_mod):
+  """NaN / +-inf / -0.0 / float16 inputs: the C restatement follows the reference, including the 26-connected
+  continuous scan's equal-voxel-below shortcut (cc3d_continuous.hpp:147-150) that joins inf with inf."""
+  ref = oracle_mod.reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built")
+  rng = np.random.default_rng(77)
+  n = 0
+  for it in range(45):
+    dims = int(rng.integers(2, 4))
+    shape = tuple(int(rng.integers(2, 30)) for _ in range(dims))
+    dt = [np.float16, np.float32, np.float64][it % 3]
+    vals = np.array([0.0, -0.0, 1.0, 2.0, 2.5, np.inf, -np.inf, np.nan, 1e-3, 65000.0], dtype=dt)
+    x = np.asarray(vals[rng.integers(0, len(vals), shape)], order="F" if rng.random() < 0.5 else "C")
+    conns = [4, 6, 18, 26] if x.ndim == 2 else [6, 18, 26]
+    c = int(conns[rng.integers(len(conns))])
+    for kw in ([dict()] if dt == np.float16 else [dict(), dict(delta=float(rng.choice([0.5, 1.0, 1e30])))]):
+      try:
+        want, Nw = ref.connected_components(x, connectivity=c, return_N=True, **kw)
+      except (RuntimeError, ValueError):
+        continue
+      got, N = oracle_mod.connected_components(x, connectivity=c, return_N=True, **kw)
+      assert N == Nw and got.dtype == want.dtype and np.array_equal(got, want), (shape, dt, c, kw)
+      n += 1
+  assert n > 50
