@@ -1347,12 +1347,12 @@ def each(labels, binary: bool = False, in_place: bool = False):
 
 
 def connected_components_stack(stacked_images, connectivity: int = 26, return_N: bool = False,
-                               binary_image: bool = False, out_dtype=None, out=None, scratch_dir=None):
+                               binary_image: bool = False, out_dtype=None, out=None, scratch_dir=None, order=None):
   """Streaming (out-of-GPU-memory) labelling of an iterable of z-slabs; see sharded.connected_components_stack
   (counterpart of cc3d.connected_components_stack, cc3d/__init__.py:353-501)."""
   from .sharded import connected_components_stack as _stack
   return _stack(stacked_images, connectivity=connectivity, return_N=return_N, binary_image=binary_image,
-                out_dtype=out_dtype, out=out, scratch_dir=scratch_dir)
+                out_dtype=out_dtype, out=out, scratch_dir=scratch_dir, order=order)
 
 
 from . import fastcc3d  # noqa: E402  (namespace alias: the reference exposes runs / draw as cc3d.fastcc3d.*)

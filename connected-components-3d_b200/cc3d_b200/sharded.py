@@ -576,7 +576,7 @@ def connected_components_slabs(slabs, connectivity: int = 26, return_N: bool = F
 
 def connected_components_stack(stacked_images, connectivity: int = 26, return_N: bool = False,
                                binary_image: bool = False, out_dtype: Optional[Any] = None, out=None, backend=None,
-                               scratch_dir: Optional[str] = None):
+                               scratch_dir: Optional[str] = None, order: Optional[str] = None):
   """Streaming front end for volumes larger than GPU memory: the counterpart of the reference's
   connected_components_stack (cc3d/__init__.py:353-501). `stacked_images` is an iterable of 3-D images of equal
   width and height (x, y) and arbitrary depth, sequenced from z = 0 upwards; only ONE slab (plus the previous
@@ -587,11 +587,14 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
   labels back. Then the host merge of the interface graph (cc3d_b200_merge_slabs, replaces the Python DisjointSet
   :296-321), and pass 2: every slab is renumbered through its remap table on the GPU into the result.
 
-  Differences from the reference: the result is a plain Fortran-ordered numpy array (sx, sy, sz_total) - or `out`,
-  e.g. an np.memmap of that shape - instead of a CrackleArray (crackle is not a dependency), connectivity 18 is
-  accepted, and the numbering is the first-appearance numbering of the whole volume: bit-identical to
-  connected_components(np.concatenate(images, axis=2)), where the reference only promises equality up to
-  renumbering (automated_test.py:1628-1641). The out-dtype rule is the monolithic one applied to the totals.
+  Differences from the reference: the result is a plain numpy array (sx, sy, sz_total) - or `out`, e.g. an np.memmap
+  of that shape - instead of a CrackleArray (crackle is not a dependency), connectivity 18 is accepted, and the
+  numbering is the first-appearance numbering of the whole volume walked x-fastest / z-slowest: bit-identical to
+  connected_components(np.asfortranarray(np.concatenate(images, axis=2))), where the reference only promises equality
+  up to renumbering (automated_test.py:1628-1641). The result's memory order follows the first image like the
+  reference's per-image labelling does (Fortran-ordered images give a Fortran-ordered result, anything else a
+  C-ordered one; `order=` overrides; `out` decides when given). The out-dtype rule is the monolithic one applied to
+  the totals.
 
   Host memory: between the two passes every slab's LOCAL labels (uint32, 4 bytes per voxel) are kept; by default in
   RAM, with `scratch_dir=` in memory-mapped files under that directory (deleted afterwards), so that together with
@@ -617,6 +620,8 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
     if sx is None:
       sx, sy = image.shape[:2]
       kind, binary_image, epl_skipped, delta_arr = _normalise(image.dtype, 0, binary_image)
+      if order is None:
+        order = "F" if image.flags.f_contiguous else "C"
     elif image.shape[:2] != (sx, sy):
       raise ValueError(f"All images of a stack must share width and height: {image.shape[:2]} vs {(sx, sy)}")
     if image.shape[2] == 0:
@@ -657,17 +662,23 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
   epl_total = voxels_total if epl_skipped else sum(epl_r)
   out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
   if out is None:
-    out = np.zeros((sx, sy, sz_total), dtype=out_dtype, order="F")
-  elif tuple(out.shape) != (sx, sy, sz_total) or out.dtype != out_dtype or not out.flags.f_contiguous:
-    raise ValueError(f"out must be a Fortran-ordered {out_dtype} array of shape {(sx, sy, sz_total)}")
+    out = np.zeros((sx, sy, sz_total), dtype=out_dtype, order="F" if order in (None, "F") else "C")
+  elif tuple(out.shape) != (sx, sy, sz_total) or out.dtype != out_dtype or not (out.flags.f_contiguous or out.flags.c_contiguous):
+    raise ValueError(f"out must be a contiguous {out_dtype} array of shape {(sx, sy, sz_total)}")
+  direct = out.flags.f_contiguous
   N_total = 0
   z0 = 0
   for r, local in enumerate(locals_):
     N_total, remap = _merge_native(N_r, pair_lists, r)
     if N_total > np.iinfo(np.uint32).max:
       raise ValueError("connected_components_stack: more than 2^32 - 1 components")
-    dst = out[:, :, z0:z0 + depths[r]].T         # (sz, sy, sx) C-contiguous view of the result
+    if direct:
+      dst = out[:, :, z0:z0 + depths[r]].T       # (sz, sy, sx) C-contiguous view of the result
+    else:                                        # C-ordered result: renumber into a slab buffer, then a strided copy
+      dst = np.empty((depths[r], sy, sx), dtype=out_dtype)
     backend.remap_host(np.ascontiguousarray(local), np.ascontiguousarray(remap, dtype=np.uint32), dst)
+    if not direct:
+      out[:, :, z0:z0 + depths[r]] = dst.T
     locals_[r] = None
     del local
     z0 += depths[r]

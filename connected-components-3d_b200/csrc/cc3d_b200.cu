@@ -163,10 +163,6 @@ void marks_collect(bool append) {
   g_marks.clear();
 }
 
-__global__ void k_init_counters(Counters* c, u32* ctl) {
-  c->epl = 0; c->first_row = INT64_MAX; c->last_row = -1; c->N = 0; c->nruns = 0;
-  if (ctl) { for (int k = 0; k < 8; k++) ctl[k] = 0; }
-}
 
 Geom make_geom(i64 sx, i64 sy, i64 sz) {
   Geom g;
@@ -226,9 +222,18 @@ struct cc3d_b200_session {
   u32* L = nullptr;   // final label of every run, at the run's first voxel
   u32* M = nullptr;   // edge bitmaps (F and X planes are what the expansion needs)
   Counters* ctr = nullptr;   // device-side counters of the resolve phase
+  Counters* hctr = nullptr;  // this session's pinned landing slot for the counters (never shared between sessions)
   bool epl_is_runs = false;  // multilabel: epl (cc3d.hpp:287-315) = number of x-runs, counted by scan S
   const void* din = nullptr; // device copy of the input (the caller's buffer, or the staged copy of a host buffer)
   u64 N = 0;
+  u32 lmask = 0xFFFFFFFFu;   // 0x7FFFFFFF when L holds CC_LABEL_TAG | label (fused rank kernel)
+  // what a host-driven redo after an edge-queue overflow needs (see redo_unions_global)
+  LabelArgs args;
+  int in_kind = 0;
+  bool periodic = false, block_order = false, inline_fallback = false, redone = false;
+  u32 *GR = nullptr, *cnt = nullptr, *prefix = nullptr;
+  u64* status2 = nullptr;    // look-back status words of the C stage
+  i64 status2_words = 0, nwords2 = 0, maxruns = 0, nbwords = 0;
 };
 
 // (definitions below inherit C linkage from their declarations in include/cc3d_b200.h)
@@ -309,8 +314,7 @@ int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64
   Counters* ctr = (Counters*)ar.take(sizeof(Counters));
   void* range2 = ar.take(16);
   Geom g = make_geom(sx, sy, sz);
-  k_init_counters<<<1, 1, 0, s>>>(ctr, nullptr);
-  g_launches += 1;
+  cudaMemsetAsync(ctr, 0, sizeof(Counters), s);
   prepass_dispatch(din, in_kind, g, ctr, range2, ar, s);
   Counters h;
   unsigned char hr[16];
@@ -320,8 +324,8 @@ int cc3d_b200_prepass(const void* in, int in_kind, int64_t sx, int64_t sy, int64
   arena_release(ar);
   if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e));
   if (epl) *epl = h.epl;
-  if (first_row) *first_row = h.epl ? h.first_row : -1;
-  if (last_row) *last_row = h.epl ? h.last_row : -1;
+  if (first_row) *first_row = h.epl ? (int64_t)~h.first_inv : -1;
+  if (last_row) *last_row = h.epl ? (int64_t)h.last_p1 - 1 : -1;
   if (vmin) memcpy(vmin, hr, es);
   if (vmax) memcpy(vmax, hr + es, es);
   return 0;
@@ -346,33 +350,56 @@ static void c8_edges_typed(const T* in, u32* M, const Geom& g, const void* delta
   g_launches += 1;
 }
 
-// Reads the counters of an enqueued resolve phase (one stream synchronisation).
-// pinned landing zone of the counters so that their copy is truly asynchronous (one per host thread)
-static Counters* pinned_counters() {
-  thread_local Counters* hpin = nullptr;
-  if (!hpin && cudaMallocHost((void**)&hpin, sizeof(Counters)) != cudaSuccess) hpin = nullptr;
-  return hpin;
+// Pinned landing slots for the counters, so that their copy back is truly asynchronous. One slot per live session
+// (a thread-local slot would be overwritten by a second enqueue-only session of the same thread before the first one
+// is read); slots are recycled through a free list.
+static std::vector<Counters*> g_pin_free;
+static Counters* pinned_slot_take() {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pin_free.empty()) { Counters* h = g_pin_free.back(); g_pin_free.pop_back(); return h; }
+  }
+  Counters* h = nullptr;
+  if (cudaMallocHost((void**)&h, sizeof(Counters)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return h;
 }
+static void pinned_slot_give(Counters* h) {
+  if (!h) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pin_free.push_back(h);
+}
+static int redo_unions_global(cc3d_b200_session* S, cudaStream_t s);
+// Reads the counters of an enqueued resolve phase (one stream synchronisation). If the global edge queue overflowed
+// (and the fallback kernel was not launched inline) the unions are redone on the global forest here.
 static int resolve_finish(cc3d_b200_session* S, cudaStream_t s, cc3d_b200_resolve_info* info) {
   if (S->voxels == 0) return 0;
   Counters hloc;
-  Counters* h = pinned_counters();
-  cudaError_t e = cudaSuccess;
-  if (!h) { h = &hloc; e = cudaMemcpyAsync(h, S->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s); }   // else: enqueued by resolve_enqueue
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e));
-  S->N = h->N;
-  info->N = h->N;
-  info->epl = S->epl_is_runs ? h->nruns : h->epl;
-  info->first_foreground_row = h->nruns ? h->first_row : -1;
-  info->last_foreground_row = h->nruns ? h->last_row : -1;
-  return 0;
+  for (int pass = 0; pass < 2; pass++) {
+    Counters* h = S->hctr;
+    cudaError_t e = cudaSuccess;
+    if (!h || pass) { h = h ? h : &hloc; e = cudaMemcpyAsync(h, S->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s); }   // pass 0: enqueued by resolve_enqueue
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("label_resolve: ") + cudaGetErrorString(e));
+    if (h->gq_ovf && !S->inline_fallback && !S->redone) {
+      if (int rc = redo_unions_global(S, s)) return rc;
+      continue;
+    }
+    S->N = h->N;
+    info->N = h->N;
+    info->epl = S->epl_is_runs ? h->nruns : h->epl;
+    info->first_foreground_row = h->nruns ? (int64_t)~h->first_inv : -1;
+    info->last_foreground_row = h->nruns ? (int64_t)h->last_p1 - 1 : -1;
+    return 0;
+  }
+  return fail(CC3D_B200_ERR_CUDA, "label_resolve: redo did not converge");
 }
 
 static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
                            const void* delta, int binary_image, int periodic_boundary, int mem_space,
-                           void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session);
+                           void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session,
+                           bool inline_fallback = false);
+static void enqueue_rank_stage(cc3d_b200_session* S, cudaStream_t s, bool cleared);
 
 int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
                             const void* delta, int binary_image, int periodic_boundary, int mem_space,
@@ -388,7 +415,8 @@ int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy,
 
 static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
                            const void* delta, int binary_image, int periodic_boundary, int mem_space,
-                           void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session) {
+                           void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session,
+                           bool inline_fallback) {
   if (!info || !session) return fail(CC3D_B200_ERR_ARGUMENT, "info/session must not be NULL");
   *session = nullptr;
   info->N = 0; info->epl = 0; info->first_foreground_row = -1; info->last_foreground_row = -1;
@@ -433,20 +461,30 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   const i64 nblocks2d = block_order ? ((sx + 1) / 2) * ((sy + 1) / 2) : 0;
   const i64 nbwords = (nblocks2d + 31) / 32;
 
+  // fused rank kernel (C stage in one launch): run ids and labels must stay below 2^31, block-order numbering keeps
+  // the three-kernel path
+  const bool fused_rank = !block_order && maxruns < (i64(1) << 31);
+  const i64 nb_rank = (maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS;
+  const i64 status2_words = (fused_rank ? nb_rank : nb2) + 2;
+  // control block: Counters | scan-S status | C-stage status, zeroed by ONE memset per call
+  const size_t ctl_bytes = ((sizeof(Counters) + 255) & ~size_t(255)) + (size_t)(nb + 2) * 8 + (size_t)status2_words * 8;
+
   size_t need = 4096;
   auto add = [&](size_t b) { need += ((b + 255) & ~size_t(255)) + 256; };
   if (mem_space == CC3D_B200_HOST) { add((size_t)voxels * es); add((size_t)voxels * 4 + 512); }   // staged input + (u16/u32) output
   add((size_t)maxruns * 4);                // L
   add(bitmap_words(g, c8) * 4);            // M
   add((size_t)nwords2 * 4 * 3);            // GR cnt prefix
-  add((size_t)(nb + 1) * 8); add((size_t)(nb2 + 1) * 8);   // scan block sums
+  add(ctl_bytes);
   size_t gqcap = (size_t)std::min<i64>(8 * nwords + 4096, 0x7FFFFFFF);   // global edge queue entries
   if (g_queue_cap_override.load()) gqcap = (size_t)g_queue_cap_override.load();
   add(gqcap * 8); add(64);
-  add(sizeof(Counters)); add(64); add(148 * 8 * 8 * 2 + 512);
+  add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
   if (int rc = arena_acquire(need, &S->arena, (cudaStream_t)stream, true)) { delete S; return rc; }
   Arena& ar = S->arena;
+  // enqueue-only sessions (slab_begin) never read the counters on the host: no landing slot, no copy
+  S->hctr = inline_fallback ? nullptr : pinned_slot_take();
 
   marks_begin(s);
   const void* din = in;
@@ -462,31 +500,31 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   u32* GR = (u32*)ar.take((size_t)nwords2 * 4);
   u32* cnt = (u32*)ar.take((size_t)nwords2 * 4);
   u32* prefix = (u32*)ar.take((size_t)nwords2 * 4);
-  u64* bsum = (u64*)ar.take((size_t)(nb + 1) * 8);
-  u64* bsum2 = (u64*)ar.take((size_t)(nb2 + 1) * 8);
-  Counters* ctr = (Counters*)ar.take(sizeof(Counters));
+  char* ctl = (char*)ar.take(ctl_bytes);
+  Counters* ctr = (Counters*)ctl;
+  u64* bsum = (u64*)(ctl + ((sizeof(Counters) + 255) & ~size_t(255)));
+  u64* bsum2 = bsum + (nb + 2);
   u64* gqbuf = (u64*)ar.take(gqcap * 8);
-  u32* gqctl = (u32*)ar.take(64);   // [0] count, [1] overflow flag
-  S->L = L; S->M = M; S->din = din;
+  S->L = L; S->M = M; S->din = din; S->ctr = ctr;
   S->epl_is_runs = (mode == MODE_EQ);
+  S->in_kind = in_kind; S->periodic = periodic_boundary && (connectivity == 4 || connectivity == 8 || connectivity == 6);
+  S->block_order = block_order; S->inline_fallback = inline_fallback;
+  S->GR = GR; S->cnt = cnt; S->prefix = prefix; S->status2 = bsum2; S->status2_words = status2_words;
+  S->nwords2 = nwords2; S->maxruns = maxruns; S->nbwords = nbwords;
+  S->lmask = fused_rank ? 0x7FFFFFFFu : 0xFFFFFFFFu;
 
-  bool scans_cleared = false;
-#if defined(CC_PDL) && !defined(CC_SCAN_THREEPASS)
-  // the look-back status words of both scans are zeroed up front so that no memset sits between the kernels
-  cudaMemsetAsync(bsum, 0, (size_t)(std::max<i64>(nb, 1) + 1) * 8, s);
-  cudaMemsetAsync(bsum2, 0, (size_t)(std::max<i64>(nb2, 1) + 1) * 8, s);
-  scans_cleared = true;
-#endif
-  k_init_counters<<<1, 1, 0, s>>>(ctr, gqctl);
-  g_launches += 1;
+  // counters, edge-queue control and the look-back status words of both scans: one memset, no init kernel
+  cudaMemsetAsync(ctl, 0, ctl_bytes, s);
+  const bool scans_cleared = true;
 
-  LabelArgs a;
-  a.GQ.q = gqbuf; a.GQ.count = gqctl; a.GQ.ovf = gqctl + 1; a.GQ.cap = (u32)gqcap;
+  LabelArgs& a = S->args;
+  a.GQ.q = gqbuf; a.GQ.count = &ctr->gq_count; a.GQ.ovf = &ctr->gq_ovf; a.GQ.cap = (u32)gqcap;
   int stage_launches = 0;
   a.launches = &stage_launches;
   a.in = din; a.M = M; a.L = L; a.ctr = ctr; a.g = g; a.mode = mode;
   a.connectivity = connectivity; a.stream = s;
   a.mark = g_timing ? mark : nullptr;
+  a.inline_fallback = inline_fallback;
   memset(a.delta, 0, 8);
   if (delta) memcpy(a.delta, delta, es);
   int rc = 0;
@@ -512,20 +550,43 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
     rc = -1;
     CC_KIND_SWITCH(in_kind, rc = run_union_stage<KT>(a));
   }
-  if (rc == 0 && periodic_boundary && (connectivity == 4 || connectivity == 8 || connectivity == 6)) {
+  if (rc == 0 && S->periodic) {
     CC_KIND_SWITCH(in_kind, rc = run_periodic_stage<KT>(a));
     mark("P_periodic", s);
   }
-  if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
-
   g_launches += stage_launches;
+  a.launches = nullptr;
+  if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
+  enqueue_rank_stage(S, s, scans_cleared);
+  if (S->hctr) cudaMemcpyAsync(S->hctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s);
+  *session = S;
+  return 0;
+}
+
+// C stage: root flags, their scan and the final label of every run (fused k_rank, or the three-kernel path for
+// block-order numbering / >= 2^31 runs). cleared: the status words were zeroed earlier in the stream.
+static void enqueue_rank_stage(cc3d_b200_session* S, cudaStream_t s, bool cleared) {
+  Counters* ctr = S->ctr;
+  u32 *L = S->L, *GR = S->GR, *cnt = S->cnt, *prefix = S->prefix;
+  const Geom& g = S->g;
+  if (S->lmask != 0xFFFFFFFFu) {
+    const i64 nb_rank = std::max<i64>(1, (S->maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS);
+    if (!cleared) cudaMemsetAsync(S->status2, 0, (size_t)S->status2_words * 8, s);
+    const unsigned grid = (unsigned)std::min<i64>(nb_rank, 148 * 6);
+    cc_launch(k_rank, dim3(grid), dim3(256), 0, s, L, GR, prefix, (unsigned long long*)S->status2, (u32)nb_rank, &ctr->nruns, &ctr->N);
+    g_launches += 1;
+    mark("C_rank", s);
+    return;
+  }
   cc_launch(k_compress, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, cnt, &ctr->nruns);
   g_launches += 1;
   mark("C1_compress", s);
-  scan_counts(cnt, prefix, bsum2, nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s, nullptr, 1, scans_cleared);
+  scan_counts(cnt, prefix, S->status2, S->nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s, nullptr, 1, cleared);
   mark("C2_scan", s);
-  if (block_order) {
-    u32* K = (u32*)ar.take((size_t)maxruns * 4);
+  if (S->block_order) {
+    Arena& ar = S->arena;
+    const i64 nbwords = S->nbwords, nwords = g.nwords;
+    u32* K = (u32*)ar.take((size_t)S->maxruns * 4);
     u32* BK = (u32*)ar.take((size_t)nbwords * 4);
     u32* bcnt = (u32*)ar.take((size_t)nbwords * 4);
     u32* bprefix = (u32*)ar.take((size_t)nbwords * 4);
@@ -533,7 +594,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
     u64* dummyN = (u64*)ar.take(8);
     cudaMemsetAsync(BK, 0, (size_t)nbwords * 4, s);
     k_fill_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(K, CC_BG, &ctr->nruns);
-    k_blockkey_min<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(L, M, K, g);
+    k_blockkey_min<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(L, S->M, K, g);
     k_blockkey_mark<<<CC_GRID_BLOCKS, 256, 0, s>>>(K, GR, BK, &ctr->nruns);
     k_popc<<<(unsigned)((nbwords + 255) / 256), 256, 0, s>>>(BK, bcnt, nbwords);
     scan_counts(bcnt, bprefix, bsum3, nbwords, nullptr, 0, dummyN, nullptr, s);
@@ -545,15 +606,47 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
     g_launches += 1;
     mark("C3_assign", s);
   }
-  S->ctr = ctr;
-  if (Counters* h = pinned_counters()) cudaMemcpyAsync(h, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s);
-  *session = S;
+}
+
+// The global edge queue overflowed (B1 raised gq_ovf) and the fallback kernel was not part of the enqueued pipeline:
+// reset the forest and unite EVERY edge on it (k_union_global), then the wrap edges and the C stage again. Rare (the
+// queue holds 8 entries per bitmap word); costs one extra synchronisation only when it happens.
+__global__ void __launch_bounds__(256) k_iota_n(u32* __restrict__ p, const u64* __restrict__ n_dev) {
+  const u32 n = (u32)*n_dev;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+}
+static int redo_unions_global(cc3d_b200_session* S, cudaStream_t s) {
+  S->redone = true;
+  LabelArgs& a = S->args;
+  int launches = 0;
+  a.launches = &launches;
+  a.stream = s;
+  a.mark = nullptr;
+  k_iota_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(S->L, &S->ctr->nruns);
+  g_launches += 1;
+  int rc = -1;
+  CC_KIND_SWITCH(S->in_kind, rc = run_union_global_stage<KT>(a));
+  if (rc == 0 && S->periodic) { CC_KIND_SWITCH(S->in_kind, rc = run_periodic_stage<KT>(a)); }
+  g_launches += launches;
+  a.launches = nullptr;
+  if (rc != 0) return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration");
+  cudaMemsetAsync(&S->ctr->N, 0, sizeof(u64), s);
+  enqueue_rank_stage(S, s, false);
   return 0;
 }
 
 void cc3d_b200_session_release(cc3d_b200_session* S) {
   if (!S) return;
   arena_release(S->arena);
+  pinned_slot_give(S->hctr);
+  delete S;
+}
+// release while work enqueued on `s` may still use the session's workspace (enqueue-only paths, error paths)
+static void session_release_after(cc3d_b200_session* S, cudaStream_t s) {
+  if (!S) return;
+  arena_release_after(S->arena, s);
+  // the pinned slot may still receive the counters copy enqueued on s: recycle it only once the stream has passed it
+  if (S->hctr) { cudaStreamSynchronize(s); pinned_slot_give(S->hctr); }
   delete S;
 }
 
@@ -564,9 +657,9 @@ static void launch_write(const cc3d_b200_session* S, OUT* dout, i64 row0, i64 nr
   const unsigned nchunks = (unsigned)((g.W + 31) / 32);
   const i64 nwarps = nrows * nchunks;
   const unsigned blocks = (unsigned)((nwarps + 7) / 8);
-  if (!remap) k_expand<OUT, 0><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap);
-  else if (remap_kind == CC3D_B200_U32) k_expand<OUT, 1><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap);
-  else k_expand<OUT, 2><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap);
+  if (!remap) k_expand<OUT, 0><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap, S->lmask);
+  else if (remap_kind == CC3D_B200_U32) k_expand<OUT, 1><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap, S->lmask);
+  else k_expand<OUT, 2><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap, S->lmask);
   g_launches += 1;
 }
 
@@ -713,7 +806,8 @@ int cc3d_b200_slab_begin(const void* in, int in_kind, int64_t sx, int64_t sy, in
   if (sx <= 0 || sy <= 0 || sz <= 0) return fail(CC3D_B200_ERR_ARGUMENT, "empty slab");
   cc3d_b200_resolve_info info;
   cc3d_b200_session* S = nullptr;
-  int rc = resolve_enqueue(in, in_kind, sx, sy, sz, connectivity, delta, binary_image, 0, CC3D_B200_DEVICE, stream, &info, &S);
+  int rc = resolve_enqueue(in, in_kind, sx, sy, sz, connectivity, delta, binary_image, 0, CC3D_B200_DEVICE, stream, &info, &S,
+                           /*inline_fallback=*/true);   // nothing synchronises here: the overflow fallback rides along
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (labels_first_plane) launch_write<uint32_t>(S, labels_first_plane, 0, sy, nullptr, 0, s);
@@ -721,7 +815,7 @@ int cc3d_b200_slab_begin(const void* in, int in_kind, int64_t sx, int64_t sy, in
   k_slab_facts<<<1, 1, 0, s>>>(S->ctr, S->epl_is_runs ? 1 : 0, (long long)sz, (long long*)facts);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { session_release_after(S, s); return fail(CC3D_B200_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)); }
   *session = S;
   return 0;
 }
@@ -741,6 +835,7 @@ int cc3d_b200_slab_finish(cc3d_b200_session* S, const void* remap, int remap_kin
     if (rc == 0 && cudaGetLastError() != cudaSuccess) rc = fail(CC3D_B200_ERR_CUDA, "slab_finish: launch failed");
   }
   arena_release_after(S->arena, s);
+  pinned_slot_give(S->hctr);   // nullptr for slab sessions
   delete S;
   return rc;
 }
@@ -797,6 +892,8 @@ int cc3d_b200_label_with_info(const void* in, int in_kind, int64_t sx, int64_t s
   }
   rc = write_impl(S, out, out_kind, mem_space, stream, 0, S->g.sy * S->g.sz, nullptr, 0, 0, false, false);
   if (rc == 0) rc = resolve_finish(S, (cudaStream_t)stream, info);
+  if (rc == 0 && S->redone)   // the edge queue overflowed: the labels written above predate the redo
+    rc = write_impl(S, out, out_kind, mem_space, stream, 0, S->g.sy * S->g.sz, nullptr, 0, 0, false, false);
   if (rc == 0 && ((out_kind == CC3D_B200_U16 && info->N > 0xFFFFull)))
     rc = fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind");
   cc3d_b200_session_release(S);
@@ -1179,7 +1276,7 @@ static void expand_mask_typed(const cc3d_b200_session* S, const IT* img, IT* out
   const Geom& g = S->g;
   const unsigned nchunks = (unsigned)((g.W + 31) / 32);
   const i64 nwarps = g.sy * g.sz * nchunks;
-  k_expand_mask<IT><<<(unsigned)((nwarps + 7) / 8), 256, 0, s>>>(S->L, S->M, img, out, g, nchunks, (u32)nwarps, keep);
+  k_expand_mask<IT><<<(unsigned)((nwarps + 7) / 8), 256, 0, s>>>(S->L, S->M, img, out, g, nchunks, (u32)nwarps, keep, S->lmask);
 }
 
 int cc3d_b200_dust(const void* img, void* out, int kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
@@ -1208,7 +1305,7 @@ int cc3d_b200_dust(const void* img, void* out, int kind, int64_t sx, int64_t sy,
   unsigned long long* dmasked = (unsigned long long*)ar.take(8);
   cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s);
   cudaMemsetAsync(dmasked, 0, 8, s);
-  k_run_counts<<<148 * 4, 256, 0, s>>>(S->L, S->M, S->g, counts);
+  k_run_counts<<<148 * 4, 256, 0, s>>>(S->L, S->M, S->g, counts, S->lmask);
   k_dust_keep<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(counts, keep, n, (long long)lo, (long long)hi, invert, dmasked);
   // host images are masked in place in their staged copy; device images go straight to `out` (which may be `img`)
   void* dout = mem_space == CC3D_B200_HOST ? const_cast<void*>(S->din) : out;

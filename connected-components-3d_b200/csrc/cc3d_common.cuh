@@ -85,13 +85,22 @@ struct Geom {
 #define CC_TILE_LQ 2048      // queue of tile-local edges (packed 16+16 bit local run ids)
 #define CC_TILE_GQ 1024      // staging buffer of edges that leave the tile (64-bit: two run ids)
 
-struct Counters {      // device-side results of a labelling pass
+// Device-side results of a labelling pass. The block is valid after being ZEROED (one memset clears it together with
+// the scan status words that follow it in memory), hence the encodings of the foreground row range.
+struct Counters {
   u64 epl;
-  i64 first_row;       // initialised to INT64_MAX
-  i64 last_row;        // initialised to -1
+  u64 first_inv;       // max over rows with foreground of ~row (0 = no foreground): first row = ~first_inv
+  u64 last_p1;         // max over rows with foreground of row + 1 (0 = none): last row = last_p1 - 1
   u64 N;
   u64 nruns;           // number of x-runs (scan S)
+  u32 gq_count;        // entries in the global edge queue (B1 -> B2)
+  u32 gq_ovf;          // the queue overflowed: the unions have to be redone on the global forest
+  u32 pad[2];
 };
+__device__ __forceinline__ void track_rows(Counters* c, u64 first_row, u64 last_row) {
+  atomicMax((unsigned long long*)&c->first_inv, (unsigned long long)~first_row);
+  atomicMax((unsigned long long*)&c->last_p1, (unsigned long long)(last_row + 1));
+}
 
 template <typename T> struct is_float_t { static constexpr bool value = false; };
 template <> struct is_float_t<float> { static constexpr bool value = true; };

@@ -18,6 +18,9 @@ struct LabelArgs {
   EdgeQueue GQ;      // edges that leave their union tile
   void (*mark)(const char*, cudaStream_t);  // optional timing hook (per-kernel CUDA events)
   int* launches;     // incremented once per kernel launch
+  bool inline_fallback;   // launch the overflow fallback kernel (k_union_global, a no-op unless the edge queue overflowed)
+                          // as part of the pipeline; false: the host checks the overflow flag at its next
+                          // synchronisation and redoes the unions (run_union_global_stage)
 };
 #define CC_QUEUE_BLOCKS (148 * 8)
 
@@ -36,6 +39,7 @@ struct PerDeviceOnce {
 template <typename T> int run_faces_stage(const LabelArgs& a);     // kernel A
 template <typename T> int run_union_stage(const LabelArgs& a);     // kernel B
 template <typename T> int run_periodic_stage(const LabelArgs& a);  // kernel P (after kernel B)
+template <typename T> int run_union_global_stage(const LabelArgs& a);   // every edge on the global forest (overflow redo)
 
 #ifdef CC3D_INSTANTIATE
 template <typename T, int MODE, int NW>
@@ -96,12 +100,17 @@ template <typename T> int run_faces_stage(const LabelArgs& a) {
 }
 
 template <typename T, int MODE, int CONN>
-static int launch_union(const LabelArgs& a) {
+static int launch_union(const LabelArgs& a, bool global_only = false) {
   Edge<T, MODE> E;
   memcpy(&E.delta, a.delta, sizeof(T));
   E.zeq = 0;
   const Geom& g = a.g;
   const T* in = static_cast<const T*>(a.in);
+  if (global_only) {
+    k_union_global<T, MODE, CONN><<<CC_QUEUE_BLOCKS, 256, 0, a.stream>>>(in, a.M, a.L, g, E, nullptr);
+    *a.launches += 1;
+    return 0;
+  }
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
   static PerDeviceOnce once;
   const bool set_attr = once.first();
@@ -121,35 +130,40 @@ static int launch_union(const LabelArgs& a) {
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);
   cc_launch(k_union_queue, dim3(CC_QUEUE_BLOCKS * 4), dim3(256), (size_t)(0), a.stream, a.L, a.GQ);
-  cc_launch(k_union_global<T, MODE, CONN>, dim3(CC_QUEUE_BLOCKS), dim3(256), (size_t)(0), a.stream, in, a.M, a.L, g, E, a.GQ.ovf);
+  *a.launches += 2;
+  if (a.inline_fallback) {
+    cc_launch(k_union_global<T, MODE, CONN>, dim3(CC_QUEUE_BLOCKS), dim3(256), (size_t)(0), a.stream, in, a.M, a.L, g, E, (const u32*)a.GQ.ovf);
+    *a.launches += 1;
+  }
   if (a.mark) a.mark("B2_union_queue", a.stream);
-  *a.launches += 3;
   return 0;
 }
 
 // Voxel values are only read for the diagonal candidates of EQ / DELTA with 8/18/26 neighbours; every
 // other configuration runs the uint8_t instantiation.
 template <typename T, int MODE>
-static int launch_union_conn(const LabelArgs& a) {
+static int launch_union_conn(const LabelArgs& a, bool global_only = false) {
   switch (a.connectivity) {
-    case 4: return launch_union<uint8_t, MODE == MODE_DELTA ? MODE_EQ : MODE, 4>(a);
-    case 6: return launch_union<uint8_t, MODE == MODE_DELTA ? MODE_EQ : MODE, 6>(a);
-    case 8: return launch_union<T, MODE, 8>(a);
-    case 18: return launch_union<T, MODE, 18>(a);
-    case 26: return launch_union<T, MODE, 26>(a);
+    case 4: return launch_union<uint8_t, MODE == MODE_DELTA ? MODE_EQ : MODE, 4>(a, global_only);
+    case 6: return launch_union<uint8_t, MODE == MODE_DELTA ? MODE_EQ : MODE, 6>(a, global_only);
+    case 8: return launch_union<T, MODE, 8>(a, global_only);
+    case 18: return launch_union<T, MODE, 18>(a, global_only);
+    case 26: return launch_union<T, MODE, 26>(a, global_only);
   }
   return -1;
 }
 
-template <typename T> int run_union_stage(const LabelArgs& a) {
+template <typename T> static int union_stage(const LabelArgs& a, bool global_only) {
   switch (a.mode) {
-    case MODE_EQ: return launch_union_conn<T, MODE_EQ>(a);
-    case MODE_NONZERO: return launch_union_conn<uint8_t, MODE_NONZERO>(a);
-    case MODE_DELTA: return launch_union_conn<T, MODE_DELTA>(a);
-    case MODE_MASK: return launch_union<uint8_t, MODE_MASK, 8>(a);
+    case MODE_EQ: return launch_union_conn<T, MODE_EQ>(a, global_only);
+    case MODE_NONZERO: return launch_union_conn<uint8_t, MODE_NONZERO>(a, global_only);
+    case MODE_DELTA: return launch_union_conn<T, MODE_DELTA>(a, global_only);
+    case MODE_MASK: return launch_union<uint8_t, MODE_MASK, 8>(a, global_only);
   }
   return -1;
 }
+template <typename T> int run_union_stage(const LabelArgs& a) { return union_stage<T>(a, false); }
+template <typename T> int run_union_global_stage(const LabelArgs& a) { return union_stage<T>(a, true); }
 
 template <typename T, int MODE, int CONN>
 static int launch_periodic(const LabelArgs& a) {

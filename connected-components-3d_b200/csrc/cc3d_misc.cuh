@@ -45,8 +45,7 @@ k_prepass(const T* __restrict__ in, Geom g, Counters* __restrict__ ctr, T* __res
   if (threadIdx.x == 0) {
     if (s_epl) {
       atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)s_epl);
-      atomicMin((long long*)&ctr->first_row, s_rmin);
-      atomicMax((long long*)&ctr->last_row, s_rmax);
+      track_rows(ctr, (u64)s_rmin, (u64)s_rmax);
     }
     T a = s_mn[0], b = s_mx[0];
     for (int k = 1; k < 8; k++) { if (s_mn[k] < a) a = s_mn[k]; if (s_mx[k] > b) b = s_mx[k]; }

@@ -74,8 +74,7 @@ k_scan_reduce(const u32* __restrict__ cnt, u64* __restrict__ bsum, i64 n_host, c
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_min != 0xFFFFFFFFu) {
-      atomicMin((long long*)&track->first_row, (long long)(s_min / W));
-      atomicMax((long long*)&track->last_row, (long long)(s_max / W));
+      track_rows(track, (u64)(s_min / W), (u64)(s_max / W));
     }
   }
 }
@@ -246,8 +245,138 @@ k_scan_onepass(const u32* cnt, u32* prefix, unsigned long long* __restrict__ sta
     for (int k = 0; k < CC_SCAN_ITEMS; k++) { if (base + k < n) prefix[base + k] = ex; ex += v[k]; }
   }
   if (track && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) {
-    atomicMin((long long*)&track->first_row, (long long)(s_min / W));
-    atomicMax((long long*)&track->last_row, (long long)(s_max / W));
+    track_rows(track, (u64)(s_min / W), (u64)(s_max / W));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// C (fused): compress + scan of root flags + assign in ONE launch (replaces k_compress / k_scan_onepass / k_assign on
+// the label path). Chunks of CC_RANK_RUNS consecutive runs are handed out in order by a ticket (persistent CTAs):
+//   1. every run of the chunk is chased to its root (L1-cached loads; a stale parent is still an ancestor); root flags
+//      are balloted, 32 per word;
+//   2. the words' popcounts are scanned in the block; the chunk publishes its flags (GR), the chunk-relative prefix of
+//      every flag word (LP) and its aggregate, then looks back for its exclusive prefix (decoupled look-back,
+//      status[c] = flag << 32 | value as in k_scan_onepass) and publishes the inclusive one;
+//   3. every run gets the final label of its root, written in place as CC_LABEL_TAG | label. A root in the same chunk is
+//      ranked from shared memory; a root in an earlier chunk c' is either already tagged (its label is read directly)
+//      or ranked as inclusive(c'-1) + LP[word] + popc(GR[word] & bits below) - chunk c' has published both before its
+//      aggregate, and every chunk below ours has published its aggregate before our look-back could finish.
+// A chase that meets a tagged entry stops there: the tag carries the final label of the whole component. That is what
+// makes the in-place update safe while later chunks are still chasing through this chunk's runs.
+// Needs run ids and labels below 2^31 (the host falls back to the three-kernel path otherwise). Readers of L mask the
+// tag off (`lmask`). *total = number of components.
+// ---------------------------------------------------------------------------------------------
+#define CC_RANK_WORDS 256
+#define CC_RANK_RUNS (CC_RANK_WORDS * 32)
+#define CC_LABEL_TAG 0x80000000u
+
+__global__ void __launch_bounds__(256)
+k_rank(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ LP, unsigned long long* __restrict__ status, u32 nb_max,
+       const u64* __restrict__ n_dev, u64* __restrict__ total) {
+  CC_PDL_WAIT();
+  __shared__ u32 s_res[CC_RANK_RUNS];
+  __shared__ u32 s_mask[CC_RANK_WORDS], s_lp[CC_RANK_WORDS];
+  __shared__ u32 s_chunk, s_prev;
+  const u32 n = (u32)*n_dev;
+  const u32 nb = (n + CC_RANK_RUNS - 1) / CC_RANK_RUNS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = (u32)atomicAdd(&status[nb_max], 1ull);
+    __syncthreads();
+    const u32 chunk = s_chunk;
+    if (chunk >= nb) {
+      if (nb == 0 && chunk == 0 && threadIdx.x == 0) *total = 0;
+      return;
+    }
+    const u32 base = chunk * CC_RANK_RUNS;
+    // ---- 1. roots ----
+    u32 mymask = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) {
+      const u32 li = ((u32)(warp * 32 + j) << 5) + lane;
+      const u32 i = base + li;
+      u32 res = CC_LABEL_TAG;       // beyond the last run: label 0, never read
+      bool isroot = false;
+      if (i < n) {
+        u32 r = i;
+        while (true) {
+          const u32 p = __ldca(&L[r]);
+          if (p & CC_LABEL_TAG) { res = p; break; }
+          if (p == r) { res = r; isroot = (r == i); break; }
+          r = p;
+        }
+      }
+      s_res[li] = res;
+      const u32 m = __ballot_sync(CC_FULL, isroot);
+      if (lane == j) mymask = m;
+    }
+    // ---- 2. scan ----
+    u32 tot;
+    const u32 lp = block_exclusive_scan((u32)__popc(mymask), &tot);
+    s_mask[threadIdx.x] = mymask; s_lp[threadIdx.x] = lp;
+    const u32 gw = (base >> 5) + threadIdx.x;
+    if ((gw << 5) < n) { GR[gw] = mymask; LP[gw] = lp; }
+    __syncthreads();
+    if (warp == 0) {
+      u32 prev = 0;
+      if (chunk > 0) {
+        if (lane == 0) { __threadfence(); atomicExch(&status[chunk], CC_SCAN_FLAG_A | tot); }
+        i64 idx = (i64)chunk - 1;
+        while (true) {
+          const i64 j = idx - lane;
+          unsigned long long st = CC_SCAN_FLAG_P;   // before chunk 0: prefix 0
+          if (j >= 0) { do { st = *(volatile unsigned long long*)&status[j]; } while ((st >> 32) == 0); }
+          const u32 isp = __ballot_sync(CC_FULL, (st >> 32) == 2);
+          const int stop = isp ? (__ffs(isp) - 1) : 32;
+          const u32 part = lane <= stop ? (u32)st : 0u;
+          prev += __reduce_add_sync(CC_FULL, part);
+          if (isp) break;
+          idx -= 32;
+        }
+      }
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&status[chunk], CC_SCAN_FLAG_P | (unsigned long long)(prev + tot));
+        s_prev = prev;
+        if (chunk == nb - 1) *total = (u64)prev + tot;
+      }
+    }
+    __syncthreads();
+    __threadfence();    // acquire side of the look-back: GR / LP of the chunks below are visible from here on
+    const u32 prev = s_prev;
+    // ---- 3. labels ----
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) {
+      const u32 li = ((u32)(warp * 32 + j) << 5) + lane;
+      const u32 i = base + li;
+      if (i >= n) continue;
+      u32 lab = s_res[li];
+      if (!(lab & CC_LABEL_TAG)) {
+        const u32 r = lab;
+        const u32 below = (1u << (r & 31)) - 1u;
+        if (r >= base) {
+          const u32 lw = (r - base) >> 5;
+          lab = prev + s_lp[lw] + __popc(s_mask[lw] & below) + 1u;
+        } else {
+          const u32 q = __ldcg(&L[r]);
+          if (q & CC_LABEL_TAG) lab = q;
+          else {
+            const u32 cr = r / CC_RANK_RUNS;
+            u32 pb = 0;
+            if (cr > 0) {
+              unsigned long long st;
+              do { st = *(volatile unsigned long long*)&status[cr - 1]; } while ((st >> 32) != 2);
+              pb = (u32)st;
+            }
+            lab = pb + __ldcg(&LP[r >> 5]) + __popc(__ldcg(&GR[r >> 5]) & below) + 1u;
+          }
+        }
+        lab |= CC_LABEL_TAG;
+      }
+      L[i] = lab;
+    }
   }
 }
 
@@ -276,7 +405,7 @@ k_assign(u32* __restrict__ L, const u32* __restrict__ GR, const u32* __restrict_
 template <typename OUT, int REMAP>
 __global__ void __launch_bounds__(256)
 k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__ out, Geom g, unsigned nchunks,
-         u32 row0, u32 nwarps_total, const void* __restrict__ remap) {
+         u32 row0, u32 nwarps_total, const void* __restrict__ remap, u32 lmask) {
   __shared__ uint4 s_words[8][32];   // per warp: {F, run starts, id of the run that enters the word, -}
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -307,7 +436,7 @@ k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__
   auto label_of = [&](const uint4 wv) -> OUT {
     OUT v = 0;
     if (wv.x & bit) {
-      const u32 lab = L[wv.z + __popc(wv.y & below)];
+      const u32 lab = L[wv.z + __popc(wv.y & below)] & lmask;
       if (REMAP == 1) v = (OUT)__ldg(reinterpret_cast<const u32*>(remap) + lab);
       else if (REMAP == 2) v = (OUT)__ldg(reinterpret_cast<const u64*>(remap) + lab);
       else v = (OUT)lab;
@@ -329,7 +458,7 @@ k_expand(const u32* __restrict__ L, const u32* __restrict__ M, OUT* __restrict__
 // One thread per bitmap word: every piece of a run inside the word adds its length to its component's count
 // (per-CTA shared-memory hash table first, one global atomic per label and CTA).
 __global__ void __launch_bounds__(256)
-k_run_counts(const u32* __restrict__ L, const u32* __restrict__ M, Geom g, u32* __restrict__ counts) {
+k_run_counts(const u32* __restrict__ L, const u32* __restrict__ M, Geom g, u32* __restrict__ counts, u32 lmask) {
   __shared__ u32 s_key[CC_CNT_SLOTS], s_cnt[CC_CNT_SLOTS];
   for (int i = threadIdx.x; i < CC_CNT_SLOTS; i += blockDim.x) { s_key[i] = 0; s_cnt[i] = 0; }
   __syncthreads();
@@ -348,7 +477,7 @@ k_run_counts(const u32* __restrict__ L, const u32* __restrict__ M, Geom g, u32* 
       const int b = __ffs(starts) - 1; starts &= starts - 1;
       const u32 rest = b == 31 ? 0u : (stops >> (b + 1));
       const u32 len = rest ? (u32)__ffs(rest) : (u32)(32 - b);
-      const u32 lab = L[rid0 + __popc(runstarts & (CC_FULL >> (31 - b)))];
+      const u32 lab = L[rid0 + __popc(runstarts & (CC_FULL >> (31 - b)))] & lmask;
       u32 h = (lab * 2654435761u) >> 21;   // 11 bits
       bool done = false;
 #pragma unroll 1
@@ -389,7 +518,7 @@ k_dust_keep(const u32* __restrict__ counts, unsigned char* __restrict__ keep, u6
 template <typename IT>
 __global__ void __launch_bounds__(256)
 k_expand_mask(const u32* __restrict__ L, const u32* __restrict__ M, const IT* img, IT* out, Geom g, unsigned nchunks,
-              u32 nwarps_total, const unsigned char* __restrict__ keep) {
+              u32 nwarps_total, const unsigned char* __restrict__ keep, u32 lmask) {
   __shared__ uint4 s_words[8][32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -421,7 +550,7 @@ k_expand_mask(const u32* __restrict__ L, const u32* __restrict__ M, const IT* im
     const uint4 wv = s_words[warp][j];
     const IT v = img[base + (j << 5)];
     bool k = false;
-    if (wv.x & bit) k = keep[L[wv.z + __popc(wv.y & below)]] != 0;
+    if (wv.x & bit) k = keep[L[wv.z + __popc(wv.y & below)] & lmask] != 0;
     out[base + (j << 5)] = k ? v : (IT)0;
   }
 }

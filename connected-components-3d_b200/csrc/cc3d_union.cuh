@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(256)
 k_union_global(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
                const u32* __restrict__ ovf) {
   CC_PDL_WAIT();
-  if (*ovf == 0) return;
+  if (ovf && *ovf == 0) return;     // ovf == nullptr: unconditional (host-driven redo after an overflow)
   const u32 W = (u32)g.W, sy = (u32)g.sy;
   WordEdges<T, MODE, CONN> we(in, M, g, E);
   auto unite = [&](u32 gp, u32 gq_, int, int, u32) { uf_union_h(L, gp, gq_); };

@@ -5,3 +5,4 @@
 template int run_faces_stage<float>(const LabelArgs&);
 template int run_union_stage<float>(const LabelArgs&);
 template int run_periodic_stage<float>(const LabelArgs&);
+template int run_union_global_stage<float>(const LabelArgs&);

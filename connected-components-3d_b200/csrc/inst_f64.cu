@@ -5,3 +5,4 @@
 template int run_faces_stage<double>(const LabelArgs&);
 template int run_union_stage<double>(const LabelArgs&);
 template int run_periodic_stage<double>(const LabelArgs&);
+template int run_union_global_stage<double>(const LabelArgs&);

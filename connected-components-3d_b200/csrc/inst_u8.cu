@@ -5,3 +5,4 @@
 template int run_faces_stage<uint8_t>(const LabelArgs&);
 template int run_union_stage<uint8_t>(const LabelArgs&);
 template int run_periodic_stage<uint8_t>(const LabelArgs&);
+template int run_union_global_stage<uint8_t>(const LabelArgs&);

@@ -273,9 +273,16 @@ def test_stack_streaming_equals_monolithic_labelling():
   n = 0
   for vol, images, kw in _stack_cases():
     want, Nw = oracle.connected_components(np.asfortranarray(vol), return_N=True, **kw)
-    got, N = sharded.connected_components_stack(iter(images), return_N=True, backend=backend, **kw)
+    got, N = sharded.connected_components_stack(iter(images), return_N=True, backend=backend, order="F", **kw)
     assert N == Nw and got.dtype == want.dtype and got.shape == want.shape and got.flags.f_contiguous, kw
     assert np.array_equal(got, want), kw
+    # default: the result's memory order follows the first image; scratch_dir spills the local labels to memmaps
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+      got_k = sharded.connected_components_stack(iter(images), backend=backend, scratch_dir=td, **kw)
+      assert os.listdir(td) == []
+    first = next(im for im in images if im.size)
+    assert got_k.flags.f_contiguous == bool(first.flags.f_contiguous) and np.array_equal(got_k, want), kw
     mm = np.zeros(want.shape, dtype=np.uint64, order="F")
     res = sharded.connected_components_stack(images, out_dtype=np.uint64, out=mm, backend=backend, **kw)
     assert res is mm and np.array_equal(mm, want)

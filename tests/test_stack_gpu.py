@@ -14,8 +14,11 @@ def test_stack_equals_monolithic_small(cc3d, oracle_mod):
   n = 0
   for vol, images, kw in _stack_cases():
     want, Nw = oracle_mod.connected_components(np.asfortranarray(vol), return_N=True, **kw)
-    got, N = cc3d.connected_components_stack(iter(images), return_N=True, **kw)
+    got, N = cc3d.connected_components_stack(iter(images), return_N=True, order="F", **kw)
     assert N == Nw and got.dtype == want.dtype and got.shape == want.shape and got.flags.f_contiguous, kw
+    got_k = cc3d.connected_components_stack(iter(images), **kw)        # memory order follows the first image
+    first = next(im for im in images if im.size)
+    assert got_k.flags.f_contiguous == bool(first.flags.f_contiguous) and np.array_equal(got_k, want), kw
     assert np.array_equal(got, want), kw
     mono, Nm = cc3d.connected_components(np.asfortranarray(vol), return_N=True, **kw)
     assert Nm == N and np.array_equal(mono, got)
