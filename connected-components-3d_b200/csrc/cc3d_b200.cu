@@ -174,12 +174,12 @@ Geom make_geom(i64 sx, i64 sy, i64 sz) {
   g.offRS = 4 * g.nwords;
   g.offA0 = g.offRS + pad4(g.nwords + 1);
   g.offC0 = g.offA0 + pad4(g.nwords);
-  // union tile: 512 words = 2^tw words x 2^ty rows x 2^tz planes
+  // union tile: CC_TILE_WORDS words = 2^tw words x 2^ty rows x 2^tz planes
   int tw = 0;
   while (tw < 4 && (i64(1) << tw) < g.W) tw++;
   g.tw = tw;
   g.tz = sz > 1 ? 2 : 0;
-  g.ty = 9 - g.tw - g.tz;
+  g.ty = CC_TILE_LOG - g.tw - g.tz;
   return g;
 }
 size_t bitmap_words(const Geom& g, bool with_diagonals) {

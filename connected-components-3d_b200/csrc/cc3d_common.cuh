@@ -80,10 +80,18 @@ struct Geom {
   i64 offRS, offA0, offC0;   // word offsets into M
   int tw, ty, tz;  // log2 of the union tile extent in words (x), rows (y) and planes (z); tw+ty+tz = 9
 };
-#define CC_TILE_WORDS 512
+#ifndef CC_TILE_LOG
+#define CC_TILE_LOG 9        // log2 of the words of a union tile (tw + ty + tz)
+#endif
+#define CC_TILE_WORDS (1 << CC_TILE_LOG)
+#ifndef CC_TILE_THREADS
+#define CC_TILE_THREADS (CC_TILE_WORDS / 2)
+#endif
 #define CC_TILE_NODES (CC_TILE_WORDS * 16)   // shared-memory forest: 16 runs per word (the binary maximum)
-#define CC_TILE_LQ 2048      // queue of tile-local edges (packed 16+16 bit local run ids)
-#define CC_TILE_GQ 1024      // staging buffer of edges that leave the tile (64-bit: two run ids)
+#define CC_TILE_LQ (CC_TILE_WORDS * 4)       // queue of tile-local edges (packed 16+16 bit local run ids)
+#define CC_TILE_GQ (CC_TILE_WORDS * 2)       // staging buffer of edges that leave the tile (64-bit: two run ids)
+#define CC_TILE_GQ_EQ CC_TILE_WORDS          // ... for multilabel volumes (fewer edges leave a tile)
+#define CC_TILE_MINB(n) ((n) * 256 / CC_TILE_THREADS)
 
 // Device-side results of a labelling pass. The block is valid after being ZEROED (one memset clears it together with
 // the scan status words that follow it in memory), hence the encodings of the foreground row range.

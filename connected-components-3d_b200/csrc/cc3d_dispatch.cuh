@@ -2,6 +2,7 @@
 // P: periodic wrap) for one element type. Each inst_<T>.cu instantiates run_*_stage<T> so that the
 // template matrix (6 types x predicates x connectivities) compiles in parallel.
 #pragma once
+#include <cstdlib>
 #include "cc3d_faces.cuh"
 #include "cc3d_union.cuh"
 
@@ -59,6 +60,63 @@ static void launch_faces_staged(const LabelArgs& a, const Edge<T, MODE>& E, bool
   else cc_launch(k_faces_async<T, MODE, true, NW>, dim3(blocks), dim3(CC_FACE_WARPS * 32), (size_t)(smem), a.stream, in, a.M, g, E, a.ctr, nych, nwg, (unsigned)ntasks);
 }
 
+
+// ---- tensor map of the input volume for k_faces_tma (driver entry point fetched through the runtime: no -lcuda) ----
+typedef CUresult (*cc_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cc_tmap_encode_fn cc_tmap_encoder() {
+  static cc_tmap_encode_fn fn = []() -> cc_tmap_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (cc_tmap_encode_fn)p;
+  }();
+  return fn;
+}
+
+// true when the TMA kernel was launched
+template <typename T, int MODE>
+static bool launch_faces_tma(const LabelArgs& a, const Edge<T, MODE>& E, bool two_d) {
+  typedef FaceTma<T> F;
+  const Geom& g = a.g;
+  const size_t es = sizeof(T);
+  if (es > 4 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || ((size_t)g.sx * es) % 16 != 0) return false;
+  if (getenv("CC3D_B200_NO_TMA")) return false;
+  cc_tmap_encode_fn enc = cc_tmap_encoder();
+  if (!enc) return false;
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.sx, (cuuint64_t)g.sy, (cuuint64_t)g.sz};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.sx * es, (cuuint64_t)g.sx * (cuuint64_t)g.sy * es};
+  const cuuint32_t box[3] = {(cuuint32_t)F::BOXX, (cuuint32_t)(F::TR + 1), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
+  if (strides[1] >= (1ull << 40)) return false;
+  if (enc(&map, dt, 3, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  const unsigned nwg = (unsigned)((g.W + F::NW - 1) / F::NW);
+  const unsigned nyb = (unsigned)((g.sy + F::TR - 1) / F::TR);
+  // z chunks: enough warps to fill the machine several times over, long enough to amortise the z - 1 halo plane
+  unsigned zchunk = 16;
+  while (zchunk > 2 && (i64)nwg * nyb * ((g.sz + zchunk - 1) / zchunk) < 148 * 24 * 4) zchunk >>= 1;
+  const unsigned nzc = (unsigned)((g.sz + zchunk - 1) / zchunk);
+  const i64 ntasks = (i64)nwg * nyb * nzc;
+  if (ntasks >= (i64(1) << 31)) return false;
+  const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
+  constexpr size_t smem = F::smem();
+  static PerDeviceOnce once;
+  if (once.first()) {
+    cudaFuncSetAttribute(k_faces_tma<T, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_faces_tma<T, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if (two_d) cc_launch(k_faces_tma<T, MODE, false>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
+  else cc_launch(k_faces_tma<T, MODE, true>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
+  return true;
+}
+
 template <typename T, int MODE>
 static int launch_faces(const LabelArgs& a) {
   Edge<T, MODE> E;
@@ -69,6 +127,10 @@ static int launch_faces(const LabelArgs& a) {
   if (two_d && g.sz != 1) return -1;
   const unsigned nych = (unsigned)((g.sy + CC_FACE_YCH - 1) / CC_FACE_YCH);
   const T* in = static_cast<const T*>(a.in);
+  // TMA variant (tensor-map bulk copies): <= 4-byte elements, 16-byte aligned base and rows; any sx / sy / sz
+  if constexpr (sizeof(T) <= 4) {
+    if (launch_faces_tma<T, MODE>(a, E, two_d)) { ++*a.launches; return 0; }
+  }
   // staged (cp.async) variants: every group of NW words lies inside the row and every row is 16-byte aligned
   bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
 #ifdef CC_FACES_NO_ASYNC
@@ -118,15 +180,15 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
     // continuous predicate: edge-parallel item lists (every word has candidates that need a value test)
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cc_launch(k_union_tile_items<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(256), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    cc_launch(k_union_tile_items<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else if constexpr (MODE == MODE_NONZERO) {
     const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(256), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else {
     const size_t smem = (size_t)HybridQueues<MODE>::SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cc_launch(k_union_tile_hybrid<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(256), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    cc_launch(k_union_tile_hybrid<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);
   cc_launch(k_union_queue, dim3(CC_QUEUE_BLOCKS * 4), dim3(256), (size_t)(0), a.stream, a.L, a.GQ);

@@ -333,3 +333,155 @@ k_c8_edges(const T* __restrict__ in, u32* __restrict__ M, Geom g, T delta, const
     M[g.offRS + idx] = __popc(F & ~X);
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Kernel A, TMA variant (sm_100a data movement: cp.async.bulk.tensor + mbarrier; inputs of <= 4-byte elements whose
+// rows are 16-byte multiples). A warp owns CC_FACE_NW bitmap words in x and TR rows in y and WALKS DOWN z through a
+// chunk of planes. Per plane ONE tensor-map bulk copy (issued by lane 0, completion on a per-buffer mbarrier) brings
+// the box [x0 - pad, x0 + 128) x [y0 - 1, y0 + TR) of plane z into a ring of three shared-memory buffers:
+//   * the -x neighbour is the same row one element to the left (the box starts `pad` elements early),
+//   * the -y neighbour of the first row is the box's halo row, the others are the previous row (kept in registers),
+//   * the -z neighbour is the SAME position in the previous buffer of the ring - every voxel crosses L2 -> SM once
+//     (plus the one-row halo) instead of twice,
+//   * everything outside the volume (x = -1, y = -1, z = -1, the ragged end of a row or of a y block) is zero-filled by
+//     the TMA unit, i.e. background: no edge cases in the kernel, any sx / sy / sz.
+// No per-lane copy instructions remain on the MIO queue (the cp.async variant issued 2-3 LDGSTS per lane and row).
+// ---------------------------------------------------------------------------------------------
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+template <typename T> struct FaceTma {
+  static constexpr int NW = CC_FACE_NW;                          // words per row of the box
+  static constexpr int PAD = 16 / (int)sizeof(T);                // elements left of the group (16 bytes)
+  static constexpr int BOXX = NW * 32 + PAD;                     // box extent in x (elements)
+  static constexpr int TR = sizeof(T) == 1 ? 16 : (sizeof(T) == 2 ? 8 : 4);   // rows per warp and plane (~2.5 KB boxes)
+  static constexpr int PITCH = BOXX * (int)sizeof(T);            // bytes per box row
+  static constexpr int BOXB = PITCH * (TR + 1);                  // bytes per box
+  static constexpr int BUFB = (BOXB + 127) & ~127;               // 128-byte aligned ring slots
+  static constexpr int NBUF = 3;
+  static constexpr size_t smem() { return (size_t)CC_FACE_WARPS * (NBUF * BUFB) + CC_FACE_WARPS * NBUF * 8 + 128; }
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "WAIT_%=:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra DONE_%=;\n\t"
+    "bra WAIT_%=;\n\t"
+    "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1, int c2) {
+  asm volatile(
+    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+    ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(reinterpret_cast<unsigned long long>(map)),
+      "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <typename T, int MODE, bool HASZ>
+__global__ void __launch_bounds__(CC_FACE_WARPS * 32)
+k_faces_tma(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
+            unsigned nyb, unsigned nwg, unsigned zchunk, unsigned ntasks) {
+  typedef FaceTma<T> F;
+  constexpr int NW = F::NW, TR = F::TR, PAD = F::PAD;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // 128-byte aligned base (dynamic shared memory is only guaranteed 16-byte alignment)
+  unsigned char* base = tma_smem + ((128u - ((unsigned)__cvta_generic_to_shared(tma_smem) & 127u)) & 127u);
+  unsigned char* ring = base + (size_t)warp * (F::NBUF * F::BUFB);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + (size_t)CC_FACE_WARPS * (F::NBUF * F::BUFB)) + warp * F::NBUF;
+  if (lane == 0) {
+#pragma unroll
+    for (int b = 0; b < F::NBUF; b++) mbar_init(bars + b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  CC_PDL_WAIT();
+  const unsigned task = blockIdx.x * CC_FACE_WARPS + warp;
+  if (task >= ntasks) return;
+  const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
+  const u32 wg = task % nwg;
+  const u32 t = task / nwg;
+  const u32 yb = t % nyb, zc = t / nyb;
+  const u32 w0 = wg * NW, y0 = yb * TR;
+  const u32 z0 = zc * zchunk, z1 = min(sz, z0 + zchunk);
+  const int cx = (int)(w0 << 5) - PAD, cy = (int)y0 - 1;
+  const u32 nrow = min(sy, y0 + TR) - y0;
+  const u32 nw = min((u32)NW, W - w0);
+  const bool rs_vec = (W & 3) == 0 && nw == NW;
+  u32 epl = 0;
+
+  // it-th plane of the walk (it = 0: plane z0 - 1, only fetched for 3D connectivities) -> ring slot it % NBUF
+  auto issue = [&](u32 it) {
+    if (lane == 0) {
+      const u32 b = it % F::NBUF;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot was last READ through the generic proxy
+      mbar_expect_tx(bars + b, (unsigned)F::BOXB);
+      tma_load_3d(ring + b * F::BUFB, &tmap, bars + b, cx, cy, (int)(z0 + it) - 1);
+    }
+  };
+  if (HASZ) issue(0);
+  issue(1);
+  if (HASZ) mbar_wait(bars + 0, 0);
+  for (u32 z = z0; z < z1; z++) {
+    const u32 it = z - z0 + 1;
+    if (z + 1 < z1) issue(it + 1);          // slot of plane z - 2: every lane finished reading it before the __syncwarp below
+    mbar_wait(bars + it % F::NBUF, (it / F::NBUF) & 1u);
+    const unsigned char* cur = ring + (it % F::NBUF) * F::BUFB;
+    const unsigned char* prv = ring + ((it - 1) % F::NBUF) * F::BUFB;
+    const u32 row0 = z * sy + y0;
+    uint4* __restrict__ mq = reinterpret_cast<uint4*>(M) + ((size_t)row0 * W + w0);
+    u32* __restrict__ rs = M + g.offRS + ((size_t)row0 * W + w0);
+    T up[NW];
+    {
+      const T* h = reinterpret_cast<const T*>(cur) + PAD + lane;     // halo row y0 - 1
+#pragma unroll
+      for (int k = 0; k < NW; k++) up[k] = h[32 * k];
+    }
+    for (u32 r = 0; r < nrow; r++) {
+      const T* sc = reinterpret_cast<const T*>(cur + (size_t)(r + 1) * F::PITCH) + PAD + lane;
+      const T* sd = reinterpret_cast<const T*>(prv + (size_t)(r + 1) * F::PITCH) + PAD + lane;
+      T c[NW], l[NW], d[NW];
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        c[k] = sc[32 * k];
+        l[k] = sc[32 * k - 1];
+        d[k] = HASZ ? sd[32 * k] : (T)0;
+      }
+      if (nw == NW) {
+        faces_eval_store<T, MODE, HASZ, NW>(E, c, l, d, up, lane, mq, rs, rs_vec, epl);
+      } else {
+        // ragged last group of a row: the words beyond W are zero-filled background, only the real ones are stored
+        u32 Fw[NW], Xw[NW], Yw[NW], Zw[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+          const bool f = E.fg(c[k]);
+          Fw[k] = __ballot_sync(CC_FULL, f);
+          Xw[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
+          Yw[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
+          Zw[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], d[k])) : 0u;
+          if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < NW; k++)
+            if ((u32)k < nw) { mq[k] = make_uint4(Fw[k], Xw[k], Yw[k], Zw[k]); rs[k] = __popc(Fw[k] & ~Xw[k]); }
+        }
+      }
+      mq += W; rs += W;
+#pragma unroll
+      for (int k = 0; k < NW; k++) up[k] = c[k];
+    }
+    __syncwarp();
+  }
+  if constexpr (MODE != MODE_EQ) {
+    if (lane == 0 && epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)epl);
+  }
+}

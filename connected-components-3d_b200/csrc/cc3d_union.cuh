@@ -277,11 +277,11 @@ struct EdgeQueue { u64* q; u32* count; u32* ovf; u32 cap; };
 
 // (binary volumes; multilabel volumes run k_union_tile_hybrid below)
 template <int MODE> struct TileQueues {
-  static constexpr u32 GQ = MODE == MODE_EQ ? 512 : CC_TILE_GQ;
+  static constexpr u32 GQ = MODE == MODE_EQ ? CC_TILE_GQ_EQ : CC_TILE_GQ;
   static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2;
 };
 template <typename T, int MODE, int CONN>
-__global__ void __launch_bounds__(256, MODE == MODE_EQ ? 6 : 0)
+__global__ void __launch_bounds__(CC_TILE_THREADS, MODE == MODE_EQ ? CC_TILE_MINB(6) : 0)
 k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
   CC_PDL_WAIT();
@@ -324,7 +324,7 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
   __syncthreads();
   const bool tile_ok = s_big == 0;   // otherwise every edge of this tile goes to kernel B2
   // dense tiles enumerate 256 words at a time so that the edge queue is drained before it overflows
-  const u32 step = s_runs > CC_TILE_LQ / 2 ? 256u : (u32)CC_TILE_WORDS;
+  const u32 step = s_runs > CC_TILE_LQ / 2 ? (u32)(CC_TILE_WORDS / 2) : (u32)CC_TILE_WORDS;
 
   auto push_global = [&](u32 gp, u32 gq_) {
     const u32 pos = atomicAdd(GQ.count, 1u);
@@ -465,12 +465,12 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
 // lists would overflow. Label volumes are latency / barrier bound here: six resident CTAs per SM (40 registers, a
 // 512-entry staging buffer) hide more of it.
 template <int MODE> struct HybridQueues {
-  static constexpr u32 GQ = MODE == MODE_EQ ? 512 : CC_TILE_GQ;
+  static constexpr u32 GQ = MODE == MODE_EQ ? CC_TILE_GQ_EQ : CC_TILE_GQ;
   static constexpr bool ITEMS = true;
   static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2 + (ITEMS ? 2 * CC_TILE_WORDS : 0);
 };
 template <typename T, int MODE, int CONN>
-__global__ void __launch_bounds__(256, MODE == MODE_EQ ? 6 : 0)
+__global__ void __launch_bounds__(CC_TILE_THREADS, MODE == MODE_EQ ? CC_TILE_MINB(6) : 0)
 k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
   CC_PDL_WAIT();
@@ -516,7 +516,7 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
   __syncthreads();
   const bool tile_ok = s_big == 0;   // otherwise every edge of this tile goes to kernel B2
   // dense tiles enumerate 256 words at a time so that the edge queue is drained before it overflows
-  const u32 step = s_runs > CC_TILE_LQ / 2 ? 256u : (u32)CC_TILE_WORDS;
+  const u32 step = s_runs > CC_TILE_LQ / 2 ? (u32)(CC_TILE_WORDS / 2) : (u32)CC_TILE_WORDS;
 
   auto push_global = [&](u32 gp, u32 gq_) {
     const u32 pos = atomicAdd(GQ.count, 1u);
@@ -797,11 +797,11 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
 // A tile whose rows hold more than 16 runs per word (possible for multilabel input only) sends all its
 // edges to B2. If GQ overflows, *ovf is raised and kernel B2s redoes every edge on the global forest.
 // ---------------------------------------------------------------------------------------------
-#define CC_TILE_ITEMS 4096    // work items per enumerate step (256 words)
+#define CC_TILE_ITEMS (CC_TILE_WORDS * 8)    // work items per enumerate step (one word per thread)
 #define CC_TILE_SMEM_WORDS (CC_TILE_NODES / 2 + CC_TILE_ITEMS + 2 * CC_TILE_GQ + 3 * CC_TILE_WORDS + CC_TILE_WORDS / 2)
 
 template <typename T, int MODE, int CONN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CC_TILE_THREADS)
 k_union_tile_items(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
   CC_PDL_WAIT();
