@@ -64,5 +64,31 @@ def build(force=False, verbose=False):
   return OUT
 
 
+def build_binding(force=False):
+  """The compiled Cython boundary cc3d_b200/fastcc3d.pyx -> cc3d_b200/fastcc3d<EXT_SUFFIX> (cdef extern from
+  include/cc3d_b200.h, linked against libcc3d_b200.so next to it through an $ORIGIN rpath)."""
+  import sysconfig
+  pkg = os.path.join(HERE, "cc3d_b200")
+  pyx = os.path.join(pkg, "fastcc3d.pyx")
+  out = os.path.join(pkg, "fastcc3d" + sysconfig.get_config_var("EXT_SUFFIX"))
+  hdr = os.path.join(HERE, "..", "include", "cc3d_b200.h")
+  lib = os.path.join(pkg, "libcc3d_b200.so")
+  if not force and not _stale(out, [pyx, hdr]) and os.path.getmtime(out) >= os.path.getmtime(pyx):
+    return out
+  os.makedirs(OBJ, exist_ok=True)
+  cpp = os.path.join(OBJ, "fastcc3d.cpp")
+  r = subprocess.run([sys.executable, "-m", "cython", "-3", "--cplus", pyx, "-o", cpp], capture_output=True, text=True)
+  if r.returncode != 0:
+    raise RuntimeError(f"cython failed:\n{r.stdout}\n{r.stderr}")
+  cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I", os.path.join(HERE, "..", "include"),
+         "-I", sysconfig.get_paths()["include"], cpp, "-o", out, "-L", pkg, "-l:libcc3d_b200.so", "-Wl,-rpath,$ORIGIN"]
+  r = subprocess.run(cmd, capture_output=True, text=True)
+  if r.returncode != 0:
+    raise RuntimeError(f"g++ failed for the Cython binding:\n{r.stdout}\n{r.stderr}")
+  return out
+
+
 if __name__ == "__main__":
   print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+  if not TAG:
+    print(build_binding(force="--force" in sys.argv))

@@ -1355,4 +1355,7 @@ def connected_components_stack(stacked_images, connectivity: int = 26, return_N:
                 out_dtype=out_dtype, out=out, scratch_dir=scratch_dir, order=order)
 
 
-from . import fastcc3d  # noqa: E402  (namespace alias: the reference exposes runs / draw as cc3d.fastcc3d.*)
+try:   # the compiled Cython boundary (fastcc3d.pyx, built by build.py); also gives cc3d.fastcc3d.runs / draw like the reference
+  from . import fastcc3d  # noqa: E402
+except ImportError:   # not built yet: everything else works through ctypes on the same C-ABI
+  fastcc3d = None

@@ -75,3 +75,30 @@ def test_no_cpu_fallback_without_gpu(cc3d):
     pass
   with pytest.raises(cc3d.CC3DB200Error):
     cc3d.connected_components(np.ones((4, 4, 4), np.uint8))
+
+
+def test_compiled_cython_binding_loads_and_validates():
+  """The Cython boundary (cc3d_b200/fastcc3d.pyx) is compiled by build(), binds the C-ABI through
+  `cdef extern from "cc3d_b200.h"` and keeps the reference's argument validation (no compute without a GPU)."""
+  import numpy as np
+  import pytest
+  import cc3d_b200
+  fc = cc3d_b200.fastcc3d
+  assert fc is not None, "cc3d_b200/fastcc3d extension not built (python connected-components-3d_b200/build.py)"
+  assert fc.__file__.endswith(".so") and "sm_100a" in fc.version()
+  src = open(os.path.join(os.path.dirname(cc3d_b200.__file__), "fastcc3d.pyx")).read()
+  assert 'cdef extern from "cc3d_b200.h"' in src
+  for name in ("connected_components", "statistics", "estimate_provisional_labels", "runs", "draw", "erase", "DimensionError"):
+    assert hasattr(fc, name), name
+  x = np.ones((4, 4, 4), np.uint8)
+  with pytest.raises(ValueError, match="Only 6, 18, and 26 connectivities are supported for 3D images"):
+    fc.connected_components(x, connectivity=5)
+  with pytest.raises(ValueError, match="periodic_boundary is not yet implemented for 26-connectivity"):
+    fc.connected_components(x, connectivity=26, periodic_boundary=True)
+  with pytest.raises(fc.DimensionError):
+    fc.connected_components(np.ones((2, 2, 2, 2), np.uint8))
+  with pytest.raises(TypeError):
+    fc.connected_components(np.ones((4, 4), np.float16), delta=1)
+  out, N = fc.connected_components(np.zeros((0, 0, 0), np.uint32), return_N=True)      # empty: no GPU needed
+  assert N == 0 and out.size == 0
+  assert fc.statistics(np.zeros((0, 0), np.uint8)) == {"voxel_counts": None, "bounding_boxes": None, "centroids": None}

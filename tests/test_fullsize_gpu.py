@@ -272,3 +272,47 @@ def test_volumes_above_the_call_limit_are_split(cc3d, oracle_mod, monkeypatch):
     cc3d.connected_components(vol, connectivity=6, periodic_boundary=True)
   with pytest.raises(ValueError):
     cc3d.connected_components(vol.reshape(45 * 40, 35), connectivity=8)
+
+
+# ---- the compiled Cython boundary (cc3d_b200/fastcc3d.pyx over `cdef extern from "cc3d_b200.h"`) ----
+def test_compiled_cython_binding_matches_reference(cc3d, oracle_mod):
+  ref = _ref(oracle_mod)
+  fc = cc3d.fastcc3d
+  assert fc is not None and fc.__file__.endswith(".so")
+  rng = np.random.default_rng(41)
+  n = 0
+  for it in range(60):
+    dims = int(rng.integers(1, 4))
+    shape = tuple(int(rng.integers(1, 60)) for _ in range(dims))
+    dt = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int32, np.int64, np.float32, np.float64, bool, np.float16][it % 11]
+    x = (rng.random(shape) < 0.5) if dt == bool else np.repeat(rng.integers(0, 4, shape), 2, axis=0)[: shape[0]].astype(dt)
+    x = np.asarray(x, order="F" if it % 2 else "C")
+    conns = [4, 8, 6, 18, 26] if dims == 2 else [6, 18, 26]
+    c = int(conns[rng.integers(len(conns))])
+    kws = [dict(), dict(out_dtype=np.uint64)]
+    if c in (4, 8, 6):
+      kws.append(dict(periodic_boundary=True))
+    if dt not in (bool, np.float16):
+      kws.append(dict(delta=1))
+    fast = x.shape[0] if x.flags.f_contiguous else x.shape[-1]
+    for kw in kws:
+      if dt == bool and c == 8 and fast % 2:
+        continue   # defect D1
+      try:
+        want, Nw = ref.connected_components(x, connectivity=c, return_N=True, **kw)
+      except RuntimeError:
+        continue   # defect D3
+      got, N = fc.connected_components(x, connectivity=c, return_N=True, **kw)
+      assert_same_labels(want, Nw, got, N, f"binding {shape} {np.dtype(dt)} conn={c} {kw}")
+      a, b = fc.statistics(got), ref.statistics(want)
+      assert np.array_equal(a["voxel_counts"], b["voxel_counts"]) and a["bounding_boxes"] == b["bounding_boxes"]
+      assert np.array_equal(a["centroids"], b["centroids"], equal_nan=True)
+      n += 1
+    assert fc.estimate_provisional_labels(x) == ref.estimate_provisional_labels(x)
+  assert n > 120
+  # same error behaviour as the reference
+  for bad in (dict(connectivity=5), dict(connectivity=26, periodic_boundary=True), dict(out_dtype=np.uint8)):
+    with pytest.raises(ValueError):
+      ref.connected_components(np.ones((4, 4, 4), np.uint8), **bad)
+    with pytest.raises(ValueError):
+      fc.connected_components(np.ones((4, 4, 4), np.uint8), **bad)
