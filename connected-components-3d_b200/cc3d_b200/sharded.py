@@ -349,12 +349,19 @@ def _out_dtype_rule(out_dtype, epl_total, voxels_total, shape_total, binary_imag
 
 _FAST_PAIR_CAP = 8192   # face pairs per rank that travel with the single all-gather of the fast path
 _fast_cap_seen = {}     # (sy, sx, connectivity) -> capacity that was enough last time (avoids the retry on the next step)
+_LABEL_CAP0 = 1 << 20   # slab labels (sum over the slabs) the device merge workspace is sized for at first
+_label_cap_seen = {}    # device index -> capacity that was enough last time
+_merge_ws = {}          # device index -> (label_cap, uint8 workspace tensor)
+_pinned_small = {}      # (device index, world) -> pinned int64 landing buffer [5 + 4 * world]
 
 
 def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, out_dtype, group, rank, world):
-  """CUDA fast path of connected_components_slab: the whole step is enqueued on the current stream
-  (cc3d_b200_slab_begin / face_pairs_async / slab_finish, NCCL point-to-point + one all-gather) and the
-  host synchronises ONCE, to read the gathered facts and face pairs for the merge."""
+  """CUDA fast path of connected_components_slab. The WHOLE step is enqueued on the current stream without a host
+  synchronisation in the middle: cc3d_b200_slab_begin (local labelling + boundary-plane labels + facts), NCCL
+  point-to-point plane exchange, cc3d_b200_face_pairs_async, ONE all-gather of [facts | pairs], the slab merge ON THE
+  DEVICE (cc3d_b200_merge_slabs_device: union-find over the slab-label ids, remap table of this slab) and
+  cc3d_b200_slab_finish (final write through the remap table). The host synchronises once, at the END of the step,
+  to read N and the overflow flags (pairs / labels beyond the buffers: the step is repeated with larger ones, rare)."""
   import torch
   import torch.distributed as dist
   L = _lib.lib()
@@ -362,6 +369,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
   sz, sy, sx = slab.shape
   stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
   cap = _fast_cap_seen.get((sy, sx, connectivity), _FAST_PAIR_CAP)
+  label_cap = _label_cap_seen.get(dev.index, _LABEL_CAP0)
   import os, time
   prof = os.environ.get("CC3D_SHARDED_TIMING") is not None
   stamps, evs = [("start", time.perf_counter())], []
@@ -369,19 +377,35 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
     if prof:
       stamps.append((name, time.perf_counter()))
       e = torch.cuda.Event(enable_timing=True); e.record(); evs.append((name, e))
-  lap("t0")
-  top_labs = torch.empty((sy, sx), dtype=torch.int32, device=dev) if rank + 1 < world else None
-  bot_labs = torch.empty((sy, sx), dtype=torch.int32, device=dev) if rank > 0 else None
-  sess = ctypes.c_void_p()
-  buf = torch.zeros((4 + cap,), dtype=torch.int64, device=dev)      # [N, epl, sz, n_pairs, pairs...]
-  with torch.cuda.device(dev):
-    _lib.check(L.cc3d_b200_slab_begin(
-      slab.data_ptr(), kind, sx, sy, sz, int(connectivity), delta_arr.ctypes.data, int(binary_image), stream,
-      ctypes.byref(sess), bot_labs.data_ptr() if bot_labs is not None else None,
-      top_labs.data_ptr() if top_labs is not None else None, buf.data_ptr()))
-  lap("begin")
-  try:
-    while True:
+  # the out dtype is only known once epl of every slab is (fastcc3d.pyx:388-434): write uint32 (or the caller's choice)
+  # and convert afterwards in the rare cases where the rule picks another width - as the single-GPU device path does
+  guess = np.dtype(np.uint32)
+  if out_dtype is not None and np.dtype(out_dtype) in (np.uint16, np.uint32, np.uint64):
+    guess = np.dtype(out_dtype)
+  tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}
+  okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}
+  key = (dev.index, world)
+  if key not in _pinned_small:
+    _pinned_small[key] = torch.empty((5 + 4 * world,), dtype=torch.int64, pin_memory=True)
+  host = _pinned_small[key]
+  while True:
+    lap("t0")
+    ws_entry = _merge_ws.get(dev.index)
+    if ws_entry is None or ws_entry[0] != label_cap:
+      ws_entry = (label_cap, torch.empty((int(L.cc3d_b200_merge_workspace_bytes(label_cap)),), dtype=torch.uint8, device=dev))
+      _merge_ws[dev.index] = ws_entry
+    ws = ws_entry[1]
+    top_labs = torch.empty((sy, sx), dtype=torch.int32, device=dev) if rank + 1 < world else None
+    bot_labs = torch.empty((sy, sx), dtype=torch.int32, device=dev) if rank > 0 else None
+    sess = ctypes.c_void_p()
+    buf = torch.zeros((4 + cap,), dtype=torch.int64, device=dev)      # [N, epl, sz, n_pairs, pairs...]
+    with torch.cuda.device(dev):
+      _lib.check(L.cc3d_b200_slab_begin(
+        slab.data_ptr(), kind, sx, sy, sz, int(connectivity), delta_arr.ctypes.data, int(binary_image), stream,
+        ctypes.byref(sess), bot_labs.data_ptr() if bot_labs is not None else None,
+        top_labs.data_ptr() if top_labs is not None else None, buf.data_ptr()))
+    lap("begin")
+    try:
       if world > 1:
         top_vals = slab[sz - 1].view(torch.uint8)
         recv = _exchange_planes(dist, group, rank, world, [top_vals, top_labs] if top_labs is not None else [],
@@ -398,46 +422,55 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
         lap("all_gather")
       else:
         gathered = buf[None]
-      host = torch.empty(gathered.shape, dtype=torch.int64, pin_memory=True)
-      host.copy_(gathered, non_blocking=True)
-      lap("d2h")
-      torch.cuda.current_stream(dev).synchronize()          # the one host synchronisation of the step
+      remap_p, result_p = ctypes.c_void_p(), ctypes.c_void_p()
+      out = torch.empty((sz, sy, sx), dtype=tdt[guess], device=dev)
+      with torch.cuda.device(dev):
+        _lib.check(L.cc3d_b200_merge_slabs_device(gathered.data_ptr(), world, 4 + cap, rank, cap, ws.data_ptr(), label_cap,
+                                                  ctypes.byref(remap_p), ctypes.byref(result_p), stream))
+        lap("merge")
+        s2, sess = sess, None
+        _lib.check(L.cc3d_b200_slab_finish(s2, remap_p, _lib.U32, out.data_ptr(), okind[guess], stream))
+      lap("finish")
+      roff = result_p.value - ws.data_ptr()
+      host[:5].copy_(ws[roff:roff + 40].view(torch.int64), non_blocking=True)
+      host[5:].copy_(gathered[:, :4].reshape(-1) if world == 1 else gathered[:, :4].contiguous().view(-1), non_blocking=True)
+      torch.cuda.current_stream(dev).synchronize()          # the one host synchronisation, at the end of the step
       lap("sync")
-      facts = host.numpy()
-      counts = facts[:, 3]
-      if int(counts.max()) <= cap:
-        break
-      # rare: an interface has more pairs than fit; repeat the pair extraction with a larger buffer
-      cap = 1 << int(counts.max() - 1).bit_length()
-      _fast_cap_seen[(sy, sx, connectivity)] = cap
-      nbuf = torch.zeros((4 + cap,), dtype=torch.int64, device=dev)
-      nbuf[:3] = buf[:3]
-      buf = nbuf
-    sz_total = int(facts[:, 2].sum())
-    voxels_total = sz_total * sy * sx
-    epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
-    N_total, remap_np = _merge_fast_path(facts, counts, rank, world)
-    lap("merge")
-    out_dtype = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
-    if np.iinfo(out_dtype).max < N_total:
-      raise _lib.CC3DB200Error(-1, "N does not fit the requested output kind")
-    remap = torch.from_numpy(remap_np).pin_memory().to(dev, non_blocking=True)
-    tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}[out_dtype]
-    okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}[out_dtype]
-    out = torch.empty((sz, sy, sx), dtype=tdt, device=dev)
-    s2, sess = sess, None
-    with torch.cuda.device(dev):
-      _lib.check(L.cc3d_b200_slab_finish(s2, remap.data_ptr(), _lib.U64, out.data_ptr(), okind, stream))
-    lap("finish")
-    if prof and rank == int(os.environ.get("CC3D_SHARDED_TIMING") or 0):
-      torch.cuda.synchronize(dev)
-      host = " ".join(f"{n}={(t - stamps[i][1]) * 1e3:.3f}" for i, (n, t) in enumerate(stamps[1:]))
-      gpu = " ".join(f"{n}={evs[i][1].elapsed_time(e):.3f}" for i, (n, e) in enumerate(evs[1:]))
-      print(f"  [slab_fast rank {rank}] host ms: {host} | gpu ms: {gpu} | pairs {[int(c) for c in counts]}", flush=True)
-    return out, N_total
-  finally:
-    if sess is not None:
-      L.cc3d_b200_session_release(sess)
+    finally:
+      if sess is not None:
+        L.cc3d_b200_session_release(sess)
+    res = host[:5].numpy()
+    facts = host[5:].numpy().reshape(world, 4)
+    counts = facts[:, 3]
+    if int(res[1]) or int(res[2]):
+      # rare: more slab labels / face pairs than the buffers hold -> larger buffers, repeat the step
+      if int(res[1]):
+        label_cap = max(label_cap * 4, 1 << int(int(facts[:, 0].sum()) + 2).bit_length())
+        if label_cap > 0xFFFFFFFF:
+          raise _lib.CC3DB200Error(-5, "more than 2^32-2 slab labels")
+        _label_cap_seen[dev.index] = label_cap
+      if int(res[2]):
+        cap = 1 << int(int(counts.max()) - 1).bit_length()
+        _fast_cap_seen[(sy, sx, connectivity)] = cap
+      del out
+      continue
+    break
+  N_total = int(res[0])
+  sz_total = int(facts[:, 2].sum())
+  voxels_total = sz_total * sy * sx
+  epl_total = voxels_total if epl_skipped else int(facts[:, 1].sum())
+  final = _out_dtype_rule(out_dtype, epl_total, voxels_total, (sz_total, sy, sx), binary_image, connectivity)
+  if np.iinfo(final).max < N_total:
+    raise _lib.CC3DB200Error(-1, "N does not fit the requested output kind")
+  if final != guess:
+    signed = {2: torch.int16, 4: torch.int32, 8: torch.int64}
+    out = out.view(signed[guess.itemsize]).to(signed[final.itemsize]).view(tdt[final])
+  if prof and rank == int(os.environ.get("CC3D_SHARDED_TIMING") or 0):
+    torch.cuda.synchronize(dev)
+    hostt = " ".join(f"{n}={(t - stamps[i][1]) * 1e3:.3f}" for i, (n, t) in enumerate(stamps[1:]))
+    gpu = " ".join(f"{n}={evs[i][1].elapsed_time(e):.3f}" for i, (n, e) in enumerate(evs[1:]))
+    print(f"  [slab_fast rank {rank}] host ms: {hostt} | gpu ms: {gpu} | pairs {[int(c) for c in counts]}", flush=True)
+  return out, N_total
 
 
 def connected_components_slab(slab, connectivity: int = 26, return_N: bool = False, delta=0,

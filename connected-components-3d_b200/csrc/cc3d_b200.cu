@@ -2,6 +2,7 @@
 // No CPU fallback exists: every entry point runs CUDA kernels or fails with an error code.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -463,7 +464,8 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
 
   // fused rank kernel (C stage in one launch): run ids and labels must stay below 2^31, block-order numbering keeps
   // the three-kernel path
-  const bool fused_rank = !block_order && maxruns < (i64(1) << 31);
+  static const bool no_fused_rank = getenv("CC3D_B200_NO_FUSED_RANK") != nullptr;   // A/B switch
+  const bool fused_rank = !block_order && maxruns < (i64(1) << 31) && !no_fused_rank;
   const i64 nb_rank = (maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS;
   const i64 status2_words = (fused_rank ? nb_rank : nb2) + 2;
   // control block: Counters | scan-S status | C-stage status, zeroed by ONE memset per call
@@ -572,7 +574,7 @@ static void enqueue_rank_stage(cc3d_b200_session* S, cudaStream_t s, bool cleare
   if (S->lmask != 0xFFFFFFFFu) {
     const i64 nb_rank = std::max<i64>(1, (S->maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS);
     if (!cleared) cudaMemsetAsync(S->status2, 0, (size_t)S->status2_words * 8, s);
-    const unsigned grid = (unsigned)std::min<i64>(nb_rank, 148 * 6);
+    const unsigned grid = (unsigned)std::min<i64>(nb_rank, 148 * 8);
     cc_launch(k_rank, dim3(grid), dim3(256), 0, s, L, GR, prefix, (unsigned long long*)S->status2, (u32)nb_rank, &ctr->nruns, &ctr->N);
     g_launches += 1;
     mark("C_rank", s);
@@ -858,6 +860,56 @@ int cc3d_b200_face_pairs_async(const void* values_upper, const uint32_t* labels_
   const u32 *lP = labels_upper, *lQ = labels_lower;
   CC_KIND_SWITCH(in_kind, face_pairs_typed((const KT*)values_upper, lP, (const KT*)values_lower, lQ, sx, sy, connectivity, mode, delta, pairs, capacity, dcount, s));
   if (cudaGetLastError() != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, "face_pairs_async: launch failed");
+  return 0;
+}
+
+
+// ---- sharded volumes: slab merge on the device (enqueue-only; see cc3d_resolve.cuh) ----
+static size_t merge_ws_layout(uint64_t label_cap, size_t* o_remap, size_t* o_nr, size_t* o_cnt, size_t* o_prefix, size_t* o_status,
+                              size_t* o_result) {
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t words = (size_t)(label_cap / 32 + 2);
+  const size_t nb = (words + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  size_t off = up((size_t)label_cap * 4);          // parent
+  *o_remap = off;  off += up((size_t)label_cap * 4);
+  *o_nr = off;     off += up(words * 4);
+  *o_cnt = off;    off += up(words * 4);
+  *o_prefix = off; off += up(words * 4);
+  *o_status = off; off += up((nb + 2) * 8);
+  *o_result = off; off += 256;
+  return off;
+}
+size_t cc3d_b200_merge_workspace_bytes(uint64_t label_cap) {
+  size_t a, b, c, d, e, f;
+  return merge_ws_layout(label_cap, &a, &b, &c, &d, &e, &f);
+}
+
+int cc3d_b200_merge_slabs_device(const int64_t* gathered, int world, int64_t row_stride, int rank, uint64_t pair_cap,
+                                 void* workspace, uint64_t label_cap, uint32_t** remap, uint64_t** result, void* stream) {
+  if (!gathered || !workspace || !remap || !result || world <= 0 || world > CC_MERGE_MAX_WORLD || rank < 0 || rank >= world ||
+      row_stride < 4 + (int64_t)pair_cap || label_cap < 64 || label_cap > 0xFFFFFFFFull)
+    return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs_device: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t o_remap, o_nr, o_cnt, o_prefix, o_status, o_result;
+  merge_ws_layout(label_cap, &o_remap, &o_nr, &o_cnt, &o_prefix, &o_status, &o_result);
+  char* ws = (char*)workspace;
+  u32* parent = (u32*)ws;
+  u32* rm = (u32*)(ws + o_remap);
+  u32 *NR = (u32*)(ws + o_nr), *cnt = (u32*)(ws + o_cnt), *prefix = (u32*)(ws + o_prefix);
+  u64* status = (u64*)(ws + o_status);
+  unsigned long long* res = (unsigned long long*)(ws + o_result);
+  SlabRows f; f.rows = (const long long*)gathered; f.world = world; f.stride = row_stride;
+  const unsigned gb = 148 * 4;
+  k_merge_init<<<gb, 256, 0, s>>>(parent, f, label_cap, pair_cap, res);
+  k_merge_union<<<gb, 256, 0, s>>>(parent, f, label_cap, pair_cap);
+  k_merge_flags<<<gb, 256, 0, s>>>(parent, NR, cnt, res);
+  const i64 words = (i64)(label_cap / 32 + 2);
+  scan_counts(cnt, prefix, status, words, (const u64*)&res[3], 5, (u64*)&res[4], nullptr, s);
+  k_merge_remap<<<gb, 256, 0, s>>>(parent, NR, prefix, f, rank, rm, res);
+  g_launches += 4;
+  if (cudaGetLastError() != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, "merge_slabs_device: launch failed");
+  *remap = rm;
+  *result = (uint64_t*)res;
   return 0;
 }
 

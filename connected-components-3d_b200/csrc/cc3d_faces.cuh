@@ -353,11 +353,17 @@ template <typename T> struct FaceTma {
   static constexpr int NW = CC_FACE_NW;                          // words per row of the box
   static constexpr int PAD = 16 / (int)sizeof(T);                // elements left of the group (16 bytes)
   static constexpr int BOXX = NW * 32 + PAD;                     // box extent in x (elements)
-  static constexpr int TR = sizeof(T) == 1 ? 16 : (sizeof(T) == 2 ? 8 : 4);   // rows per warp and plane (~2.5 KB boxes)
+#ifndef CC_TMA_TR4
+#define CC_TMA_TR4 4
+#endif
+#ifndef CC_TMA_NBUF
+#define CC_TMA_NBUF 3
+#endif
+  static constexpr int TR = sizeof(T) == 1 ? 4 * CC_TMA_TR4 : (sizeof(T) == 2 ? 2 * CC_TMA_TR4 : CC_TMA_TR4);   // rows per warp and plane (~2.5 KB boxes)
   static constexpr int PITCH = BOXX * (int)sizeof(T);            // bytes per box row
   static constexpr int BOXB = PITCH * (TR + 1);                  // bytes per box
   static constexpr int BUFB = (BOXB + 127) & ~127;               // 128-byte aligned ring slots
-  static constexpr int NBUF = 3;
+  static constexpr int NBUF = CC_TMA_NBUF;     // ring slots: planes z - 1, z and NBUF - 2 planes in flight
   static constexpr size_t smem() { return (size_t)CC_FACE_WARPS * (NBUF * BUFB) + CC_FACE_WARPS * NBUF * 8 + 128; }
 };
 
@@ -427,12 +433,14 @@ k_faces_tma(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom 
       tma_load_3d(ring + b * F::BUFB, &tmap, bars + b, cx, cy, (int)(z0 + it) - 1);
     }
   };
+  constexpr u32 PD = F::NBUF - 2;            // planes in flight ahead of the one being evaluated
   if (HASZ) issue(0);
-  issue(1);
+#pragma unroll
+  for (u32 k = 0; k < PD; k++) if (z0 + k < z1) issue(1 + k);
   if (HASZ) mbar_wait(bars + 0, 0);
   for (u32 z = z0; z < z1; z++) {
     const u32 it = z - z0 + 1;
-    if (z + 1 < z1) issue(it + 1);          // slot of plane z - 2: every lane finished reading it before the __syncwarp below
+    if (z + PD < z1) issue(it + PD);        // slot of plane z - 2: every lane finished reading it before the __syncwarp below
     mbar_wait(bars + it % F::NBUF, (it / F::NBUF) & 1u);
     const unsigned char* cur = ring + (it % F::NBUF) * F::BUFB;
     const unsigned char* prv = ring + ((it - 1) % F::NBUF) * F::BUFB;

@@ -267,7 +267,9 @@ k_scan_onepass(const u32* cnt, u32* prefix, unsigned long long* __restrict__ sta
 // Needs run ids and labels below 2^31 (the host falls back to the three-kernel path otherwise). Readers of L mask the
 // tag off (`lmask`). *total = number of components.
 // ---------------------------------------------------------------------------------------------
-#define CC_RANK_WORDS 256
+#ifndef CC_RANK_WORDS
+#define CC_RANK_WORDS 32          // flag words (of 32 runs) per chunk: small chunks = short serial chains per CTA, many CTAs
+#endif
 #define CC_RANK_RUNS (CC_RANK_WORDS * 32)
 #define CC_LABEL_TAG 0x80000000u
 
@@ -292,10 +294,9 @@ k_rank(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ LP, unsigned
     }
     const u32 base = chunk * CC_RANK_RUNS;
     // ---- 1. roots ----
-    u32 mymask = 0;
 #pragma unroll 4
-    for (int j = 0; j < 32; j++) {
-      const u32 li = ((u32)(warp * 32 + j) << 5) + lane;
+    for (u32 j = warp; j < CC_RANK_WORDS; j += 8) {
+      const u32 li = (j << 5) + lane;
       const u32 i = base + li;
       u32 res = CC_LABEL_TAG;       // beyond the last run: label 0, never read
       bool isroot = false;
@@ -310,14 +311,18 @@ k_rank(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ LP, unsigned
       }
       s_res[li] = res;
       const u32 m = __ballot_sync(CC_FULL, isroot);
-      if (lane == j) mymask = m;
+      if (lane == 0) s_mask[j] = m;
     }
+    __syncthreads();
     // ---- 2. scan ----
     u32 tot;
+    const u32 mymask = threadIdx.x < CC_RANK_WORDS ? s_mask[threadIdx.x] : 0u;
     const u32 lp = block_exclusive_scan((u32)__popc(mymask), &tot);
-    s_mask[threadIdx.x] = mymask; s_lp[threadIdx.x] = lp;
-    const u32 gw = (base >> 5) + threadIdx.x;
-    if ((gw << 5) < n) { GR[gw] = mymask; LP[gw] = lp; }
+    if (threadIdx.x < CC_RANK_WORDS) {
+      s_lp[threadIdx.x] = lp;
+      const u32 gw = (base >> 5) + threadIdx.x;
+      if ((gw << 5) < n) { GR[gw] = mymask; LP[gw] = lp; }
+    }
     __syncthreads();
     if (warp == 0) {
       u32 prev = 0;
@@ -337,19 +342,18 @@ k_rank(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ LP, unsigned
         }
       }
       if (lane == 0) {
-        __threadfence();
+        __threadfence();      // release our GR / LP, acquire those of the chunks below (their flags were observed above)
         atomicExch(&status[chunk], CC_SCAN_FLAG_P | (unsigned long long)(prev + tot));
         s_prev = prev;
         if (chunk == nb - 1) *total = (u64)prev + tot;
       }
     }
     __syncthreads();
-    __threadfence();    // acquire side of the look-back: GR / LP of the chunks below are visible from here on
     const u32 prev = s_prev;
     // ---- 3. labels ----
 #pragma unroll 4
-    for (int j = 0; j < 32; j++) {
-      const u32 li = ((u32)(warp * 32 + j) << 5) + lane;
+    for (u32 j = warp; j < CC_RANK_WORDS; j += 8) {
+      const u32 li = (j << 5) + lane;
       const u32 i = base + li;
       if (i >= n) continue;
       u32 lab = s_res[li];
@@ -565,6 +569,11 @@ __global__ void __launch_bounds__(256)
 k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __restrict__ vQ, const u32* __restrict__ lQ,
              i64 sx, i64 sy, int connectivity, Edge<T, MODE> E, u64* __restrict__ pairs, unsigned long long cap,
              unsigned long long* __restrict__ count) {
+  // per-CTA direct-mapped cache of the pairs already emitted: an interface between two big components reports the same
+  // pair from thousands of voxels (a thread that finds its pair here skips it - the thread that stored it appends it)
+  __shared__ u64 s_seen[256];
+  s_seen[threadIdx.x] = ~0ull;
+  __syncthreads();
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   u64 mine[9];
@@ -598,7 +607,11 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
           if (left_same && xx > 0 && lQ[qi - 1] == lq && E(vP[i - 1], vQ[qi - 1])) continue;
           // ... or the voxel above
           if (up_same && yy > 0 && lQ[qi - sx] == lq && E(vP[i - sx], vQ[qi - sx])) continue;
-          mine[n++] = ((u64)lq << 32) | lp;
+          const u64 v = ((u64)lq << 32) | lp;
+          const u32 slot = (u32)((v * 0x9E3779B97F4A7C15ull) >> 56);
+          if (*(volatile u64*)&s_seen[slot] == v) continue;
+          s_seen[slot] = v;
+          mine[n++] = v;
         }
       }
     }
@@ -617,6 +630,108 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
   const unsigned long long off = base + total - n;
   for (int k = 0; k < n; k++)
     if (off + k < cap) pairs[off + k] = mine[k];
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Sharded volumes: the slab merge ON THE DEVICE (replaces the host union-find of the first round and, with it, the
+// host synchronisation in the middle of a sharded step; the reference does this in Python, cc3d/__init__.py:296-321,
+// 425-492). Input = the all-gathered buffer: row r = [N_r, epl_r, sz_r, n_pairs_r, pairs...] (int64), pairs packed as
+// (label in slab r-1) << 32 | (label in slab r). Global id of (slab r, local label l >= 1) = off[r] + l with
+// off[r] = N_0 + ... + N_{r-1}: id order = first-appearance order of the whole volume, so with link-to-smaller unions
+// the root of a component is its first label, and
+//     final label of a root id = id - #(non-root ids below it),
+// i.e. its rank among the roots - no per-slab bookkeeping. Every rank runs the same kernels on the same gathered data
+// (redundantly, like the redundant host solve before) and writes only its own slab's remap table.
+// result[0] = N of the whole volume, result[1] = label capacity exceeded, result[2] = pair capacity exceeded,
+// result[3] = total + 1 (ids incl. 0), result[4] = number of non-root ids.
+// ---------------------------------------------------------------------------------------------
+struct SlabRows { const long long* rows; int world; long long stride; };
+#define CC_MERGE_MAX_WORLD 64
+
+__device__ __forceinline__ void slab_offsets(const SlabRows& f, u64* s_off) {   // s_off[world + 1], one CTA
+  if (threadIdx.x == 0) {
+    u64 acc = 0;
+    for (int r = 0; r < f.world; r++) { s_off[r] = acc; acc += (u64)f.rows[(size_t)r * f.stride]; }
+    s_off[f.world] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_merge_init(u32* __restrict__ parent, SlabRows f, u64 label_cap, u64 pair_cap, unsigned long long* __restrict__ result) {
+  __shared__ u64 s_off[CC_MERGE_MAX_WORLD + 1];
+  slab_offsets(f, s_off);
+  const u64 total = s_off[f.world];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    bool pov = false;
+    for (int r = 0; r < f.world; r++) pov |= (u64)f.rows[(size_t)r * f.stride + 3] > pair_cap;
+    result[0] = 0; result[1] = (total + 1 > label_cap) ? 1ull : 0ull; result[2] = pov ? 1ull : 0ull;
+    result[3] = (total + 1 > label_cap) ? 0ull : total + 1; result[4] = 0;
+  }
+  if (total + 1 > label_cap) return;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += (u64)gridDim.x * blockDim.x) parent[i] = (u32)i;
+}
+
+__global__ void __launch_bounds__(256)
+k_merge_union(u32* __restrict__ parent, SlabRows f, u64 label_cap, u64 pair_cap) {
+  __shared__ u64 s_off[CC_MERGE_MAX_WORLD + 1];
+  slab_offsets(f, s_off);
+  if (s_off[f.world] + 1 > label_cap) return;
+  const u64 nslots = (u64)f.world * pair_cap;
+  for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nslots; t += (u64)gridDim.x * blockDim.x) {
+    const int r = (int)(t / pair_cap);
+    const u64 k = t - (u64)r * pair_cap;
+    if (r == 0) continue;
+    const long long* row = f.rows + (size_t)r * f.stride;
+    if (k >= (u64)row[3]) continue;
+    const u64 v = (u64)row[4 + k];
+    const u64 lo = v >> 32, up = v & 0xFFFFFFFFull;
+    if (lo < 1 || up < 1 || lo > (u64)f.rows[(size_t)(r - 1) * f.stride] || up > (u64)row[0]) continue;   // malformed pair
+    uf_union(parent, (u32)(s_off[r - 1] + lo), (u32)(s_off[r] + up));
+  }
+}
+
+// one warp per 32 ids: every id is pointed at its root, non-root flags are balloted into NR, popcounts into cnt
+__global__ void __launch_bounds__(256)
+k_merge_flags(u32* __restrict__ parent, u32* __restrict__ NR, u32* __restrict__ cnt, const unsigned long long* __restrict__ result) {
+  const u64 n = result[3];             // total + 1 (0 when the label capacity was exceeded)
+  const u64 nwords = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 wd = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wd < nwords; wd += nwarps) {
+    const u64 i = (wd << 5) + lane;
+    bool nonroot = false;
+    if (i >= 1 && i < n) {
+      u32 r = (u32)i, p;
+      while ((p = __ldcg(&parent[r])) != r) r = p;
+      if (r != (u32)i) { parent[i] = r; nonroot = true; }
+    }
+    const u32 m = __ballot_sync(CC_FULL, nonroot);
+    if (lane == 0) { NR[wd] = m; cnt[wd] = __popc(m); }
+  }
+}
+
+// remap[l] = final label of local label l of slab `rank` (remap[0] = 0); result[0] = N of the whole volume
+__global__ void __launch_bounds__(256)
+k_merge_remap(const u32* __restrict__ parent, const u32* __restrict__ NR, const u32* __restrict__ prefix, SlabRows f, int rank,
+              u32* __restrict__ remap, unsigned long long* __restrict__ result) {
+  __shared__ u64 s_off[CC_MERGE_MAX_WORLD + 1];
+  slab_offsets(f, s_off);
+  const u64 n = result[3];
+  if (n == 0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) result[0] = (n - 1) - result[4];
+  const u64 off = s_off[rank], nl = (u64)f.rows[(size_t)rank * f.stride];
+  for (u64 l = (u64)blockIdx.x * blockDim.x + threadIdx.x; l <= nl; l += (u64)gridDim.x * blockDim.x) {
+    u32 out = 0;
+    if (l) {
+      u32 root = parent[off + l];
+      root = parent[root];     // k_merge_flags compresses concurrently: at most one more hop to the root
+      const u32 below = __ldg(&prefix[root >> 5]) + __popc(__ldg(&NR[root >> 5]) & ((1u << (root & 31)) - 1u));
+      out = root - below;
+    }
+    remap[l] = out;
+  }
 }
 
 // union-find over compact node ids (pairs given as two u32 arrays); parent must hold 0..n-1 on entry

@@ -124,6 +124,19 @@ int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, 
 int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* const* pairs, const int64_t* n_pairs,
                           int rank, int64_t* remap, int64_t* n_total);
 
+/* Slab merge ON THE DEVICE, enqueue-only (no host synchronisation; replaces the Python DisjointSet + renumber of
+ * connected_components_stack, cc3d/__init__.py:296-321, 425-492, and the host merge cc3d_b200_merge_slabs above).
+ * `gathered` (device) is the all-gathered buffer of the slab step: `world` rows of `row_stride` int64, row r =
+ * [N_r, epl_r, sz_r, n_pairs_r, pairs...], pairs packed as (label in slab r-1) << 32 | (label in slab r), at most
+ * `pair_cap` per row. `workspace` (device, >= cc3d_b200_merge_workspace_bytes(label_cap) bytes) holds the union-find
+ * over the slab-label ids (the sum of N_r must stay below label_cap). On return *remap points at the uint32 remap
+ * table of slab `rank` inside the workspace (remap[local label] = global label, remap[0] = 0; feed it to
+ * cc3d_b200_slab_finish) and *result at five device uint64: [0] N of the whole volume, [1] label_cap exceeded,
+ * [2] pair_cap exceeded (in either case the tables are invalid: grow the capacity and repeat the step), [3..4] internal. */
+size_t cc3d_b200_merge_workspace_bytes(uint64_t label_cap);
+int cc3d_b200_merge_slabs_device(const int64_t* gathered, int world, int64_t row_stride, int rank, uint64_t pair_cap,
+                                 void* workspace, uint64_t label_cap, uint32_t** remap, uint64_t** result, void* stream);
+
 /* Sharded fast path (one process per GPU, small slabs): the three calls below only ENQUEUE work on `stream`;
  * none of them synchronises, so a whole slab step needs one host synchronisation (after the all-gather of the
  * facts and face pairs). Device memory only.
