@@ -456,8 +456,14 @@ def _connected_components_split(src, on_device, is_torch, order, shape_in, sxyz,
 # ----------------------------------------------------------------------------------------------
 # statistics (fastcc3d.pyx:682-938)
 # ----------------------------------------------------------------------------------------------
+_stat_cap = {"host": 1 << 16}     # table capacity that was enough last time (per device / host)
+
+
 def _statistics_arrays(out_labels, N: Optional[int] = None):
-  """Raw per-label arrays in ARRAY axes: counts u32[N+1], bbox u32[N+1, 2*ndim], sums u64[N+1, ndim]."""
+  """Raw per-label arrays in ARRAY axes: counts u32[N+1], bbox u32[N+1, 2*ndim], sums u64[N+1, ndim], and N.
+  N = None: the largest label is found by the SAME sweep that accumulates the statistics (cc3d_b200_statistics_auto;
+  the reference runs np.max over the volume first, fastcc3d.pyx:713-720) - the tables are sized by the capacity that
+  was enough last time and the call is repeated once if the maximum turns out larger."""
   L = _lib.lib()
   ndim = out_labels.ndim
   shape3 = list(out_labels.shape) + [1] * (3 - ndim)
@@ -466,46 +472,86 @@ def _statistics_arrays(out_labels, N: Optional[int] = None):
     out_labels = np.ascontiguousarray(out_labels)
     forder = False
   mem = shape3 if forder else shape3[::-1]
+  kind = _kind_of(out_labels.dtype)
   if N is None:
-    N = int(np.max(out_labels))
-  counts = np.empty(N + 1, dtype=np.uint32)
-  bbox = np.empty((N + 1, 6), dtype=np.uint32)
-  sums = np.empty((N + 1, 3), dtype=np.uint64)
-  _lib.check(L.cc3d_b200_statistics(
-    out_labels.ctypes.data, _kind_of(out_labels.dtype), mem[0], mem[1], mem[2], N,
-    counts.ctypes.data, bbox.ctypes.data, sums.ctypes.data, _lib.HOST, None))
+    cap = max(2, min(_stat_cap["host"], out_labels.size + 1))
+    while True:
+      counts = np.empty(cap, dtype=np.uint32)
+      bbox = np.empty((cap, 6), dtype=np.uint32)
+      sums = np.empty((cap, 3), dtype=np.uint64)
+      mx = ctypes.c_uint64(0)
+      _lib.check(L.cc3d_b200_statistics_auto(
+        out_labels.ctypes.data, kind, mem[0], mem[1], mem[2], cap, ctypes.byref(mx),
+        counts.ctypes.data, bbox.ctypes.data, sums.ctypes.data, _lib.HOST, None))
+      N = int(mx.value)
+      if N < cap or N > out_labels.size:      # N > voxels: the caller raises, nothing to repeat
+        break
+      cap = 1 << (N + 1).bit_length()
+      _stat_cap["host"] = cap
+    if N > out_labels.size:
+      return None, None, None, N
+    counts, bbox, sums = counts[:N + 1], bbox[:N + 1], sums[:N + 1]
+  else:
+    counts = np.empty(N + 1, dtype=np.uint32)
+    bbox = np.empty((N + 1, 6), dtype=np.uint32)
+    sums = np.empty((N + 1, 3), dtype=np.uint64)
+    _lib.check(L.cc3d_b200_statistics(
+      out_labels.ctypes.data, kind, mem[0], mem[1], mem[2], N,
+      counts.ctypes.data, bbox.ctypes.data, sums.ctypes.data, _lib.HOST, None))
   if not forder:  # memory axes (x fastest) -> array axes
     sums = sums[:, ::-1]
     bbox = bbox.reshape(N + 1, 3, 2)[:, ::-1, :].reshape(N + 1, 6)
-  return counts, bbox[:, : 2 * ndim], sums[:, :ndim]
+  return counts, bbox[:, : 2 * ndim], sums[:, :ndim], N
 
 
-def _statistics_arrays_device(t, N: int):
-  """Same as _statistics_arrays for a CUDA tensor (labels stay on the device; only the per-label arrays
-  come back)."""
+def _statistics_arrays_device(t, N: Optional[int] = None):
+  """Same as _statistics_arrays for a CUDA tensor (labels stay on the device; only the per-label arrays come back:
+  one sweep, one synchronisation for the maximum, one copy of the first N + 1 table entries)."""
   import torch
   L = _lib.lib()
   t, order = _torch_order(t.detach())
   ndim = t.ndim
   shape3 = list(t.shape) + [1] * (3 - ndim)
   mem = shape3 if order == "F" else shape3[::-1]
-  # one device buffer for the three per-label arrays (sums | boxes | counts): one copy back, one synchronisation
-  n1 = N + 1
-  buf = torch.empty((n1 * 52,), dtype=torch.uint8, device=t.device)
-  p_sums, p_bbox, p_counts = buf.data_ptr(), buf.data_ptr() + n1 * 24, buf.data_ptr() + n1 * 48
+  kind = _kind_of(_torch_np_dtype(t))
   stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
-  with torch.cuda.device(t.device):
-    _lib.check(L.cc3d_b200_statistics(
-      t.data_ptr(), _kind_of(_torch_np_dtype(t)), mem[0], mem[1], mem[2], N,
-      p_counts, p_bbox, p_sums, _lib.DEVICE, stream))
-  host = buf.cpu().numpy()
-  sums = host[: n1 * 24].view(np.uint64).reshape(n1, 3)
-  bbox = host[n1 * 24: n1 * 48].view(np.uint32).reshape(n1, 6)
-  counts = host[n1 * 48:].view(np.uint32)
+  key = ("cuda", t.device.index)
+  auto = N is None
+  cap = max(2, min(_stat_cap.get(key, 1 << 16), t.numel() + 1)) if auto else N + 1
+  while True:
+    # one device buffer for the three per-label tables (sums | boxes | counts): one copy back
+    buf = torch.empty((cap * 52,), dtype=torch.uint8, device=t.device)
+    p_sums, p_bbox, p_counts = buf.data_ptr(), buf.data_ptr() + cap * 24, buf.data_ptr() + cap * 48
+    with torch.cuda.device(t.device):
+      if auto:
+        mx = ctypes.c_uint64(0)
+        _lib.check(L.cc3d_b200_statistics_auto(
+          t.data_ptr(), kind, mem[0], mem[1], mem[2], cap, ctypes.byref(mx), p_counts, p_bbox, p_sums, _lib.DEVICE, stream))
+        N = int(mx.value)
+      else:
+        _lib.check(L.cc3d_b200_statistics(
+          t.data_ptr(), kind, mem[0], mem[1], mem[2], N, p_counts, p_bbox, p_sums, _lib.DEVICE, stream))
+    if not auto or N < cap or N > t.numel():
+      break
+    cap = 1 << (N + 1).bit_length()
+    _stat_cap[key] = cap
+  if N > t.numel():
+    return None, None, None, N
+  n1 = N + 1
+  if n1 == cap:
+    host = buf.cpu().numpy()
+    sums = host[: n1 * 24].view(np.uint64).reshape(n1, 3)
+    bbox = host[cap * 24: cap * 24 + n1 * 24].view(np.uint32).reshape(n1, 6)
+    counts = host[cap * 48: cap * 48 + n1 * 4].view(np.uint32)
+  else:   # only the first N + 1 entries of every table cross PCIe
+    packed = torch.cat([buf[: n1 * 24], buf[cap * 24: cap * 24 + n1 * 24], buf[cap * 48: cap * 48 + n1 * 4]]).cpu().numpy()
+    sums = packed[: n1 * 24].view(np.uint64).reshape(n1, 3)
+    bbox = packed[n1 * 24: n1 * 48].view(np.uint32).reshape(n1, 6)
+    counts = packed[n1 * 48:].view(np.uint32)
   if order != "F":  # memory axes (x fastest) -> array axes
     sums = sums[:, ::-1]
     bbox = bbox.reshape(N + 1, 3, 2)[:, ::-1, :].reshape(N + 1, 6)
-  return counts, bbox[:, : 2 * ndim], sums[:, :ndim]
+  return counts, bbox[:, : 2 * ndim], sums[:, :ndim], N
 
 
 def _torch_max(t) -> int:
@@ -521,29 +567,35 @@ def _torch_max(t) -> int:
   return int(t.max())
 
 
+def _too_large(N):
+  return ValueError(
+    f"Statistics can only be computed on volumes containing labels with values lower than the number of voxels. Max: {N}")
+
+
 def statistics(out_labels, no_slice_conversion: bool = False) -> dict:
   """Voxel counts, bounding boxes and centroids per label; same contract as cc3d.statistics.
-  CUDA tensors are processed in place on their device."""
-  device_labels = None
+  CUDA tensors are processed in place on their device. The volume is swept ONCE: the largest label is found by the
+  sweep that accumulates the statistics (the reference takes np.max first)."""
   out_labels = _adopt_device_array(out_labels)
   if _is_torch(out_labels):
     if out_labels.is_cuda and out_labels.ndim >= 2 and out_labels.dtype != __import__("torch").bool:
-      device_labels = out_labels
       voxels = out_labels.numel()
       if voxels == 0:
         return {"voxel_counts": None, "bounding_boxes": None, "centroids": None}
-      N = _torch_max(out_labels)
       np_dtype = _torch_np_dtype(out_labels)
-      if np.issubdtype(np_dtype, np.signedinteger) and int(out_labels.min()) < 0:
-        raise ValueError(
-          f"Statistics can only be computed on volumes containing labels with values >= 0. Min: {int(out_labels.min())}")
-      if N > voxels:
-        raise ValueError(
-          f"Statistics can only be computed on volumes containing labels with values lower than the number of voxels. Max: {N}")
+      signed = np.issubdtype(np_dtype, np.signedinteger)
+      counts, bbox32, sums, N = _statistics_arrays_device(out_labels, None)
+      # a negative label shows as a huge unsigned one: sort the two errors out like the reference does (max first)
+      if counts is None or (signed and N >= (1 << (8 * np_dtype.itemsize - 1))):
+        if signed and int(out_labels.min()) < 0:
+          if int(out_labels.max()) > voxels:
+            raise _too_large(int(out_labels.max()))
+          raise ValueError(
+            f"Statistics can only be computed on volumes containing labels with values >= 0. Min: {int(out_labels.min())}")
+        raise _too_large(N)
       ndim = out_labels.ndim
       shape3 = list(out_labels.shape) + [1] * (3 - ndim)
       bdtype = np.uint32 if max(shape3) > np.iinfo(np.uint16).max else np.uint16
-      counts, bbox32, sums = _statistics_arrays_device(out_labels, N)
       return _finish_statistics(counts, bbox32, sums, bdtype, voxels, no_slice_conversion)
     out_labels = out_labels.cpu().numpy()
   while out_labels.ndim < 2:
@@ -553,21 +605,19 @@ def statistics(out_labels, no_slice_conversion: bool = False) -> dict:
   voxels = out_labels.size
   if voxels == 0:
     return {"voxel_counts": None, "bounding_boxes": None, "centroids": None}
-  N = int(np.max(out_labels))
-  if N > voxels:
-    raise ValueError(
-      f"Statistics can only be computed on volumes containing labels with values lower than the number of voxels. Max: {N}")
-  if np.issubdtype(out_labels.dtype, np.signedinteger):
-    N_min = int(np.min(out_labels))
-    if N_min < 0:
+  signed = np.issubdtype(out_labels.dtype, np.signedinteger)
+  view = out_labels.view(_UNSIGNED[out_labels.dtype.itemsize]) if signed else out_labels
+  counts, bbox32, sums, N = _statistics_arrays(view, None)
+  if counts is None or (signed and N >= (1 << (8 * out_labels.dtype.itemsize - 1))):
+    if signed and int(np.min(out_labels)) < 0:
+      if int(np.max(out_labels)) > voxels:
+        raise _too_large(int(np.max(out_labels)))
       raise ValueError(
-        f"Statistics can only be computed on volumes containing labels with values >= 0. Min: {N_min}")
-    out_labels = out_labels.view(_UNSIGNED[out_labels.dtype.itemsize])
+        f"Statistics can only be computed on volumes containing labels with values >= 0. Min: {int(np.min(out_labels))}")
+    raise _too_large(N)
   ndim = out_labels.ndim
   shape3 = list(out_labels.shape) + [1] * (3 - ndim)
   bdtype = np.uint32 if max(shape3) > np.iinfo(np.uint16).max else np.uint16
-
-  counts, bbox32, sums = _statistics_arrays(out_labels, N)
   return _finish_statistics(counts, bbox32, sums, bdtype, voxels, no_slice_conversion)
 
 

@@ -80,6 +80,8 @@ def lib():
   L.cc3d_b200_label_with_info.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, ci, vp, ci, ci, p(ResolveInfo), vp]
   L.cc3d_b200_statistics.restype = ci
   L.cc3d_b200_statistics.argtypes = [vp, ci, i64, i64, i64, u64, vp, vp, vp, ci, vp]
+  L.cc3d_b200_statistics_auto.restype = ci
+  L.cc3d_b200_statistics_auto.argtypes = [vp, ci, i64, i64, i64, u64, p(u64), vp, vp, vp, ci, vp]
   L.cc3d_b200_voxel_connectivity_graph.restype = ci
   L.cc3d_b200_voxel_connectivity_graph.argtypes = [vp, ci, i64, i64, i64, ci, vp, ci, vp]
   L.cc3d_b200_color_connectivity_graph.restype = ci

@@ -1,4 +1,4 @@
-# cython: language_level=3, boundscheck=False, wraparound=False
+# cython: language_level=3
 """fastcc3d — the COMPILED Cython boundary of cc3d_b200 (the binding INTEGRATION.md describes, built by build()).
 
 It is what the reference's `cc3d/fastcc3d.pyx` becomes when its C++ template externs are replaced by the C-ABI of

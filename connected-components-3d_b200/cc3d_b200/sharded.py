@@ -109,7 +109,7 @@ class CudaBackend:
   def partial_statistics(self, labels, N):
     """(counts u32[N+1], bbox u32[N+1, 6], sums u64[N+1, 3]) of one slab in ARRAY axes, slab-local coordinates."""
     from . import _statistics_arrays_device
-    return _statistics_arrays_device(labels, int(N))
+    return _statistics_arrays_device(labels, int(N))[:3]
 
   def to_device(self, slab_np):
     """numpy (sz, sy, sx) C-contiguous slab -> device tensor (streaming front end)."""

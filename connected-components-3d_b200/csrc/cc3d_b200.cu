@@ -464,8 +464,11 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
 
   // fused rank kernel (C stage in one launch): run ids and labels must stay below 2^31, block-order numbering keeps
   // the three-kernel path
-  static const bool no_fused_rank = getenv("CC3D_B200_NO_FUSED_RANK") != nullptr;   // A/B switch
-  const bool fused_rank = !block_order && maxruns < (i64(1) << 31) && !no_fused_rank;
+  // Measured on B200 (profiles/r02_rank_ab.md): the fused kernel costs 92 us at 512^3 against 66 us for the three small
+  // kernels (its look-back sits between two block-wide phases of every chunk), so the three-kernel path stays the
+  // default; CC3D_B200_FUSED_RANK=1 selects the fused kernel (one launch less).
+  static const bool want_fused_rank = getenv("CC3D_B200_FUSED_RANK") != nullptr;
+  const bool fused_rank = !block_order && maxruns < (i64(1) << 31) && want_fused_rank;
   const i64 nb_rank = (maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS;
   const i64 status2_words = (fused_rank ? nb_rank : nb2) + 2;
   // control block: Counters | scan-S status | C-stage status, zeroed by ONE memset per call
@@ -965,12 +968,13 @@ int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t
 }
 
 template <typename LT>
-static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts, u32* bbox, u64* sums, cudaStream_t s) {
+static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts, u32* bbox, u64* sums, cudaStream_t s,
+                            unsigned long long* maxout = nullptr) {
   static PerDeviceOnce once;
   auto k = k_statistics<LT>;
   if (once.first()) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable));
   k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
-  k<<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums);
+  k<<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
   g_launches += 2;
   return 0;
 }
@@ -1014,6 +1018,63 @@ int cc3d_b200_statistics(const void* labels, int kind, int64_t sx, int64_t sy, i
   if (e == cudaSuccess) e = cudaGetLastError();
   arena_release(ar);
   if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("statistics: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+
+// statistics without knowing the largest label beforehand (the reference takes np.max first, fastcc3d.pyx:713-720; a
+// separate maximum pass would read the volume twice): ONE sweep accumulates the labels below `cap` into tables of
+// `cap` entries and tracks the true maximum. *max_label < cap: the first *max_label + 1 entries of the tables are the
+// statistics (host tables receive exactly those). Otherwise nothing useful was produced: call again with
+// cap > *max_label.
+int cc3d_b200_statistics_auto(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, uint64_t cap,
+                              uint64_t* max_label, uint32_t* counts, uint32_t* bbox, uint64_t* sums, int mem_space,
+                              void* stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  const size_t es = kind_size(kind);
+  if (!es || kind > CC3D_B200_U64) return fail(CC3D_B200_ERR_KIND, "labels must be u8/u16/u32/u64");
+  if (!max_label || cap == 0 || cap >= 0xFFFFFFFEull) return fail(CC3D_B200_ERR_ARGUMENT, "statistics_auto: bad max_label / cap");
+  *max_label = 0;
+  const i64 voxels = sx * sy * sz;
+  if (voxels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  Geom g = make_geom(sx, sy, sz);
+  Arena ar;
+  const bool host = mem_space == CC3D_B200_HOST;
+  const size_t n1 = (size_t)cap;
+  if (int rc = arena_acquire((host ? (size_t)voxels * es + n1 * (4 + 24 + 24) : 0) + 4096, &ar, s, true)) return rc;
+  const void* dl = labels;
+  u32 *dc = counts, *db = bbox;
+  u64* ds = sums;
+  if (host) {
+    void* d = ar.take((size_t)voxels * es);
+    dc = (u32*)ar.take(n1 * 4); db = (u32*)ar.take(n1 * 24); ds = (u64*)ar.take(n1 * 24);
+    cudaError_t e = cudaMemcpyAsync(d, labels, (size_t)voxels * es, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { arena_release(ar); return fail(CC3D_B200_ERR_CUDA, cudaGetErrorString(e)); }
+    dl = d;
+  }
+  unsigned long long* dmax = (unsigned long long*)ar.take(8);
+  cudaMemsetAsync(dmax, 0, 8, s);
+  switch (kind) {
+    case CC3D_B200_U8: statistics_typed((const uint8_t*)dl, g, cap - 1, dc, db, ds, s, dmax); break;
+    case CC3D_B200_U16: statistics_typed((const uint16_t*)dl, g, cap - 1, dc, db, ds, s, dmax); break;
+    case CC3D_B200_U32: statistics_typed((const uint32_t*)dl, g, cap - 1, dc, db, ds, s, dmax); break;
+    default: statistics_typed((const uint64_t*)dl, g, cap - 1, dc, db, ds, s, dmax); break;
+  }
+  unsigned long long hmax = 0;
+  cudaError_t e = cudaMemcpyAsync(&hmax, dmax, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess && host && hmax < cap) {
+    const size_t m1 = (size_t)hmax + 1;
+    e = cudaMemcpyAsync(counts, dc, m1 * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bbox, db, m1 * 24, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sums, ds, m1 * 24, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("statistics_auto: ") + cudaGetErrorString(e));
+  *max_label = hmax;
   return 0;
 }
 

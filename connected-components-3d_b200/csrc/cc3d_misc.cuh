@@ -109,7 +109,7 @@ __device__ __forceinline__ void sm_add64(u32* lo, u32* hi, unsigned long long v)
 template <typename LT>
 __global__ void __launch_bounds__(256)
 k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ counts, u32* __restrict__ bbox,
-             unsigned long long* __restrict__ sums) {
+             unsigned long long* __restrict__ sums, unsigned long long* __restrict__ maxout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StatTable& tb = *reinterpret_cast<StatTable*>(smem_raw);
   for (int i = threadIdx.x; i < CC_STAT_SLOTS; i += blockDim.x) {
@@ -228,6 +228,7 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
   // every CTA walks a contiguous range of tasks (a compact region of the volume: few labels in its table)
   const i64 per_cta = (ntasks + gridDim.x - 1) / gridDim.x;
   const i64 task_end = min(ntasks, (i64)(blockIdx.x + 1) * per_cta);
+  LT vmax = (LT)0;     // largest label this lane has seen (the caller may not know the maximum: statistics_auto)
   for (i64 task = (i64)blockIdx.x * per_cta + warp; task < task_end; task += blockDim.x >> 5) {
     const i64 w = task % W, t = task / W;
     const u32 ych = (u32)(t % nych), z = (u32)(t / nych);
@@ -239,6 +240,7 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
     const LT* __restrict__ p = labels + (((size_t)z * sy + y0) * sx + (inx ? x : 0));
     u32 cur = NONE, ystart = 0;
     auto row_step = [&](LT v, u32 r) {
+      if (inx && v > vmax) vmax = v;
       const u32 l = (inx && v <= nmax) ? (u32)v : NONE;
       const bool change = l != cur;
       if (__any_sync(CC_FULL, change)) {
@@ -259,6 +261,12 @@ k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ cou
     finish_runs(cur != NONE, cur, ystart, nrow - 1, xbase, y0, z);
     if (lane < CC_STAT_WSLOTS) spill(lane, xbase, y0, z);
     __syncwarp();
+  }
+  if (maxout) {
+    unsigned long long m = (unsigned long long)vmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(CC_FULL, m, o); if (t > m) m = t; }
+    if (lane == 0 && m > *(volatile unsigned long long*)maxout) atomicMax(maxout, m);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < CC_STAT_SLOTS; i += blockDim.x) {

@@ -180,6 +180,15 @@ int cc3d_b200_label_with_info(const void* in, int in_kind, int64_t sx, int64_t s
 int cc3d_b200_statistics(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, uint64_t N,
                          uint32_t* counts, uint32_t* bbox, uint64_t* sums, int mem_space, void* stream);
 
+/* statistics when the largest label is not known beforehand (the reference runs np.max first, fastcc3d.pyx:713-720;
+ * here the same sweep tracks the maximum): labels below `cap` are accumulated into tables of `cap` entries
+ * (counts[cap], bbox[cap][6], sums[cap][3], layout as cc3d_b200_statistics) and *max_label (host) receives the true
+ * maximum. If *max_label < cap the first *max_label + 1 entries are the statistics (host tables receive exactly those);
+ * otherwise call again with cap > *max_label. */
+int cc3d_b200_statistics_auto(const void* labels, int kind, int64_t sx, int64_t sy, int64_t sz, uint64_t cap,
+                              uint64_t* max_label, uint32_t* counts, uint32_t* bbox, uint64_t* sums, int mem_space,
+                              void* stream);
+
 /* Row a14: masking step of dust: img[i] = keep[labels[i]] ? img[i] : 0, in place.
  * keep has N+1 bytes (index = label). img_itemsize in {1,2,4,8}. */
 int cc3d_b200_mask_by_label(void* img, int img_itemsize, const void* labels, int label_kind,

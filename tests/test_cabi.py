@@ -99,6 +99,10 @@ def test_compiled_cython_binding_loads_and_validates():
     fc.connected_components(np.ones((2, 2, 2, 2), np.uint8))
   with pytest.raises(TypeError):
     fc.connected_components(np.ones((4, 4), np.float16), delta=1)
+  try:   # C-ordered input indexes shape[-1] (a module-wide wraparound=False once turned this into a wild read)
+    fc.estimate_provisional_labels(np.ones((5, 4), np.uint8))
+  except RuntimeError:
+    pass   # no GPU here: the C-ABI reports it
   out, N = fc.connected_components(np.zeros((0, 0, 0), np.uint32), return_N=True)      # empty: no GPU needed
   assert N == 0 and out.size == 0
   assert fc.statistics(np.zeros((0, 0), np.uint8)) == {"voxel_counts": None, "bounding_boxes": None, "centroids": None}

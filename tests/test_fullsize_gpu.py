@@ -316,3 +316,34 @@ def test_compiled_cython_binding_matches_reference(cc3d, oracle_mod):
       ref.connected_components(np.ones((4, 4, 4), np.uint8), **bad)
     with pytest.raises(ValueError):
       fc.connected_components(np.ones((4, 4, 4), np.uint8), **bad)
+
+
+# ---- statistics in one sweep: the maximum label is found by the sweep itself, the tables grow when it is large ----
+def test_statistics_one_sweep_capacity_and_errors(cc3d, oracle_mod):
+  import torch
+  truth = oracle_mod.reference_module() or oracle_mod
+  cc3d._stat_cap.clear(); cc3d._stat_cap["host"] = 1 << 10
+  lab = np.arange(45 ** 3, dtype=np.uint32).reshape(45, 45, 45)      # N = 91 124: larger than the first table
+  lab[3:9, :, 5] = 0
+  for x in (lab, np.asfortranarray(lab), lab.astype(np.int64), lab[:, :, 7].copy()):
+    a, b = cc3d.statistics(x, no_slice_conversion=True), truth.statistics(x, no_slice_conversion=True)
+    for k in ("voxel_counts", "bounding_boxes", "centroids"):
+      assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k], equal_nan=True), (k, x.dtype, x.shape)
+  t = torch.from_numpy(lab.view(np.int32)).cuda()
+  a, b = cc3d.statistics(t, no_slice_conversion=True), truth.statistics(lab, no_slice_conversion=True)
+  for k in ("voxel_counts", "bounding_boxes", "centroids"):
+    assert np.array_equal(a[k], b[k], equal_nan=True), k
+  assert cc3d.statistics(t) ["bounding_boxes"] == truth.statistics(lab)["bounding_boxes"]
+  # error behaviour of the reference (fastcc3d.pyx:713-747)
+  big = np.zeros((4, 4, 4), np.uint32); big[1, 1, 1] = 1000
+  neg = np.zeros((4, 4, 4), np.int32); neg[2, 2, 2] = -3
+  for bad in (big, neg):
+    with pytest.raises(ValueError) as e1:
+      truth.statistics(bad)
+    with pytest.raises(ValueError) as e2:
+      cc3d.statistics(bad)
+    assert str(e1.value) == str(e2.value)
+    with pytest.raises(ValueError) as e3:
+      cc3d.statistics(torch.from_numpy(bad.view(np.int32) if bad.dtype == np.uint32 else bad).cuda())
+    if bad is neg:
+      assert str(e3.value) == str(e1.value)
