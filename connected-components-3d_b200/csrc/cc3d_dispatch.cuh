@@ -79,9 +79,16 @@ static cc_tmap_encode_fn cc_tmap_encoder() {
 }
 
 // true when the TMA kernel was launched
+#ifndef CC_TMA_V1
+#define CC_TMA_KERNEL k_faces_tma2
+#define CC_TMA_TRAITS FaceTma2
+#else
+#define CC_TMA_KERNEL k_faces_tma
+#define CC_TMA_TRAITS FaceTma
+#endif
 template <typename T, int MODE>
 static bool launch_faces_tma(const LabelArgs& a, const Edge<T, MODE>& E, bool two_d) {
-  typedef FaceTma<T> F;
+  typedef CC_TMA_TRAITS<T> F;
   const Geom& g = a.g;
   const size_t es = sizeof(T);
   if (es > 4 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || ((size_t)g.sx * es) % 16 != 0) return false;
@@ -109,11 +116,11 @@ static bool launch_faces_tma(const LabelArgs& a, const Edge<T, MODE>& E, bool tw
   constexpr size_t smem = F::smem();
   static PerDeviceOnce once;
   if (once.first()) {
-    cudaFuncSetAttribute(k_faces_tma<T, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_faces_tma<T, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(CC_TMA_KERNEL<T, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(CC_TMA_KERNEL<T, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  if (two_d) cc_launch(k_faces_tma<T, MODE, false>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
-  else cc_launch(k_faces_tma<T, MODE, true>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
+  if (two_d) cc_launch(CC_TMA_KERNEL<T, MODE, false>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
+  else cc_launch(CC_TMA_KERNEL<T, MODE, true>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
   return true;
 }
 

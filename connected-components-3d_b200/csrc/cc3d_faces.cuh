@@ -493,3 +493,139 @@ k_faces_tma(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom 
     if (lane == 0 && epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)epl);
   }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Kernel A, TMA variant 2: as k_faces_tma, but the plane that has just been evaluated stays in REGISTERS as the -z
+// operand of the next one (TR2 x NW values per lane), so the ring only holds planes that are in flight (NBUF2 - 1 of
+// them ahead of the evaluation) and a row costs two shared-memory loads per word (voxel, -x neighbour) instead of
+// three. The plane below the first one of a z chunk is fetched like any other and only fills the registers.
+// ---------------------------------------------------------------------------------------------
+#ifndef CC_TMA2_NBUF
+#define CC_TMA2_NBUF 3
+#endif
+template <typename T> struct FaceTma2 {
+  static constexpr int NW = CC_FACE_NW;
+  static constexpr int PAD = 16 / (int)sizeof(T);
+  static constexpr int BOXX = NW * 32 + PAD;
+  static constexpr int TR = 4;
+  static constexpr int PITCH = BOXX * (int)sizeof(T);
+  static constexpr int BOXB = PITCH * (TR + 1);
+  static constexpr int BUFB = (BOXB + 127) & ~127;
+  static constexpr int NBUF = CC_TMA2_NBUF;
+  static constexpr size_t smem() { return (size_t)CC_FACE_WARPS * (NBUF * BUFB) + CC_FACE_WARPS * NBUF * 8 + 128; }
+};
+
+template <typename T, int MODE, bool HASZ>
+__global__ void __launch_bounds__(CC_FACE_WARPS * 32)
+k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
+             unsigned nyb, unsigned nwg, unsigned zchunk, unsigned ntasks) {
+  typedef FaceTma2<T> F;
+  constexpr int NW = F::NW, TR = F::TR, PAD = F::PAD;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* base = tma_smem + ((128u - ((unsigned)__cvta_generic_to_shared(tma_smem) & 127u)) & 127u);
+  unsigned char* ring = base + (size_t)warp * (F::NBUF * F::BUFB);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + (size_t)CC_FACE_WARPS * (F::NBUF * F::BUFB)) + warp * F::NBUF;
+  if (lane == 0) {
+#pragma unroll
+    for (int b = 0; b < F::NBUF; b++) mbar_init(bars + b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  CC_PDL_WAIT();
+  const unsigned task = blockIdx.x * CC_FACE_WARPS + warp;
+  if (task >= ntasks) return;
+  const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
+  const u32 wg = task % nwg;
+  const u32 t = task / nwg;
+  const u32 yb = t % nyb, zc = t / nyb;
+  const u32 w0 = wg * NW, y0 = yb * TR;
+  const u32 z0 = zc * zchunk, z1 = min(sz, z0 + zchunk);
+  const int cx = (int)(w0 << 5) - PAD, cy = (int)y0 - 1;
+  const u32 nrow = min(sy, y0 + TR) - y0;
+  const u32 nw = min((u32)NW, W - w0);
+  const bool rs_vec = (W & 3) == 0 && nw == NW;
+  u32 epl = 0;
+  // walk: step 0 = plane z0 - 1 (3D connectivities only; it just fills the registers), step s = plane z0 - 1 + s
+  const u32 first = HASZ ? 0u : 1u;
+  const u32 nsteps = z1 - z0 + 1;
+  auto issue = [&](u32 s_) {
+    if (lane == 0) {
+      const u32 b = (s_ - first) % F::NBUF;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bars + b, (unsigned)F::BOXB);
+      tma_load_3d(ring + b * F::BUFB, &tmap, bars + b, cx, cy, (int)(z0 + s_) - 1);
+    }
+  };
+  constexpr u32 PD = F::NBUF;          // a slot is refilled as soon as its plane has been evaluated: NBUF - 1 planes in flight
+#pragma unroll
+  for (u32 k = 0; k < PD; k++) if (first + k < nsteps) issue(first + k);
+  T dreg[TR][NW];
+#pragma unroll
+  for (int r = 0; r < TR; r++)
+#pragma unroll
+    for (int k = 0; k < NW; k++) dreg[r][k] = (T)0;
+  for (u32 st = first; st < nsteps; st++) {
+    const u32 q = st - first;
+    mbar_wait(bars + q % F::NBUF, (q / F::NBUF) & 1u);
+    const unsigned char* cur = ring + (q % F::NBUF) * F::BUFB;
+    if (st == 0) {
+      // plane z0 - 1: only the -z operands of the first plane
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const T* sc = reinterpret_cast<const T*>(cur + (size_t)(r + 1) * F::PITCH) + PAD + lane;
+#pragma unroll
+        for (int k = 0; k < NW; k++) dreg[r][k] = sc[32 * k];
+      }
+    } else {
+      const u32 z = z0 + st - 1;
+      const u32 row0 = z * sy + y0;
+      uint4* __restrict__ mq = reinterpret_cast<uint4*>(M) + ((size_t)row0 * W + w0);
+      u32* __restrict__ rs = M + g.offRS + ((size_t)row0 * W + w0);
+      T up[NW];
+      {
+        const T* h = reinterpret_cast<const T*>(cur) + PAD + lane;     // halo row y0 - 1
+#pragma unroll
+        for (int k = 0; k < NW; k++) up[k] = h[32 * k];
+      }
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        if ((u32)r < nrow) {
+          const T* sc = reinterpret_cast<const T*>(cur + (size_t)(r + 1) * F::PITCH) + PAD + lane;
+          T c[NW], l[NW];
+#pragma unroll
+          for (int k = 0; k < NW; k++) { c[k] = sc[32 * k]; l[k] = sc[32 * k - 1]; }
+          if (nw == NW) {
+            faces_eval_store<T, MODE, HASZ, NW>(E, c, l, dreg[r], up, lane, mq, rs, rs_vec, epl);
+          } else {
+            u32 Fw[NW], Xw[NW], Yw[NW], Zw[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+              const bool f = E.fg(c[k]);
+              Fw[k] = __ballot_sync(CC_FULL, f);
+              Xw[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
+              Yw[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
+              Zw[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], dreg[r][k])) : 0u;
+              if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < NW; k++)
+                if ((u32)k < nw) { mq[k] = make_uint4(Fw[k], Xw[k], Yw[k], Zw[k]); rs[k] = __popc(Fw[k] & ~Xw[k]); }
+            }
+          }
+          mq += W; rs += W;
+#pragma unroll
+          for (int k = 0; k < NW; k++) { up[k] = c[k]; dreg[r][k] = c[k]; }
+        }
+      }
+    }
+    __syncwarp();                                   // every lane has read the slot: it can be refilled
+    if (st + PD < nsteps) issue(st + PD);
+  }
+  if constexpr (MODE != MODE_EQ) {
+    if (lane == 0 && epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)epl);
+  }
+}
