@@ -945,6 +945,49 @@ int cc3d_b200_label_with_info(const void* in, int in_kind, int64_t sx, int64_t s
     marks_collect(false);
     return cc3d_b200_label_write(S, out, out_kind, mem_space, stream);
   }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mem_space == CC3D_B200_DEVICE && S->voxels > 0 && S->hctr &&
+      (out_kind == CC3D_B200_U16 || out_kind == CC3D_B200_U32 || out_kind == CC3D_B200_U64)) {
+    // Device-resident call: the host only needs the counters, which are final BEFORE the expansion kernel runs. An
+    // event marks their copy; D is enqueued behind it and the host returns as soon as the event has fired - the output
+    // is stream-ordered like any other CUDA result, and the caller's next enqueue overlaps with D instead of waiting
+    // for it (the workspace goes back to the cache behind an event of its own).
+    thread_local cudaEvent_t ev = nullptr;
+    if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+    if (ev) {
+      cudaEventRecord(ev, s);
+      const i64 nrows = S->g.sy * S->g.sz;
+      auto write = [&]() {
+        if (out_kind == CC3D_B200_U16) launch_write<uint16_t>(S, (uint16_t*)out, 0, nrows, nullptr, 0, s);
+        else if (out_kind == CC3D_B200_U32) launch_write<uint32_t>(S, (uint32_t*)out, 0, nrows, nullptr, 0, s);
+        else launch_write<uint64_t>(S, (uint64_t*)out, 0, nrows, nullptr, 0, s);
+      };
+      write();
+      cudaError_t e = cudaEventSynchronize(ev);
+      if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) { session_release_after(S, s); return fail(CC3D_B200_ERR_CUDA, std::string("label: ") + cudaGetErrorString(e)); }
+      const Counters* h = S->hctr;
+      if (h->gq_ovf) {
+        // rare: the edge queue overflowed - redo the unions on the global forest (synchronises), write again
+        rc = resolve_finish(S, s, info);
+        if (rc == 0) { write(); if (cudaStreamSynchronize(s) != cudaSuccess) rc = fail(CC3D_B200_ERR_CUDA, "label: redo failed"); }
+        cc3d_b200_session_release(S);
+        if (rc == 0 && out_kind == CC3D_B200_U16 && info->N > 0xFFFFull) rc = fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind");
+        return rc;
+      }
+      S->N = h->N;
+      info->N = h->N;
+      info->epl = S->epl_is_runs ? h->nruns : h->epl;
+      info->first_foreground_row = h->nruns ? (int64_t)~h->first_inv : -1;
+      info->last_foreground_row = h->nruns ? (int64_t)h->last_p1 - 1 : -1;
+      rc = (out_kind == CC3D_B200_U16 && info->N > 0xFFFFull) ? fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind") : 0;
+      // the copy into the pinned slot has completed (the event fired): the slot can be recycled now, the arena after D
+      arena_release_after(S->arena, s);
+      pinned_slot_give(S->hctr);
+      delete S;
+      return rc;
+    }
+  }
   rc = write_impl(S, out, out_kind, mem_space, stream, 0, S->g.sy * S->g.sz, nullptr, 0, 0, false, false);
   if (rc == 0) rc = resolve_finish(S, (cudaStream_t)stream, info);
   if (rc == 0 && S->redone)   // the edge queue overflowed: the labels written above predate the redo

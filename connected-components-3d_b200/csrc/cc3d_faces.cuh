@@ -502,7 +502,7 @@ k_faces_tma(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom 
 // three. The plane below the first one of a z chunk is fetched like any other and only fills the registers.
 // ---------------------------------------------------------------------------------------------
 #ifndef CC_TMA2_NBUF
-#define CC_TMA2_NBUF 3
+#define CC_TMA2_NBUF 2     // measured on B200 (profiles/r02_faces_ab.md): 2 slots 0.170-0.174 ms, 3 slots 0.174-0.176, 4 slots 0.196 (512^3 u32)
 #endif
 template <typename T> struct FaceTma2 {
   static constexpr int NW = CC_FACE_NW;

@@ -107,7 +107,7 @@ __device__ __forceinline__ void sm_add64(u32* lo, u32* hi, unsigned long long v)
 }
 
 template <typename LT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)     // 148 * 4 persistent CTAs: all of them have to be resident (<= 64 registers)
 k_statistics(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ counts, u32* __restrict__ bbox,
              unsigned long long* __restrict__ sums, unsigned long long* __restrict__ maxout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

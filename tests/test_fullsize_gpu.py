@@ -308,7 +308,8 @@ def test_compiled_cython_binding_matches_reference(cc3d, oracle_mod):
       assert np.array_equal(a["voxel_counts"], b["voxel_counts"]) and a["bounding_boxes"] == b["bounding_boxes"]
       assert np.array_equal(a["centroids"], b["centroids"], equal_nan=True)
       n += 1
-    assert fc.estimate_provisional_labels(x) == ref.estimate_provisional_labels(x)
+    if dt != np.float16:      # both refuse float16 here (TypeError)
+      assert fc.estimate_provisional_labels(x) == ref.estimate_provisional_labels(x)
   assert n > 120
   # same error behaviour as the reference
   for bad in (dict(connectivity=5), dict(connectivity=26, periodic_boundary=True), dict(out_dtype=np.uint8)):
@@ -325,7 +326,8 @@ def test_statistics_one_sweep_capacity_and_errors(cc3d, oracle_mod):
   cc3d._stat_cap.clear(); cc3d._stat_cap["host"] = 1 << 10
   lab = np.arange(45 ** 3, dtype=np.uint32).reshape(45, 45, 45)      # N = 91 124: larger than the first table
   lab[3:9, :, 5] = 0
-  for x in (lab, np.asfortranarray(lab), lab.astype(np.int64), lab[:, :, 7].copy()):
+  flat2d = np.arange(300 * 310, dtype=np.uint32).reshape(300, 310)      # 2D, N = 92 999 < voxels
+  for x in (lab, np.asfortranarray(lab), lab.astype(np.int64), flat2d, np.asfortranarray(flat2d)):
     a, b = cc3d.statistics(x, no_slice_conversion=True), truth.statistics(x, no_slice_conversion=True)
     for k in ("voxel_counts", "bounding_boxes", "centroids"):
       assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k], equal_nan=True), (k, x.dtype, x.shape)
