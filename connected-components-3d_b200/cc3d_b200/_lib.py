@@ -88,6 +88,8 @@ def lib():
   L.cc3d_b200_color_connectivity_graph.argtypes = [vp, ci, i64, i64, i64, ci, vp, p(u64), ci, vp]
   L.cc3d_b200_contacts.restype = ci
   L.cc3d_b200_contacts.argtypes = [vp, ci, i64, i64, i64, ci, vp, vp, u64, p(u64), ci, vp]
+  L.cc3d_b200_crackle_v0_decode.restype = ci
+  L.cc3d_b200_crackle_v0_decode.argtypes = [vp, vp, i64, i64, i64, vp, u64, vp, p(u64), ci, vp]
   L.cc3d_b200_remap_labels.restype = ci
   L.cc3d_b200_remap_labels.argtypes = [vp, ci, i64, vp, u64, vp, ci, ci, vp]
   L.cc3d_b200_runs.restype = ci

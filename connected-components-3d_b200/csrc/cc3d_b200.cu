@@ -1310,6 +1310,80 @@ int cc3d_b200_color_connectivity_graph(const void* vcg, int vcg_kind, int64_t sx
   return 0;
 }
 
+
+// ---- crackle v0 decode on the device: crack codes -> 4-bit pixel graph (k_crackle_cuts),
+// coloured slice by slice as ONE 6-connected graph without z links (k_vcg_union + the rank kernels: components are
+// numbered in raster order, i.e. slice by slice, which is the order of the file's key table), then out[i] =
+// lut[component of i]. Replaces the per-slice cc3d.color_connectivity_graph calls of a crackle decoder
+// (cc3d_graphs.hpp:1018-1074 is the colouring it would call). ----
+int cc3d_b200_crackle_v0_decode(const uint8_t* stream, const uint64_t* slice_off, int64_t sx, int64_t sy, int64_t sz,
+                                const uint32_t* lut, uint64_t n_lut, uint32_t* out, uint64_t* n_components, int mem_space,
+                                void* cuda_stream) {
+  if (int rc = check_shape(sx, sy, sz)) return rc;
+  if (!stream || !slice_off || !lut || !out) return fail(CC3D_B200_ERR_ARGUMENT, "crackle_v0_decode: NULL argument");
+  const i64 voxels = sx * sy * sz;
+  if (n_components) *n_components = 0;
+  if (voxels == 0) return 0;
+  if ((u64)voxels >= 0xFFFFFFFFull) return fail(CC3D_B200_ERR_TOO_LARGE, "crackle_v0_decode: >= 2^32-1 voxels");
+  if (sx >= 65536 || sy >= 65536 || ((sx * sy) & 3)) return fail(CC3D_B200_ERR_ARGUMENT, "crackle_v0_decode: slices must be < 65536 wide / high and sx * sy a multiple of 4");
+  if (mem_space != CC3D_B200_HOST) return fail(CC3D_B200_ERR_ARGUMENT, "crackle_v0_decode: the code stream is parsed from host memory (the labels may stay on the device: see out)");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const size_t total = (size_t)slice_off[sz];
+  const i64 nwords2 = (voxels + 31) / 32;
+  const i64 nb2 = (nwords2 + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+  cudaPointerAttributes pa;
+  const bool out_on_device = cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  size_t need = 8192 + total + 256 + (size_t)(sz + 1) * 8 + 256 + (size_t)voxels + 256 + 8 * total + 256 + (size_t)n_lut * 4 + 256 +
+                (size_t)nwords2 * 12 + 1024 + (size_t)(nb2 + 2) * 8 + 256 + (out_on_device ? 0 : (size_t)voxels * 4 + 256);
+  Arena ar;
+  if (int rc = arena_acquire(need, &ar, s, true)) return rc;
+  unsigned char* dstream = (unsigned char*)ar.take(total + 16);
+  unsigned long long* doff = (unsigned long long*)ar.take((size_t)(sz + 1) * 8);
+  unsigned char* vcg = (unsigned char*)ar.take((size_t)voxels);
+  u32* stack = (u32*)ar.take(8 * total + 16);
+  u32* dlut = (u32*)ar.take((size_t)n_lut * 4);
+  u32* GR = (u32*)ar.take((size_t)nwords2 * 4);
+  u32* cnt = (u32*)ar.take((size_t)nwords2 * 4);
+  u32* prefix = (u32*)ar.take((size_t)nwords2 * 4);
+  u64* bsum = (u64*)ar.take((size_t)(nb2 + 2) * 8);
+  u64* small = (u64*)ar.take(64);          // [0] voxels, [1] N, [2] error flags
+  u32* dout = out_on_device ? out : (u32*)ar.take((size_t)voxels * 4);
+  cudaMemcpyAsync(dstream, stream, total, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(doff, slice_off, (size_t)(sz + 1) * 8, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(dlut, lut, (size_t)n_lut * 4, cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(vcg, 0x0F, (size_t)voxels, s);
+  cudaMemsetAsync(small, 0, 64, s);
+  k_set_u64<<<1, 1, 0, s>>>(small, (u64)voxels);
+  k_crackle_cuts<<<(unsigned)((sz + 31) / 32), 32, 0, s>>>(dstream, doff, (int)sx, (int)sy, (int)sz, vcg, stack, (u32*)(small + 2));
+  VcgDirs D;
+  D.n = 0;
+  auto add = [&](int dx, int dy, int dz, int bit_number) {
+    D.d[D.n][0] = (signed char)dx; D.d[D.n][1] = (signed char)dy; D.d[D.n][2] = (signed char)dz;
+    D.mask[D.n] = 1u << (bit_number - 1); D.n++;
+  };
+  add(-1, 0, 0, 2); add(0, -1, 0, 4);      // the slices are independent images: no z links
+  const unsigned blocks = (unsigned)std::min<i64>((voxels + 255) / 256, 148 * 64);
+  k_iota<<<(unsigned)((voxels + 255) / 256), 256, 0, s>>>(dout, voxels);
+  k_vcg_union<uint8_t><<<blocks, 256, 0, s>>>(vcg, dout, sx, sy, sz, D);
+  k_compress<<<CC_GRID_BLOCKS, 256, 0, s>>>(dout, GR, cnt, small);
+  scan_counts(cnt, prefix, bsum, nwords2, nullptr, 0, small + 1, nullptr, s);
+  k_assign<<<CC_GRID_BLOCKS, 256, 0, s>>>(dout, GR, prefix, small);
+  k_remap_labels<u32, u32><<<(unsigned)std::min<i64>((voxels + 255) / 256, 148 * 32), 256, 0, s>>>(dout, dlut, n_lut ? n_lut - 1 : 0, dout, voxels);
+  g_launches += 7;
+  u64 h[3] = {0, 0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, small, 24, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && !out_on_device) e = cudaMemcpyAsync(out, dout, (size_t)voxels * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  arena_release(ar);
+  if (e != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, std::string("crackle_v0_decode: ") + cudaGetErrorString(e));
+  if (h[2]) return fail(CC3D_B200_ERR_ARGUMENT, "crackle_v0_decode: malformed crack code stream (flags " + std::to_string(h[2]) + ")");
+  if (h[1] + 1 > n_lut) return fail(CC3D_B200_ERR_ARGUMENT, "crackle_v0_decode: more components than keys");
+  if (n_components) *n_components = h[1];
+  return 0;
+}
+
 template <typename LT>
 static void remap_typed(const LT* labels, const u32* table, u64 N, void* out, int out_kind, i64 n, cudaStream_t s) {
   const unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 32);

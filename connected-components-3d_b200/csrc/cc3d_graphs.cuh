@@ -176,3 +176,83 @@ k_contacts_compact(ContactTable tb, unsigned long long* __restrict__ out_keys, u
     reinterpret_cast<uint4*>(out_vals)[pos] = reinterpret_cast<const uint4*>(tb.vals)[s];
   }
 }
+
+// ---- crackle v0 crack codes -> per-pixel 4-bit connectivity graph (the colouring step that
+// follows is color_connectivity_graph, cc3d_graphs.hpp:583-1106). One THREAD per z slice: the chain parse is a stack
+// machine over a difference-coded 2-bit symbol stream whose chains start where the previous one ended, i.e. it is
+// sequential within a slice; the 512 slices of the benchmark volume run in parallel.
+//   slice blob = u32 index_bytes | u16 n_rows, n_rows x { y_delta, n, n x x_delta } (chain start corners)
+//              | symbols, 4 per byte, LSB first; dir[i] = (sym[0] + ... + sym[i]) mod 4, 0 up 1 right 2 down 3 left
+//   a reversal ((d - last) mod 4 == 2) is a control symbol: the pending move is dropped; up / left terminate a branch
+//   (pop the position), right / down open one (push the position); a chain ends when no branch is open.
+//   a move from corner (x, y) cuts one pixel adjacency: clear the facing bit on both pixels (bit0 +x, bit1 -x,
+//   bit2 +y, bit3 -y; the graph starts as 0b1111 everywhere).
+// Cuts are fire-and-forget atomicAnd on the containing 32-bit word (no other thread touches the slice), so the only
+// dependent chain is symbol fetch + control.
+__global__ void __launch_bounds__(32)
+k_crackle_cuts(const unsigned char* __restrict__ stream, const unsigned long long* __restrict__ slice_off, int sx, int sy, int sz,
+               unsigned char* __restrict__ vcg, u32* __restrict__ stack, u32* __restrict__ err) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= sz) return;
+  const unsigned char* blob = stream + slice_off[z];
+  const size_t blob_len = (size_t)(slice_off[z + 1] - slice_off[z]);
+  if (blob_len < 6) { if (blob_len) atomicOr(err, 1u); return; }
+  const u32 index_bytes = (u32)blob[0] | ((u32)blob[1] << 8) | ((u32)blob[2] << 16) | ((u32)blob[3] << 24);
+  if (4 + (size_t)index_bytes > blob_len) { atomicOr(err, 1u); return; }
+  const unsigned char* idx = blob + 4;
+  auto rd16 = [&](u32 p) -> u32 { return (u32)idx[2 * p] | ((u32)idx[2 * p + 1] << 8); };
+  const unsigned char* codes = blob + 4 + index_bytes;
+  const size_t nsym = (blob_len - 4 - index_bytes) * 4;
+  u32* stk = stack + 2 * (size_t)slice_off[z];          // room for one entry per two symbols of this slice
+  const size_t stk_cap = 2 * blob_len;
+  u32* plane = reinterpret_cast<u32*>(vcg + (size_t)z * sx * sy);   // sx * sy is a multiple of 4 (checked by the host)
+  auto clear_bit = [&](int px, int py, int bit) {
+    if (px < 0 || px >= sx || py < 0 || py >= sy) return;
+    const size_t i = (size_t)py * sx + px;
+    atomicAnd(plane + (i >> 2), ~((1u << bit) << (8 * (i & 3))));
+  };
+  size_t i = 0;
+  u32 acc = 0;
+  u32 p = 0;
+  const u32 nidx = index_bytes / 2;
+  if (nidx == 0) return;
+  const u32 n_rows = rd16(p++);
+  int y0 = 0;
+  for (u32 r = 0; r < n_rows; r++) {
+    if (p + 2 > nidx) { atomicOr(err, 2u); return; }
+    y0 += (int)rd16(p); const u32 n = rd16(p + 1); p += 2;
+    int x0 = 0;
+    for (u32 k = 0; k < n; k++) {
+      if (p >= nidx) { atomicOr(err, 2u); return; }
+      x0 += (int)rd16(p++);
+      int x = x0, y = y0;
+      int branches = 1, last = -1;
+      size_t sp = 0;
+      while (branches > 0) {
+        if (i >= nsym) { atomicOr(err, 4u); return; }
+        acc = (acc + ((codes[i >> 2] >> (2 * (i & 3))) & 3u)) & 3u;
+        i++;
+        const int d = (int)acc;
+        if (last >= 0 && ((d - last) & 3) == 2) {
+          if (d == 0 || d == 3) {
+            branches--;
+            if (sp) { const u32 v = stk[--sp]; x = (int)(v & 0xFFFFu); y = (int)(v >> 16); }
+          } else {
+            branches++;
+            if (sp >= stk_cap) { atomicOr(err, 8u); return; }
+            stk[sp++] = (u32)x | ((u32)y << 16);
+          }
+          last = -1;
+          continue;
+        }
+        if (last >= 0) {
+          if (last == 0) { clear_bit(x - 1, y - 1, 0); clear_bit(x, y - 1, 1); y--; }
+          else if (last == 2) { clear_bit(x - 1, y, 0); clear_bit(x, y, 1); y++; }
+          else if (last == 3) { clear_bit(x - 1, y - 1, 2); clear_bit(x - 1, y, 3); x--; }
+          else { clear_bit(x, y - 1, 2); clear_bit(x, y, 3); x++; }
+        }
+        last = d;
+      }
+    }
+  }
+}

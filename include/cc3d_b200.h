@@ -219,6 +219,17 @@ int cc3d_b200_contacts(const void* labels, int kind, int64_t sx, int64_t sy, int
                        uint64_t* pairs, uint32_t* class_counts, uint64_t capacity, uint64_t* count, int mem_space,
                        void* stream);
 
+/* crackle v0 decode on the device (the on-disk format either side of the labelling path;
+ * its colouring step is color_connectivity_graph, cc3d_graphs.hpp:583-1106, 1018-1074). `stream` (HOST) holds the
+ * concatenated per-slice crack-code blobs, slice z = bytes [slice_off[z], slice_off[z+1]); the crack codes are turned
+ * into the 4-bit pixel graph by one thread per slice, all slices are coloured at once (4-connected, numbered slice by
+ * slice in raster order = the order of the file's key table) and out[i] = lut[component of i] (lut[0] unused, n_lut
+ * entries, HOST). `out` (uint32, x fastest, sx*sy*sz) may be a HOST or a DEVICE pointer. *n_components = total number
+ * of per-slice components. Flat labels / "impermissible" crack format only (the format of the reference's fixture). */
+int cc3d_b200_crackle_v0_decode(const uint8_t* stream, const uint64_t* slice_off, int64_t sx, int64_t sy, int64_t sz,
+                                const uint32_t* lut, uint64_t n_lut, uint32_t* out, uint64_t* n_components, int mem_space,
+                                void* cuda_stream);
+
 /* out[i] = table[labels[i]] (labels above N give 0): the relabelling step of cc3d.largest_k
  * (cc3d/__init__.py:262-276, fastremap.mask_except + renumber / runs + draw). out kind u8/u16/u32/u64. */
 int cc3d_b200_remap_labels(const void* labels, int label_kind, int64_t voxels, const uint32_t* table, uint64_t N,

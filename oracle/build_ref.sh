@@ -11,7 +11,9 @@ mkdir -p "$OUT"
 PY=${PYTHON:-python3}
 SUFFIX=$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')
 # the reference's own test file travels with the build (git-ignored): tests/test_reference_suite.py runs it against the drop-in
-if [ -f "$REF/automated_test.py" ]; then cp "$REF/automated_test.py" "$OUT/automated_test.py"; fi
+if [ -f "$REF/automated_test.py" ]; then cp -f "$REF/automated_test.py" "$OUT/automated_test.py" && chmod u+w "$OUT/automated_test.py"; fi
+# the crackle-v0 benchmark volume itself (3 MB data file): input of the GPU crackle decoder test
+if [ -f "$REF/benchmarks/connectomics.npy.ckl.gz" ]; then cp -f "$REF/benchmarks/connectomics.npy.ckl.gz" "$OUT/connectomics.npy.ckl.gz" && chmod u+w "$OUT/connectomics.npy.ckl.gz"; fi
 if [ -f "$OUT/fastcc3d$SUFFIX" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "oracle/_ref/fastcc3d$SUFFIX already built"; exit 0
 fi

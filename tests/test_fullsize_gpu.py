@@ -349,3 +349,32 @@ def test_statistics_one_sweep_capacity_and_errors(cc3d, oracle_mod):
       cc3d.statistics(torch.from_numpy(bad.view(np.int32) if bad.dtype == np.uint32 else bad).cuda())
     if bad is neg:
       assert str(e3.value) == str(e1.value)
+
+
+# ---- crackle v0 decode on the GPU (chain parse -> pixel graph -> colouring -> key table) ----
+def test_crackle_v0_decode_of_the_benchmark_volume(cc3d):
+  import hashlib
+  import os
+  import time
+  from cc3d_b200 import crackle
+  from oracle import decode_connectomics
+  path = os.path.join(os.path.dirname(decode_connectomics.DST), "connectomics.npy.ckl.gz")
+  if not os.path.exists(path):
+    pytest.skip("oracle/_ref/connectomics.npy.ckl.gz did not travel (copied by oracle/build_ref.sh)")
+  raw = open(path, "rb").read()
+  crackle.decompress(raw)                      # warm-up (workspace allocation)
+  t0 = time.perf_counter()
+  vol = crackle.decompress(raw)
+  dt = time.perf_counter() - t0
+  assert vol.shape == (512, 512, 512) and vol.dtype == np.uint32 and vol.flags.f_contiguous
+  assert hashlib.sha256(vol.tobytes(order="F")).hexdigest() == decode_connectomics.SHA
+  assert dt < 1.0, f"decode took {dt:.2f} s"
+  fix = decode_connectomics.load_fixture()
+  if fix is not None:
+    assert np.array_equal(vol, fix)
+  t = crackle.decompress(raw, device="cuda")   # stays on the device
+  assert t.is_cuda and tuple(t.shape) == (512, 512, 512)
+  lab, N = cc3d.connected_components(t, connectivity=26, return_N=True)
+  assert N == 3619
+  with pytest.raises(ValueError):
+    crackle.decompress(b"nope" + raw[4:100])
