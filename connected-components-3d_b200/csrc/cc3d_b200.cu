@@ -1014,10 +1014,14 @@ template <typename LT>
 static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts, u32* bbox, u64* sums, cudaStream_t s,
                             unsigned long long* maxout = nullptr) {
   static PerDeviceOnce once;
-  auto k = k_statistics<LT>;
-  if (once.first()) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable));
+  static const bool v1 = getenv("CC3D_B200_STATS_V1") != nullptr;     // vertical-run formulation (A/B)
+  if (once.first()) {
+    cudaFuncSetAttribute(k_statistics<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable));
+    cudaFuncSetAttribute(k_statistics2<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable2));
+  }
   k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
-  k<<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
+  if (v1) k_statistics<LT><<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
+  else k_statistics2<LT><<<148 * 4, 256, sizeof(StatTable2), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
   g_launches += 2;
   return 0;
 }
