@@ -960,13 +960,15 @@ def color_connectivity_graph(vcg, connectivity: int = 26, return_N: bool = False
   """Labels the components of a voxel connectivity graph; same contract as cc3d.color_connectivity_graph
   (fastcc3d.pyx:941-1018): uint32 labels, every voxel labelled, numbered by first appearance in Fortran order."""
   L = _lib.lib()
+  vcg = _adopt_device_array(vcg)
   if _is_torch(vcg):
-    dev = vcg.device
-    out = color_connectivity_graph(vcg.cpu().numpy(), connectivity, return_N)
+    if vcg.is_cuda:
+      return _color_connectivity_graph_device(vcg, connectivity, return_N)
     import torch
+    out = color_connectivity_graph(vcg.numpy(), connectivity, return_N)
     if return_N:
-      return torch.from_numpy(out[0].view(np.int32)).to(dev).view(torch.uint32), out[1]
-    return torch.from_numpy(out.view(np.int32)).to(dev).view(torch.uint32)
+      return torch.from_numpy(out[0].view(np.int32)).view(torch.uint32), out[1]
+    return torch.from_numpy(out.view(np.int32)).view(torch.uint32)
   dims = len(vcg.shape)
   if dims not in (2, 3):
     raise DimensionError("Only 2D, and 3D arrays supported. Got: " + str(dims))
@@ -996,6 +998,57 @@ def color_connectivity_graph(vcg, connectivity: int = 26, return_N: bool = False
   return out_labels
 
 
+def _fortran_flat_device(t):
+  """(flat tensor in Fortran memory order, i.e. first axis fastest; (sx, sy, sz)) of a 2-D / 3-D CUDA tensor - a view
+  when the tensor already is Fortran-ordered, else one transposing copy on the device."""
+  shape = list(t.shape) + [1] * (3 - t.ndim)
+  rev = t.permute(*reversed(range(t.ndim)))       # (.., y, x): C-contiguous iff t is Fortran-ordered
+  return rev.contiguous().reshape(-1), tuple(shape)
+
+
+def _color_connectivity_graph_device(vcg, connectivity, return_N):
+  """color_connectivity_graph of a CUDA tensor without leaving the device (zero copy for Fortran-ordered graphs)."""
+  import torch
+  L = _lib.lib()
+  dims = vcg.ndim
+  if dims not in (2, 3):
+    raise DimensionError("Only 2D, and 3D arrays supported. Got: " + str(dims))
+  if dims == 2 and connectivity not in [4, 8, 6, 26]:
+    raise ValueError(f"Only 4 and 8 connectivity is supported for 2D images. Got: {connectivity}")
+  elif dims != 2 and connectivity not in [6, 26]:
+    raise ValueError(f"Only 6 and 26 connectivity are supported for 3D images. Got: {connectivity}")
+  np_dt = _torch_np_dtype(vcg)
+  if np_dt.kind == "i" and np_dt.itemsize in (1, 4):
+    np_dt = np.dtype(_UNSIGNED[np_dt.itemsize])     # torch spells uint32 graphs as int32 more often than not
+  if np_dt not in (np.uint8, np.uint32):
+    raise ValueError(f"Only uint8 and uint32 are supported. Got: {np_dt}")
+  if vcg.numel() == 0:
+    return torch.zeros([0] * dims, dtype=torch.uint32, device=vcg.device)
+  flat, (sx, sy, sz) = _fortran_flat_device(vcg.detach())
+  if connectivity in [18, 26] and sz > 1 and np_dt != np.uint32:
+    raise ValueError(f"Only uint32 is supported for 18 and 26 connected. Got: {np_dt}")
+  out = torch.empty((sx * sy * sz,), dtype=torch.uint32, device=vcg.device)
+  N = ctypes.c_uint64(0)
+  with torch.cuda.device(vcg.device):
+    _lib.check(L.cc3d_b200_color_connectivity_graph(
+      flat.data_ptr(), _kind_of(np_dt), sx, sy, sz, int(connectivity), out.data_ptr(), ctypes.byref(N), _lib.DEVICE,
+      ctypes.c_void_p(torch.cuda.current_stream(vcg.device).cuda_stream)))
+  out = out.reshape(tuple(reversed(vcg.shape))).permute(*reversed(range(dims)))      # Fortran-ordered like the reference's
+  return (out, int(N.value)) if return_N else out
+
+
+def _contacts_wide_labels(labels, connectivity, surface_area, anisotropy):
+  """contacts for uint64 label VALUES >= 2^32 (the pair keys of the kernel pack two 32-bit labels): the labels are
+  replaced by their ranks among the distinct values (order preserving, 0 stays 0), the ranks go through the kernel and
+  the pairs are mapped back. cc3d_graphs.hpp:300-468 handles any label width."""
+  uniq, inv = np.unique(labels, return_inverse=True)
+  inv = np.asarray(inv).reshape(labels.shape)
+  shift = 0 if (uniq.size and uniq[0] == 0) else 1          # rank 0 must mean background
+  ranks = np.asfortranarray((inv + shift).astype(np.uint32))
+  res = contacts(ranks, connectivity=connectivity, surface_area=surface_area, anisotropy=anisotropy)
+  return {(int(uniq[a - shift]), int(uniq[b - shift])): v for (a, b), v in res.items()}
+
+
 def contacts(labels, connectivity: int = 26, surface_area: bool = True, anisotropy=(1, 1, 1)) -> dict:
   """Region adjacency graph with contact areas; same contract as cc3d.contacts (fastcc3d.pyx:1196-1252):
   {(label_1, label_2): float} with label_1 < label_2. The GPU counts the contacts of every pair per direction
@@ -1003,8 +1056,14 @@ def contacts(labels, connectivity: int = 26, surface_area: bool = True, anisotro
   agree whenever the reference's running sum stays exactly representable, e.g. integer areas below 2^24).
   Label values must be < 2^32."""
   L = _lib.lib()
+  labels = _adopt_device_array(labels)
+  device_flat = None
   if _is_torch(labels):
-    labels = labels.cpu().numpy() if labels.is_cuda else labels.numpy()
+    if labels.is_cuda and labels.ndim in (2, 3) and _torch_np_dtype(labels).kind in "iu" and labels.numel():
+      # the label volume stays on the device; only the pair table comes back
+      device_flat, dshape = _fortran_flat_device(labels.detach())
+      dkind = _kind_of(_torch_np_dtype(labels))
+    labels = (labels[:1].cpu() if device_flat is not None else labels.cpu()).numpy()   # dtype / rank checks below
   labels = np.asarray(labels)
   while labels.ndim < 3:
     labels = labels[..., np.newaxis]
@@ -1018,18 +1077,37 @@ def contacts(labels, connectivity: int = 26, surface_area: bool = True, anisotro
   labels = np.asfortranarray(_view_as_unsigned(labels))
   if labels.dtype == bool:
     labels = labels.view(np.uint8)
-  sx, sy, sz = labels.shape
+  sx, sy, sz = labels.shape if device_flat is None else dshape
   if connectivity in (4, 8) and sz != 1:
     raise RuntimeError("z thickness must be 1 for 2d region graph extraction.")
   if labels.size == 0:
     return {}
   cap = 1 << 16
   while True:
-    keys = np.empty(cap, dtype=np.uint64)
-    vals = np.empty((cap, 4), dtype=np.uint32)
     n = ctypes.c_uint64(0)
-    _lib.check(L.cc3d_b200_contacts(labels.ctypes.data, _kind_of(labels.dtype), sx, sy, sz, int(connectivity),
-                                    keys.ctypes.data, vals.ctypes.data, cap, ctypes.byref(n), _lib.HOST, None))
+    try:
+      if device_flat is not None:
+        import torch
+        dkeys = torch.empty((cap,), dtype=torch.int64, device=device_flat.device)
+        dvals = torch.empty((cap, 4), dtype=torch.int32, device=device_flat.device)
+        with torch.cuda.device(device_flat.device):
+          _lib.check(L.cc3d_b200_contacts(device_flat.data_ptr(), dkind, sx, sy, sz, int(connectivity), dkeys.data_ptr(),
+                                          dvals.data_ptr(), cap, ctypes.byref(n), _lib.DEVICE,
+                                          ctypes.c_void_p(torch.cuda.current_stream(device_flat.device).cuda_stream)))
+        if n.value <= cap:
+          keys, vals = dkeys[: n.value].cpu().numpy().view(np.uint64), dvals[: n.value].cpu().numpy().view(np.uint32)
+      else:
+        keys = np.empty(cap, dtype=np.uint64)
+        vals = np.empty((cap, 4), dtype=np.uint32)
+        _lib.check(L.cc3d_b200_contacts(labels.ctypes.data, _kind_of(labels.dtype), sx, sy, sz, int(connectivity),
+                                        keys.ctypes.data, vals.ctypes.data, cap, ctypes.byref(n), _lib.HOST, None))
+    except CC3DB200Error as e:
+      if e.code != -5 or "2^32" not in str(e):
+        raise
+      # label values >= 2^32: go through order-preserving ranks (host arrays; device tensors come to the host for it)
+      wide = labels if device_flat is None else np.asfortranarray(
+        device_flat.cpu().numpy().view(_UNSIGNED[device_flat.element_size()]).reshape((sx, sy, sz), order="F"))
+      return _contacts_wide_labels(wide, connectivity, surface_area, anisotropy)
     if n.value <= cap:
       break
     cap = 1 << int(n.value - 1).bit_length()

@@ -378,3 +378,37 @@ def test_crackle_v0_decode_of_the_benchmark_volume(cc3d):
   assert N == 3619
   with pytest.raises(ValueError):
     crackle.decompress(b"nope" + raw[4:100])
+
+
+# ---- SURVEY 8(f)1/3 on device tensors (zero copy) and contacts with 64-bit label values ----
+def test_graph_rows_on_device_tensors_and_wide_labels(cc3d, oracle_mod):
+  import torch
+  from helpers import blobs
+  ref = _ref(oracle_mod)
+  rng = np.random.default_rng(33)
+  for it in range(12):
+    dims = 3 if it % 3 else 2
+    shape = tuple(int(rng.integers(5, 50)) for _ in range(dims))
+    x = blobs(rng, shape, 5, int(rng.integers(1, 4))).astype(np.uint32)
+    conn = int(rng.choice([6, 26] if dims == 3 else [4, 8]))
+    for order in ("C", "F"):
+      xa = np.asarray(x, order=order)
+      t = torch.from_numpy(xa.view(np.int32)).cuda()
+      if order == "F":
+        t = torch.from_numpy(np.ascontiguousarray(xa.T).view(np.int32)).cuda().permute(*reversed(range(dims)))   # F-ordered tensor
+      assert ref.contacts(xa, connectivity=conn, anisotropy=(2, 3, 5)) == cc3d.contacts(t, connectivity=conn, anisotropy=(2, 3, 5))
+      g = ref.voxel_connectivity_graph(xa, connectivity=conn)
+      g[rng.random(g.shape) < 0.05] &= g.dtype.type(0x15)
+      want, Nw = ref.color_connectivity_graph(g, connectivity=conn, return_N=True)
+      gt = torch.from_numpy(np.ascontiguousarray(g).view(np.int32 if g.dtype == np.uint32 else np.uint8)).cuda()
+      got, N = cc3d.color_connectivity_graph(gt, connectivity=conn, return_N=True)
+      assert got.is_cuda and N == Nw and np.array_equal(got.cpu().numpy().view(np.uint32), want), (shape, conn, order)
+  # uint64 label VALUES above 2^32 (configs[2] uses 62-bit ids): the reference handles any width
+  big = (blobs(rng, (30, 25, 20), 6, 3).astype(np.uint64) * np.uint64(0x1234567890ABCDEF // 7)) & np.uint64((1 << 62) - 1)
+  for conn in (6, 18, 26):
+    assert ref.contacts(big, connectivity=conn) == cc3d.contacts(big, connectivity=conn)
+    assert ref.region_graph(big, connectivity=conn) == cc3d.region_graph(big, connectivity=conn)
+  nz = big + np.uint64(1 << 40)     # no background at all: rank 0 must not alias a real label
+  assert ref.contacts(nz, connectivity=26) == cc3d.contacts(nz, connectivity=26)
+  tb = torch.from_numpy(big.view(np.int64)).cuda()
+  assert ref.contacts(big, connectivity=26) == cc3d.contacts(tb, connectivity=26)
