@@ -319,15 +319,15 @@ k_mask_by_label(IT* __restrict__ img, const LT* __restrict__ labels, const unsig
 //           region of the volume: few labels) and flush their table with global atomics once.
 // Labels above N are ignored; the largest label seen goes to *maxout (statistics_auto).
 // ---------------------------------------------------------------------------------------------
-#define CC_ST2_RECS 1024
+#define CC_ST2_WRECS 128          // records per warp and span (a span of 1024 voxels rarely has more runs; the rest is applied directly)
+#define CC_ST2_LOADS 8           // words whose loads are issued back to back (memory-level parallelism)
 struct StatTable2 {
   u32 key[CC_STAT_SLOTS];   // label + 1, 0 = empty
   u32 cnt[CC_STAT_SLOTS];
   u32 bb[CC_STAT_SLOTS][6];
   u32 sumlo[CC_STAT_SLOTS][3];
   u32 sumhi[CC_STAT_SLOTS][3];
-  uint4 rec[CC_ST2_RECS];   // {label, first x, length, row}
-  u32 nrec;
+  uint4 rec[8][CC_ST2_WRECS];   // per warp: {label, first x, length, row}
 };
 
 template <typename LT>
@@ -343,7 +343,6 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
     tb.sumlo[i][0] = tb.sumlo[i][1] = tb.sumlo[i][2] = 0;
     tb.sumhi[i][0] = tb.sumhi[i][1] = tb.sumhi[i][2] = 0;
   }
-  if (threadIdx.x == 0) tb.nrec = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 sx = (u32)g.sx, sy = (u32)g.sy;
@@ -352,6 +351,7 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
   const i64 nspans = nspr * g.rows;
   const LT nmax = (u64)(LT)~(LT)0 <= N ? (LT)~(LT)0 : (LT)N;   // labels above N are ignored
   LT vmax = (LT)0;
+  uint4* __restrict__ wrec = tb.rec[warp];
 
   // cnt voxels of label l with absolute sums and box -> per-CTA table (global memory when the table is full)
   auto cta_add = [&](u32 l, u32 cnt, unsigned long long sumx, unsigned long long sumy, unsigned long long sumz,
@@ -390,99 +390,102 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
     sm_add64(&tb.sumlo[slot][1], &tb.sumhi[slot][1], sumy);
     sm_add64(&tb.sumlo[slot][2], &tb.sumhi[slot][2], sumz);
   };
-  // one record, handled by one lane (list overflow only)
-  auto apply_record = [&](u32 l, u32 x, u32 len, u32 row) {
-    const u32 z = row / sy, y = row - z * sy;
-    cta_add(l, len, (unsigned long long)len * x + (unsigned long long)len * (len - 1) / 2, (unsigned long long)len * y,
-            (unsigned long long)len * z, x, x + len - 1, y, y, z, z);
-  };
 
+  // every CTA owns a contiguous range of spans (a compact region of the volume: few labels in its table); its warps
+  // take them round robin and never wait for each other
   const i64 per_cta = (nspans + gridDim.x - 1) / gridDim.x;
   const i64 span_end = min(nspans, (i64)(blockIdx.x + 1) * per_cta);
-  for (i64 batch = (i64)blockIdx.x * per_cta; batch < span_end; batch += 8) {
-    // ---- phase 1: the runs of 8 spans -> records ----
-    const i64 span = batch + warp;
-    if (span < span_end) {
-      const u32 row = (u32)(span / nspr);
-      const u32 w0 = (u32)(span - (i64)row * nspr) * 32;
-      const u32 nwd = min(32u, (u32)W - w0);
-      const LT* __restrict__ p = labels + ((size_t)row * sx + ((size_t)w0 << 5) + lane);
-      LT carry = (LT)0;            // value of the voxel left of the current word (uniform); unused for the first word
-      u32 run_start = w0 << 5;     // first x of the run that is open at the beginning of the current word (uniform)
-      bool have_open = false;      // a run is open (false only before the first voxel of the span)
-#pragma unroll 2
-      for (u32 j = 0; j < nwd; j++) {
-        const u32 x = ((w0 + j) << 5) + lane;
-        const bool in = x < sx;
-        LT v = (LT)0;
-        if (in) v = p[(size_t)j << 5];
-        if (in && v > vmax) vmax = v;
-        LT left = __shfl_up_sync(CC_FULL, v, 1);
-        if (lane == 0) left = carry;
-        // a run starts here: first voxel of the span, value change, or the first voxel beyond the row (closes the last run)
-        const bool first = (j == 0 && lane == 0);
-        const bool head = first || (in ? (v != left) : (x == sx));
-        const u32 H = __ballot_sync(CC_FULL, head);
-        if (H) {
-          // the lane that starts a run emits the run that ended at x - 1 (label `left`, start = previous head or run_start)
-          const u32 below = H & ((1u << lane) - 1u);
-          const u32 xs = below ? (((w0 + j) << 5) + (31u - __clz(below))) : run_start;
-          const bool emit = head && !first && (below != 0u || have_open) && left <= nmax;
-          const u32 E = __ballot_sync(CC_FULL, emit);
-          if (E) {
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(&tb.nrec, (u32)__popc(E));
-            base = __shfl_sync(CC_FULL, base, 0);
+  for (i64 span = (i64)blockIdx.x * per_cta + warp; span < span_end; span += 8) {
+    const u32 row = (u32)(span / nspr);
+    const u32 z = row / sy, y = row - z * sy;
+    const u32 w0 = (u32)(span - (i64)row * nspr) * 32;
+    const u32 nwd = min(32u, (u32)W - w0);
+    const LT* __restrict__ p = labels + ((size_t)row * sx + ((size_t)w0 << 5) + lane);
+    LT carry = (LT)0;            // value of the voxel left of the current word (uniform); unused for the first word
+    u32 run_start = w0 << 5;     // first x of the run that is open at the beginning of the current word (uniform)
+    bool have_open = false;      // a run is open (false only before the first voxel of the span)
+    u32 nrec = 0;                // records of this span so far (uniform)
+    // ---- phase 1 (voxel-parallel): the runs of the span -> records ----
+    for (u32 j0 = 0; j0 < nwd; j0 += CC_ST2_LOADS) {
+      LT vv[CC_ST2_LOADS];
+#pragma unroll
+      for (int k = 0; k < CC_ST2_LOADS; k++) {
+        const u32 x = ((w0 + j0 + k) << 5) + lane;
+        vv[k] = (LT)0;
+        if (j0 + k < nwd && x < sx) vv[k] = p[(size_t)(j0 + k) << 5];
+      }
+#pragma unroll
+      for (int k = 0; k < CC_ST2_LOADS; k++) {
+        const u32 j = j0 + k;
+        if (j < nwd) {                                  // warp-uniform
+          const u32 x = ((w0 + j) << 5) + lane;
+          const bool in = x < sx;
+          const LT v = vv[k];
+          if (in && v > vmax) vmax = v;
+          LT left = __shfl_up_sync(CC_FULL, v, 1);
+          if (lane == 0) left = carry;
+          // a run starts here: first voxel of the span, value change, or the first voxel beyond the row (closes the last run)
+          const bool first = (j == 0 && lane == 0);
+          const bool head = first || (in ? (v != left) : (x == sx));
+          const u32 H = __ballot_sync(CC_FULL, head);
+          if (H) {
+            // the lane that starts a run emits the run that ended at x - 1 (label `left`, start = previous head or run_start)
+            const u32 below = H & ((1u << lane) - 1u);
+            const u32 xs = below ? (((w0 + j) << 5) + (31u - __clz(below))) : run_start;
+            const bool emit = head && !first && (below != 0u || have_open) && left <= nmax;
+            const u32 E = __ballot_sync(CC_FULL, emit);
             if (emit) {
-              const u32 pos = base + __popc(E & ((1u << lane) - 1u));
-              if (pos < CC_ST2_RECS) tb.rec[pos] = make_uint4((u32)left, xs, x - xs, row);
-              else apply_record((u32)left, xs, x - xs, row);
+              const u32 pos = nrec + __popc(E & ((1u << lane) - 1u));
+              if (pos < CC_ST2_WRECS) wrec[pos] = make_uint4((u32)left, xs, x - xs, 0u);
+              else {
+                const u32 len = x - xs;
+                cta_add((u32)left, len, (unsigned long long)len * xs + (unsigned long long)len * (len - 1) / 2,
+                        (unsigned long long)len * y, (unsigned long long)len * z, xs, x - 1, y, y, z, z);
+              }
             }
+            nrec += __popc(E);
+            run_start = ((w0 + j) << 5) + (31u - __clz(H));
+            have_open = true;
           }
-          run_start = ((w0 + j) << 5) + (31u - __clz(H));
-          have_open = true;
+          carry = __shfl_sync(CC_FULL, v, 31);
         }
-        carry = __shfl_sync(CC_FULL, v, 31);
-      }
-      // the run that is still open at the end of the span (rows that end inside the last word were closed by x == sx)
-      const u32 xend = min(sx, (w0 + nwd) << 5);
-      if (lane == 0 && have_open && run_start < xend && carry <= nmax) {
-        // carry = value of the last voxel of the span when the row fills its last word; otherwise the run was closed above
-        const u32 pos = atomicAdd(&tb.nrec, 1u);
-        if (pos < CC_ST2_RECS) tb.rec[pos] = make_uint4((u32)carry, run_start, xend - run_start, row);
-        else apply_record((u32)carry, run_start, xend - run_start, row);
       }
     }
-    __syncthreads();
-    // ---- phase 2: one record per thread; lanes with the same label are combined ----
-    const u32 nrec = min(tb.nrec, (u32)CC_ST2_RECS);
-    for (u32 base = 0; base < nrec; base += blockDim.x) {
-      const u32 i = base + threadIdx.x;
+    // the run that is still open at the end of the span (rows that end inside the last word were closed by x == sx)
+    const u32 xend = min(sx, (w0 + nwd) << 5);
+    if (have_open && run_start < xend && carry <= nmax) {
+      if (lane == 0) {
+        if (nrec < CC_ST2_WRECS) wrec[nrec] = make_uint4((u32)carry, run_start, xend - run_start, 0u);
+        else {
+          const u32 len = xend - run_start;
+          cta_add((u32)carry, len, (unsigned long long)len * run_start + (unsigned long long)len * (len - 1) / 2,
+                  (unsigned long long)len * y, (unsigned long long)len * z, run_start, xend - 1, y, y, z, z);
+        }
+      }
+      nrec++;
+    }
+    __syncwarp();
+    // ---- phase 2 (record-parallel): one record per lane; lanes with the same label are combined ----
+    nrec = min(nrec, (u32)CC_ST2_WRECS);
+    for (u32 base = 0; base < nrec; base += 32) {
+      const u32 i = base + lane;
       const bool have = i < nrec;
-      uint4 r = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-      if (have) r = tb.rec[i];
       const u32 act = __ballot_sync(CC_FULL, have);
-      if (!have) continue;
-      const u32 len = r.z, x = r.y;
-      const u32 z = r.w / sy, y = r.w - z * sy;
-      const unsigned long long sxv = (unsigned long long)len * x + (unsigned long long)len * (len - 1) / 2;
-      const unsigned long long syv = (unsigned long long)len * y, szv = (unsigned long long)len * z;
-      const u32 grp = __match_any_sync(act, r.x);
-      const u32 cnt = __reduce_add_sync(grp, len);
-      // 64-bit sums of up to 32 values below 2^42: two 21-bit digits each, every digit sum fits 32 bits
-      const u32 ax = __reduce_add_sync(grp, (u32)(sxv & 0x1FFFFFu)), bx = __reduce_add_sync(grp, (u32)(sxv >> 21));
-      const u32 ay = __reduce_add_sync(grp, (u32)(syv & 0x1FFFFFu)), by = __reduce_add_sync(grp, (u32)(syv >> 21));
-      const u32 az = __reduce_add_sync(grp, (u32)(szv & 0x1FFFFFu)), bz = __reduce_add_sync(grp, (u32)(szv >> 21));
-      const u32 xmin = __reduce_min_sync(grp, x), xmax = __reduce_max_sync(grp, x + len - 1);
-      const u32 ymin = __reduce_min_sync(grp, y), ymax = __reduce_max_sync(grp, y);
-      const u32 zmin = __reduce_min_sync(grp, z), zmax = __reduce_max_sync(grp, z);
-      if (lane == __ffs(grp) - 1)
-        cta_add(r.x, cnt, (unsigned long long)ax + ((unsigned long long)bx << 21), (unsigned long long)ay + ((unsigned long long)by << 21),
-                (unsigned long long)az + ((unsigned long long)bz << 21), xmin, xmax, ymin, ymax, zmin, zmax);
+      if (have) {
+        const uint4 r = wrec[i];
+        const u32 len = r.z, x = r.y;
+        const unsigned long long sxv = (unsigned long long)len * x + (unsigned long long)len * (len - 1) / 2;
+        const u32 grp = __match_any_sync(act, r.x);
+        const u32 cnt = __reduce_add_sync(grp, len);
+        // 64-bit sums of up to 32 values below 2^42: two 21-bit digits each, every digit sum fits 32 bits
+        const u32 ax = __reduce_add_sync(grp, (u32)(sxv & 0x1FFFFFu)), bx = __reduce_add_sync(grp, (u32)(sxv >> 21));
+        const u32 xmin = __reduce_min_sync(grp, x), xmax = __reduce_max_sync(grp, x + len - 1);
+        if (lane == __ffs(grp) - 1)
+          cta_add(r.x, cnt, (unsigned long long)ax + ((unsigned long long)bx << 21), (unsigned long long)cnt * y,
+                  (unsigned long long)cnt * z, xmin, xmax, y, y, z, z);
+      }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) tb.nrec = 0;
-    __syncthreads();
+    __syncwarp();
   }
   if (maxout) {
     unsigned long long m = (unsigned long long)vmax;
