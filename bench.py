@@ -374,6 +374,27 @@ def main():
               "pipeline_frac": alg_bytes / (ms / args.steps / 1e3) / 1e9 / peak}
 
   # ---- e2e: public API on pinned host buffers (H2D + kernels + D2H inside the timed region) ----
+  # NUMA: the pinned staging buffers should live on the memory node of this rank's GPU (r01: with every rank on node 0
+  # the 8-GPU e2e collapsed). Bind this process to the CPUs of the GPU's node before allocating them, if the cpuset
+  # allows it; report what was possible.
+  numa = {"gpu_node": None, "bound": False, "affinity_before": len(os.sched_getaffinity(0))}
+  try:
+    props = torch.cuda.get_device_properties(local_rank)
+    bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+    node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+    numa["gpu_node"] = node
+    if node >= 0:
+      cpus = set()
+      for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+      allowed = cpus & os.sched_getaffinity(0)
+      if allowed:
+        os.sched_setaffinity(0, allowed)
+        numa["bound"] = True
+      numa["node_cpus_allowed"] = len(allowed)
+  except Exception as e:   # noqa: BLE001 - informational only
+    numa["error"] = repr(e)[:120]
   xh = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
   xh.copy_(x)
   np_out_dtype = {"uint16": np.uint16, "uint32": np.uint32, "uint64": np.uint64}[out_dtype]
@@ -402,9 +423,33 @@ def main():
   barrier()
   e2e_ms = max_over_ranks(e0.elapsed_time(e1))
   assert N2 == N
+  # the two copies alone, every rank at the same time (what the PCIe / host-memory path of this box gives each GPU)
+  def copy_gbs(fn, nbytes):
+    fn(); barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+      fn()
+    c1.record(); barrier()
+    return nbytes * 3 / (c0.elapsed_time(c1) / 1e3) / 1e9
+  xd_tmp = torch.empty_like(x)
+  od_tmp = torch.empty((voxels * out_bytes,), dtype=torch.uint8, device=dev)
+  h2d_gbs = copy_gbs(lambda: xd_tmp.copy_(xh, non_blocking=True), voxels * x.element_size())
+  d2h_gbs = copy_gbs(lambda: oh.copy_(od_tmp, non_blocking=True), voxels * out_bytes)
+  del xd_tmp, od_tmp
+  if world > 1:
+    tt = torch.tensor([h2d_gbs, d2h_gbs], dtype=torch.float64, device=dev)
+    allt = [torch.empty_like(tt) for _ in range(world)]
+    dist.all_gather(allt, tt)
+    per_rank = [[round(float(v), 1) for v in t_.tolist()] for t_ in allt]
+  else:
+    per_rank = [[round(h2d_gbs, 1), round(d2h_gbs, 1)]]
   e2e = {"value": world * voxels * e2e_steps / (e2e_ms / 1e3) / 1e9, "unit": UNIT,
          "h2d_bytes_per_step": voxels * x.element_size(), "d2h_bytes_per_step": voxels * out_bytes + 32,
-         "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_memory": "pinned"}
+         "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_memory": "pinned",
+         "copy_GBps_per_rank_h2d_d2h": per_rank, "numa": numa,
+         "note": "e2e is bounded by the two PCIe copies (h2d + d2h bytes / the per-rank copy rates above); "
+                 "copy rates are measured with every rank copying at the same time"}
 
   # ---- other BASELINE workloads, same timing method (N=1 only) ----
   also = []

@@ -88,9 +88,15 @@ struct Geom {
 #define CC_TILE_THREADS (CC_TILE_WORDS / 2)
 #endif
 #define CC_TILE_NODES (CC_TILE_WORDS * 16)   // shared-memory forest: 16 runs per word (the binary maximum)
-#define CC_TILE_LQ (CC_TILE_WORDS * 4)       // queue of tile-local edges (packed 16+16 bit local run ids)
+#ifndef CC_TILE_LQ_FACTOR
+#define CC_TILE_LQ_FACTOR 4
+#endif
+#define CC_TILE_LQ (CC_TILE_WORDS * CC_TILE_LQ_FACTOR)   // queue of tile-local edges (packed 16+16 bit local run ids)
 #define CC_TILE_GQ (CC_TILE_WORDS * 2)       // staging buffer of edges that leave the tile (64-bit: two run ids)
 #define CC_TILE_GQ_EQ CC_TILE_WORDS          // ... for multilabel volumes (fewer edges leave a tile)
+#ifndef CC_B1_MINB
+#define CC_B1_MINB 6
+#endif
 #define CC_TILE_MINB(n) ((n) * 256 / CC_TILE_THREADS)
 
 // Device-side results of a labelling pass. The block is valid after being ZEROED (one memset clears it together with

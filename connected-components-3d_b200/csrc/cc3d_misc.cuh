@@ -319,7 +319,7 @@ k_mask_by_label(IT* __restrict__ img, const LT* __restrict__ labels, const unsig
 //           region of the volume: few labels) and flush their table with global atomics once.
 // Labels above N are ignored; the largest label seen goes to *maxout (statistics_auto).
 // ---------------------------------------------------------------------------------------------
-#define CC_ST2_WRECS 128          // records per warp and span (a span of 1024 voxels rarely has more runs; the rest is applied directly)
+#define CC_ST2_WRECS 256          // run starts per warp and span kept in shared memory (a span has at most 1024 + 1)
 #define CC_ST2_LOADS 8           // words whose loads are issued back to back (memory-level parallelism)
 struct StatTable2 {
   u32 key[CC_STAT_SLOTS];   // label + 1, 0 = empty
@@ -327,7 +327,7 @@ struct StatTable2 {
   u32 bb[CC_STAT_SLOTS][6];
   u32 sumlo[CC_STAT_SLOTS][3];
   u32 sumhi[CC_STAT_SLOTS][3];
-  uint4 rec[8][CC_ST2_WRECS];   // per warp: {label, first x, length, row}
+  uint2 rec[8][CC_ST2_WRECS + 1];   // per warp: {label, first x} of every run of the span, in x order (+ end sentinel)
 };
 
 template <typename LT>
@@ -350,12 +350,13 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
   const i64 nspr = (W + 31) / 32;                 // spans per row
   const i64 nspans = nspr * g.rows;
   const LT nmax = (u64)(LT)~(LT)0 <= N ? (LT)~(LT)0 : (LT)N;   // labels above N are ignored
+  constexpr u32 IGNORE = 0xFFFFFFFFu;             // record label of a run whose value is above N
   LT vmax = (LT)0;
-  uint4* __restrict__ wrec = tb.rec[warp];
+  uint2* __restrict__ wrec = tb.rec[warp];
 
   // cnt voxels of label l with absolute sums and box -> per-CTA table (global memory when the table is full)
   auto cta_add = [&](u32 l, u32 cnt, unsigned long long sumx, unsigned long long sumy, unsigned long long sumz,
-                     u32 xmin, u32 xmax, u32 ymin, u32 ymax, u32 zmin, u32 zmax) {
+                     u32 xmin, u32 xmax, u32 y, u32 z) {
     u32 h = (l * 2654435761u) >> 23;  // 9 bits
     int slot = -1;
 #pragma unroll 1
@@ -372,8 +373,8 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
       atomicAdd(&counts[l], cnt);
       u32* b = bbox + 6 * (size_t)l;
       atomicMin(&b[0], xmin); atomicMax(&b[1], xmax);
-      atomicMin(&b[2], ymin); atomicMax(&b[3], ymax);
-      atomicMin(&b[4], zmin); atomicMax(&b[5], zmax);
+      atomicMin(&b[2], y); atomicMax(&b[3], y);
+      atomicMin(&b[4], z); atomicMax(&b[5], z);
       unsigned long long* sg = sums + 3 * (size_t)l;
       atomicAdd(&sg[0], sumx); atomicAdd(&sg[1], sumy); atomicAdd(&sg[2], sumz);
       return;
@@ -382,13 +383,42 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
     volatile u32* b = tb.bb[slot];   // most additions do not move the box: read before the atomic
     if (xmin < b[0]) atomicMin(&tb.bb[slot][0], xmin);
     if (xmax > b[1]) atomicMax(&tb.bb[slot][1], xmax);
-    if (ymin < b[2]) atomicMin(&tb.bb[slot][2], ymin);
-    if (ymax > b[3]) atomicMax(&tb.bb[slot][3], ymax);
-    if (zmin < b[4]) atomicMin(&tb.bb[slot][4], zmin);
-    if (zmax > b[5]) atomicMax(&tb.bb[slot][5], zmax);
+    if (y < b[2]) atomicMin(&tb.bb[slot][2], y);
+    if (y > b[3]) atomicMax(&tb.bb[slot][3], y);
+    if (z < b[4]) atomicMin(&tb.bb[slot][4], z);
+    if (z > b[5]) atomicMax(&tb.bb[slot][5], z);
     sm_add64(&tb.sumlo[slot][0], &tb.sumhi[slot][0], sumx);
     sm_add64(&tb.sumlo[slot][1], &tb.sumhi[slot][1], sumy);
     sm_add64(&tb.sumlo[slot][2], &tb.sumhi[slot][2], sumz);
+  };
+
+  // Phase 2 on `n` runs whose starts are in wrec[0..n] (wrec[n] = end sentinel): one run per lane; the lanes are
+  // combined label by label with FULL-mask redux (a redux over a sub-mask that differs from lane to lane runs once
+  // per distinct mask), then the lanes that lead a label update the CTA table together.
+  auto accumulate = [&](u32 n, u32 y, u32 z) {
+    for (u32 base = 0; base < n; base += 32) {
+      const u32 i = base + lane;
+      u32 lab = IGNORE, x = 0, len = 0;
+      if (i < n) { const uint2 r = wrec[i]; lab = r.x; x = r.y; len = wrec[i + 1].y - x; }
+      const unsigned long long sxv = (unsigned long long)len * x + (unsigned long long)len * (len - 1) / 2;   // < 2^42
+      u32 todo = __ballot_sync(CC_FULL, lab != IGNORE);
+      u32 mycnt = 0, myxmin = 0, myxmax = 0;
+      unsigned long long mysx = 0;
+      bool leader = false;
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        const u32 cur = __shfl_sync(CC_FULL, lab, src);
+        const bool mine = lab == cur;
+        todo &= ~__ballot_sync(CC_FULL, mine);
+        const u32 c = __reduce_add_sync(CC_FULL, mine ? len : 0u);
+        const u32 a = __reduce_add_sync(CC_FULL, mine ? (u32)(sxv & 0x1FFFFFu) : 0u);     // two 21-bit digits: each sum fits 32 bits
+        const u32 b = __reduce_add_sync(CC_FULL, mine ? (u32)(sxv >> 21) : 0u);
+        const u32 mn = __reduce_min_sync(CC_FULL, mine ? x : 0xFFFFFFFFu);
+        const u32 mx = __reduce_max_sync(CC_FULL, mine ? x + len - 1 : 0u);
+        if (lane == src) { leader = true; mycnt = c; mysx = (unsigned long long)a + ((unsigned long long)b << 21); myxmin = mn; myxmax = mx; }
+      }
+      if (leader) cta_add(lab, mycnt, mysx, (unsigned long long)mycnt * y, (unsigned long long)mycnt * z, myxmin, myxmax, y, z);
+    }
   };
 
   // every CTA owns a contiguous range of spans (a compact region of the volume: few labels in its table); its warps
@@ -400,12 +430,12 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
     const u32 z = row / sy, y = row - z * sy;
     const u32 w0 = (u32)(span - (i64)row * nspr) * 32;
     const u32 nwd = min(32u, (u32)W - w0);
+    const u32 xend = min(sx, (w0 + nwd) << 5);
     const LT* __restrict__ p = labels + ((size_t)row * sx + ((size_t)w0 << 5) + lane);
     LT carry = (LT)0;            // value of the voxel left of the current word (uniform); unused for the first word
-    u32 run_start = w0 << 5;     // first x of the run that is open at the beginning of the current word (uniform)
-    bool have_open = false;      // a run is open (false only before the first voxel of the span)
-    u32 nrec = 0;                // records of this span so far (uniform)
-    // ---- phase 1 (voxel-parallel): the runs of the span -> records ----
+    u32 nrec = 0;                // run starts recorded so far (uniform; at most CC_ST2_WRECS: flushed before it could overflow)
+    bool force_head = true;      // the next word's first voxel starts a record whatever lies to its left (uniform)
+    // ---- phase 1 (voxel-parallel): {label, x} of every run start of the span, in x order ----
     for (u32 j0 = 0; j0 < nwd; j0 += CC_ST2_LOADS) {
       LT vv[CC_ST2_LOADS];
 #pragma unroll
@@ -421,70 +451,32 @@ k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ co
           const u32 x = ((w0 + j) << 5) + lane;
           const bool in = x < sx;
           const LT v = vv[k];
-          if (in && v > vmax) vmax = v;
+          if (v > vmax) vmax = v;                       // out-of-row lanes hold 0
           LT left = __shfl_up_sync(CC_FULL, v, 1);
           if (lane == 0) left = carry;
-          // a run starts here: first voxel of the span, value change, or the first voxel beyond the row (closes the last run)
-          const bool first = (j == 0 && lane == 0);
-          const bool head = first || (in ? (v != left) : (x == sx));
+          const bool head = in && (v != left || (lane == 0 && force_head));
+          force_head = false;
           const u32 H = __ballot_sync(CC_FULL, head);
-          if (H) {
-            // the lane that starts a run emits the run that ended at x - 1 (label `left`, start = previous head or run_start)
-            const u32 below = H & ((1u << lane) - 1u);
-            const u32 xs = below ? (((w0 + j) << 5) + (31u - __clz(below))) : run_start;
-            const bool emit = head && !first && (below != 0u || have_open) && left <= nmax;
-            const u32 E = __ballot_sync(CC_FULL, emit);
-            if (emit) {
-              const u32 pos = nrec + __popc(E & ((1u << lane) - 1u));
-              if (pos < CC_ST2_WRECS) wrec[pos] = make_uint4((u32)left, xs, x - xs, 0u);
-              else {
-                const u32 len = x - xs;
-                cta_add((u32)left, len, (unsigned long long)len * xs + (unsigned long long)len * (len - 1) / 2,
-                        (unsigned long long)len * y, (unsigned long long)len * z, xs, x - 1, y, y, z, z);
-              }
-            }
-            nrec += __popc(E);
-            run_start = ((w0 + j) << 5) + (31u - __clz(H));
-            have_open = true;
-          }
+          if (head) wrec[nrec + __popc(H & ((1u << lane) - 1u))] = make_uint2(v <= nmax ? (u32)v : IGNORE, x);
+          nrec += __popc(H);
           carry = __shfl_sync(CC_FULL, v, 31);
+          if (nrec > CC_ST2_WRECS - 32 && j + 1 < nwd) {
+            // (rare: a run every few voxels) the next word could overflow the list: account for what it holds now. The
+            // open run is cut at the word boundary; the next word's first voxel starts a new record for its remainder.
+            if (lane == 0) wrec[nrec] = make_uint2(IGNORE, min(sx, ((w0 + j) << 5) + 32u));
+            __syncwarp();
+            accumulate(nrec, y, z);
+            __syncwarp();
+            nrec = 0;
+            force_head = true;
+          }
         }
       }
     }
-    // the run that is still open at the end of the span (rows that end inside the last word were closed by x == sx)
-    const u32 xend = min(sx, (w0 + nwd) << 5);
-    if (have_open && run_start < xend && carry <= nmax) {
-      if (lane == 0) {
-        if (nrec < CC_ST2_WRECS) wrec[nrec] = make_uint4((u32)carry, run_start, xend - run_start, 0u);
-        else {
-          const u32 len = xend - run_start;
-          cta_add((u32)carry, len, (unsigned long long)len * run_start + (unsigned long long)len * (len - 1) / 2,
-                  (unsigned long long)len * y, (unsigned long long)len * z, run_start, xend - 1, y, y, z, z);
-        }
-      }
-      nrec++;
-    }
+    if (lane == 0) wrec[nrec] = make_uint2(IGNORE, xend);
     __syncwarp();
-    // ---- phase 2 (record-parallel): one record per lane; lanes with the same label are combined ----
-    nrec = min(nrec, (u32)CC_ST2_WRECS);
-    for (u32 base = 0; base < nrec; base += 32) {
-      const u32 i = base + lane;
-      const bool have = i < nrec;
-      const u32 act = __ballot_sync(CC_FULL, have);
-      if (have) {
-        const uint4 r = wrec[i];
-        const u32 len = r.z, x = r.y;
-        const unsigned long long sxv = (unsigned long long)len * x + (unsigned long long)len * (len - 1) / 2;
-        const u32 grp = __match_any_sync(act, r.x);
-        const u32 cnt = __reduce_add_sync(grp, len);
-        // 64-bit sums of up to 32 values below 2^42: two 21-bit digits each, every digit sum fits 32 bits
-        const u32 ax = __reduce_add_sync(grp, (u32)(sxv & 0x1FFFFFu)), bx = __reduce_add_sync(grp, (u32)(sxv >> 21));
-        const u32 xmin = __reduce_min_sync(grp, x), xmax = __reduce_max_sync(grp, x + len - 1);
-        if (lane == __ffs(grp) - 1)
-          cta_add(r.x, cnt, (unsigned long long)ax + ((unsigned long long)bx << 21), (unsigned long long)cnt * y,
-                  (unsigned long long)cnt * z, xmin, xmax, y, y, z, z);
-      }
-    }
+    // ---- phase 2 (run-parallel) ----
+    accumulate(nrec, y, z);
     __syncwarp();
   }
   if (maxout) {
