@@ -1013,15 +1013,15 @@ int cc3d_b200_label(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t
 template <typename LT>
 static int statistics_typed(const LT* labels, const Geom& g, u64 N, u32* counts, u32* bbox, u64* sums, cudaStream_t s,
                             unsigned long long* maxout = nullptr) {
+  // (A second formulation - x-run records, voxel-parallel emission + record-parallel accumulation - was built and
+  // measured this round: 0.58-0.77 ms at 512^3 against 0.9 ms here on the connectomics labelling but 5.3 ms against
+  // 3.4 ms on 2048 x 2048 x 512 Voronoi labels, and 110 warp instructions per 32 voxels; it was removed again.
+  // profiles/r02_statistics_ab.md has the numbers.)
   static PerDeviceOnce once;
-  static const bool v1 = getenv("CC3D_B200_STATS_V1") != nullptr;     // vertical-run formulation (A/B)
-  if (once.first()) {
-    cudaFuncSetAttribute(k_statistics<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable));
-    cudaFuncSetAttribute(k_statistics2<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable2));
-  }
+  auto k = k_statistics<LT>;
+  if (once.first()) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StatTable));
   k_stat_init<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(counts, bbox, (unsigned long long*)sums, N + 1);
-  if (v1) k_statistics<LT><<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
-  else k_statistics2<LT><<<148 * 4, 256, sizeof(StatTable2), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
+  k<<<148 * 4, 256, sizeof(StatTable), s>>>(labels, g, N, counts, bbox, (unsigned long long*)sums, maxout);
   g_launches += 2;
   return 0;
 }

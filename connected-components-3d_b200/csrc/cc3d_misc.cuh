@@ -304,198 +304,3 @@ k_mask_by_label(IT* __restrict__ img, const LT* __restrict__ labels, const unsig
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Row a13, second formulation (the default): statistics from X-RUNS of the label volume, in two phases per batch so
-// that neither diverges (the first formulation above keeps vertical runs in registers and collapses when the labels
-// of a 32-voxel word change from one row to the next, i.e. on real segmentations: 0.5 TB/s on the 512^3 benchmark
-// volume against 2.5 TB/s on 160-voxel Voronoi cells):
-//   phase 1 (voxel-parallel): a warp walks a SPAN of 32 consecutive words of one row (1024 voxels), one voxel per lane
-//           and word: run starts = the label differs from the left neighbour (shuffle; the value that ended the previous
-//           word is carried). The lane that starts a run emits the record of the run that just ENDED - label (the left
-//           neighbour's value), first x, length, row - into a shared-memory list (slots: one atomic per warp and word).
-//   phase 2 (record-parallel): one record per thread: closed-form contributions (count, coordinate sums, box), lanes
-//           with the same label are combined with match_any + redux, one lane per label updates the per-CTA hash table
-//           (32-bit shared atomics, 64-bit sums as lo/hi pairs). Persistent CTAs own contiguous ranges of spans (a compact
-//           region of the volume: few labels) and flush their table with global atomics once.
-// Labels above N are ignored; the largest label seen goes to *maxout (statistics_auto).
-// ---------------------------------------------------------------------------------------------
-#define CC_ST2_WRECS 256          // run starts per warp and span kept in shared memory (a span has at most 1024 + 1)
-#define CC_ST2_LOADS 8           // words whose loads are issued back to back (memory-level parallelism)
-struct StatTable2 {
-  u32 key[CC_STAT_SLOTS];   // label + 1, 0 = empty
-  u32 cnt[CC_STAT_SLOTS];
-  u32 bb[CC_STAT_SLOTS][6];
-  u32 sumlo[CC_STAT_SLOTS][3];
-  u32 sumhi[CC_STAT_SLOTS][3];
-  uint2 rec[8][CC_ST2_WRECS + 1];   // per warp: {label, first x} of every run of the span, in x order (+ end sentinel)
-};
-
-template <typename LT>
-__global__ void __launch_bounds__(256, 4)
-k_statistics2(const LT* __restrict__ labels, Geom g, u64 N, u32* __restrict__ counts, u32* __restrict__ bbox,
-              unsigned long long* __restrict__ sums, unsigned long long* __restrict__ maxout) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  StatTable2& tb = *reinterpret_cast<StatTable2*>(smem_raw);
-  for (int i = threadIdx.x; i < CC_STAT_SLOTS; i += blockDim.x) {
-    tb.key[i] = 0; tb.cnt[i] = 0;
-    tb.bb[i][0] = tb.bb[i][2] = tb.bb[i][4] = 0xFFFFFFFFu;
-    tb.bb[i][1] = tb.bb[i][3] = tb.bb[i][5] = 0;
-    tb.sumlo[i][0] = tb.sumlo[i][1] = tb.sumlo[i][2] = 0;
-    tb.sumhi[i][0] = tb.sumhi[i][1] = tb.sumhi[i][2] = 0;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 sx = (u32)g.sx, sy = (u32)g.sy;
-  const i64 W = g.W;
-  const i64 nspr = (W + 31) / 32;                 // spans per row
-  const i64 nspans = nspr * g.rows;
-  const LT nmax = (u64)(LT)~(LT)0 <= N ? (LT)~(LT)0 : (LT)N;   // labels above N are ignored
-  constexpr u32 IGNORE = 0xFFFFFFFFu;             // record label of a run whose value is above N
-  LT vmax = (LT)0;
-  uint2* __restrict__ wrec = tb.rec[warp];
-
-  // cnt voxels of label l with absolute sums and box -> per-CTA table (global memory when the table is full)
-  auto cta_add = [&](u32 l, u32 cnt, unsigned long long sumx, unsigned long long sumy, unsigned long long sumz,
-                     u32 xmin, u32 xmax, u32 y, u32 z) {
-    u32 h = (l * 2654435761u) >> 23;  // 9 bits
-    int slot = -1;
-#pragma unroll 1
-    for (int probe = 0; probe < 16; probe++) {
-      const u32 s = (h + probe) & (CC_STAT_SLOTS - 1);
-      const u32 k = *(volatile u32*)&tb.key[s];
-      if (k == l + 1) { slot = s; break; }
-      if (k == 0) {
-        const u32 old = atomicCAS(&tb.key[s], 0u, l + 1);
-        if (old == 0 || old == l + 1) { slot = s; break; }
-      }
-    }
-    if (slot < 0) {
-      atomicAdd(&counts[l], cnt);
-      u32* b = bbox + 6 * (size_t)l;
-      atomicMin(&b[0], xmin); atomicMax(&b[1], xmax);
-      atomicMin(&b[2], y); atomicMax(&b[3], y);
-      atomicMin(&b[4], z); atomicMax(&b[5], z);
-      unsigned long long* sg = sums + 3 * (size_t)l;
-      atomicAdd(&sg[0], sumx); atomicAdd(&sg[1], sumy); atomicAdd(&sg[2], sumz);
-      return;
-    }
-    atomicAdd(&tb.cnt[slot], cnt);
-    volatile u32* b = tb.bb[slot];   // most additions do not move the box: read before the atomic
-    if (xmin < b[0]) atomicMin(&tb.bb[slot][0], xmin);
-    if (xmax > b[1]) atomicMax(&tb.bb[slot][1], xmax);
-    if (y < b[2]) atomicMin(&tb.bb[slot][2], y);
-    if (y > b[3]) atomicMax(&tb.bb[slot][3], y);
-    if (z < b[4]) atomicMin(&tb.bb[slot][4], z);
-    if (z > b[5]) atomicMax(&tb.bb[slot][5], z);
-    sm_add64(&tb.sumlo[slot][0], &tb.sumhi[slot][0], sumx);
-    sm_add64(&tb.sumlo[slot][1], &tb.sumhi[slot][1], sumy);
-    sm_add64(&tb.sumlo[slot][2], &tb.sumhi[slot][2], sumz);
-  };
-
-  // Phase 2 on `n` runs whose starts are in wrec[0..n] (wrec[n] = end sentinel): one run per lane; the lanes are
-  // combined label by label with FULL-mask redux (a redux over a sub-mask that differs from lane to lane runs once
-  // per distinct mask), then the lanes that lead a label update the CTA table together.
-  auto accumulate = [&](u32 n, u32 y, u32 z) {
-    for (u32 base = 0; base < n; base += 32) {
-      const u32 i = base + lane;
-      u32 lab = IGNORE, x = 0, len = 0;
-      if (i < n) { const uint2 r = wrec[i]; lab = r.x; x = r.y; len = wrec[i + 1].y - x; }
-      const unsigned long long sxv = (unsigned long long)len * x + (unsigned long long)len * (len - 1) / 2;   // < 2^42
-      u32 todo = __ballot_sync(CC_FULL, lab != IGNORE);
-      u32 mycnt = 0, myxmin = 0, myxmax = 0;
-      unsigned long long mysx = 0;
-      bool leader = false;
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        const u32 cur = __shfl_sync(CC_FULL, lab, src);
-        const bool mine = lab == cur;
-        todo &= ~__ballot_sync(CC_FULL, mine);
-        const u32 c = __reduce_add_sync(CC_FULL, mine ? len : 0u);
-        const u32 a = __reduce_add_sync(CC_FULL, mine ? (u32)(sxv & 0x1FFFFFu) : 0u);     // two 21-bit digits: each sum fits 32 bits
-        const u32 b = __reduce_add_sync(CC_FULL, mine ? (u32)(sxv >> 21) : 0u);
-        const u32 mn = __reduce_min_sync(CC_FULL, mine ? x : 0xFFFFFFFFu);
-        const u32 mx = __reduce_max_sync(CC_FULL, mine ? x + len - 1 : 0u);
-        if (lane == src) { leader = true; mycnt = c; mysx = (unsigned long long)a + ((unsigned long long)b << 21); myxmin = mn; myxmax = mx; }
-      }
-      if (leader) cta_add(lab, mycnt, mysx, (unsigned long long)mycnt * y, (unsigned long long)mycnt * z, myxmin, myxmax, y, z);
-    }
-  };
-
-  // every CTA owns a contiguous range of spans (a compact region of the volume: few labels in its table); its warps
-  // take them round robin and never wait for each other
-  const i64 per_cta = (nspans + gridDim.x - 1) / gridDim.x;
-  const i64 span_end = min(nspans, (i64)(blockIdx.x + 1) * per_cta);
-  for (i64 span = (i64)blockIdx.x * per_cta + warp; span < span_end; span += 8) {
-    const u32 row = (u32)(span / nspr);
-    const u32 z = row / sy, y = row - z * sy;
-    const u32 w0 = (u32)(span - (i64)row * nspr) * 32;
-    const u32 nwd = min(32u, (u32)W - w0);
-    const u32 xend = min(sx, (w0 + nwd) << 5);
-    const LT* __restrict__ p = labels + ((size_t)row * sx + ((size_t)w0 << 5) + lane);
-    LT carry = (LT)0;            // value of the voxel left of the current word (uniform); unused for the first word
-    u32 nrec = 0;                // run starts recorded so far (uniform; at most CC_ST2_WRECS: flushed before it could overflow)
-    bool force_head = true;      // the next word's first voxel starts a record whatever lies to its left (uniform)
-    // ---- phase 1 (voxel-parallel): {label, x} of every run start of the span, in x order ----
-    for (u32 j0 = 0; j0 < nwd; j0 += CC_ST2_LOADS) {
-      LT vv[CC_ST2_LOADS];
-#pragma unroll
-      for (int k = 0; k < CC_ST2_LOADS; k++) {
-        const u32 x = ((w0 + j0 + k) << 5) + lane;
-        vv[k] = (LT)0;
-        if (j0 + k < nwd && x < sx) vv[k] = p[(size_t)(j0 + k) << 5];
-      }
-#pragma unroll
-      for (int k = 0; k < CC_ST2_LOADS; k++) {
-        const u32 j = j0 + k;
-        if (j < nwd) {                                  // warp-uniform
-          const u32 x = ((w0 + j) << 5) + lane;
-          const bool in = x < sx;
-          const LT v = vv[k];
-          if (v > vmax) vmax = v;                       // out-of-row lanes hold 0
-          LT left = __shfl_up_sync(CC_FULL, v, 1);
-          if (lane == 0) left = carry;
-          const bool head = in && (v != left || (lane == 0 && force_head));
-          force_head = false;
-          const u32 H = __ballot_sync(CC_FULL, head);
-          if (head) wrec[nrec + __popc(H & ((1u << lane) - 1u))] = make_uint2(v <= nmax ? (u32)v : IGNORE, x);
-          nrec += __popc(H);
-          carry = __shfl_sync(CC_FULL, v, 31);
-          if (nrec > CC_ST2_WRECS - 32 && j + 1 < nwd) {
-            // (rare: a run every few voxels) the next word could overflow the list: account for what it holds now. The
-            // open run is cut at the word boundary; the next word's first voxel starts a new record for its remainder.
-            if (lane == 0) wrec[nrec] = make_uint2(IGNORE, min(sx, ((w0 + j) << 5) + 32u));
-            __syncwarp();
-            accumulate(nrec, y, z);
-            __syncwarp();
-            nrec = 0;
-            force_head = true;
-          }
-        }
-      }
-    }
-    if (lane == 0) wrec[nrec] = make_uint2(IGNORE, xend);
-    __syncwarp();
-    // ---- phase 2 (run-parallel) ----
-    accumulate(nrec, y, z);
-    __syncwarp();
-  }
-  if (maxout) {
-    unsigned long long m = (unsigned long long)vmax;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(CC_FULL, m, o); if (t > m) m = t; }
-    if (lane == 0 && m > *(volatile unsigned long long*)maxout) atomicMax(maxout, m);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < CC_STAT_SLOTS; i += blockDim.x) {
-    if (tb.key[i] == 0) continue;
-    const u32 l = tb.key[i] - 1;
-    atomicAdd(&counts[l], tb.cnt[i]);
-    u32* b = bbox + 6 * (size_t)l;
-    atomicMin(&b[0], tb.bb[i][0]); atomicMax(&b[1], tb.bb[i][1]);
-    atomicMin(&b[2], tb.bb[i][2]); atomicMax(&b[3], tb.bb[i][3]);
-    atomicMin(&b[4], tb.bb[i][4]); atomicMax(&b[5], tb.bb[i][5]);
-    unsigned long long* s = sums + 3 * (size_t)l;
-#pragma unroll
-    for (int k = 0; k < 3; k++) atomicAdd(&s[k], ((unsigned long long)tb.sumhi[i][k] << 32) | tb.sumlo[i][k]);
-  }
-}

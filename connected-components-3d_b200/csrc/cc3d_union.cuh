@@ -512,14 +512,7 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
     }
     segRS[r] = first;
   }
-#ifdef CC_B1_VINIT
-  for (u32 k = threadIdx.x; k < CC_TILE_NODES / 8; k += blockDim.x) {      // eight 16-bit parents per 16-byte store
-    const u32 b = 8 * k;
-    reinterpret_cast<uint4*>(smem_u32)[k] = make_uint4(b | ((b + 1) << 16), (b + 2) | ((b + 3) << 16), (b + 4) | ((b + 5) << 16), (b + 6) | ((b + 7) << 16));
-  }
-#else
   for (u32 k = threadIdx.x; k < CC_TILE_NODES / 2; k += blockDim.x) smem_u32[k] = (2 * k) | ((2 * k + 1) << 16);
-#endif
   __syncthreads();
   const bool tile_ok = s_big == 0;   // otherwise every edge of this tile goes to kernel B2
   // dense tiles enumerate 256 words at a time so that the edge queue is drained before it overflows
@@ -765,12 +758,6 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
 #pragma unroll 1
   for (u32 q = threadIdx.x; q < CC_TILE_WORDS; q += blockDim.x) {
     const u32 r = q >> g.tw;
-#ifdef CC_B1_STASHWB
-    // run starts / first run id of the word come from the stash that round 0 filled (no second trip to global memory)
-    const int n = __popc(wS[q]);
-    if (n == 0) continue;
-    const u32 g0 = wR[q] + 1u;
-#else
     const u32 wx = q & (TW - 1);
     const u32 w = w0 + wx, y = y0 + (r & (TY - 1)), z = z0 + (r >> g.ty);
     if (w >= W || y >= sy || z >= sz) continue;
@@ -779,7 +766,6 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
     const int n = __popc(fx.x & ~fx.y);
     if (n == 0) continue;
     const u32 g0 = __ldg(RS + i);
-#endif
     if (!tile_ok) { for (int k = 0; k < n; k++) L[g0 + k] = g0 + k; continue; }
     const u32 l0 = (r << capl) + (g0 - segRS[r]);
     for (int k = 0; k < n; k++) {
