@@ -428,13 +428,18 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
         _lib.check(L.cc3d_b200_merge_slabs_device(gathered.data_ptr(), world, 4 + cap, rank, cap, ws.data_ptr(), label_cap,
                                                   ctypes.byref(remap_p), ctypes.byref(result_p), stream))
         lap("merge")
+        # everything the host needs (N, overflow flags, the slabs' facts) is final here: copy it out and mark the spot
+        # BEFORE the expansion is enqueued, so that the host returns while the final write still runs (the output is
+        # stream-ordered like any CUDA result; the next step's enqueue overlaps with it)
+        roff = result_p.value - ws.data_ptr()
+        host[:5].copy_(ws[roff:roff + 40].view(torch.int64), non_blocking=True)
+        host[5:].copy_(gathered[:, :4].reshape(-1) if world == 1 else gathered[:, :4].contiguous().view(-1), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
         s2, sess = sess, None
         _lib.check(L.cc3d_b200_slab_finish(s2, remap_p, _lib.U32, out.data_ptr(), okind[guess], stream))
       lap("finish")
-      roff = result_p.value - ws.data_ptr()
-      host[:5].copy_(ws[roff:roff + 40].view(torch.int64), non_blocking=True)
-      host[5:].copy_(gathered[:, :4].reshape(-1) if world == 1 else gathered[:, :4].contiguous().view(-1), non_blocking=True)
-      torch.cuda.current_stream(dev).synchronize()          # the one host synchronisation, at the end of the step
+      ready.synchronize()          # the one host synchronisation of the step
       lap("sync")
     finally:
       if sess is not None:
