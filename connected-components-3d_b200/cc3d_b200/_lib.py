@@ -105,6 +105,8 @@ def lib():
   L.cc3d_b200_launch_count.restype = ctypes.c_ulonglong
   L.cc3d_b200_debug_set_queue_capacity.restype = None
   L.cc3d_b200_debug_set_queue_capacity.argtypes = [u64]
+  L.cc3d_b200_debug_set_big_tiles.restype = None
+  L.cc3d_b200_debug_set_big_tiles.argtypes = [ci]
   L.cc3d_b200_set_timing.restype = None
   L.cc3d_b200_set_timing.argtypes = [ci]
   L.cc3d_b200_last_timings.restype = ci

@@ -386,7 +386,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
   okind = {np.dtype(np.uint16): _lib.U16, np.dtype(np.uint32): _lib.U32, np.dtype(np.uint64): _lib.U64}
   key = (dev.index, world)
   if key not in _pinned_small:
-    _pinned_small[key] = torch.empty((5 + 4 * world,), dtype=torch.int64, pin_memory=True)
+    _pinned_small[key] = torch.empty((8 + 4 * world,), dtype=torch.int64, pin_memory=True)
   host = _pinned_small[key]
   while True:
     lap("t0")
@@ -432,8 +432,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
         # BEFORE the expansion is enqueued, so that the host returns while the final write still runs (the output is
         # stream-ordered like any CUDA result; the next step's enqueue overlaps with it)
         roff = result_p.value - ws.data_ptr()
-        host[:5].copy_(ws[roff:roff + 40].view(torch.int64), non_blocking=True)
-        host[5:].copy_(gathered[:, :4].reshape(-1) if world == 1 else gathered[:, :4].contiguous().view(-1), non_blocking=True)
+        host.copy_(ws[roff:roff + 8 * (8 + 4 * world)].view(torch.int64), non_blocking=True)   # result + every slab's facts
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))
         s2, sess = sess, None
@@ -445,7 +444,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
       if sess is not None:
         L.cc3d_b200_session_release(sess)
     res = host[:5].numpy()
-    facts = host[5:].numpy().reshape(world, 4)
+    facts = host[8:].numpy().reshape(world, 4)
     counts = facts[:, 3]
     if int(res[1]) or int(res[2]):
       # rare: more slab labels / face pairs than the buffers hold -> larger buffers, repeat the step

@@ -136,7 +136,8 @@ void arena_release_after(Arena& a, cudaStream_t s) {
 }
 
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<unsigned long long> g_queue_cap_override{0};   // tests: force the global edge queue to overflow
+std::atomic<unsigned long long> g_queue_cap_override{0};
+std::atomic<bool> g_seen_big_tiles{false};   // a volume with > 16 runs per word was labelled: later calls add the RL = 5 launch   // tests: force the global edge queue to overflow
 
 // ---- optional per-kernel timing ----
 thread_local bool g_timing = false;
@@ -249,6 +250,7 @@ int cc3d_b200_last_timings(const char** names, float* ms, int cap) {
 }
 unsigned long long cc3d_b200_launch_count(void) { return g_launches.load(); }
 void cc3d_b200_debug_set_queue_capacity(uint64_t entries) { g_queue_cap_override.store(entries); }
+void cc3d_b200_debug_set_big_tiles(int seen) { g_seen_big_tiles.store(seen != 0); }
 size_t cc3d_b200_workspace_bytes(void) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
   size_t n = 0;
@@ -386,6 +388,7 @@ static int resolve_finish(cc3d_b200_session* S, cudaStream_t s, cc3d_b200_resolv
       if (int rc = redo_unions_global(S, s)) return rc;
       continue;
     }
+    if (h->pad[0]) g_seen_big_tiles.store(true);
     S->N = h->N;
     info->N = h->N;
     info->epl = S->epl_is_runs ? h->nruns : h->epl;
@@ -472,7 +475,10 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   const i64 nb_rank = (maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS;
   const i64 status2_words = (fused_rank ? nb_rank : nb2) + 2;
   // control block: Counters | scan-S status | C-stage status, zeroed by ONE memset per call
-  const size_t ctl_bytes = ((sizeof(Counters) + 255) & ~size_t(255)) + (size_t)(nb + 2) * 8 + (size_t)status2_words * 8;
+  const i64 ntiles = ((g.W + (i64(1) << g.tw) - 1) >> g.tw) * ((sy + (i64(1) << g.ty) - 1) >> g.ty) * ((sz + (i64(1) << g.tz) - 1) >> g.tz);
+  const bool defer_big = g_seen_big_tiles.load() && (mode == MODE_EQ || c8);
+  const size_t ctl_bytes = ((sizeof(Counters) + 255) & ~size_t(255)) + (size_t)(nb + 2) * 8 + (size_t)status2_words * 8 +
+                           (defer_big ? (size_t)ntiles * 4 : 0);
 
   size_t need = 4096;
   auto add = [&](size_t b) { need += ((b + 255) & ~size_t(255)) + 256; };
@@ -509,6 +515,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   Counters* ctr = (Counters*)ctl;
   u64* bsum = (u64*)(ctl + ((sizeof(Counters) + 255) & ~size_t(255)));
   u64* bsum2 = bsum + (nb + 2);
+  u32* bigflags = defer_big ? (u32*)(bsum2 + status2_words) : nullptr;
   u64* gqbuf = (u64*)ar.take(gqcap * 8);
   S->L = L; S->M = M; S->din = din; S->ctr = ctr;
   S->epl_is_runs = (mode == MODE_EQ);
@@ -530,6 +537,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   a.connectivity = connectivity; a.stream = s;
   a.mark = g_timing ? mark : nullptr;
   a.inline_fallback = inline_fallback;
+  a.bigflags = bigflags; a.nbig = &ctr->pad[0]; a.defer_big = defer_big;
   memset(a.delta, 0, 8);
   if (delta) memcpy(a.delta, delta, es);
   int rc = 0;
@@ -879,7 +887,7 @@ static size_t merge_ws_layout(uint64_t label_cap, size_t* o_remap, size_t* o_nr,
   *o_cnt = off;    off += up(words * 4);
   *o_prefix = off; off += up(words * 4);
   *o_status = off; off += up((nb + 2) * 8);
-  *o_result = off; off += 256;
+  *o_result = off; off += 8 * (8 + 4 * CC_MERGE_MAX_WORLD) + 256;
   return off;
 }
 size_t cc3d_b200_merge_workspace_bytes(uint64_t label_cap) {
@@ -975,6 +983,7 @@ int cc3d_b200_label_with_info(const void* in, int in_kind, int64_t sx, int64_t s
         if (rc == 0 && out_kind == CC3D_B200_U16 && info->N > 0xFFFFull) rc = fail(CC3D_B200_ERR_OUT_RANGE, "N does not fit the requested output kind");
         return rc;
       }
+      if (h->pad[0]) g_seen_big_tiles.store(true);
       S->N = h->N;
       info->N = h->N;
       info->epl = S->epl_is_runs ? h->nruns : h->epl;

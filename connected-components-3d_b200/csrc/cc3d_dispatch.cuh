@@ -19,6 +19,9 @@ struct LabelArgs {
   EdgeQueue GQ;      // edges that leave their union tile
   void (*mark)(const char*, cudaStream_t);  // optional timing hook (per-kernel CUDA events)
   int* launches;     // incremented once per kernel launch
+  u32* bigflags;          // one word per union tile (zeroed): set by B1 for tiles with > 16 runs per word
+  u32* nbig;              // device counter of such tiles
+  bool defer_big;         // the process has met such volumes: flagged tiles are relabelled by the RL = 5 launch
   bool inline_fallback;   // launch the overflow fallback kernel (k_union_global, a no-op unless the edge queue overflowed)
                           // as part of the pipeline; false: the host checks the overflow flag at its next
                           // synchronisation and redoes the unions (run_union_global_stage)
@@ -193,9 +196,17 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
     if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else {
-    const size_t smem = (size_t)HybridQueues<MODE>::SMEM_WORDS * 4;
-    if (set_attr) cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cc_launch(k_union_tile_hybrid<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    const size_t smem = (size_t)HybridQueues<MODE, 4>::SMEM_WORDS * 4, smem5 = (size_t)HybridQueues<MODE, 5>::SMEM_WORDS * 4;
+    if (set_attr) {
+      cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+    }
+    BigTiles big; big.flags = a.bigflags; big.count = a.nbig; big.defer = a.defer_big ? 1 : 0;
+    cc_launch(k_union_tile_hybrid<T, MODE, CONN, 4>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ, big);
+    if (a.defer_big) {
+      cc_launch(k_union_tile_hybrid<T, MODE, CONN, 5>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem5), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ, big);
+      *a.launches += 1;
+    }
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);
   cc_launch(k_union_queue, dim3(CC_QUEUE_BLOCKS * 4), dim3(256), (size_t)(0), a.stream, a.L, a.GQ);

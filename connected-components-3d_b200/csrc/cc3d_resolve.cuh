@@ -644,7 +644,7 @@ k_face_pairs(const T* __restrict__ vP, const u32* __restrict__ lP, const T* __re
 // i.e. its rank among the roots - no per-slab bookkeeping. Every rank runs the same kernels on the same gathered data
 // (redundantly, like the redundant host solve before) and writes only its own slab's remap table.
 // result[0] = N of the whole volume, result[1] = label capacity exceeded, result[2] = pair capacity exceeded,
-// result[3] = total + 1 (ids incl. 0), result[4] = number of non-root ids.
+// result[3] = total + 1 (ids incl. 0), result[4] = number of non-root ids, result[8 + 4 r + k] = fact k of slab r.
 // ---------------------------------------------------------------------------------------------
 struct SlabRows { const long long* rows; int world; long long stride; };
 #define CC_MERGE_MAX_WORLD 64
@@ -668,6 +668,9 @@ k_merge_init(u32* __restrict__ parent, SlabRows f, u64 label_cap, u64 pair_cap, 
     for (int r = 0; r < f.world; r++) pov |= (u64)f.rows[(size_t)r * f.stride + 3] > pair_cap;
     result[0] = 0; result[1] = (total + 1 > label_cap) ? 1ull : 0ull; result[2] = pov ? 1ull : 0ull;
     result[3] = (total + 1 > label_cap) ? 0ull : total + 1; result[4] = 0;
+    // the slabs' facts [N, epl, sz, n_pairs] ride along (result[8 + 4 r + k]): the host reads everything with ONE copy
+    for (int r = 0; r < f.world; r++)
+      for (int k = 0; k < 4; k++) result[8 + 4 * r + k] = (unsigned long long)f.rows[(size_t)r * f.stride + k];
   }
   if (total + 1 > label_cap) return;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += (u64)gridDim.x * blockDim.x) parent[i] = (u32)i;

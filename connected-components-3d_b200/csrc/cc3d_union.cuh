@@ -464,21 +464,29 @@ k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restric
 // of running the candidate loop per word. Tiles with many runs (dense noise) keep the per-word loop: their item
 // lists would overflow. Label volumes are latency / barrier bound here: six resident CTAs per SM (40 registers, a
 // 512-entry staging buffer) hide more of it.
-template <int MODE> struct HybridQueues {
+// RL = log2 of the runs per word the shared-memory forest has room for: 4 (16 runs per word - every label volume and every
+// binary image) for the first launch; tiles whose rows hold more (multilabel noise: up to 32 runs per word, the
+// maximum) are flagged and - once the process has met such a volume (BigTiles::defer) - relabelled by a second launch
+// with RL = 5 instead of sending every one of their edges through the global queue.
+struct BigTiles { u32* flags; u32* count; int defer; };
+template <int MODE, int RL = 4> struct HybridQueues {
   static constexpr u32 GQ = MODE == MODE_EQ ? CC_TILE_GQ_EQ : CC_TILE_GQ;
   static constexpr bool ITEMS = true;
-  static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2 + (ITEMS ? 2 * CC_TILE_WORDS : 0);
+  static constexpr u32 NODES = CC_TILE_WORDS << RL;
+  static constexpr u32 SMEM_WORDS = NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2 + (ITEMS ? 2 * CC_TILE_WORDS : 0);
 };
-template <typename T, int MODE, int CONN>
-__global__ void __launch_bounds__(CC_TILE_THREADS, MODE == MODE_EQ ? CC_TILE_MINB(CC_B1_MINB) : 0)
+template <typename T, int MODE, int CONN, int RL>
+__global__ void __launch_bounds__(CC_TILE_THREADS, (MODE == MODE_EQ && RL == 4) ? CC_TILE_MINB(CC_B1_MINB) : 0)
 k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
-             u32 ntx, u32 nty, EdgeQueue GQ) {
+             u32 ntx, u32 nty, EdgeQueue GQ, BigTiles big) {
   CC_PDL_WAIT();
-  constexpr u32 GQN = HybridQueues<MODE>::GQ;
-  constexpr bool ITEMS = HybridQueues<MODE>::ITEMS;   // round 1 through item lists (needs the wS / wR stash)
+  if constexpr (RL != 4) { if (big.flags[blockIdx.x] == 0) return; }      // second launch: flagged tiles only
+  constexpr u32 GQN = HybridQueues<MODE, RL>::GQ;
+  constexpr bool ITEMS = HybridQueues<MODE, RL>::ITEMS;   // round 1 through item lists (needs the wS / wR stash)
+  constexpr u32 NODES = HybridQueues<MODE, RL>::NODES;
   extern __shared__ __align__(16) u32 smem_u32[];
-  uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [CC_TILE_NODES] 16-bit parents
-  u32* lq = smem_u32 + CC_TILE_NODES / 2;                  // [CC_TILE_LQ]
+  uint16_t* lab = reinterpret_cast<uint16_t*>(smem_u32);   // [NODES] 16-bit parents
+  u32* lq = smem_u32 + NODES / 2;                          // [CC_TILE_LQ]
   u64* gq = reinterpret_cast<u64*>(lq + CC_TILE_LQ);       // [GQN]
   u32* segRS = lq + CC_TILE_LQ + 2 * GQN;           // [CC_TILE_WORDS] first run id of every row segment
   uint16_t* todo = reinterpret_cast<uint16_t*>(segRS + CC_TILE_WORDS);   // [CC_TILE_WORDS]
@@ -488,7 +496,7 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
   const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
   const u32 TW = 1u << g.tw, TY = 1u << g.ty;
   const u32 nseg = CC_TILE_WORDS >> g.tw;        // TY * TZ
-  const u32 capl = g.tw + 4;                     // log2(runs a segment can hold locally)
+  const u32 capl = g.tw + RL;                    // log2(runs a segment can hold locally)
   u32 t = blockIdx.x;
   const u32 bx = t % ntx; t /= ntx;
   const u32 by = t % nty;
@@ -512,8 +520,14 @@ k_union_tile_hybrid(const T* __restrict__ in, const u32* __restrict__ M, u32* __
     }
     segRS[r] = first;
   }
-  for (u32 k = threadIdx.x; k < CC_TILE_NODES / 2; k += blockDim.x) smem_u32[k] = (2 * k) | ((2 * k + 1) << 16);
+  for (u32 k = threadIdx.x; k < NODES / 2; k += blockDim.x) smem_u32[k] = (2 * k) | ((2 * k + 1) << 16);
   __syncthreads();
+  if constexpr (RL == 4) {
+    if (s_big) {      // block-uniform
+      if (threadIdx.x == 0) { atomicAdd(big.count, 1u); if (big.defer) big.flags[blockIdx.x] = 1u; }
+      if (big.defer) return;     // the RL = 5 launch relabels this tile
+    }
+  }
   const bool tile_ok = s_big == 0;   // otherwise every edge of this tile goes to kernel B2
   // dense tiles enumerate 256 words at a time so that the edge queue is drained before it overflows
   const u32 step = s_runs > CC_TILE_LQ / 2 ? (u32)(CC_TILE_WORDS / 2) : (u32)CC_TILE_WORDS;

@@ -132,7 +132,8 @@ int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* co
  * over the slab-label ids (the sum of N_r must stay below label_cap). On return *remap points at the uint32 remap
  * table of slab `rank` inside the workspace (remap[local label] = global label, remap[0] = 0; feed it to
  * cc3d_b200_slab_finish) and *result at five device uint64: [0] N of the whole volume, [1] label_cap exceeded,
- * [2] pair_cap exceeded (in either case the tables are invalid: grow the capacity and repeat the step), [3..4] internal. */
+ * [2] pair_cap exceeded (in either case the tables are invalid: grow the capacity and repeat the step), [3..4] internal,
+ * [8 + 4 r + k] = fact k (N, epl, sz, n_pairs) of slab r, so that one small copy gives the host all it needs. */
 size_t cc3d_b200_merge_workspace_bytes(uint64_t label_cap);
 int cc3d_b200_merge_slabs_device(const int64_t* gathered, int world, int64_t row_stride, int rank, uint64_t pair_cap,
                                  void* workspace, uint64_t label_cap, uint32_t** remap, uint64_t** result, void* stream);
@@ -270,6 +271,9 @@ void cc3d_b200_release_workspace(void);
 /* Testing aid: capacity (entries) of the global edge queue between the tile kernel and the global union
  * kernel; 0 restores the default (8 per bitmap word). A tiny value forces the overflow fallback path. */
 void cc3d_b200_debug_set_queue_capacity(uint64_t entries);
+/* Tests: multilabel tiles with more than 16 runs per word are relabelled by a second launch with a larger shared-memory
+ * forest once the process has met such a volume; this sets / clears that memory (1 / 0). */
+void cc3d_b200_debug_set_big_tiles(int seen);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 unsigned long long cc3d_b200_launch_count(void);

@@ -8,6 +8,10 @@ sys.path.insert(0, os.path.join(ROOT, "connected-components-3d_b200")); sys.path
 import cc3d_b200, benchdata
 dev = "cuda"
 
+def marks(fn):
+    cc3d_b200.set_timing(True); fn(); tm = cc3d_b200.last_timings(); cc3d_b200.set_timing(False)
+    print("   kernels: " + " ".join(f"{k}={v:.3f}" for k, v in tm), flush=True)
+
 def timed(name, fn, vox, reps=4, bytes_per_vox=None):
     fn(); torch.cuda.synchronize()
     ts = []
@@ -22,17 +26,17 @@ def timed(name, fn, vox, reps=4, bytes_per_vox=None):
 n = int(os.environ.get("N", "1024"))
 x = benchdata.three_tone_noise((n, n, n), cell=64, seed=3, device=dev)
 r = timed(f"configs[3] continuous {n}^3 f32 delta=10 conn26", lambda: cc3d_b200.connected_components(x, connectivity=26, delta=10, return_N=True), x.numel(), bytes_per_vox=8)
-print("   N =", r[1], r[0].dtype); del x, r
+print("   N =", r[1], r[0].dtype); marks(lambda: cc3d_b200.connected_components(x, connectivity=26, delta=10, return_N=True)); del x, r
 g = torch.Generator(device=dev); g.manual_seed(4)
 x = torch.randint(0, 4, (n, n, n), generator=g, device=dev, dtype=torch.int32)
 r = timed(f"configs[4] periodic 6-conn {n}^3 u32 random labels 0..3", lambda: cc3d_b200.connected_components(x, connectivity=6, periodic_boundary=True, return_N=True), x.numel(), bytes_per_vox=8)
-print("   N =", r[1], r[0].dtype); del x, r
+print("   N =", r[1], r[0].dtype); marks(lambda: cc3d_b200.connected_components(x, connectivity=6, periodic_boundary=True, return_N=True)); del x, r
 m = int(os.environ.get("M", "16384"))
 x = benchdata.random_binary((m, m), 0.5, 5, dev)
 r = timed(f"configs[4] 2D {m}^2 u8 8-conn binary_image=True", lambda: cc3d_b200.connected_components(x, connectivity=8, binary_image=True, return_N=True), x.numel(), bytes_per_vox=5)
-print("   N =", r[1], r[0].dtype)
+print("   N =", r[1], r[0].dtype); marks(lambda: cc3d_b200.connected_components(x, connectivity=8, binary_image=True, return_N=True))
 r = timed(f"configs[4] 2D {m}^2 u8 8-conn multilabel call", lambda: cc3d_b200.connected_components(x, connectivity=8, return_N=True), x.numel(), bytes_per_vox=5)
-print("   N =", r[1], r[0].dtype); del x, r
+print("   N =", r[1], r[0].dtype); marks(lambda: cc3d_b200.connected_components(x, connectivity=8, return_N=True)); del x, r
 zs = int(os.environ.get("Z", "512"))
 x = benchdata.voronoi_multilabel((2048, 2048, 2048), cell=160, seed=2, device=dev, dtype=torch.int64, id_bits=62, z_range=(0, zs))
 lab, N = cc3d_b200.connected_components(x, connectivity=26, return_N=True)

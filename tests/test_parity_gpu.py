@@ -341,13 +341,32 @@ def test_edge_queue_overflow_fallback(cc3d, oracle_mod):
 def test_many_runs_per_word_tiles(cc3d, oracle_mod):
   """Multilabel rows with more than 16 runs per 32-voxel word do not fit the shared-memory forest of a tile;
   those tiles send every edge to the global phase."""
+  from cc3d_b200 import _lib
+  L = _lib.lib()
   rng = np.random.default_rng(6)
   x = rng.integers(1, 4, (64, 96, 160)).astype(np.uint16)
   x[:, :48] = np.repeat(np.repeat(np.repeat(rng.integers(0, 3, (16, 12, 40)), 4, 0), 4, 1), 4, 2)  # mixed: coarse half
-  for conn in (6, 18, 26):
-    a, Na = _truth(oracle_mod).connected_components(x, connectivity=conn, return_N=True)
-    b, Nb = cc3d.connected_components(x, connectivity=conn, return_N=True)
-    assert_same_labels(a, Na, b, Nb, f"dense runs conn={conn}")
+  x2 = rng.integers(0, 3, (300, 700)).astype(np.uint8)                                            # 2D noise
+  try:
+    for seen in (0, 1):     # 0: every edge of such a tile goes through the global queue; 1: second launch, 32 runs per word
+      for conn in (6, 18, 26):
+        L.cc3d_b200_debug_set_big_tiles(seen)
+        a, Na = _truth(oracle_mod).connected_components(x, connectivity=conn, return_N=True)
+        b, Nb = cc3d.connected_components(x, connectivity=conn, return_N=True)
+        assert_same_labels(a, Na, b, Nb, f"dense runs conn={conn} seen={seen}")
+      for conn, kw in ((4, {}), (8, {}), (8, dict(periodic_boundary=True)), (6, dict(periodic_boundary=True))):
+        L.cc3d_b200_debug_set_big_tiles(seen)
+        a, Na = _truth(oracle_mod).connected_components(x2, connectivity=conn, return_N=True, **kw)
+        b, Nb = cc3d.connected_components(x2, connectivity=conn, return_N=True, **kw)
+        assert_same_labels(a, Na, b, Nb, f"dense 2D conn={conn} {kw} seen={seen}")
+    # the first noisy volume switches the second launch on for the calls that follow
+    L.cc3d_b200_debug_set_big_tiles(0)
+    cc3d.connected_components(x, connectivity=26)
+    b, Nb = cc3d.connected_components(x, connectivity=26, return_N=True)
+    a, Na = _truth(oracle_mod).connected_components(x, connectivity=26, return_N=True)
+    assert_same_labels(a, Na, b, Nb, "dense runs after the switch")
+  finally:
+    L.cc3d_b200_debug_set_big_tiles(0)
 
 
 def test_voxel_and_color_connectivity_graph(cc3d, oracle_mod):
