@@ -97,6 +97,9 @@ struct Geom {
 #ifndef CC_B1_MINB
 #define CC_B1_MINB 6
 #endif
+#ifndef CC_B1W_MINB
+#define CC_B1W_MINB 6
+#endif
 #define CC_TILE_MINB(n) ((n) * 256 / CC_TILE_THREADS)
 
 // Device-side results of a labelling pass. The block is valid after being ZEROED (one memset clears it together with

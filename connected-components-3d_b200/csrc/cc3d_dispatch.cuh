@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "cc3d_faces.cuh"
 #include "cc3d_union.cuh"
+#include "cc3d_union_w.cuh"
 
 struct LabelArgs {
   const void* in;    // device pointer, element kind T
@@ -171,6 +172,11 @@ template <typename T> int run_faces_stage(const LabelArgs& a) {
   return -1;
 }
 
+// CC3D_B200_B1=phased selects the CTA-phased tile kernels of round 1 (k_union_tile_hybrid) for A/B runs
+static inline bool b1_phased() {
+  static const bool v = []() { const char* e = getenv("CC3D_B200_B1"); return e && e[0] == 'p'; }();
+  return v;
+}
 template <typename T, int MODE, int CONN>
 static int launch_union(const LabelArgs& a, bool global_only = false) {
   Edge<T, MODE> E;
@@ -195,6 +201,20 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
     const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+  } else if (!b1_phased() && nty < 65536 && ntz < 65536) {
+    // warp-owned tiles (cc3d_union_w.cuh): compact 32-bit forest of up to 4 096 runs per tile; tiles with more runs
+    // (multilabel noise) are flagged and relabelled by a second launch with room for the maximum (16 384)
+    const size_t smem = (size_t)WarpTile<MODE, 4096>::SMEM_WORDS * 4, smem2 = (size_t)WarpTile<MODE, 16384>::SMEM_WORDS * 4;
+    if (set_attr) {
+      cudaFuncSetAttribute(k_union_tile_w<T, MODE, CONN, 4096, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_union_tile_w<T, MODE, CONN, 16384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    }
+    BigTiles big; big.flags = a.bigflags; big.count = a.nbig; big.defer = a.defer_big ? 1 : 0;
+    cc_launch(k_union_tile_w<T, MODE, CONN, 4096, false>, dim3((unsigned)ntx, (unsigned)nty, (unsigned)ntz), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, a.GQ, big);
+    if (a.defer_big) {
+      cc_launch(k_union_tile_w<T, MODE, CONN, 16384, true>, dim3((unsigned)ntx, (unsigned)nty, (unsigned)ntz), dim3(CC_TILE_THREADS), (size_t)(smem2), a.stream, in, a.M, a.L, g, E, a.GQ, big);
+      *a.launches += 1;
+    }
   } else {
     const size_t smem = (size_t)HybridQueues<MODE, 4>::SMEM_WORDS * 4, smem5 = (size_t)HybridQueues<MODE, 5>::SMEM_WORDS * 4;
     if (set_attr) {

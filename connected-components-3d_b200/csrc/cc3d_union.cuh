@@ -119,12 +119,20 @@ struct WordEdges {
         any |= nZ & nXr & ~(P.Z >> 1) & ~(D.X >> 1) & ((D.F >> 1) | 0x80000000u);  // C1
         if (hasU) {
           any |= nZ & ~P.Y & ~U.Z & ~D.Y;                                          // B2
-          if constexpr (CORNER) any |= nZ & ~P.Y & (~P.X | nXr);                   // A2, C2
+          if constexpr (CORNER) {
+            const u32 c2 = nZ & ~P.Y;       // A2, C2: neither p nor q = (x -+ 1, y - 1, z - 1) has a face link into the 2x2x2 block
+            any |= c2 & ~P.X & ~(U.Z << 1) & ~(D.Y << 1);          // (links of q seen from rows U and D; shifted-in bits unknown -> possible)
+            any |= c2 & nXr & ~(U.Z >> 1) & ~(D.Y >> 1);
+          }
         }
         if (hasV && nZ) {
           const Q4 V = ldq(M, i + W);
           any |= nZ & ~V.Y & ~V.Z;                                                 // B3
-          if constexpr (CORNER) any |= nZ & ~V.Y & (~P.X | nXr);                   // A3, C3
+          if constexpr (CORNER) {
+            const u32 c3 = nZ & ~V.Y;       // A3, C3
+            any |= c3 & ~P.X & ~(V.Z << 1);
+            any |= c3 & nXr & ~(V.Z >> 1);
+          }
         }
       }
     }
