@@ -86,9 +86,11 @@ static cc_tmap_encode_fn cc_tmap_encoder() {
 #ifndef CC_TMA_V1
 #define CC_TMA_KERNEL k_faces_tma2
 #define CC_TMA_TRAITS FaceTma2
+#define CC_TMA_WARPS_ CC_TMA2_WARPS
 #else
 #define CC_TMA_KERNEL k_faces_tma
 #define CC_TMA_TRAITS FaceTma
+#define CC_TMA_WARPS_ CC_FACE_WARPS
 #endif
 template <typename T, int MODE>
 static bool launch_faces_tma(const LabelArgs& a, const Edge<T, MODE>& E, bool two_d) {
@@ -113,18 +115,19 @@ static bool launch_faces_tma(const LabelArgs& a, const Edge<T, MODE>& E, bool tw
   // z chunks: enough warps to fill the machine several times over, long enough to amortise the z - 1 halo plane
   unsigned zchunk = 16;
   while (zchunk > 2 && (i64)nwg * nyb * ((g.sz + zchunk - 1) / zchunk) < 148 * 24 * 4) zchunk >>= 1;
+  { static const int zc_env = []() { const char* e = getenv("CC3D_B200_ZCHUNK"); return e ? atoi(e) : 0; }(); if (zc_env > 0) zchunk = (unsigned)zc_env; }
   const unsigned nzc = (unsigned)((g.sz + zchunk - 1) / zchunk);
   const i64 ntasks = (i64)nwg * nyb * nzc;
   if (ntasks >= (i64(1) << 31)) return false;
-  const unsigned blocks = (unsigned)((ntasks + CC_FACE_WARPS - 1) / CC_FACE_WARPS);
+  const unsigned blocks = (unsigned)((ntasks + CC_TMA_WARPS_ - 1) / CC_TMA_WARPS_);
   constexpr size_t smem = F::smem();
   static PerDeviceOnce once;
   if (once.first()) {
     cudaFuncSetAttribute(CC_TMA_KERNEL<T, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(CC_TMA_KERNEL<T, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  if (two_d) cc_launch(CC_TMA_KERNEL<T, MODE, false>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
-  else cc_launch(CC_TMA_KERNEL<T, MODE, true>, dim3(blocks), dim3(CC_FACE_WARPS * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
+  if (two_d) cc_launch(CC_TMA_KERNEL<T, MODE, false>, dim3(blocks), dim3(CC_TMA_WARPS_ * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
+  else cc_launch(CC_TMA_KERNEL<T, MODE, true>, dim3(blocks), dim3(CC_TMA_WARPS_ * 32), smem, a.stream, map, a.M, g, E, a.ctr, nyb, nwg, zchunk, (unsigned)ntasks);
   return true;
 }
 

@@ -9,11 +9,18 @@
 #ifndef CC_FACE_YCH
 #define CC_FACE_YCH 32   // rows of one plane a warp walks through
 #endif
+#ifndef CC_FACE_LANES
+#define CC_FACE_LANES true
+#endif
 #define CC_FACE_NW 4     // bitmap words (of one row) a warp handles per row step
 
 // Faces of one row of CC_FACE_NW words (c: voxels, l: -x neighbours, d: -z neighbours, up: -y neighbours);
 // lane 0 stores the group's four {F,X,Y,Z} and run-start counts.
-template <typename T, int MODE, bool HASZ, int NW>
+// LANES (NW == 4): lanes 0..3 each pick the {F,X,Y,Z} of one word (12 selects on the ALU pipe) and the group leaves the warp
+// as ONE 64-byte store, one POPC and one 16-byte store of the run-start counts instead of four 16-byte stores, four
+// POPCs and a store issued by lane 0: the memory-instruction queue (LDS + STG + POPC) is what throttles the unrolled
+// kernel (ncu: mio_throttle 25 % of the stall samples).
+template <typename T, int MODE, bool HASZ, int NW, bool LANES = false>
 __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T* c, const T* l, const T* d, const T* up,
                                                  int lane, uint4* __restrict__ mq, u32* __restrict__ rs, bool rs_vec, u32& epl) {
   u32 F[NW], X[NW], Y[NW], Z[NW];
@@ -26,6 +33,16 @@ __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T
     Z[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], d[k])) : 0u;
     // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
     if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
+  }
+  if constexpr (LANES && NW == 4) {
+    const bool b0 = lane & 1, b1 = lane & 2;
+    auto pick = [&](const u32* a) { const u32 lo = b0 ? a[1] : a[0], hi = b0 ? a[3] : a[2]; return b1 ? hi : lo; };
+    const uint4 v = make_uint4(pick(F), pick(X), pick(Y), pick(Z));
+    if (lane < 4) {
+      mq[lane] = v;
+      rs[lane] = __popc(v.x & ~v.y);
+    }
+    return;
   }
   if (lane == 0) {
 #pragma unroll
@@ -504,20 +521,30 @@ k_faces_tma(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom 
 #ifndef CC_TMA2_NBUF
 #define CC_TMA2_NBUF 2     // measured on B200 (profiles/r02_faces_ab.md): 2 slots 0.170-0.174 ms, 3 slots 0.174-0.176, 4 slots 0.196 (512^3 u32)
 #endif
+#ifndef CC_TMA2_TR
+#define CC_TMA2_TR 8      // measured on B200 (profiles/r02b_faces_variants.md): 4 rows / 8 warps 0.148 ms, 8 rows / 8 warps 0.137, 8 rows / 4 warps 0.128, 16 rows / 2 warps 0.142
+#endif
+#ifndef CC_TMA2_MINB
+#define CC_TMA2_MINB 1
+#endif
+#ifndef CC_TMA2_WARPS
+#define CC_TMA2_WARPS 4
+#endif
 template <typename T> struct FaceTma2 {
+  static constexpr int WARPS = CC_TMA2_WARPS;
   static constexpr int NW = CC_FACE_NW;
   static constexpr int PAD = 16 / (int)sizeof(T);
   static constexpr int BOXX = NW * 32 + PAD;
-  static constexpr int TR = 4;
+  static constexpr int TR = CC_TMA2_TR;
   static constexpr int PITCH = BOXX * (int)sizeof(T);
   static constexpr int BOXB = PITCH * (TR + 1);
   static constexpr int BUFB = (BOXB + 127) & ~127;
   static constexpr int NBUF = CC_TMA2_NBUF;
-  static constexpr size_t smem() { return (size_t)CC_FACE_WARPS * (NBUF * BUFB) + CC_FACE_WARPS * NBUF * 8 + 128; }
+  static constexpr size_t smem() { return (size_t)WARPS * (NBUF * BUFB) + WARPS * NBUF * 8 + 128; }
 };
 
 template <typename T, int MODE, bool HASZ>
-__global__ void __launch_bounds__(CC_FACE_WARPS * 32)
+__global__ void __launch_bounds__(CC_TMA2_WARPS * 32, CC_TMA2_MINB)
 k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom g, Edge<T, MODE> E, Counters* __restrict__ ctr,
              unsigned nyb, unsigned nwg, unsigned zchunk, unsigned ntasks) {
   typedef FaceTma2<T> F;
@@ -526,7 +553,7 @@ k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* base = tma_smem + ((128u - ((unsigned)__cvta_generic_to_shared(tma_smem) & 127u)) & 127u);
   unsigned char* ring = base + (size_t)warp * (F::NBUF * F::BUFB);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + (size_t)CC_FACE_WARPS * (F::NBUF * F::BUFB)) + warp * F::NBUF;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + (size_t)F::WARPS * (F::NBUF * F::BUFB)) + warp * F::NBUF;
   if (lane == 0) {
 #pragma unroll
     for (int b = 0; b < F::NBUF; b++) mbar_init(bars + b, 1);
@@ -535,7 +562,7 @@ k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom
   }
   __syncwarp();
   CC_PDL_WAIT();
-  const unsigned task = blockIdx.x * CC_FACE_WARPS + warp;
+  const unsigned task = blockIdx.x * F::WARPS + warp;
   if (task >= ntasks) return;
   const u32 W = (u32)g.W, sy = (u32)g.sy, sz = (u32)g.sz;
   const u32 wg = task % nwg;
@@ -562,6 +589,80 @@ k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom
   constexpr u32 PD = F::NBUF;          // a slot is refilled as soon as its plane has been evaluated: NBUF - 1 planes in flight
 #pragma unroll
   for (u32 k = 0; k < PD; k++) if (first + k < nsteps) issue(first + k);
+#ifndef CC_TMA2_NO_FAST
+  if (nrow == (u32)TR && rs_vec) {
+    // ---- full blocks (every block of a volume whose sy is a multiple of 4 and whose rows are multiples of 128 voxels):
+    //      rows unrolled without conditions, the planes z - 1 / z ping-pong between two register sets (no register
+    //      moves), ONE 32-bit word index per row instead of two 64-bit pointers. ncu of the conditional loop below
+    //      (profiles/r02_ncu_full_summary.md): 110 instructions per row of four words, of which 19 were pointer
+    //      arithmetic and 16 register moves. ----
+    T A[TR][NW], B[TR][NW];
+#pragma unroll
+    for (int r = 0; r < TR; r++)
+#pragma unroll
+      for (int k = 0; k < NW; k++) A[r][k] = (T)0;
+    uint4* __restrict__ M4 = reinterpret_cast<uint4*>(M);
+    u32* __restrict__ RSb = M + g.offRS;
+    const u32 wplane = sy * W;
+    u32 widx = (z0 * sy + y0) * W + w0;
+    auto eval_plane = [&](const T (&prev)[TR][NW], T (&cur)[TR][NW], const unsigned char* buf, u32 wrow) {
+      T up[NW];
+      {
+        const T* h = reinterpret_cast<const T*>(buf) + PAD + lane;     // halo row y0 - 1
+#pragma unroll
+        for (int k = 0; k < NW; k++) up[k] = h[32 * k];
+      }
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const T* sc = reinterpret_cast<const T*>(buf + (size_t)(r + 1) * F::PITCH) + PAD + lane;
+        T l[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) { cur[r][k] = sc[32 * k]; l[k] = sc[32 * k - 1]; }
+        faces_eval_store<T, MODE, HASZ, NW, CC_FACE_LANES>(E, cur[r], l, prev[r], r == 0 ? up : cur[r > 0 ? r - 1 : 0], lane, M4 + wrow, RSb + wrow, true, epl);
+        wrow += W;
+      }
+    };
+    u32 st = first;
+    if (HASZ) {
+      // plane z0 - 1: only the -z operands of the first plane
+      mbar_wait(bars, 0u);
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const T* sc = reinterpret_cast<const T*>(ring + (size_t)(r + 1) * F::PITCH) + PAD + lane;
+#pragma unroll
+        for (int k = 0; k < NW; k++) A[r][k] = sc[32 * k];
+      }
+      __syncwarp();
+      if (st + PD < nsteps) issue(st + PD);
+      st++;
+    }
+    while (st < nsteps) {
+      {
+        const u32 q = st - first;
+        mbar_wait(bars + q % F::NBUF, (q / F::NBUF) & 1u);
+        eval_plane(A, B, ring + (q % F::NBUF) * F::BUFB, widx);
+        widx += wplane;
+        __syncwarp();
+        if (st + PD < nsteps) issue(st + PD);
+        st++;
+      }
+      if (st >= nsteps) break;
+      {
+        const u32 q = st - first;
+        mbar_wait(bars + q % F::NBUF, (q / F::NBUF) & 1u);
+        eval_plane(B, A, ring + (q % F::NBUF) * F::BUFB, widx);
+        widx += wplane;
+        __syncwarp();
+        if (st + PD < nsteps) issue(st + PD);
+        st++;
+      }
+    }
+    if constexpr (MODE != MODE_EQ) {
+      if (lane == 0 && epl) atomicAdd((unsigned long long*)&ctr->epl, (unsigned long long)epl);
+    }
+    return;
+  }
+#endif
   T dreg[TR][NW];
 #pragma unroll
   for (int r = 0; r < TR; r++)

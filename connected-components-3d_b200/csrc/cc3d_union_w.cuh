@@ -153,40 +153,73 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
     if (w < W && y < sy && z < sz) {
       const u32 row = z * sy + y;
       if (we.load(row * W + w, row, w, y, z)) {
-        const u32 sg = r >> sshift;
-        const u32 Sp = we.Sp, dP = segD[sg], nbr = nb[sg];
+        const u32 Sp = we.Sp;
         const u32 gP = we.RSp;                                   // global id of the first run that starts in the word, minus 1
-        u32 need = we.need_y(), need2 = we.need_z();
-        // neighbour word of the current direction: run starts, global id base, and - when its row lies in the tile -
-        // first local id of its segment and global - local of that segment
-        u32 Sq = we.U.F & ~we.U.X, gQ = 0, mQ = 0, dQ = 0; bool inQ = false;
-        u32 Sq2 = we.D.F & ~we.D.X, gQ2 = 0, mQ2 = 0, dQ2 = 0; bool inQ2 = false;
-        if (need) {
-          gQ = __ldg(RS + we.i - W) - 1u;
-          if (tile_ok && ly > 0) { const u32 s2 = (r - 1) >> sshift; mQ = nb[s2]; dQ = segD[s2]; inQ = true; }
+        const u32 needY = we.need_y(), needZ = we.need_z();
+        // an edge is tile-local when both of its runs START in the tile: the neighbour row lies in the tile and neither
+        // voxel belongs to a run that enters the tile from the left. Such a run exists only when the tile does not begin
+        // at x = 0, and it owns the bits below the first run start of a word as long as no run has started in the tile
+        // row before that word (local id base == first local id of the row segment - 1).
+        const u32 SqY = we.U.F & ~we.U.X, SqZ = we.D.F & ~we.D.X;
+        u32 locY = 0, locZ = 0, gQY = 0, gQZ = 0, lQY = 0, lQZ = 0;
+        const u32 sgP = r >> sshift;
+        const u32 dP = segD[sgP];
+        auto from_first_start = [](u32 S) { return S ? ~((S & (0u - S)) - 1u) : 0u; };
+        u32 locP = CC_FULL;
+        if (w0 != 0 && gP - dP + 1u == nb[sgP]) locP = from_first_start(Sp);
+        if (needY) {
+          gQY = __ldg(RS + we.i - W) - 1u;
+          if (tile_ok && ly > 0) {
+            const u32 sgQ = (r - 1) >> sshift;
+            lQY = gQY - segD[sgQ];
+            locY = locP;
+            if (w0 != 0 && lQY + 1u == nb[sgQ]) locY &= from_first_start(SqY);
+          }
         }
-        if (need2) {
-          gQ2 = __ldg(RS + we.i - W * sy) - 1u;
-          if (tile_ok && lz > 0) { const u32 s2 = (r - TY) >> sshift; mQ2 = nb[s2]; dQ2 = segD[s2]; inQ2 = true; }
+        if (needZ) {
+          gQZ = __ldg(RS + we.i - W * sy) - 1u;
+          if (tile_ok && lz > 0) {
+            const u32 sgQ = (r - TY) >> sshift;
+            lQZ = gQZ - segD[sgQ];
+            locZ = locP;
+            if (w0 != 0 && lQZ + 1u == nb[sgQ]) locZ &= from_first_start(SqZ);
+          }
         }
-        if (!need) { need = need2; need2 = 0; Sq = Sq2; gQ = gQ2; mQ = mQ2; dQ = dQ2; inQ = inQ2; }
-        while (need) {
-          const int b = __ffs(need) - 1; need &= need - 1;
-          const u32 below = CC_FULL >> (31 - b);
-          const u32 ga = gP + __popc(Sp & below), gc = gQ + __popc(Sq & below);
-          const u32 a = ga - dP, c = gc - dQ;
-          // signed compares: a run that enters the tile from the left has the id of its segment's first run minus 1
-          if (inQ && (int)(a - nbr) >= 0 && (int)(c - mQ) >= 0) {
+        // tile-local edges: first link by one atomicMin
+        {
+          const u32 lP = gP - dP;
+          u32 need = needY & locY, need2 = needZ & locZ, Sq = SqY, lQ = lQY;
+          if (!need) { need = need2; need2 = 0; Sq = SqZ; lQ = lQZ; }
+          while (need) {
+            const int b = __ffs(need) - 1; need &= need - 1;
+            const u32 below = CC_FULL >> (31 - b);
+            const u32 a = lP + __popc(Sp & below), c = lQ + __popc(Sq & below);
             const u32 old = atomicMin(&lab[a], c);
             if (old != a && old != c) {             // a already had a parent: union(old, c) is still owed
               const u32 pos = atomicAdd(&s_wqn[warp], 1u);
               if (pos < WQ) wq[pos] = old | (c << 16);
               else sm_union32(lab, old, c);
             }
-          } else {
-            stage_global(ga, gc);
+            if (!need) { need = need2; need2 = 0; Sq = SqZ; lQ = lQZ; }
           }
-          if (!need) { need = need2; need2 = 0; Sq = Sq2; gQ = gQ2; mQ = mQ2; dQ = dQ2; inQ = inQ2; }
+        }
+        // edges that leave the tile: one reservation per word in the staging buffer
+        {
+          u32 need = needY & ~locY, need2 = needZ & ~locZ, Sq = SqY, gQ = gQY;
+          const u32 n = __popc(need) + __popc(need2);
+          if (n) {
+            u32 pos = atomicAdd(&s_gn, n);
+            if (!need) { need = need2; need2 = 0; Sq = SqZ; gQ = gQZ; }
+            while (need) {
+              const int b = __ffs(need) - 1; need &= need - 1;
+              const u32 below = CC_FULL >> (31 - b);
+              const u32 ga = gP + __popc(Sp & below), gc = gQ + __popc(Sq & below);
+              if (pos < GQN) gq[pos] = (u64)ga | ((u64)gc << 32);
+              else push_global(ga, gc);
+              pos++;
+              if (!need) { need = need2; need2 = 0; Sq = SqZ; gQ = gQZ; }
+            }
+          }
         }
         td = we.may_have_diagonals();
       }

@@ -107,6 +107,31 @@ def test_differential_fuzz_wide(cc3d, oracle_mod):
   assert _fuzz(cc3d, _truth(oracle_mod), seed=505, ncase=160, maxdim=24, wide=True) > 120
 
 
+def test_long_runs_across_x_tiles(cc3d, oracle_mod):
+  """Rows of 1 100 .. 2 100 voxels (three to five union tiles side by side) with runs of hundreds of voxels: a run that
+  enters a tile from the left keeps owning the leading bits of the tile's second, third ... word (regression: the
+  warp-owned B1 treated those bits as tile-local; only a 2048-wide full-size test saw it)."""
+  truth = _truth(oracle_mod)
+  rng = np.random.default_rng(77)
+  checked = 0
+  for it in range(24):
+    sx = int(rng.choice([1100, 1536, 2048, 2100, int(rng.integers(1025, 2200))]))
+    sy, sz = int(rng.integers(9, 40)), int(rng.integers(1, 11))
+    coarse = rng.integers(0 if it % 3 == 0 else 1, 5, (sz // 3 + 1, sy // 5 + 1, sx // int(rng.integers(90, 400)) + 1))
+    x = np.repeat(np.repeat(np.repeat(coarse, 3, 0), 5, 1), 400, 2)
+    shift = rng.integers(0, 300, (x.shape[0], x.shape[1]))
+    rows = np.arange(x.shape[2])[None, None, :] + shift[:, :, None]
+    x = np.take_along_axis(x, np.minimum(rows, x.shape[2] - 1), axis=2)[:sz, :sy, :sx]
+    x = np.ascontiguousarray(x).astype([np.uint32, np.uint64, np.uint8, np.uint16][it % 4])
+    for conn in ((6, 18, 26) if sz > 1 else (4, 8)):
+      xx = x if sz > 1 else x[0]
+      a, Na = truth.connected_components(xx, connectivity=conn, return_N=True)
+      b, Nb = cc3d.connected_components(xx, connectivity=conn, return_N=True)
+      assert_same_labels(a, Na, b, Nb, f"{xx.shape} conn={conn} case {it}")
+      checked += 1
+  assert checked >= 48
+
+
 def test_c_oracle_agrees_too(cc3d, oracle_mod):
   assert _fuzz(cc3d, oracle_mod, seed=303, ncase=200, maxdim=40) > 150
 
