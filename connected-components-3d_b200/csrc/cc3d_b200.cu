@@ -15,6 +15,7 @@
 #include "cc3d_graphs.cuh"
 #include "cc3d_resolve.cuh"
 #include "cc3d_runs.cuh"
+#include "cc3d_blocks.cuh"
 
 namespace {
 
@@ -492,6 +493,20 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   add(gqcap * 8); add(64);
   add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
+  // binary 26-connected volumes: the unions are solved on the grid of 2x2x2 blocks (cc3d_blocks.cuh)
+  static const bool no_blocks = getenv("CC3D_B200_NO_BLOCKS") != nullptr;
+  const bool use_blocks = mode == MODE_NONZERO && connectivity == 26 && !no_blocks;
+  Geom g2 = {};
+  i64 maxruns_b = 0, nb_b = 0; size_t gqcap_b = 0, ctl_b = 0, occ_b = 0;
+  if (use_blocks) {
+    g2 = make_geom((sx + 1) / 2, (sy + 1) / 2, (sz + 1) / 2);
+    maxruns_b = g2.rows * g2.sx;          // neighbouring occupied blocks need not be joined: up to one run per block
+    nb_b = (g2.nwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK;
+    gqcap_b = (size_t)std::min<i64>(8 * g2.nwords + 4096, 0x7FFFFFFF);
+    ctl_b = ((sizeof(Counters) + 255) & ~size_t(255)) + (size_t)(nb_b + 2) * 8;
+    occ_b = (size_t)g2.sx * g2.sy * g2.sz + 64;
+    add(occ_b); add(bitmap_words(g2, false) * 4); add((size_t)maxruns_b * 4); add((size_t)maxruns_b * 4); add(gqcap_b * 8); add(ctl_b);
+  }
   if (int rc = arena_acquire(need, &S->arena, (cudaStream_t)stream, true)) { delete S; return rc; }
   Arena& ar = S->arena;
   // enqueue-only sessions (slab_begin) never read the counters on the host: no landing slot, no copy
@@ -560,8 +575,50 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
     scan_counts(RS, RS, bsum, nwords, nullptr, 0, &ctr->nruns, RS + nwords, s, ctr, (u32)g.W, scans_cleared);
     mark("S_scan_runs", s);
     // B: unions
-    rc = -1;
-    CC_KIND_SWITCH(in_kind, rc = run_union_stage<KT>(a));
+    if (use_blocks) {
+      // the same pipeline one level up, on the occupancy bytes of the 2x2x2 blocks
+      uint8_t* occ = (uint8_t*)ar.take(occ_b);
+      u32* M2 = (u32*)ar.take(bitmap_words(g2, false) * 4);
+      u32* L2 = (u32*)ar.take((size_t)maxruns_b * 4);
+      u32* minrun = (u32*)ar.take((size_t)maxruns_b * 4);
+      u64* gq2 = (u64*)ar.take(gqcap_b * 8);
+      char* ctl2 = (char*)ar.take(ctl_b);
+      Counters* ctr2 = (Counters*)ctl2;
+      u64* bsum_b = (u64*)(ctl2 + ((sizeof(Counters) + 255) & ~size_t(255)));
+      cudaMemsetAsync(ctl2, 0, ctl_b, s);
+      const u32 BX = (u32)g2.sx, BY = (u32)g2.sy, BZ = (u32)g2.sz;
+      const i64 nthr = g.W * (i64)BY * BZ;
+      k_block_occ<<<(unsigned)((nthr + 255) / 256), 256, 0, s>>>(M, g, occ, BX, BY, BZ);
+      mark("Bb_occupancy", s);
+      LabelArgs b = a;
+      int launches_b = 0;
+      b.launches = &launches_b;
+      b.in = occ; b.M = M2; b.L = L2; b.ctr = ctr2; b.g = g2; b.mode = MODE_BLOCK; b.connectivity = 26;
+      b.GQ.q = gq2; b.GQ.count = &ctr2->gq_count; b.GQ.ovf = &ctr2->gq_ovf; b.GQ.cap = (u32)gqcap_b;
+      b.mark = nullptr; b.inline_fallback = true; b.bigflags = nullptr; b.nbig = nullptr; b.defer_big = false;
+      memset(b.delta, 0, 8);
+      rc = run_faces_stage<uint8_t>(b);
+      mark("Bb_faces", s);
+      if (rc == 0) {
+        u32* RS2 = M2 + g2.offRS;
+        scan_counts(RS2, RS2, bsum_b, g2.nwords, nullptr, 0, &ctr2->nruns, RS2 + g2.nwords, s, nullptr, 1, true);
+        mark("Bb_scan", s);
+        rc = run_union_stage<uint8_t>(b);
+        mark("Bb_unions", s);
+      }
+      if (rc == 0) {
+        k_block_flatten<<<CC_GRID_BLOCKS, 256, 0, s>>>(L2, &ctr2->nruns);
+        k_fill_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(minrun, CC_BG, &ctr2->nruns);
+        mark("Bb_flatten", s);
+        k_block_minrun<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(M, g, M2, g2, L2, L, minrun);
+        k_block_assign<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, minrun, &ctr->nruns);
+        stage_launches += launches_b + 5;
+      }
+      mark("Bb_minrun_assign", s);
+    } else {
+      rc = -1;
+      CC_KIND_SWITCH(in_kind, rc = run_union_stage<KT>(a));
+    }
   }
   if (rc == 0 && S->periodic) {
     CC_KIND_SWITCH(in_kind, rc = run_periodic_stage<KT>(a));

@@ -40,7 +40,7 @@ typedef int64_t i64;
 #define CC_BG 0xFFFFFFFFu
 #define CC_FULL 0xFFFFFFFFu
 
-enum { MODE_EQ = 0, MODE_NONZERO = 1, MODE_DELTA = 2, MODE_MASK = 3 };
+enum { MODE_EQ = 0, MODE_NONZERO = 1, MODE_DELTA = 2, MODE_MASK = 3, MODE_BLOCK = 4 };
 
 // Backward-direction codes. Order follows the reference's compute_neighborhood
 // (cc3d_continuous.hpp:38-73).
@@ -134,13 +134,40 @@ template <typename T, int MODE> struct Edge {
   // difference is NaN. zeq = 1 reproduces that on the straight -z edge.
   int zeq;
   __device__ __forceinline__ bool fg(T v) const { return v != (T)0; }
+  // BLOCK (binary 26-connected volumes, cc3d_blocks.cuh): a "voxel" is the occupancy byte of a 2x2x2 block (bit
+  // x + 2y + 4z); two blocks are joined in backward direction (dx, dy, dz) when p has a voxel on the side that faces q
+  // and q has one on the side that faces p (all such voxel pairs are 26-adjacent).
+  static __device__ __forceinline__ u32 side_mask(int d, u32 lo, u32 hi) { return d < 0 ? lo : (d > 0 ? hi : 0xFFu); }
+  static __device__ __forceinline__ bool block_edge(u32 p, u32 q, int dx, int dy, int dz) {
+    const u32 mp = side_mask(dx, 0x55u, 0xAAu) & side_mask(dy, 0x33u, 0xCCu) & side_mask(dz, 0x0Fu, 0xF0u);
+    const u32 mq = side_mask(-dx, 0x55u, 0xAAu) & side_mask(-dy, 0x33u, 0xCCu) & side_mask(-dz, 0x0Fu, 0xF0u);
+    return (p & mp) != 0 && (q & mq) != 0;
+  }
+  __device__ __forceinline__ bool xedge(T p, T q) const {
+    if constexpr (MODE == MODE_BLOCK) return block_edge((u32)p, (u32)q, -1, 0, 0);
+    else return (*this)(p, q);
+  }
+  __device__ __forceinline__ bool yedge(T p, T q) const {
+    if constexpr (MODE == MODE_BLOCK) return block_edge((u32)p, (u32)q, 0, -1, 0);
+    else return (*this)(p, q);
+  }
   __device__ __forceinline__ bool zedge(T p, T q) const {
+    if constexpr (MODE == MODE_BLOCK) return block_edge((u32)p, (u32)q, 0, 0, -1);
     if constexpr (MODE == MODE_DELTA && is_float_t<T>::value) { if (zeq && p == q && p != (T)0) return true; }
     return (*this)(p, q);
   }
+  // diagonal direction t of WordEdges::diag_masks: 0 A0, 1 C0, 2 A1, 3 C1, 4 B2, 5 A2, 6 C2, 7 B3, 8 A3, 9 C3
+  __device__ __forceinline__ bool diag(int t, T p, T q) const {
+    if constexpr (MODE == MODE_BLOCK) {
+      const int dx = (int)((0x86188u >> (2 * t)) & 3u) - 1;      // -1 +1 -1 +1 0 -1 +1 0 -1 +1
+      const int dy = t < 2 ? -1 : (t < 4 ? 0 : (t < 7 ? -1 : 1));
+      const int dz = t < 2 ? 0 : -1;
+      return block_edge((u32)p, (u32)q, dx, dy, dz);
+    } else return (*this)(p, q);
+  }
   __device__ __forceinline__ bool operator()(T p, T q) const {
     if constexpr (MODE == MODE_EQ) { return p == q && p != (T)0; }
-    else if constexpr (MODE == MODE_NONZERO) { return p != (T)0 && q != (T)0; }
+    else if constexpr (MODE == MODE_NONZERO || MODE == MODE_BLOCK) { return p != (T)0 && q != (T)0; }
     else {
       if (p == (T)0 || q == (T)0) return false;
       if constexpr (is_float_t<T>::value) { return fabs(p - q) <= delta; }

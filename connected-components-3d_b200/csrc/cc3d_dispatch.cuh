@@ -171,6 +171,9 @@ template <typename T> int run_faces_stage(const LabelArgs& a) {
     case MODE_EQ: return launch_faces<T, MODE_EQ>(a);
     case MODE_NONZERO: return launch_faces<T, MODE_NONZERO>(a);
     case MODE_DELTA: return launch_faces<T, MODE_DELTA>(a);
+    case MODE_BLOCK:      // occupancy bytes of 2x2x2 blocks (cc3d_blocks.cuh)
+      if constexpr (sizeof(T) == 1) return launch_faces<T, MODE_BLOCK>(a);
+      else return -1;
   }
   return -1;
 }
@@ -195,8 +198,8 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
   static PerDeviceOnce once;
   const bool set_attr = once.first();
-  if constexpr (MODE == MODE_DELTA) {
-    // continuous predicate: edge-parallel item lists (every word has candidates that need a value test)
+  if constexpr (MODE == MODE_DELTA || MODE == MODE_BLOCK) {
+    // continuous predicate (and block nodes, whose predicate is not transitive either): edge-parallel item lists (every word has candidates that need a value test)
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cc_launch(k_union_tile_items<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
@@ -262,6 +265,9 @@ template <typename T> static int union_stage(const LabelArgs& a, bool global_onl
     case MODE_NONZERO: return launch_union_conn<uint8_t, MODE_NONZERO>(a, global_only);
     case MODE_DELTA: return launch_union_conn<T, MODE_DELTA>(a, global_only);
     case MODE_MASK: return launch_union<uint8_t, MODE_MASK, 8>(a, global_only);
+    case MODE_BLOCK:
+      if constexpr (sizeof(T) == 1) return launch_union<uint8_t, MODE_BLOCK, 26>(a, global_only);
+      else return -1;
   }
   return -1;
 }

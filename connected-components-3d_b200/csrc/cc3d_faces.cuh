@@ -28,8 +28,8 @@ __device__ __forceinline__ void faces_eval_store(const Edge<T, MODE>& E, const T
   for (int k = 0; k < NW; k++) {
     const bool f = E.fg(c[k]);
     F[k] = __ballot_sync(CC_FULL, f);
-    X[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
-    Y[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
+    X[k] = __ballot_sync(CC_FULL, E.xedge(c[k], l[k]));
+    Y[k] = __ballot_sync(CC_FULL, E.yedge(c[k], up[k]));
     Z[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], d[k])) : 0u;
     // cc3d.hpp:300-303: a provisional label per x-transition into a non-zero value
     if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
@@ -145,8 +145,8 @@ k_faces(const T* __restrict__ in, u32* __restrict__ M, Geom g, Edge<T, MODE> E, 
         if (inx) { c = *p; if (x > 0) l = *(p - 1); if (hasz) d = *(p - plane); }
         const bool f = E.fg(c);
         const u32 F = __ballot_sync(CC_FULL, f);
-        const u32 X = __ballot_sync(CC_FULL, E(c, l));
-        const u32 Y = __ballot_sync(CC_FULL, E(c, up));
+        const u32 X = __ballot_sync(CC_FULL, E.xedge(c, l));
+        const u32 Y = __ballot_sync(CC_FULL, E.yedge(c, up));
         const u32 Z = HASZ ? __ballot_sync(CC_FULL, E.zedge(c, d)) : 0u;
         if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c != l));
         if (lane == 0) {
@@ -489,8 +489,8 @@ k_faces_tma(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom 
         for (int k = 0; k < NW; k++) {
           const bool f = E.fg(c[k]);
           Fw[k] = __ballot_sync(CC_FULL, f);
-          Xw[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
-          Yw[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
+          Xw[k] = __ballot_sync(CC_FULL, E.xedge(c[k], l[k]));
+          Yw[k] = __ballot_sync(CC_FULL, E.yedge(c[k], up[k]));
           Zw[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], d[k])) : 0u;
           if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
         }
@@ -706,8 +706,8 @@ k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom
             for (int k = 0; k < NW; k++) {
               const bool f = E.fg(c[k]);
               Fw[k] = __ballot_sync(CC_FULL, f);
-              Xw[k] = __ballot_sync(CC_FULL, E(c[k], l[k]));
-              Yw[k] = __ballot_sync(CC_FULL, E(c[k], up[k]));
+              Xw[k] = __ballot_sync(CC_FULL, E.xedge(c[k], l[k]));
+              Yw[k] = __ballot_sync(CC_FULL, E.yedge(c[k], up[k]));
               Zw[k] = HASZ ? __ballot_sync(CC_FULL, E.zedge(c[k], dreg[r][k])) : 0u;
               if constexpr (MODE != MODE_EQ) epl += __popc(__ballot_sync(CC_FULL, f && c[k] != l[k]));
             }

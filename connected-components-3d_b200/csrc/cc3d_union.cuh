@@ -257,7 +257,7 @@ struct WordEdges {
           const u32 rowQ = row + DY[t] + DZ[t] * (int)sy;
           const u32 xq = x0 + b + DX[t];
           bool joined = true;
-          if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA) joined = E(in[row * sx + x0 + b], in[rowQ * sx + xq]);
+          if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA || MODE == MODE_BLOCK) joined = E.diag(t, in[row * sx + x0 + b], in[rowQ * sx + xq]);
           if (joined) emit(gp, run_id(M, g, rowQ * W, xq), DY[t], DZ[t], xq);
         }
       }
@@ -903,9 +903,9 @@ k_union_tile_items(const T* __restrict__ in, const u32* __restrict__ M, u32* __r
     const u32 rowP = (z0 + lz) * sy + y0 + ly;
     const u32 rowQ = (u32)((int)rowP + dy + dz * (int)sy);
     const u32 xq = (u32)((int)((w0 << 5)) + xl);
-    if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA) {
+    if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA || MODE == MODE_BLOCK) {
       if (tdir >= 2) {   // diagonal candidate: test the predicate on the two voxel values
-        if (!E(in[(size_t)rowP * sx + ((w0 + wx) << 5) + b], in[(size_t)rowQ * sx + xq])) return;
+        if (!E.diag((int)tdir - 2, in[(size_t)rowP * sx + ((w0 + wx) << 5) + b], in[(size_t)rowQ * sx + xq])) return;
       }
     }
     u32 gq_, rq = 0;

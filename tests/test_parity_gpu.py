@@ -132,6 +132,34 @@ def test_long_runs_across_x_tiles(cc3d, oracle_mod):
   assert checked >= 48
 
 
+def test_binary26_block_nodes(cc3d, oracle_mod):
+  """Binary 26-connected volumes solve their unions on the grid of 2x2x2 blocks (cc3d_blocks.cuh): odd and tiny extents
+  (partial blocks, one block per row), sparse and dense occupancies, numbering by the first VOXEL of every component."""
+  truth = _truth(oracle_mod)
+  rng = np.random.default_rng(2626)
+  checked = 0
+  for it in range(220):
+    if it % 4 == 0:
+      shape = (int(rng.integers(1, 6)), int(rng.integers(1, 70)), int(rng.integers(1, 70)))
+    elif it % 4 == 1:
+      shape = (int(rng.integers(1, 140)), int(rng.integers(1, 30)), int(rng.integers(1, 6)))
+    else:
+      shape = tuple(int(rng.integers(1, 75)) for _ in range(3))
+    if it % 7 == 0:
+      shape = shape[:2]     # a 2D array labelled with a 3D connectivity
+    p = float(rng.choice([0.03, 0.1, 0.2, 0.35, 0.5, 0.8, 0.97]))
+    dt = [np.uint8, bool, np.uint16, np.float32, np.int64][it % 5]
+    x = np.asarray((rng.random(shape) < p).astype(dt), order="F" if it % 2 else "C")
+    try:
+      a, Na = truth.connected_components(x, connectivity=26, return_N=True, binary_image=True)
+    except RuntimeError:
+      continue   # reference union-find overflow (defect D3)
+    b, Nb = cc3d.connected_components(x, connectivity=26, return_N=True, binary_image=True)
+    assert_same_labels(a, Na, b, Nb, f"{shape} {np.dtype(dt)} p={p} case {it}")
+    checked += 1
+  assert checked > 150
+
+
 def test_c_oracle_agrees_too(cc3d, oracle_mod):
   assert _fuzz(cc3d, oracle_mod, seed=303, ncase=200, maxdim=40) > 150
 
