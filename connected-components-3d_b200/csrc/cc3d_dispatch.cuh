@@ -198,30 +198,53 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
   const i64 ntx = (g.W + (1 << g.tw) - 1) >> g.tw, nty = (g.sy + (1 << g.ty) - 1) >> g.ty, ntz = (g.sz + (1 << g.tz) - 1) >> g.tz;
   static PerDeviceOnce once;
   const bool set_attr = once.first();
+  // Which tile kernel (measured on B200, 512^3, profiles/r02b_b1_by_mode.md): the warp-owned kernel wins wherever the
+  // diagonal candidates are sparse or absent (label volumes 0.28 -> 0.20 ms, binary 6-connected noise 0.76 -> 0.61 ms);
+  // where every word carries candidates (binary 18/26-connected noise, continuous values, block grids, multilabel noise)
+  // its per-warp item lists overflow and the CTA-phased kernels of round 1 stay ahead (18-conn. noise 2.5 vs 4.8 ms,
+  // continuous 0.66 vs 1.13 ms, blocks 0.44 vs 0.76 ms).
+  constexpr bool DIAG = CONN == 8 || CONN == 18 || CONN == 26;
+  const bool use_w = !b1_phased() && nty < 65536 && ntz < 65536;
   if constexpr (MODE == MODE_DELTA || MODE == MODE_BLOCK) {
-    // continuous predicate (and block nodes, whose predicate is not transitive either): edge-parallel item lists (every word has candidates that need a value test)
+    // continuous predicate / block nodes: edge-parallel item lists (every word has candidates that need a value test)
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cc_launch(k_union_tile_items<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
   } else if constexpr (MODE == MODE_NONZERO) {
-    const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
-    if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
-  } else if (!b1_phased() && nty < 65536 && ntz < 65536) {
-    // warp-owned tiles (cc3d_union_w.cuh): compact 32-bit forest of up to 4 096 runs per tile; tiles with more runs
-    // (multilabel noise) are flagged and relabelled by a second launch with room for the maximum (16 384)
-    const size_t smem = (size_t)WarpTile<MODE, 4096>::SMEM_WORDS * 4, smem2 = (size_t)WarpTile<MODE, 16384>::SMEM_WORDS * 4;
-    if (set_attr) {
-      cudaFuncSetAttribute(k_union_tile_w<T, MODE, CONN, 4096, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_union_tile_w<T, MODE, CONN, 16384, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (!DIAG && use_w) {
+      // binary images hold at most 16 runs per word: 8 192 per tile
+      if constexpr (!DIAG) {
+        const size_t smem = (size_t)WarpTile<MODE, 8192>::SMEM_WORDS * 4;
+        if (set_attr) cudaFuncSetAttribute(k_union_tile_w<T, MODE, CONN, 8192, false, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        BigTiles big; big.flags = nullptr; big.count = nullptr; big.defer = 0;
+        cc_launch(k_union_tile_w<T, MODE, CONN, 8192, false, 8192>, dim3((unsigned)ntx, (unsigned)nty, (unsigned)ntz), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, a.GQ, big);
+      }
+    } else {
+      const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
+      if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
     }
-    BigTiles big; big.flags = a.bigflags; big.count = a.nbig; big.defer = a.defer_big ? 1 : 0;
-    cc_launch(k_union_tile_w<T, MODE, CONN, 4096, false>, dim3((unsigned)ntx, (unsigned)nty, (unsigned)ntz), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, a.GQ, big);
-    if (a.defer_big) {
-      cc_launch(k_union_tile_w<T, MODE, CONN, 16384, true>, dim3((unsigned)ntx, (unsigned)nty, (unsigned)ntz), dim3(CC_TILE_THREADS), (size_t)(smem2), a.stream, in, a.M, a.L, g, E, a.GQ, big);
-      *a.launches += 1;
+  } else if (MODE == MODE_EQ && use_w) {
+    if constexpr (MODE == MODE_EQ) {
+      // warp-owned tiles (cc3d_union_w.cuh): compact 32-bit forest of up to 4 096 runs per tile. Tiles with more runs - with
+      // diagonals: more than 3 072, i.e. noise, where the candidates are dense - are flagged and, once the process has met
+      // such a volume, relabelled by a second launch of the CTA-phased kernel with a 32-runs-per-word forest (measured faster on
+      // noise than the warp-owned kernel with room for 16 384 runs: periodic 6-connected 1024^3 B1 6.4 vs 9.7 ms).
+      constexpr u32 DENSE = DIAG ? 3072u : 4096u;
+      const size_t smem = (size_t)WarpTile<MODE, 4096>::SMEM_WORDS * 4;
+      const size_t smem5 = (size_t)HybridQueues<MODE, 5>::SMEM_WORDS * 4;
+      if (set_attr) {
+        cudaFuncSetAttribute(k_union_tile_w<T, MODE, CONN, 4096, false, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+      }
+      BigTiles big; big.flags = a.bigflags; big.count = a.nbig; big.defer = a.defer_big ? 1 : 0;
+      cc_launch(k_union_tile_w<T, MODE, CONN, 4096, false, DENSE>, dim3((unsigned)ntx, (unsigned)nty, (unsigned)ntz), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, a.GQ, big);
+      if (a.defer_big) {
+        cc_launch(k_union_tile_hybrid<T, MODE, CONN, 5>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem5), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ, big);
+        *a.launches += 1;
+      }
     }
-  } else {
+  } else if constexpr (MODE == MODE_EQ || MODE == MODE_MASK) {
     const size_t smem = (size_t)HybridQueues<MODE, 4>::SMEM_WORDS * 4, smem5 = (size_t)HybridQueues<MODE, 5>::SMEM_WORDS * 4;
     if (set_attr) {
       cudaFuncSetAttribute(k_union_tile_hybrid<T, MODE, CONN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

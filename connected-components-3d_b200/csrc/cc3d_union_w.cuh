@@ -58,7 +58,8 @@ template <int MODE, u32 CAPN> struct WarpTile {
 };
 
 // grid = (tiles in x, tiles in y, tiles in z)
-template <typename T, int MODE, int CONN, u32 CAPN, bool SECOND>
+// DENSE: tiles with more runs are flagged for the second launch (<= CAPN)
+template <typename T, int MODE, int CONN, u32 CAPN, bool SECOND, u32 DENSE>
 __global__ void __launch_bounds__(CC_TILE_THREADS, CAPN <= 4096 ? CC_TILE_MINB(CC_B1W_MINB) : (CAPN <= 8192 ? CC_TILE_MINB(4) : CC_TILE_MINB(2)))
 k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
                EdgeQueue GQ, BigTiles big) {
@@ -116,7 +117,7 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
   }
   if (lane == 0) { nb[nsegE] = ntot; s_wqn[warp] = 0; }
   if (threadIdx.x == 0) s_gn = 0;
-  const bool tile_ok = ntot <= CAPN;                   // block-uniform
+  const bool tile_ok = ntot <= (DENSE < CAPN ? DENSE : CAPN);                   // block-uniform
   if constexpr (!SECOND) {
     if (!tile_ok && big.count) {
       if (threadIdx.x == 0) { atomicAdd(big.count, 1u); if (big.defer) big.flags[tile] = 1u; }
@@ -263,8 +264,8 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
       const u32 rowQ = (u32)((int)rowP + dy + dz * (int)sy);
       const u32 xp = ((w0 + wx) << 5) + b;
       const u32 xq = (u32)((int)(w0 << 5) + xl);
-      if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA) {
-        if (!E(in[(size_t)rowP * sx + xp], in[(size_t)rowQ * sx + xq])) return;
+      if constexpr (MODE == MODE_EQ || MODE == MODE_DELTA || MODE == MODE_BLOCK) {
+        if (!E.diag((int)tdir, in[(size_t)rowP * sx + xp], in[(size_t)rowQ * sx + xq])) return;
       }
       const u32 gp = run_id(M, g, rowP * W, xp), gq_ = run_id(M, g, rowQ * W, xq);
       bool local = tile_ok && inside;
