@@ -4,7 +4,10 @@
 #pragma once
 #include "cc3d_common.cuh"
 
-#define CC_GRID_BLOCKS (148 * 8)   // grid of the kernels that loop over a device-side count
+#ifndef CC_GRID_BLOCKS
+#define CC_GRID_BLOCKS (148 * 8)
+#endif
+//  // grid of the kernels that loop over a device-side count
 
 // Length of a device-sized array: n_dev == nullptr -> n_host, else ceil(*n_dev / 2^shift)
 __device__ __forceinline__ u32 dev_len(i64 n_host, const u64* __restrict__ n_dev, int shift) {
