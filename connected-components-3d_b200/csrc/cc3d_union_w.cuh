@@ -116,6 +116,7 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
     ntot += __shfl_sync(CC_FULL, inc, 31);
   }
   if (lane == 0) { nb[nsegE] = ntot; s_wqn[warp] = 0; }
+  if (nsegE < 4 && lane >= nsegE + 1 && lane < 4) nb[lane] = 0xFFFFFFFFu;      // pads for the compare chain of the write-back
   if (threadIdx.x == 0) s_gn = 0;
   const bool tile_ok = ntot <= (DENSE < CAPN ? DENSE : CAPN);                   // block-uniform
   if constexpr (!SECOND) {
@@ -331,6 +332,7 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
   if (threadIdx.x == 0 && gn) s_gbase = atomicAdd(GQ.count, gn);
   if (tile_ok) {
     auto seg_of = [&](u32 k) {
+      if (nsegE <= 4) return (u32)(k >= nb[1]) + (u32)(k >= nb[2]) + (u32)(k >= nb[3]);     // plane segments: no search
       u32 lo = 0, len = nsegE;
       while (len > 1) {
         const u32 half = len >> 1;
