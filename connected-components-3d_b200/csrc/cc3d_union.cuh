@@ -64,6 +64,25 @@ struct WordEdges {
     Sp = P.F & ~P.X;
     return true;
   }
+  // Same as load(), but every word the straight edges can need - P, its left neighbour, U, D and the run ids of U and D -
+  // is requested before the first of them is looked at: one level of dependent loads instead of three (load() waits
+  // for P.F before it asks for the neighbours, and the callers ask for the neighbours' run ids after the need masks).
+  u32 RSu, RSd;
+  __device__ __forceinline__ bool load_eager(u32 i_, u32 row_, u32 w_, u32 y_, u32 z_) {
+    i = i_; row = row_; w = w_; y = y_; z = z_;
+    W = (u32)g.W; sy = (u32)g.sy; sx = (u32)g.sx; WS = W * sy; x0 = w << 5;
+    hasL = w > 0; hasR = w + 1 < W; hasU = y > 0; hasD = NR >= 2 && z > 0; hasV = y + 1 < sy;
+    const Q4 Z4 = {0u, 0u, 0u, 0u};
+    P = ldq(M, i);
+    Pl = hasL ? ldq(M, i - 1) : Z4;
+    U = hasU ? ldq(M, i - W) : Z4;
+    D = hasD ? ldq(M, i - WS) : Z4;
+    RSp = __ldg(RS + i) - 1u;
+    RSu = hasU ? __ldg(RS + i - W) - 1u : 0u;
+    RSd = hasD ? __ldg(RS + i - WS) - 1u : 0u;
+    Sp = P.F & ~P.X;
+    return P.F != 0;
+  }
   __device__ __forceinline__ u32 pid(int b) const { return RSp + __popc(Sp & (CC_FULL >> (31 - b))); }
 
   // straight edges that have to be united (x rule and square rule applied)

@@ -154,7 +154,9 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
     bool td = false;
     if (w < W && y < sy && z < sz) {
       const u32 row = z * sy + y;
-      if (we.load(row * W + w, row, w, y, z)) {
+      // eager: every word the straight edges can need is requested at once - the kernel is bound by its chains of
+      // dependent loads, not by instruction issue (profiles/r02_experiments.md section 8)
+      if (we.load_eager(row * W + w, row, w, y, z)) {
         const u32 Sp = we.Sp;
         const u32 gP = we.RSp;                                   // global id of the first run that starts in the word, minus 1
         const u32 needY = we.need_y(), needZ = we.need_z();
@@ -170,7 +172,7 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
         u32 locP = CC_FULL;
         if (w0 != 0 && gP - dP + 1u == nb[sgP]) locP = from_first_start(Sp);
         if (needY) {
-          gQY = __ldg(RS + we.i - W) - 1u;
+          gQY = we.RSu;
           if (tile_ok && ly > 0) {
             const u32 sgQ = (r - 1) >> sshift;
             lQY = gQY - segD[sgQ];
@@ -179,7 +181,7 @@ k_union_tile_w(const T* __restrict__ in, const u32* __restrict__ M, u32* __restr
           }
         }
         if (needZ) {
-          gQZ = __ldg(RS + we.i - W * sy) - 1u;
+          gQZ = we.RSd;
           if (tile_ok && lz > 0) {
             const u32 sgQ = (r - TY) >> sshift;
             lQZ = gQZ - segD[sgQ];
