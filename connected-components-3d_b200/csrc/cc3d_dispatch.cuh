@@ -205,7 +205,16 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
   // continuous 0.66 vs 1.13 ms, blocks 0.44 vs 0.76 ms).
   constexpr bool DIAG = CONN == 8 || CONN == 18 || CONN == 26;
   const bool use_w = !b1_phased() && nty < 65536 && ntz < 65536;
-  if constexpr (MODE == MODE_DELTA || MODE == MODE_BLOCK) {
+  // block grids: the per-word candidate loop with the balanced edge queue (k_union_tile) measured ahead of the item lists
+  // (random binary 512^3: 0.380 vs 0.448 ms); CC3D_B200_BLOCK_ITEMS=1 selects the item lists
+  static const bool block_items = getenv("CC3D_B200_BLOCK_ITEMS") != nullptr;
+  if (MODE == MODE_BLOCK && !block_items) {
+    if constexpr (MODE == MODE_BLOCK) {
+      const size_t smem = (size_t)TileQueues<MODE>::SMEM_WORDS * 4;
+      if (set_attr) cudaFuncSetAttribute(k_union_tile<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cc_launch(k_union_tile<T, MODE, CONN>, dim3((unsigned)(ntx * nty * ntz)), dim3(CC_TILE_THREADS), (size_t)(smem), a.stream, in, a.M, a.L, g, E, (u32)ntx, (u32)nty, a.GQ);
+    }
+  } else if constexpr (MODE == MODE_DELTA || MODE == MODE_BLOCK) {
     // continuous predicate / block nodes: edge-parallel item lists (every word has candidates that need a value test)
     const size_t smem = (size_t)CC_TILE_SMEM_WORDS * 4;
     if (set_attr) cudaFuncSetAttribute(k_union_tile_items<T, MODE, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
