@@ -72,6 +72,8 @@ def lib():
   L.cc3d_b200_merge_workspace_bytes.argtypes = [u64]
   L.cc3d_b200_merge_slabs_device.restype = ci
   L.cc3d_b200_merge_slabs_device.argtypes = [vp, ci, i64, ci, u64, vp, u64, p(vp), p(vp), vp]
+  L.cc3d_b200_merge_slabs_device_small.restype = ci
+  L.cc3d_b200_merge_slabs_device_small.argtypes = [vp, ci, i64, ci, u64, vp, u64, p(vp), p(vp), vp]
   L.cc3d_b200_session_release.restype = None
   L.cc3d_b200_session_release.argtypes = [vp]
   L.cc3d_b200_label.restype = ci

@@ -355,6 +355,10 @@ _merge_ws = {}          # device index -> (label_cap, uint8 workspace tensor)
 _pinned_small = {}      # (device index, world) -> pinned int64 landing buffer [5 + 4 * world]
 
 
+_side_streams = {}      # per device: stream of the small result copy of the sharded step
+_small_merge = {}       # (device, world) -> False once a step had more slab labels than the single-CTA merge handles
+
+
 def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, out_dtype, group, rank, world):
   """CUDA fast path of connected_components_slab. The WHOLE step is enqueued on the current stream without a host
   synchronisation in the middle: cc3d_b200_slab_begin (local labelling + boundary-plane labels + facts), NCCL
@@ -425,16 +429,28 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
       remap_p, result_p = ctypes.c_void_p(), ctypes.c_void_p()
       out = torch.empty((sz, sy, sx), dtype=tdt[guess], device=dev)
       with torch.cuda.device(dev):
-        _lib.check(L.cc3d_b200_merge_slabs_device(gathered.data_ptr(), world, 4 + cap, rank, cap, ws.data_ptr(), label_cap,
-                                                  ctypes.byref(remap_p), ctypes.byref(result_p), stream))
+        # small interface graphs (the sum of the slabs' label counts below 65 535, as seen in the last step): ONE
+        # single-CTA launch instead of four kernels + a scan; result[5] tells when the guess was wrong
+        small = _small_merge.get((dev.index, world), True)
+        merge_fn = L.cc3d_b200_merge_slabs_device_small if small else L.cc3d_b200_merge_slabs_device
+        _lib.check(merge_fn(gathered.data_ptr(), world, 4 + cap, rank, cap, ws.data_ptr(), label_cap,
+                            ctypes.byref(remap_p), ctypes.byref(result_p), stream))
         lap("merge")
         # everything the host needs (N, overflow flags, the slabs' facts) is final here: copy it out and mark the spot
         # BEFORE the expansion is enqueued, so that the host returns while the final write still runs (the output is
         # stream-ordered like any CUDA result; the next step's enqueue overlaps with it)
         roff = result_p.value - ws.data_ptr()
-        host.copy_(ws[roff:roff + 8 * (8 + 4 * world)].view(torch.int64), non_blocking=True)   # result + every slab's facts
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(dev))
+        # ... on a side stream, so that the small device-to-host copy does not sit between the merge and the final write
+        merged = torch.cuda.Event()
+        merged.record(torch.cuda.current_stream(dev))
+        side = _side_streams.get(dev.index)
+        if side is None:
+          side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+        side.wait_event(merged)
+        with torch.cuda.stream(side):
+          host.copy_(ws[roff:roff + 8 * (8 + 4 * world)].view(torch.int64), non_blocking=True)   # result + every slab's facts
+          ready = torch.cuda.Event()
+          ready.record(side)
         s2, sess = sess, None
         _lib.check(L.cc3d_b200_slab_finish(s2, remap_p, _lib.U32, out.data_ptr(), okind[guess], stream))
       lap("finish")
@@ -446,6 +462,10 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
     res = host[:5].numpy()
     facts = host[8:].numpy().reshape(world, 4)
     counts = facts[:, 3]
+    if small and int(host[5]):
+      _small_merge[(dev.index, world)] = False      # more slab labels than the single-CTA merge handles: general kernels
+      del out
+      continue
     if int(res[1]) or int(res[2]):
       # rare: more slab labels / face pairs than the buffers hold -> larger buffers, repeat the step
       if int(res[1]):

@@ -981,6 +981,25 @@ int cc3d_b200_merge_slabs_device(const int64_t* gathered, int world, int64_t row
   return 0;
 }
 
+int cc3d_b200_merge_slabs_device_small(const int64_t* gathered, int world, int64_t row_stride, int rank, uint64_t pair_cap,
+                                       void* workspace, uint64_t label_cap, uint32_t** remap, uint64_t** result, void* stream) {
+  if (!gathered || !workspace || !remap || !result || world <= 0 || world > CC_MERGE_MAX_WORLD || rank < 0 || rank >= world ||
+      row_stride < 4 + (int64_t)pair_cap || label_cap < 64 || label_cap > 0xFFFFFFFFull)
+    return fail(CC3D_B200_ERR_ARGUMENT, "merge_slabs_device_small: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t o_remap, o_nr, o_cnt, o_prefix, o_status, o_result;
+  merge_ws_layout(label_cap, &o_remap, &o_nr, &o_cnt, &o_prefix, &o_status, &o_result);
+  char* ws = (char*)workspace;
+  unsigned long long* res = (unsigned long long*)(ws + o_result);
+  SlabRows f; f.rows = (const long long*)gathered; f.world = world; f.stride = row_stride;
+  k_merge_small<<<1, 1024, 0, s>>>((u32*)ws, f, rank, label_cap, pair_cap, (u32*)(ws + o_remap), res);
+  g_launches += 1;
+  if (cudaGetLastError() != cudaSuccess) return fail(CC3D_B200_ERR_CUDA, "merge_slabs_device_small: launch failed");
+  *remap = (u32*)(ws + o_remap);
+  *result = (uint64_t*)res;
+  return 0;
+}
+
 int cc3d_b200_solve_pairs(uint32_t* parent, int64_t n_nodes, const uint32_t* a, const uint32_t* b, int64_t n_pairs,
                           void* stream) {
   if (n_nodes <= 0) return 0;

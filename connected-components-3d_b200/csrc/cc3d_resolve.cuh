@@ -670,7 +670,7 @@ k_merge_init(u32* __restrict__ parent, SlabRows f, u64 label_cap, u64 pair_cap, 
     bool pov = false;
     for (int r = 0; r < f.world; r++) pov |= (u64)f.rows[(size_t)r * f.stride + 3] > pair_cap;
     result[0] = 0; result[1] = (total + 1 > label_cap) ? 1ull : 0ull; result[2] = pov ? 1ull : 0ull;
-    result[3] = (total + 1 > label_cap) ? 0ull : total + 1; result[4] = 0;
+    result[3] = (total + 1 > label_cap) ? 0ull : total + 1; result[4] = 0; result[5] = 0;
     // the slabs' facts [N, epl, sz, n_pairs] ride along (result[8 + 4 r + k]): the host reads everything with ONE copy
     for (int r = 0; r < f.world; r++)
       for (int k = 0; k < 4; k++) result[8 + 4 * r + k] = (unsigned long long)f.rows[(size_t)r * f.stride + k];
@@ -735,6 +735,93 @@ k_merge_remap(const u32* __restrict__ parent, const u32* __restrict__ NR, const 
       root = parent[root];     // k_merge_flags compresses concurrently: at most one more hop to the root
       const u32 below = __ldg(&prefix[root >> 5]) + __popc(__ldg(&NR[root >> 5]) & ((1u << (root & 31)) - 1u));
       out = root - below;
+    }
+    remap[l] = out;
+  }
+}
+
+// The same merge in ONE launch of ONE CTA for small interface graphs (at most CC_MERGE_SMALL slab-label ids: the
+// connectomics benchmark has 29 k over eight slabs): the four kernels + scan above are latency, not work (30 us of a
+// 0.66 ms sharded step). Phases separated by block barriers; the non-root flags and their prefix live in shared memory.
+// result[5] = 1: more ids than this kernel handles - nothing else was written, the caller repeats with the general path.
+#define CC_MERGE_SMALL 65536
+__global__ void __launch_bounds__(1024)
+k_merge_small(u32* __restrict__ parent, SlabRows f, int rank, u64 label_cap, u64 pair_cap, u32* __restrict__ remap,
+              unsigned long long* __restrict__ result) {
+  __shared__ u64 s_off[CC_MERGE_MAX_WORLD + 1];
+  __shared__ u32 s_nr[CC_MERGE_SMALL / 32], s_pre[CC_MERGE_SMALL / 32], s_wsum[32], s_nonroot;
+  slab_offsets(f, s_off);
+  const u64 total = s_off[f.world];
+  const bool fits = total + 1 <= CC_MERGE_SMALL && total + 1 <= label_cap;
+  if (threadIdx.x == 0) {
+    bool pov = false;
+    for (int r = 0; r < f.world; r++) pov |= (u64)f.rows[(size_t)r * f.stride + 3] > pair_cap;
+    result[0] = 0; result[1] = (total + 1 > label_cap) ? 1ull : 0ull; result[2] = pov ? 1ull : 0ull;
+    result[3] = fits ? total + 1 : 0ull; result[4] = 0; result[5] = (total + 1 > CC_MERGE_SMALL) ? 1ull : 0ull;
+    for (int r = 0; r < f.world; r++)
+      for (int k = 0; k < 4; k++) result[8 + 4 * r + k] = (unsigned long long)f.rows[(size_t)r * f.stride + k];
+  }
+  if (!fits) return;
+  const u32 n = (u32)total + 1u;
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) parent[i] = i;
+  __syncthreads();
+  for (int r = 1; r < f.world; r++) {
+    const long long* row = f.rows + (size_t)r * f.stride;
+    const u64 np = min((u64)row[3], pair_cap);
+    const u64 nlo = (u64)f.rows[(size_t)(r - 1) * f.stride], nup = (u64)row[0];
+    for (u64 k = threadIdx.x; k < np; k += blockDim.x) {
+      const u64 v = (u64)row[4 + k];
+      const u64 lo = v >> 32, up = v & 0xFFFFFFFFull;
+      if (lo < 1 || up < 1 || lo > nlo || up > nup) continue;   // malformed pair
+      uf_union(parent, (u32)(s_off[r - 1] + lo), (u32)(s_off[r] + up));
+    }
+  }
+  __syncthreads();
+  // every id -> its root; non-root flags per 32 ids
+  const u32 nwords = (n + 31) >> 5;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (u32 wd = warp; wd < nwords; wd += blockDim.x >> 5) {
+    const u32 i = (wd << 5) + lane;
+    bool nonroot = false;
+    if (i >= 1 && i < n) {
+      u32 r = i, p;
+      while ((p = __ldcg(&parent[r])) != r) r = p;
+      if (r != i) { parent[i] = r; nonroot = true; }
+    }
+    const u32 m = __ballot_sync(CC_FULL, nonroot);
+    if (lane == 0) s_nr[wd] = m;
+  }
+  __syncthreads();
+  // exclusive prefix of the popcounts over the words (two words per thread at most)
+  {
+    const u32 w0 = 2 * threadIdx.x, w1 = w0 + 1;
+    const u32 c0 = w0 < nwords ? __popc(s_nr[w0]) : 0u, c1 = w1 < nwords ? __popc(s_nr[w1]) : 0u;
+    u32 inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(CC_FULL, inc, o); if ((int)lane >= o) inc += v; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      u32 v = s_wsum[lane], si = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(CC_FULL, si, o); if ((int)lane >= o) si += t; }
+      s_wsum[lane] = si - v;
+      if (lane == 31) s_nonroot = si;
+    }
+    __syncthreads();
+    const u32 excl = s_wsum[warp] + inc - (c0 + c1);
+    if (w0 < nwords) s_pre[w0] = excl;
+    if (w1 < nwords) s_pre[w1] = excl + c0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { result[4] = s_nonroot; result[0] = (unsigned long long)(n - 1u - s_nonroot); }
+  const u32 off = (u32)s_off[rank], nl = (u32)f.rows[(size_t)rank * f.stride];
+  for (u32 l = threadIdx.x; l <= nl; l += blockDim.x) {
+    u32 out = 0;
+    if (l) {
+      u32 root = parent[off + l];
+      root = parent[root];
+      out = root - (s_pre[root >> 5] + __popc(s_nr[root >> 5] & ((1u << (root & 31)) - 1u)));
     }
     remap[l] = out;
   }

@@ -137,6 +137,10 @@ int cc3d_b200_merge_slabs(int world, const int64_t* n_labels, const uint64_t* co
 size_t cc3d_b200_merge_workspace_bytes(uint64_t label_cap);
 int cc3d_b200_merge_slabs_device(const int64_t* gathered, int world, int64_t row_stride, int rank, uint64_t pair_cap,
                                  void* workspace, uint64_t label_cap, uint32_t** remap, uint64_t** result, void* stream);
+/* The same merge in ONE single-CTA launch for small interface graphs (the sum of N_r below 65 535; same arguments,
+ * workspace and results). result[5] = 1: the graph is larger - nothing was computed, call cc3d_b200_merge_slabs_device. */
+int cc3d_b200_merge_slabs_device_small(const int64_t* gathered, int world, int64_t row_stride, int rank, uint64_t pair_cap,
+                                 void* workspace, uint64_t label_cap, uint32_t** remap, uint64_t** result, void* stream);
 
 /* Sharded fast path (one process per GPU, small slabs): the three calls below only ENQUEUE work on `stream`;
  * none of them synchronises, so a whole slab step needs one host synchronisation (after the all-gather of the

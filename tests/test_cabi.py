@@ -23,7 +23,7 @@ def test_header_declares_expected_entry_points():
   for s in ["cc3d_b200_prepass", "cc3d_b200_label_resolve", "cc3d_b200_label_write", "cc3d_b200_label",
             "cc3d_b200_statistics", "cc3d_b200_mask_by_label", "cc3d_b200_last_error",
             "cc3d_b200_dust", "cc3d_b200_face_pairs", "cc3d_b200_merge_slabs", "cc3d_b200_slab_begin",
-            "cc3d_b200_face_pairs_async", "cc3d_b200_slab_finish", "cc3d_b200_voxel_connectivity_graph",
+            "cc3d_b200_face_pairs_async", "cc3d_b200_slab_finish", "cc3d_b200_merge_slabs_device", "cc3d_b200_merge_slabs_device_small", "cc3d_b200_voxel_connectivity_graph",
             "cc3d_b200_color_connectivity_graph", "cc3d_b200_contacts", "cc3d_b200_remap_labels",
             "cc3d_b200_runs", "cc3d_b200_draw"]:
     assert s in syms

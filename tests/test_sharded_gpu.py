@@ -9,16 +9,17 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _device_merge(L, torch, _lib, rows, world, cap, rank, label_cap):
+def _device_merge(L, torch, _lib, rows, world, cap, rank, label_cap, small=False):
   gathered = torch.from_numpy(rows).cuda()
   ws = torch.empty((int(L.cc3d_b200_merge_workspace_bytes(label_cap)),), dtype=torch.uint8, device="cuda")
   remap_p, result_p = ctypes.c_void_p(), ctypes.c_void_p()
   st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-  _lib.check(L.cc3d_b200_merge_slabs_device(gathered.data_ptr(), world, rows.shape[1], rank, cap, ws.data_ptr(), label_cap,
-                                            ctypes.byref(remap_p), ctypes.byref(result_p), st))
+  fn = L.cc3d_b200_merge_slabs_device_small if small else L.cc3d_b200_merge_slabs_device
+  _lib.check(fn(gathered.data_ptr(), world, rows.shape[1], rank, cap, ws.data_ptr(), label_cap,
+                ctypes.byref(remap_p), ctypes.byref(result_p), st))
   torch.cuda.synchronize()
   roff = result_p.value - ws.data_ptr()
-  res = ws[roff:roff + 40].view(torch.int64).cpu().numpy()
+  res = ws[roff:roff + 48].view(torch.int64).cpu().numpy()
   n = int(rows[rank, 0])
   moff = remap_p.value - ws.data_ptr()
   remap = ws[moff:moff + 4 * (n + 1)].view(torch.int32).cpu().numpy().view(np.uint32)
@@ -56,6 +57,14 @@ def test_device_merge_equals_host_merge(cc3d):
       assert int(res[1]) == 0 and int(res[2]) == 0
       assert int(res[0]) == want_N, (trial, rank)
       assert np.array_equal(remap.astype(np.int64), want), (trial, rank)
+      # the single-CTA merge: same tables when the graph is small enough, result[5] raised otherwise
+      res_s, remap_s = _device_merge(L, torch, _lib, rows, world, cap, rank, label_cap, small=True)
+      if sum(N_r) + 1 <= 65536:
+        assert int(res_s[5]) == 0 and int(res_s[0]) == want_N and int(res_s[1]) == 0 and int(res_s[2]) == 0, (trial, rank)
+        assert np.array_equal(remap_s.astype(np.int64), want), (trial, rank)
+        assert np.array_equal(res_s[8:8 + 4 * world], res[8:8 + 4 * world])
+      else:
+        assert int(res_s[5]) == 1
   # capacity flags
   rows = np.zeros((2, 4 + 8), np.int64)
   rows[0, 0] = 100; rows[1, 0] = 100; rows[1, 3] = 20          # 20 pairs reported, room for 8
