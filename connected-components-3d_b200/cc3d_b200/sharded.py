@@ -356,7 +356,7 @@ _pinned_small = {}      # (device index, world) -> pinned int64 landing buffer [
 
 
 _side_streams = {}      # per device: stream of the small result copy of the sharded step
-_small_merge = {}       # (device, world) -> False once a step had more slab labels than the single-CTA merge handles
+_small_merge = {}       # (device, world) -> the last step's interface graph was small enough for the single-CTA merge
 
 
 def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, out_dtype, group, rank, world):
@@ -431,7 +431,7 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
       with torch.cuda.device(dev):
         # small interface graphs (the sum of the slabs' label counts below 65 535, as seen in the last step): ONE
         # single-CTA launch instead of four kernels + a scan; result[5] tells when the guess was wrong
-        small = _small_merge.get((dev.index, world), True)
+        small = _small_merge.get((dev.index, world), False)
         merge_fn = L.cc3d_b200_merge_slabs_device_small if small else L.cc3d_b200_merge_slabs_device
         _lib.check(merge_fn(gathered.data_ptr(), world, 4 + cap, rank, cap, ws.data_ptr(), label_cap,
                             ctypes.byref(remap_p), ctypes.byref(result_p), stream))
@@ -466,6 +466,9 @@ def _slab_fast(slab, connectivity, delta_arr, kind, binary_image, epl_skipped, o
       _small_merge[(dev.index, world)] = False      # more slab labels than the single-CTA merge handles: general kernels
       del out
       continue
+    # the single-CTA merge pays off for small interface graphs only (2 slabs of the connectomics volume: 7 k labels and
+    # 3.5 k pairs, 18 us against 30 us; 8 slabs: 21 k labels and 24 k pairs, 62 us against 35 us): decide from this step
+    _small_merge[(dev.index, world)] = int(facts[:, 0].sum()) <= 12000 and int(counts.sum()) <= 6000
     if int(res[1]) or int(res[2]):
       # rare: more slab labels / face pairs than the buffers hold -> larger buffers, repeat the step
       if int(res[1]):
