@@ -5,9 +5,8 @@
 #include "cc3d_common.cuh"
 
 #ifndef CC_GRID_BLOCKS
-#define CC_GRID_BLOCKS (148 * 8)
+#define CC_GRID_BLOCKS (148 * 8)   // grid of the kernels that loop over a device-side count (148 x 16 / x 32 measured flat)
 #endif
-//  // grid of the kernels that loop over a device-side count
 
 // Length of a device-sized array: n_dev == nullptr -> n_host, else ceil(*n_dev / 2^shift)
 __device__ __forceinline__ u32 dev_len(i64 n_host, const u64* __restrict__ n_dev, int shift) {
