@@ -472,7 +472,10 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   // kernels (its look-back sits between two block-wide phases of every chunk), so the three-kernel path stays the
   // default; CC3D_B200_FUSED_RANK=1 selects the fused kernel (one launch less).
   static const bool want_fused_rank = getenv("CC3D_B200_FUSED_RANK") != nullptr;
-  const bool fused_rank = !block_order && maxruns < (i64(1) << 31) && want_fused_rank;
+  // binary 26-connected volumes: the unions are solved on the grid of 2x2x2 blocks, which also ranks (cc3d_blocks.cuh)
+  static const bool no_blocks = getenv("CC3D_B200_NO_BLOCKS") != nullptr;
+  const bool use_blocks = mode == MODE_NONZERO && connectivity == 26 && !no_blocks;
+  const bool fused_rank = !block_order && !use_blocks && maxruns < (i64(1) << 31) && want_fused_rank;
   const i64 nb_rank = (maxruns + CC_RANK_RUNS - 1) / CC_RANK_RUNS;
   const i64 status2_words = (fused_rank ? nb_rank : nb2) + 2;
   // control block: Counters | scan-S status | C-stage status, zeroed by ONE memset per call
@@ -493,9 +496,6 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   add(gqcap * 8); add(64);
   add(64); add(148 * 8 * 8 * 2 + 512);
   if (block_order) { add((size_t)maxruns * 4); add((size_t)nbwords * 4 * 3 + 64); add(((nbwords + CC_SCAN_CHUNK - 1) / CC_SCAN_CHUNK + 1) * 8); }
-  // binary 26-connected volumes: the unions are solved on the grid of 2x2x2 blocks (cc3d_blocks.cuh)
-  static const bool no_blocks = getenv("CC3D_B200_NO_BLOCKS") != nullptr;
-  const bool use_blocks = mode == MODE_NONZERO && connectivity == 26 && !no_blocks;
   Geom g2 = {};
   i64 maxruns_b = 0, nb_b = 0; size_t gqcap_b = 0, ctl_b = 0, occ_b = 0;
   if (use_blocks) {
@@ -556,6 +556,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   memset(a.delta, 0, 8);
   if (delta) memcpy(a.delta, delta, es);
   int rc = 0;
+  bool ranked = false;     // the block path numbers its components itself
   // A: face bitmaps
   if (c8) {
     // epl + value range, then the reference's per-pixel edge rule straight into the bitmaps
@@ -610,11 +611,19 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
         k_block_flatten<<<CC_GRID_BLOCKS, 256, 0, s>>>(L2, &ctr2->nruns);
         k_fill_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(minrun, CC_BG, &ctr2->nruns);
         mark("Bb_flatten", s);
+        cudaMemsetAsync(GR, 0, (size_t)nwords2 * 4, s);
         k_block_minrun<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(M, g, M2, g2, L2, L, minrun);
-        k_block_assign<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, minrun, &ctr->nruns);
-        stage_launches += launches_b + 5;
+        mark("Bb_minrun", s);
+        // C stage of this path: root flags from the block roots, scan, one pass over the voxel runs (cc3d_blocks.cuh)
+        k_block_rootflags<<<CC_GRID_BLOCKS, 256, 0, s>>>(L2, minrun, GR, &ctr2->nruns);
+        k_popc_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(GR, cnt, &ctr->nruns);
+        scan_counts(cnt, prefix, bsum2, nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s, nullptr, 1, scans_cleared);
+        mark("C2_scan", s);
+        k_block_assign_rank<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, minrun, GR, prefix, &ctr->nruns);
+        mark("C3_assign", s);
+        stage_launches += launches_b + 7;
+        ranked = true;
       }
-      mark("Bb_minrun_assign", s);
     } else {
       rc = -1;
       CC_KIND_SWITCH(in_kind, rc = run_union_stage<KT>(a));
@@ -627,7 +636,7 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
   g_launches += stage_launches;
   a.launches = nullptr;
   if (rc != 0) { cc3d_b200_session_release(S); return fail(CC3D_B200_ERR_ARGUMENT, "no kernel for this configuration"); }
-  enqueue_rank_stage(S, s, scans_cleared);
+  if (!ranked) enqueue_rank_stage(S, s, scans_cleared);
   if (S->hctr) cudaMemcpyAsync(S->hctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s);
   *session = S;
   return 0;
@@ -648,7 +657,10 @@ static void enqueue_rank_stage(cc3d_b200_session* S, cudaStream_t s, bool cleare
     mark("C_rank", s);
     return;
   }
-  cc_launch(k_compress, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, cnt, &ctr->nruns);
+  // CC3D_B200_C_ILP=0: one run per lane (rounds 1-2c); default: four (k_compress4 / k_assign4, round 2d)
+  static const bool ilp4 = !(getenv("CC3D_B200_C_ILP") && atoi(getenv("CC3D_B200_C_ILP")) == 0);
+  if (ilp4) cc_launch(k_compress4, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, cnt, &ctr->nruns);
+  else cc_launch(k_compress, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, cnt, &ctr->nruns);
   g_launches += 1;
   mark("C1_compress", s);
   scan_counts(cnt, prefix, S->status2, S->nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s, nullptr, 1, cleared);
@@ -672,7 +684,8 @@ static void enqueue_rank_stage(cc3d_b200_session* S, cudaStream_t s, bool cleare
     g_launches += 5;
     mark("C3_assign_blockorder", s);
   } else {
-    cc_launch(k_assign, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, prefix, &ctr->nruns);
+    if (ilp4) cc_launch(k_assign4, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, prefix, &ctr->nruns);
+    else cc_launch(k_assign, dim3(CC_GRID_BLOCKS), dim3(256), 0, s, L, GR, prefix, &ctr->nruns);
     g_launches += 1;
     mark("C3_assign", s);
   }

@@ -14,7 +14,8 @@
 //   k_block_minrun   every voxel run -> root of the block run that holds its first voxel; per root the minimum voxel
 //                    run id (= the run of the component's first voxel in raster order: first-appearance numbering
 //                    is decided on VOXEL runs, block order does not matter)
-//   k_block_assign   L[run] = minimum run id of its component: the forest the C stage expects (roots point to themselves)
+//   k_block_rootflags / k_popc_n / scan / k_block_assign_rank   root flags of the voxel-run table from the block roots'
+//                    minimum runs, then L[run] = first-appearance rank of its component (the C stage of this path)
 // The session keeps its voxel-level run table, so every consumer (expansion, dust, slabs, statistics) is unchanged.
 #pragma once
 #include "cc3d_common.cuh"
@@ -122,8 +123,49 @@ k_block_minrun(const u32* __restrict__ M, Geom g, const u32* __restrict__ M2, Ge
   }
 }
 
+// The C stage of the block path (round 2d). After k_block_minrun the first run of every component is known per ROOT BLOCK
+// RUN, so the root flags of the voxel-run table are set by the (few) block roots instead of a sweep over all voxel runs
+// (k_compress), and the final write L[run] = rank(minrun[root]) replaces k_block_assign + k_assign: one pass over the
+// voxel runs instead of three. GR must be zero on entry.
 static __global__ void __launch_bounds__(256)
-k_block_assign(u32* __restrict__ L, const u32* __restrict__ minrun, const u64* __restrict__ n_dev) {
+k_block_rootflags(const u32* __restrict__ L2, const u32* __restrict__ minrun, u32* __restrict__ GR, const u64* __restrict__ n2_dev) {
+  const u32 n = (u32)*n2_dev;
+  for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    if (__ldg(&L2[r]) != r) continue;
+    const u32 m = __ldg(&minrun[r]);
+    if (m != CC_BG) atomicOr(&GR[m >> 5], 1u << (m & 31));
+  }
+}
+static __global__ void __launch_bounds__(256)
+k_popc_n(const u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restrict__ n_dev) {
+  const u32 nw = (u32)((*n_dev + 31) >> 5);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) cnt[i] = __popc(GR[i]);
+}
+// four runs per lane: three dependent gathers per run, four chains in flight (see k_compress4)
+static __global__ void __launch_bounds__(256)
+k_block_assign_rank(u32* __restrict__ L, const u32* __restrict__ minrun, const u32* __restrict__ GR,
+                    const u32* __restrict__ prefix, const u64* __restrict__ n_dev) {
   const u32 n = (u32)*n_dev;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) L[i] = __ldg(&minrun[L[i]]);
+  const u32 ngroups = (n + 127) >> 7;
+  const int lane = threadIdx.x & 31;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += nwarps) {
+    const u32 base = (grp << 7) + lane;
+    u32 m[4], pw[4], gw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const u32 i = base + 32u * k; m[k] = i < n ? L[i] : 0u; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const u32 i = base + 32u * k; m[k] = i < n ? __ldg(&minrun[m[k]]) : 0u; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      pw[k] = i < n ? __ldg(&prefix[m[k] >> 5]) : 0u;
+      gw[k] = i < n ? __ldg(&GR[m[k] >> 5]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      if (i < n) L[i] = pw[k] + __popc(gw[k] & ((1u << (m[k] & 31)) - 1u)) + 1u;
+    }
+  }
 }

@@ -3,6 +3,7 @@
 // template matrix (6 types x predicates x connectivities) compiles in parallel.
 #pragma once
 #include <cstdlib>
+#include <algorithm>
 #include "cc3d_faces.cuh"
 #include "cc3d_union.cuh"
 #include "cc3d_union_w.cuh"
@@ -141,6 +142,22 @@ static int launch_faces(const LabelArgs& a) {
   if (two_d && g.sz != 1) return -1;
   const unsigned nych = (unsigned)((g.sy + CC_FACE_YCH - 1) / CC_FACE_YCH);
   const T* in = static_cast<const T*>(a.in);
+  // binary images of 1-byte elements: the foreground bitmap comes from byte-parallel arithmetic (one thread per word),
+  // the links are word logic on it (k_fg_bitmap_u8 / k_faces_from_fg, cc3d_faces.cuh; the bitmap borrows the forest
+  // array, which nothing touches before B1). CC3D_B200_BIN_A=0: generic kernel
+  if constexpr (MODE == MODE_NONZERO && sizeof(T) == 1) {
+    static const bool bin_a = !(getenv("CC3D_B200_BIN_A") && atoi(getenv("CC3D_B200_BIN_A")) == 0);
+    if (bin_a) {
+      u32* Fb = a.L;
+      const int vec_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (g.sx & 15) == 0) ? 1 : 0;
+      const unsigned nb = (unsigned)((g.nwords + 255) / 256);
+      cc_launch(k_fg_bitmap_u8, dim3(std::min(nb, 148u * 16u)), dim3(256), (size_t)0, a.stream, reinterpret_cast<const uint8_t*>(in), Fb, g, a.ctr, vec_ok);
+      if (two_d) cc_launch(k_faces_from_fg<false>, dim3(nb), dim3(256), (size_t)0, a.stream, (const u32*)Fb, a.M, g);
+      else cc_launch(k_faces_from_fg<true>, dim3(nb), dim3(256), (size_t)0, a.stream, (const u32*)Fb, a.M, g);
+      *a.launches += 2;
+      return 0;
+    }
+  }
   // TMA variant (tensor-map bulk copies): <= 4-byte elements, 16-byte aligned base and rows; any sx / sy / sz
   if constexpr (sizeof(T) <= 4) {
     if (launch_faces_tma<T, MODE>(a, E, two_d)) { ++*a.launches; return 0; }
@@ -267,7 +284,10 @@ static int launch_union(const LabelArgs& a, bool global_only = false) {
     }
   }
   if (a.mark) a.mark("B1_union_tile", a.stream);
-  cc_launch(k_union_queue, dim3(CC_QUEUE_BLOCKS * 4), dim3(256), (size_t)(0), a.stream, a.L, a.GQ);
+  // dense queues (noise) elect one lane per pair of tile roots; CC3D_B200_B2=1: never, =2: always
+  static const int b2_mode = getenv("CC3D_B200_B2") ? atoi(getenv("CC3D_B200_B2")) : 0;
+  const u32 dense_above = b2_mode == 1 ? 0xFFFFFFFFu : (b2_mode == 2 ? 0u : (u32)(g.nwords >> 1));
+  cc_launch(k_union_queue, dim3(CC_QUEUE_BLOCKS * 4), dim3(256), (size_t)(0), a.stream, a.L, a.GQ, dense_above);
   *a.launches += 2;
   if (a.inline_fallback) {
     cc_launch(k_union_global<T, MODE, CONN>, dim3(CC_QUEUE_BLOCKS), dim3(256), (size_t)(0), a.stream, in, a.M, a.L, g, E, (const u32*)a.GQ.ovf);

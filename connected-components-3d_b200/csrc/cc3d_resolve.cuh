@@ -37,6 +37,48 @@ k_compress(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, con
   }
 }
 
+// C1, four runs per lane (round 2d). The sweep is bound by latency x occupancy (one dependent chain per thread: ~1 us per
+// iteration with 2 048 resident threads per SM), so a lane takes runs i, i+32, i+64, i+96 of a 128-run group and walks
+// the four chains together: four loads in flight per lane, coalesced per k, one ballot per flag word.
+__global__ void __launch_bounds__(256)
+k_compress4(u32* __restrict__ L, u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restrict__ n_dev) {
+  CC_PDL_WAIT();
+  const u32 n = (u32)*n_dev;
+  const u32 nwords2 = (n + 31) >> 5;
+  const u32 ngroups = (n + 127) >> 7;
+  const int lane = threadIdx.x & 31;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += nwarps) {
+    const u32 base = (grp << 7) + lane;
+    u32 cur[4], nxt[4], first[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      cur[k] = i;
+      nxt[k] = i < n ? __ldca(&L[i]) : i;
+      first[k] = nxt[k];
+    }
+    while (true) {
+      bool mv[4], any = false;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { mv[k] = nxt[k] != cur[k]; any |= mv[k]; }
+      if (!any) break;
+      // L1-cached loads: tile roots are shared by many runs; a stale parent is still an ancestor
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (mv[k]) { cur[k] = nxt[k]; nxt[k] = __ldca(&L[cur[k]]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      const bool isroot = i < n && cur[k] == i;
+      if (i < n && cur[k] != first[k]) L[i] = cur[k];
+      const u32 m = __ballot_sync(CC_FULL, isroot);
+      const u32 wd = (grp << 2) + k;
+      if (lane == 0 && wd < nwords2) { GR[wd] = m; cnt[wd] = __popc(m); }
+    }
+  }
+}
+
 // C2 / S: exclusive scan of u32 counts, three small kernels (block reduce, scan of block sums, apply).
 // The length is either a host value or derived from a device-side count (see dev_len); the kernels
 // loop over 4096-element chunks, so the grid does not depend on the length.
@@ -399,6 +441,40 @@ k_assign(u32* __restrict__ L, const u32* __restrict__ GR, const u32* __restrict_
     const bool isroot = (GR[i >> 5] >> (i & 31)) & 1u;
     const u32 r = isroot ? i : L[i];
     L[i] = rank_in_bitmap(GR, prefix, r >> 5, (int)(r & 31)) + 1u;
+  }
+}
+
+// C3, four runs per lane (see k_compress4): four independent gather chains per thread.
+__global__ void __launch_bounds__(256)
+k_assign4(u32* __restrict__ L, const u32* __restrict__ GR, const u32* __restrict__ prefix, const u64* __restrict__ n_dev) {
+  CC_PDL_WAIT();
+  const u32 n = (u32)*n_dev;
+  const u32 ngroups = (n + 127) >> 7;
+  const int lane = threadIdx.x & 31;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += nwarps) {
+    const u32 base = (grp << 7) + lane;
+    u32 r[4], fl[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      r[k] = i < n ? L[i] : 0u;
+      fl[k] = (grp << 2) + k < ((n + 31) >> 5) ? __ldg(&GR[(grp << 2) + k]) : 0u;
+    }
+    u32 pw[4], gw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      if ((fl[k] >> lane) & 1u) r[k] = i;
+      const bool ok = i < n;
+      pw[k] = ok ? __ldg(&prefix[r[k] >> 5]) : 0u;
+      gw[k] = ok ? __ldg(&GR[r[k] >> 5]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 i = base + 32u * k;
+      if (i < n) L[i] = pw[k] + __popc(gw[k] & ((1u << (r[k] & 31)) - 1u)) + 1u;
+    }
   }
 }
 

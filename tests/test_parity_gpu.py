@@ -160,6 +160,62 @@ def test_binary26_block_nodes(cc3d, oracle_mod):
   assert checked > 150
 
 
+def test_binary_one_byte_kernel_a(cc3d, oracle_mod):
+  """Binary images of 1-byte elements take their own kernel A (k_fg_bitmap_u8 + k_faces_from_fg: byte-parallel foreground
+  bits, links as word logic). RAW values (any non-zero byte is foreground), rows that are / are not multiples of 16 and 32
+  voxels, misaligned base pointers, every connectivity, the maximum delta (which the reference turns into the binary
+  kernel AFTER it has estimated epl on the raw values, fastcc3d.pyx:388-395), and epl itself through the C-ABI."""
+  import ctypes
+  from cc3d_b200 import _lib
+  L = _lib.lib()
+  truth = _truth(oracle_mod)
+  rng = np.random.default_rng(8080)
+  checked = 0
+  for it in range(120):
+    sx = int(rng.choice([16, 32, 48, 64, 96, 128, 160, 37, 100, 130, 1, 7, int(rng.integers(1, 200))]))
+    dims = 2 if it % 5 == 0 else 3
+    rest = (int(rng.integers(1, 60)),) if dims == 2 else (int(rng.integers(1, 20)), int(rng.integers(1, 12)))
+    dt = [np.uint8, np.int8, bool][it % 3]
+    p = float(rng.choice([0.05, 0.3, 0.5, 0.8, 1.0]))
+    vals = rng.integers(1, 6 if it % 2 else 256, (sx,) + rest) * (rng.random((sx,) + rest) < p)
+    base = np.zeros(vals.size + 3, dtype=np.uint8)
+    off = int(rng.integers(0, 4)) if it % 4 == 0 else 0           # misaligned base pointer
+    view = base[off:off + vals.size].reshape((sx,) + rest, order="F")
+    view[...] = vals.astype(np.uint8)
+    x = view.view(np.int8) if dt == np.int8 else ((view != 0) if dt == bool else view)
+    conns = [4, 8] if dims == 2 else [6, 18, 26]
+    c = conns[it % len(conns)]
+    if c == 8 and sx % 2 == 1:
+      continue  # reference defect D1 (SURVEY A.3)
+    if c == 4:
+      # reference defect: the first row of the binary 2D 4-connected kernel joins EQUAL values instead of non-zero ones
+      # (cc3d_binary.hpp:832 `in_labels[loc] == in_labels[loc + B]`), so raw values split runs of row 0 that every other
+      # row - and scipy - join; the drop-in joins them. One non-zero value keeps the comparison meaningful.
+      view[...] = (view != 0) * np.uint8(7)
+      x = view.view(np.int8) if dt == np.int8 else ((view != 0) if dt == bool else view)
+    kws = [dict(binary_image=True)]
+    if dt != bool:
+      kws.append(dict(delta=int(np.iinfo(dt).max)))
+    for kw in kws:
+      try:
+        a, Na = truth.connected_components(x, connectivity=c, return_N=True, **kw)
+      except RuntimeError:
+        continue  # reference union-find overflow (defect D3)
+      b, Nb = cc3d.connected_components(x, connectivity=c, return_N=True, **kw)
+      assert_same_labels(a, Na, b, Nb, f"{x.shape} {np.dtype(dt)} off={off} conn={c} {kw} case {it}")
+      checked += 1
+    if dt == np.uint8:
+      # info.epl of the binary call = the reference's transition count on the raw values (cc3d.hpp:287-315)
+      sy, sz = (rest[0], 1) if dims == 2 else rest
+      info, sess = _lib.ResolveInfo(), ctypes.c_void_p()
+      zero = np.zeros(1, np.uint8)
+      assert L.cc3d_b200_label_resolve(x.ctypes.data, _lib.U8, sx, sy, sz, 6 if dims == 3 else 4, zero.ctypes.data, 1, 0,
+                                       _lib.HOST, None, ctypes.byref(info), ctypes.byref(sess)) == 0
+      L.cc3d_b200_session_release(sess)
+      assert int(info.epl) == oracle_mod.estimate_provisional_labels(x)[0], f"epl {x.shape} off={off} case {it}"
+  assert checked > 120
+
+
 def test_c_oracle_agrees_too(cc3d, oracle_mod):
   assert _fuzz(cc3d, oracle_mod, seed=303, ncase=200, maxdim=40) > 150
 
