@@ -181,7 +181,7 @@ Geom make_geom(i64 sx, i64 sy, i64 sz) {
   int tw = 0;
   while (tw < 4 && (i64(1) << tw) < g.W) tw++;
   g.tw = tw;
-  g.tz = sz > 1 ? 2 : 0;
+  g.tz = sz > 1 ? CC_TILE_TZ : 0;
   g.ty = CC_TILE_LOG - g.tw - g.tz;
   return g;
 }

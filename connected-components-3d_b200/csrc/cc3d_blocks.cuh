@@ -83,15 +83,16 @@ k_block_minrun(const u32* __restrict__ M, Geom g, const u32* __restrict__ M2, Ge
       x0 = w << 5;
     }
   }
-  // block words this voxel word can touch: 16 blocks = half a block word; cache the {F, X} / RS of that word
-  u32 cw = 0xFFFFFFFFu, cS = 0, cR = 0;
+  // the 16 blocks under a voxel word lie in ONE block word: its {F, X} / RS are loaded once, the roots of the word's
+  // runs are then gathered four at a time (independent loads in flight instead of one dependent load per run)
+  u32 cS = 0, cR = 0;
+  if (starts) {
+    const u32 j = row2w + (x0 >> 6);
+    const uint2 fx2 = __ldg(reinterpret_cast<const uint2*>(M2) + 2 * (size_t)j);
+    cS = fx2.x & ~fx2.y; cR = __ldg(M2 + g2.offRS + j) - 1u;
+  }
   auto root_of = [&](u32 x) -> u32 {
     const u32 bx = x >> 1;
-    const u32 j = row2w + (bx >> 5);
-    if (j != cw) {
-      const uint2 fx2 = __ldg(reinterpret_cast<const uint2*>(M2) + 2 * (size_t)j);
-      cS = fx2.x & ~fx2.y; cR = __ldg(M2 + g2.offRS + j) - 1u; cw = j;
-    }
     const u32 br = cR + __popc(cS & (CC_FULL >> (31 - (bx & 31))));      // 32-bit sum: cR is 'first id - 1' and may be 0xFFFFFFFF
     return __ldg(L2 + br);
   };
@@ -112,13 +113,22 @@ k_block_minrun(const u32* __restrict__ M, Geom g, const u32* __restrict__ M2, Ge
   }
   u32 last = root;
   while (starts) {
-    const int b = __ffs(starts) - 1; starts &= starts - 1;
-    id++;
-    const u32 r = root_of(x0 + b);
-    L[id] = r;
-    if (r != last) {
-      if (id < __ldcg(&minrun[r])) atomicMin(&minrun[r], id);
-      last = r;
+    u32 r[4]; int nr = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      r[k] = 0;
+      if (starts) { const int b = __ffs(starts) - 1; starts &= starts - 1; r[k] = root_of(x0 + b); nr = k + 1; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < nr) {
+        id++;
+        L[id] = r[k];
+        if (r[k] != last) {
+          if (id < __ldcg(&minrun[r[k]])) atomicMin(&minrun[r[k]], id);
+          last = r[k];
+        }
+      }
     }
   }
 }

@@ -84,6 +84,9 @@ struct Geom {
 #define CC_TILE_LOG 9        // log2 of the words of a union tile (tw + ty + tz)
 #endif
 #define CC_TILE_WORDS (1 << CC_TILE_LOG)
+#ifndef CC_TILE_TZ
+#define CC_TILE_TZ 2         // log2 of the planes of a union tile (3D volumes)
+#endif
 #ifndef CC_TILE_THREADS
 #define CC_TILE_THREADS (CC_TILE_WORDS / 2)
 #endif
