@@ -236,6 +236,12 @@ struct cc3d_b200_session {
   bool periodic = false, block_order = false, inline_fallback = false, redone = false;
   u32 *GR = nullptr, *cnt = nullptr, *prefix = nullptr;
   u64* status2 = nullptr;    // look-back status words of the C stage
+  // block path (binary 26-connected, cc3d_blocks.cuh): labels live on the BLOCK runs (LB); the voxel-run labels L are
+  // filled in on demand (ensure_run_labels) for the consumers that work on the run table
+  const u32* M2 = nullptr;
+  u32* LB = nullptr;
+  Geom g2 = {};
+  bool L_lazy = false;
   i64 status2_words = 0, nwords2 = 0, maxruns = 0, nbwords = 0;
 };
 
@@ -405,6 +411,14 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
                            void* stream, cc3d_b200_resolve_info* info, cc3d_b200_session** session,
                            bool inline_fallback = false);
 static void enqueue_rank_stage(cc3d_b200_session* S, cudaStream_t s, bool cleared);
+
+// Block-path sessions keep their labels on the block runs; consumers of the voxel-level run table call this first.
+static void ensure_run_labels(cc3d_b200_session* S, cudaStream_t s) {
+  if (!S->L_lazy) return;
+  k_block_fill_L<<<(unsigned)((S->g.nwords + 255) / 256), 256, 0, s>>>(S->M, S->g, S->M2, S->g2, S->LB, S->L);
+  g_launches += 1;
+  S->L_lazy = false;
+}
 
 int cc3d_b200_label_resolve(const void* in, int in_kind, int64_t sx, int64_t sy, int64_t sz, int connectivity,
                             const void* delta, int binary_image, int periodic_boundary, int mem_space,
@@ -612,17 +626,21 @@ static int resolve_enqueue(const void* in, int in_kind, int64_t sx, int64_t sy, 
         k_fill_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(minrun, CC_BG, &ctr2->nruns);
         mark("Bb_flatten", s);
         cudaMemsetAsync(GR, 0, (size_t)nwords2 * 4, s);
-        k_block_minrun<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(M, g, M2, g2, L2, L, minrun);
+        k_block_minrun<<<(unsigned)((g2.nwords + 255) / 256), 256, 0, s>>>(M, g, occ, M2, g2, L2, minrun);
         mark("Bb_minrun", s);
-        // C stage of this path: root flags from the block roots, scan, one pass over the voxel runs (cc3d_blocks.cuh)
+        // C stage of this path: root flags from the block roots, scan, labels on the block runs (cc3d_blocks.cuh)
         k_block_rootflags<<<CC_GRID_BLOCKS, 256, 0, s>>>(L2, minrun, GR, &ctr2->nruns);
         k_popc_n<<<CC_GRID_BLOCKS, 256, 0, s>>>(GR, cnt, &ctr->nruns);
         scan_counts(cnt, prefix, bsum2, nwords2, &ctr->nruns, 5, &ctr->N, nullptr, s, nullptr, 1, scans_cleared);
         mark("C2_scan", s);
-        k_block_assign_rank<<<CC_GRID_BLOCKS, 256, 0, s>>>(L, minrun, GR, prefix, &ctr->nruns);
+        k_block_labels<<<CC_GRID_BLOCKS, 256, 0, s>>>(L2, minrun, GR, prefix, &ctr2->nruns);
         mark("C3_assign", s);
         stage_launches += launches_b + 7;
         ranked = true;
+        S->M2 = M2; S->LB = L2; S->g2 = g2; S->L_lazy = true;
+        // CC3D_B200_BLOCK_LAZY=0: fill the voxel-run labels right away and expand from them (round 2c behaviour)
+        static const bool eager = getenv("CC3D_B200_BLOCK_LAZY") && atoi(getenv("CC3D_B200_BLOCK_LAZY")) == 0;
+        if (eager) { ensure_run_labels(S, s); S->LB = nullptr; mark("C3_fill_L", s); }
       }
     } else {
       rc = -1;
@@ -740,6 +758,14 @@ static void launch_write(const cc3d_b200_session* S, OUT* dout, i64 row0, i64 nr
   const unsigned nchunks = (unsigned)((g.W + 31) / 32);
   const i64 nwarps = nrows * nchunks;
   const unsigned blocks = (unsigned)((nwarps + 7) / 8);
+  if (S->LB) {
+    // block path: straight from the labels of the block runs
+    if (!remap) k_expand_blocks<OUT, 0><<<blocks, 256, 0, s>>>(S->LB, S->M, S->M2, dout, g, S->g2, nchunks, (u32)row0, (u32)nwarps, remap);
+    else if (remap_kind == CC3D_B200_U32) k_expand_blocks<OUT, 1><<<blocks, 256, 0, s>>>(S->LB, S->M, S->M2, dout, g, S->g2, nchunks, (u32)row0, (u32)nwarps, remap);
+    else k_expand_blocks<OUT, 2><<<blocks, 256, 0, s>>>(S->LB, S->M, S->M2, dout, g, S->g2, nchunks, (u32)row0, (u32)nwarps, remap);
+    g_launches += 1;
+    return;
+  }
   if (!remap) k_expand<OUT, 0><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap, S->lmask);
   else if (remap_kind == CC3D_B200_U32) k_expand<OUT, 1><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap, S->lmask);
   else k_expand<OUT, 2><<<blocks, 256, 0, s>>>(S->L, S->M, dout, g, nchunks, (u32)row0, (u32)nwarps, remap, S->lmask);
@@ -1637,6 +1663,7 @@ int cc3d_b200_dust(const void* img, void* out, int kind, int64_t sx, int64_t sy,
   unsigned long long* dmasked = (unsigned long long*)ar.take(8);
   cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s);
   cudaMemsetAsync(dmasked, 0, 8, s);
+  ensure_run_labels(S, s);      // block-path sessions: the run table's labels are filled in on demand
   k_run_counts<<<148 * 4, 256, 0, s>>>(S->L, S->M, S->g, counts, S->lmask);
   k_dust_keep<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(counts, keep, n, (long long)lo, (long long)hi, invert, dmasked);
   // host images are masked in place in their staged copy; device images go straight to `out` (which may be `img`)

@@ -11,12 +11,14 @@
 //   k_block_occ      voxel foreground bitmap F -> occupancy byte per block (bit x + 2y + 4z)
 //   A / S / B1 / B2  on the block grid with the BLOCK predicate (non-transitive: the continuous-value code path)
 //   k_block_flatten  every block run -> its root block run
-//   k_block_minrun   every voxel run -> root of the block run that holds its first voxel; per root the minimum voxel
-//                    run id (= the run of the component's first voxel in raster order: first-appearance numbering
-//                    is decided on VOXEL runs, block order does not matter)
-//   k_block_rootflags / k_popc_n / scan / k_block_assign_rank   root flags of the voxel-run table from the block roots'
-//                    minimum runs, then L[run] = first-appearance rank of its component (the C stage of this path)
-// The session keeps its voxel-level run table, so every consumer (expansion, dust, slabs, statistics) is unchanged.
+//   k_block_minrun   per root block run the minimum voxel-run id of its component (= the run of the component's first
+//                    voxel in raster order: first-appearance numbering is decided on VOXEL runs, block order does not
+//                    matter), from the first voxel of every block-run piece (one thread per block word)
+//   k_block_rootflags / k_popc_n / scan / k_block_labels   root flags of the voxel-run table from the block roots'
+//                    minimum runs, their scan, then every BLOCK run gets the rank of its component (the C stage)
+//   k_expand_blocks  D: out[voxel] = label of the block run of its block (REMAP / row ranges as k_expand)
+//   k_block_fill_L   only for consumers of the voxel-level run table (fused dust): L[run] = label, on demand
+// Nothing sweeps the 33 M voxel runs of a noise volume any more (round 2c: three sweeps; 2d: one).
 #pragma once
 #include "cc3d_common.cuh"
 
@@ -61,82 +63,82 @@ static __global__ void __launch_bounds__(256) k_block_flatten(u32* __restrict__ 
   }
 }
 
-// One thread per voxel bitmap word: every run that starts in the word -> L[run] = root block run (flattened forest L2 of
-// the block grid, bitmaps M2); minrun[root] = min(run id). A warp first settles the FIRST run of its 32 words with one
-// atomic per distinct root (match + min reduction: on noise every lane meets the same giant root), later runs of a word
-// only act when their root differs from the previous one; a plain read of the current minimum keeps all but the first
-// wave of warps off the atomic.
+// One thread per BLOCK bitmap word (32 blocks of a block row): every piece of a block run inside the word reports the
+// voxel run that holds the piece's first voxel in raster order; minrun[root] = the smallest of them = the run of the
+// component's first voxel (a voxel run lies inside ONE block run, and the first voxel of the component is the first voxel
+// of its piece). Bit b of an occupancy byte is voxel (x, y, z) = (b & 1, b >> 1 & 1, b >> 2), so voxel row q = b >> 1 of
+// the block row comes first in raster order for the smallest q; per q a mask of the blocks that have a voxel in that
+// row (and of those whose voxel at x even is set) comes from byte-parallel arithmetic on the 32 occupancy bytes.
+// Lanes that may lower a minimum (a plain read first) elect one lane per root: on noise every piece of the first wave
+// meets the same giant root.
 static __global__ void __launch_bounds__(256)
-k_block_minrun(const u32* __restrict__ M, Geom g, const u32* __restrict__ M2, Geom g2, const u32* __restrict__ L2,
-               u32* __restrict__ L, u32* __restrict__ minrun) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 W = (u32)g.W, W2 = (u32)g2.W;
-  u32 starts = 0, id = 0, row2w = 0, x0 = 0;
-  if (i < (u32)g.nwords) {
-    const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)i);
-    starts = fx.x & ~fx.y;
-    if (starts) {
-      id = __ldg(M + g.offRS + i);
-      const u32 row = i / W, w = i - row * W;
-      const u32 z = row / (u32)g.sy, y = row - z * (u32)g.sy;
-      row2w = ((z >> 1) * (u32)g2.sy + (y >> 1)) * W2;
-      x0 = w << 5;
+k_block_minrun(const u32* __restrict__ M, Geom g, const uint8_t* __restrict__ occ, const u32* __restrict__ M2, Geom g2,
+               const u32* __restrict__ L2, u32* __restrict__ minrun) {
+  const u32 j2 = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 W2 = (u32)g2.W, BX = (u32)g2.sx, BY = (u32)g2.sy;
+  u32 F2 = 0, starts2 = 0, id2 = 0, w2 = 0, by = 0, bz = 0;
+  u32 mrow[4] = {0, 0, 0, 0}, meven[4] = {0, 0, 0, 0};
+  if (j2 < (u32)g2.nwords) {
+    const uint2 fx2 = __ldg(reinterpret_cast<const uint2*>(M2) + 2 * (size_t)j2);
+    F2 = fx2.x; starts2 = fx2.x & ~fx2.y;
+  }
+  if (F2) {
+    id2 = __ldg(M2 + g2.offRS + j2) - 1u;      // may be 0xFFFFFFFF: 32-bit sums below
+    const u32 brow = j2 / W2;
+    w2 = j2 - brow * W2; bz = brow / BY; by = brow - bz * BY;
+    const uint8_t* __restrict__ p = occ + ((size_t)brow * BX + (w2 << 5));
+    const u32 n = min(32u, BX - (w2 << 5));
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      u32 v = 0;
+      if ((BX & 3u) == 0) { if (4u * k < n) v = __ldg(reinterpret_cast<const u32*>(p) + k); }
+      else {
+#pragma unroll
+        for (int b = 0; b < 4; b++) if (4u * k + b < n) v |= (u32)p[4 * k + b] << (8 * b);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        mrow[q] |= cc_nz_nibble4(v & (0x03030303u << (2 * q))) << (4 * k);
+        meven[q] |= cc_nz_nibble4(v & (0x01010101u << (2 * q))) << (4 * k);
+      }
     }
   }
-  // the 16 blocks under a voxel word lie in ONE block word: its {F, X} / RS are loaded once, the roots of the word's
-  // runs are then gathered four at a time (independent loads in flight instead of one dependent load per run)
-  u32 cS = 0, cR = 0;
-  if (starts) {
-    const u32 j = row2w + (x0 >> 6);
-    const uint2 fx2 = __ldg(reinterpret_cast<const uint2*>(M2) + 2 * (size_t)j);
-    cS = fx2.x & ~fx2.y; cR = __ldg(M2 + g2.offRS + j) - 1u;
-  }
-  auto root_of = [&](u32 x) -> u32 {
-    const u32 bx = x >> 1;
-    const u32 br = cR + __popc(cS & (CC_FULL >> (31 - (bx & 31))));      // 32-bit sum: cR is 'first id - 1' and may be 0xFFFFFFFF
-    return __ldg(L2 + br);
-  };
-  // first run of every word: warp-aggregated
-  u32 root = 0xFFFFFFFFu;
-  if (starts) {
-    const int b = __ffs(starts) - 1; starts &= starts - 1;
-    root = root_of(x0 + b);
-    L[id] = root;
-  }
-  {
-    const u32 active = __ballot_sync(CC_FULL, root != 0xFFFFFFFFu);
-    if (root != 0xFFFFFFFFu) {
+  const u32 cont = F2 & ~starts2;      // blocks that continue a run from their left neighbour
+  u32 rem = F2;
+  while (__any_sync(CC_FULL, rem != 0)) {
+    u32 root = 0, id = 0;
+    bool need = false;
+    if (rem) {
+      const int s = __ffs(rem) - 1;
+      const u32 t = s == 31 ? 0u : (cont >> (s + 1));
+      const int len = 1 + (__ffs(~t) - 1);                       // ~t != 0: t has at most 31 - s bits
+      const u32 pm = (len >= 32 ? CC_FULL : ((1u << len) - 1u)) << s;
+      rem &= ~pm;
+      root = __ldg(L2 + (id2 + __popc(starts2 & (CC_FULL >> (31 - s)))));
+      // first voxel row of the block row that the piece touches (it holds at least one voxel); no dynamic indexing
+      const u32 c0 = mrow[0] & pm, c1 = mrow[1] & pm, c2 = mrow[2] & pm, c3 = mrow[3] & pm;
+      const int q = c0 ? 0 : (c1 ? 1 : (c2 ? 2 : 3));
+      const u32 cm = c0 ? c0 : (c1 ? c1 : (c2 ? c2 : c3));
+      const u32 ev = c0 ? meven[0] : (c1 ? meven[1] : (c2 ? meven[2] : meven[3]));
+      const int b = __ffs(cm) - 1;
+      const u32 x = 2u * ((w2 << 5) + b) + (((ev >> b) & 1u) ? 0u : 1u);
+      const u32 y = 2u * by + (q & 1), z = 2u * bz + (q >> 1);
+      id = run_id(M, g, (z * (u32)g.sy + y) * (u32)g.W, x);
+      need = id < __ldcg(&minrun[root]);
+    }
+    const u32 active = __ballot_sync(CC_FULL, need);
+    if (need) {
       const u32 grp = __match_any_sync(active, root);
       const u32 m = __reduce_min_sync(grp, id);
-      if ((u32)(__ffs(grp) - 1) == (threadIdx.x & 31u) && m < __ldcg(&minrun[root])) atomicMin(&minrun[root], m);
-    }
-  }
-  u32 last = root;
-  while (starts) {
-    u32 r[4]; int nr = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      r[k] = 0;
-      if (starts) { const int b = __ffs(starts) - 1; starts &= starts - 1; r[k] = root_of(x0 + b); nr = k + 1; }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (k < nr) {
-        id++;
-        L[id] = r[k];
-        if (r[k] != last) {
-          if (id < __ldcg(&minrun[r[k]])) atomicMin(&minrun[r[k]], id);
-          last = r[k];
-        }
-      }
+      if ((u32)(__ffs(grp) - 1) == (threadIdx.x & 31u)) atomicMin(&minrun[root], m);
     }
   }
 }
 
 // The C stage of the block path (round 2d). After k_block_minrun the first run of every component is known per ROOT BLOCK
 // RUN, so the root flags of the voxel-run table are set by the (few) block roots instead of a sweep over all voxel runs
-// (k_compress), and the final write L[run] = rank(minrun[root]) replaces k_block_assign + k_assign: one pass over the
-// voxel runs instead of three. GR must be zero on entry.
+// (k_compress), and every BLOCK run takes the rank of its component (k_block_labels): no sweep over the voxel runs at all.
+// GR must be zero on entry.
 static __global__ void __launch_bounds__(256)
 k_block_rootflags(const u32* __restrict__ L2, const u32* __restrict__ minrun, u32* __restrict__ GR, const u64* __restrict__ n2_dev) {
   const u32 n = (u32)*n2_dev;
@@ -151,31 +153,93 @@ k_popc_n(const u32* __restrict__ GR, u32* __restrict__ cnt, const u64* __restric
   const u32 nw = (u32)((*n_dev + 31) >> 5);
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) cnt[i] = __popc(GR[i]);
 }
-// four runs per lane: three dependent gathers per run, four chains in flight (see k_compress4)
+// every block run -> the first-appearance rank of its component, in place (L2: root block run -> label)
 static __global__ void __launch_bounds__(256)
-k_block_assign_rank(u32* __restrict__ L, const u32* __restrict__ minrun, const u32* __restrict__ GR,
-                    const u32* __restrict__ prefix, const u64* __restrict__ n_dev) {
-  const u32 n = (u32)*n_dev;
-  const u32 ngroups = (n + 127) >> 7;
+k_block_labels(u32* __restrict__ L2, const u32* __restrict__ minrun, const u32* __restrict__ GR,
+               const u32* __restrict__ prefix, const u64* __restrict__ n2_dev) {
+  const u32 n = (u32)*n2_dev;
+  for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const u32 m = __ldg(&minrun[L2[r]]);      // every thread reads and writes its own entry of L2 only
+    L2[r] = __ldg(&prefix[m >> 5]) + __popc(__ldg(&GR[m >> 5]) & ((1u << (m & 31)) - 1u)) + 1u;
+  }
+}
+
+// D for the block path: out[voxel] = label of the block run of its 2x2x2 block (same walk as k_expand: one warp per
+// (row, chunk of 32 voxel words); lane j stages voxel word j and the block word above it, then one voxel per lane).
+// The voxel-level run labels are not needed for this: they are only filled in (k_block_fill_L) for the consumers that
+// work on the run table (fused dust).
+template <typename OUT, int REMAP>
+__global__ void __launch_bounds__(256)
+k_expand_blocks(const u32* __restrict__ LB, const u32* __restrict__ M, const u32* __restrict__ M2, OUT* __restrict__ out,
+                Geom g, Geom g2, unsigned nchunks, u32 row0, u32 nwarps_total, const void* __restrict__ remap) {
+  __shared__ uint4 s_words[8][32];   // per warp: {F of the voxel word, run starts of the block word, id of the run that enters it, -}
   const int lane = threadIdx.x & 31;
-  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += nwarps) {
-    const u32 base = (grp << 7) + lane;
-    u32 m[4], pw[4], gw[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { const u32 i = base + 32u * k; m[k] = i < n ? L[i] : 0u; }
-#pragma unroll
-    for (int k = 0; k < 4; k++) { const u32 i = base + 32u * k; m[k] = i < n ? __ldg(&minrun[m[k]]) : 0u; }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const u32 i = base + 32u * k;
-      pw[k] = i < n ? __ldg(&prefix[m[k] >> 5]) : 0u;
-      gw[k] = i < n ? __ldg(&GR[m[k] >> 5]) : 0u;
+  const int warp = threadIdx.x >> 5;
+  const u32 wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= nwarps_total) return;
+  const u32 rrel = wid / nchunks;
+  const u32 chunk = wid - rrel * nchunks;
+  const u32 row = row0 + rrel;
+  const u32 W = (u32)g.W, sx = (u32)g.sx, sy = (u32)g.sy;
+  const u32 z = row / sy, y = row - z * sy;
+  const u32 row2w = ((z >> 1) * (u32)g2.sy + (y >> 1)) * (u32)g2.W;
+  const u32 wl = (chunk << 5) + lane;
+  {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (wl < W) {
+      v.x = __ldg(M + 4 * ((size_t)row * W + wl));
+      const u32 j2 = row2w + (wl >> 1);
+      const uint2 fx2 = __ldg(reinterpret_cast<const uint2*>(M2) + 2 * (size_t)j2);
+      v.y = fx2.x & ~fx2.y;
+      v.z = __ldg(M2 + g2.offRS + j2) - 1u;
     }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const u32 i = base + 32u * k;
-      if (i < n) L[i] = pw[k] + __popc(gw[k] & ((1u << (m[k] & 31)) - 1u)) + 1u;
+    s_words[warp][lane] = v;
+  }
+  __syncwarp();
+  const u32 nwd = min(32u, W - (chunk << 5));
+  const u32 bit = 1u << lane;
+  const u32 below0 = CC_FULL >> (31 - (lane >> 1)), below1 = CC_FULL >> (15 - (lane >> 1));   // block bit of the lane in an even / odd voxel word
+  u32 x = (chunk << 10) + lane;
+  OUT* __restrict__ o = out + ((size_t)rrel * sx + x);
+  auto label_of = [&](const uint4 wv, u32 j) -> OUT {
+    OUT v = 0;
+    if (wv.x & bit) {
+      const u32 lab = LB[wv.z + __popc(wv.y & ((j & 1u) ? below1 : below0))];
+      if (REMAP == 1) v = (OUT)__ldg(reinterpret_cast<const u32*>(remap) + lab);
+      else if (REMAP == 2) v = (OUT)__ldg(reinterpret_cast<const u64*>(remap) + lab);
+      else v = (OUT)lab;
     }
+    return v;
+  };
+  const u32 nfull = (x - lane + (nwd << 5) <= sx) ? nwd : nwd - 1;   // words that lie fully inside the row
+#pragma unroll 4
+  for (u32 j = 0; j < nfull; j++) o[j << 5] = label_of(s_words[warp][j], j);
+  if (nfull < nwd) {
+    const OUT v = label_of(s_words[warp][nfull], nfull);
+    if (x + (nfull << 5) < sx) o[nfull << 5] = v;
+  }
+}
+
+// The voxel-level run labels of a block-path session, on demand: L[run] = label of the block run that holds the run's
+// first voxel. One thread per voxel bitmap word; the 16 blocks under it lie in one block word.
+static __global__ void __launch_bounds__(256)
+k_block_fill_L(const u32* __restrict__ M, Geom g, const u32* __restrict__ M2, Geom g2, const u32* __restrict__ LB,
+               u32* __restrict__ L) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (u32)g.nwords) return;
+  const uint2 fx = __ldg(reinterpret_cast<const uint2*>(M) + 2 * (size_t)i);
+  u32 starts = fx.x & ~fx.y;
+  if (!starts) return;
+  u32 id = __ldg(M + g.offRS + i);
+  const u32 W = (u32)g.W;
+  const u32 row = i / W, w = i - row * W;
+  const u32 z = row / (u32)g.sy, y = row - z * (u32)g.sy;
+  const u32 j2 = ((z >> 1) * (u32)g2.sy + (y >> 1)) * (u32)g2.W + (w >> 1);
+  const uint2 fx2 = __ldg(reinterpret_cast<const uint2*>(M2) + 2 * (size_t)j2);
+  const u32 cS = fx2.x & ~fx2.y, cR = __ldg(M2 + g2.offRS + j2) - 1u;
+  const u32 half = (w & 1u) << 4;
+  while (starts) {
+    const int b = __ffs(starts) - 1; starts &= starts - 1;
+    L[id++] = __ldg(LB + (cR + __popc(cS & (CC_FULL >> (31 - (half + (b >> 1)))))));
   }
 }

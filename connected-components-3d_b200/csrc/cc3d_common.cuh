@@ -179,6 +179,11 @@ template <typename T, int MODE> struct Edge {
   }
 };
 
+// Byte-parallel helpers (four 1-byte voxels / blocks per 32-bit word): bit 7 of every byte that is non-zero, and the
+// gather of those four flags into a nibble (one multiply: the partial products land on distinct bits).
+__device__ __forceinline__ u32 cc_nz_flags4(u32 v) { return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u; }
+__device__ __forceinline__ u32 cc_nz_nibble4(u32 v) { return (cc_nz_flags4(v) * 0x00204081u) >> 28; }
+
 // Lock-free union with link-to-smaller: the root of every set is its minimum index, which is what
 // makes the final scan reproduce first-appearance numbering. `A` is shared or global memory.
 __device__ __forceinline__ u32 uf_find(volatile u32* A, u32 i) {

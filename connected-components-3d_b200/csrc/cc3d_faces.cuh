@@ -743,7 +743,6 @@ k_faces_tma2(const __grid_constant__ CUtensorMap tmap, u32* __restrict__ M, Geom
 // ~4 warp instructions per bitmap word instead of 18. The compact F bitmap (1/8 byte per voxel) lives in the not yet
 // used forest array L.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 cc_nz_flags4(u32 v) { return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u; }
 
 static __global__ void __launch_bounds__(256)
 k_fg_bitmap_u8(const uint8_t* __restrict__ in, u32* __restrict__ Fb, Geom g, Counters* __restrict__ ctr, int vec_ok) {

@@ -216,6 +216,22 @@ def test_binary_one_byte_kernel_a(cc3d, oracle_mod):
   assert checked > 120
 
 
+def test_binary26_block_path_consumers(cc3d, oracle_mod):
+  """Block-path sessions (binary 26-connected) keep their labels on the block runs; the consumers of the voxel-level run
+  table (fused dust: component sizes from the run table, masked expansion) fill the run labels in on demand."""
+  truth = oracle_mod.reference_package() or oracle_mod
+  rng = np.random.default_rng(2627)
+  for it in range(12):
+    shape = tuple(int(rng.integers(3, 90)) for _ in range(3))
+    p = float(rng.choice([0.05, 0.15, 0.3, 0.5]))
+    img = np.asarray((rng.integers(1, 200, shape) * (rng.random(shape) < p)).astype([np.uint8, np.uint16, np.uint32][it % 3]),
+                     order="F" if it % 2 else "C")
+    for thr, inv in ((3, False), (6, True), ((2, 40), False)):
+      a, Na = truth.dust(img, thr, connectivity=26, binary_image=True, invert=inv, return_N=True)
+      b, Nb = cc3d.dust(img, thr, connectivity=26, binary_image=True, invert=inv, return_N=True)
+      assert Na == Nb and a.dtype == b.dtype and np.array_equal(a, b), (shape, p, thr, inv)
+
+
 def test_c_oracle_agrees_too(cc3d, oracle_mod):
   assert _fuzz(cc3d, oracle_mod, seed=303, ncase=200, maxdim=40) > 150
 
