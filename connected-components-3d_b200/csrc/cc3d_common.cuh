@@ -100,6 +100,9 @@ struct Geom {
 #ifndef CC_B1_MINB
 #define CC_B1_MINB 6
 #endif
+#ifndef CC_BLOCK_MINB
+#define CC_BLOCK_MINB 0      // resident CTAs per SM asked of k_union_tile on block grids (0: whatever 48 registers allow)
+#endif
 #ifndef CC_B1W_MINB
 #define CC_B1W_MINB 6
 #endif

@@ -308,7 +308,7 @@ template <int MODE> struct TileQueues {
   static constexpr u32 SMEM_WORDS = CC_TILE_NODES / 2 + CC_TILE_LQ + 2 * GQ + CC_TILE_WORDS + CC_TILE_WORDS / 2;
 };
 template <typename T, int MODE, int CONN>
-__global__ void __launch_bounds__(CC_TILE_THREADS, MODE == MODE_EQ ? CC_TILE_MINB(6) : 0)
+__global__ void __launch_bounds__(CC_TILE_THREADS, MODE == MODE_EQ ? CC_TILE_MINB(6) : (MODE == MODE_BLOCK ? CC_TILE_MINB(CC_BLOCK_MINB) : 0))
 k_union_tile(const T* __restrict__ in, const u32* __restrict__ M, u32* __restrict__ L, Geom g, Edge<T, MODE> E,
              u32 ntx, u32 nty, EdgeQueue GQ) {
   CC_PDL_WAIT();

@@ -11,7 +11,8 @@ def blobs(shape, nvals, scale):
         coarse = np.repeat(coarse, scale, ax)
     return coarse[tuple(slice(0, s) for s in shape)]
 vols = [blobs((40, 50, 256), 5, 6).astype(np.uint32), (rng.random((33, 47, 130)) < 0.5).astype(np.uint8),
-        blobs((20, 30, 97), 4, 3).astype(np.uint64), blobs((300, 384), 4, 7).astype(np.uint16)]
+        blobs((20, 30, 97), 4, 3).astype(np.uint64), blobs((300, 384), 4, 7).astype(np.uint16),
+        ((rng.random((21, 30, 96)) < 0.4) * rng.integers(1, 200, (21, 30, 96))).astype(np.uint8)]   # 1-byte binary kernel A, 16-byte rows
 for v in vols:
     conns = (6, 18, 26) if v.ndim == 3 else (4, 8)
     for c in conns:
@@ -24,6 +25,7 @@ for v in vols:
     lab = cc3d_b200.connected_components(v, connectivity=conns[-1])
     cc3d_b200.statistics(lab)
     cc3d_b200.dust(v, threshold=20, connectivity=conns[-1])
+    cc3d_b200.dust(v, threshold=5, connectivity=conns[-1], binary_image=True)     # block-path session: run labels on demand
     cc3d_b200.largest_k(v, 3, connectivity=conns[-1])
     g = cc3d_b200.voxel_connectivity_graph(v, connectivity=conns[-1])
     cc3d_b200.color_connectivity_graph(g, connectivity=conns[-1])
